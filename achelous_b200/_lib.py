@@ -1,0 +1,105 @@
+"""ctypes binding of libachelous_b200.so (include/achelous_b200.h).
+
+This is the stub a maintainer of the reference would add to call the sm_100a kernels
+(INTEGRATION.md).  There is NO fallback: if the library is missing or a call fails this
+module raises - the product path never silently computes on the CPU or through ATen.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libachelous_b200.so")
+
+c_float_p = C.c_void_p  # device pointers travel as integers
+LL = C.c_longlong
+I = C.c_int
+F = C.c_float
+VP = C.c_void_p
+
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+
+
+class AchPwConv(C.Structure):
+    _fields_ = [("x0", VP), ("x1", VP), ("wt", VP), ("scale", VP), ("bias", VP), ("pbias", VP), ("res", VP),
+                ("gamma", VP), ("out", VP),
+                ("x0_bs", LL), ("x1_bs", LL), ("wt_bs", LL), ("res_bs", LL), ("out_bs", LL),
+                ("c0", I), ("c1", I), ("ldw", I), ("B", I), ("O", I), ("P", I),
+                ("ln", I), ("ln_eps", F), ("act", I), ("reduce_max", I)]
+
+
+class AchDwConv(C.Structure):
+    _fields_ = [("x", VP), ("xadd", VP), ("w", VP), ("scale", VP), ("bias", VP), ("post", VP), ("out", VP),
+                ("x_bs", LL), ("xadd_bs", LL), ("out_bs", LL),
+                ("B", I), ("C", I), ("H", I), ("W", I), ("Ho", I), ("Wo", I), ("k", I), ("stride", I), ("act", I)]
+
+
+class AchConvDense(C.Structure):
+    _fields_ = [("x", VP), ("w", VP), ("scale", VP), ("bias", VP), ("ln_w", VP), ("ln_b", VP), ("out", VP),
+                ("x_bs", LL), ("out_bs", LL),
+                ("B", I), ("Cin", I), ("H", I), ("W", I), ("O", I), ("ldo", I), ("Ho", I), ("Wo", I), ("k", I),
+                ("stride", I), ("pad", I), ("act", I), ("ln_out", I), ("ln_eps", F)]
+
+
+class AchRcDeform(C.Structure):
+    _fields_ = [("x", VP), ("pooled", VP), ("w_om", VP), ("b_om", VP), ("w_reg", VP), ("w1", VP), ("scale", VP),
+                ("bias", VP), ("out", VP), ("x_bs", LL), ("pooled_bs", LL), ("out_bs", LL),
+                ("B", I), ("C", I), ("H", I), ("W", I)]
+
+
+_SIGNATURES = {
+    "ach_version": ([], I),
+    "ach_pw_conv": ([C.POINTER(AchPwConv), VP], I),
+    "ach_dw_conv": ([C.POINTER(AchDwConv), VP], I),
+    "ach_conv_dense": ([C.POINTER(AchConvDense), VP], I),
+    "ach_layernorm_cf": ([VP, LL, VP, VP, VP, LL, I, I, I, F, VP], I),
+    "ach_upsample2x": ([VP, LL, VP, LL, I, I, I, I, VP], I),
+    "ach_spp_maxpool": ([VP, LL, VP, VP, VP, LL, I, I, I, I, VP], I),
+    "ach_shuffle_attention": ([VP, LL, VP, LL, VP, VP, VP, VP, VP, VP, I, I, I, I, F, VP], I),
+    "ach_plane_mean": ([VP, LL, VP, LL, VP, I, I, I, VP], I),
+    "ach_eca_fuse": ([VP, LL, VP, LL, VP, VP, I, VP, VP, VP, LL, I, I, I, VP], I),
+    "ach_avgpool3": ([VP, LL, VP, LL, I, I, I, I, VP], I),
+    "ach_rc_deform": ([C.POINTER(AchRcDeform), VP], I),
+    "ach_xca_fold": ([VP, LL, VP, VP, I, VP, LL, I, I, I, I, VP], I),
+    "ach_fc": ([VP, LL, VP, VP, VP, VP, LL, I, I, I, I, VP], I),
+    "ach_logsoftmax_t": ([VP, LL, VP, LL, I, I, I, VP], I),
+    "ach_copy_add": ([VP, LL, VP, VP, LL, I, I, I, VP], I),
+    "ach_add": ([VP, LL, VP, LL, VP, LL, I, I, I, VP], I),
+    "ach_fill": ([VP, LL, F, VP], I),
+    "ach_decode_outputs": ([C.POINTER(VP), C.POINTER(LL), C.POINTER(I), C.POINTER(I), I, VP, I, I, F, F, VP], I),
+    "ach_nms_workspace_bytes": ([I, I], LL),
+    "ach_nms": ([VP, I, I, I, F, F, VP, VP, VP, VP, LL, VP], I),
+}
+
+EXPORTED_SYMBOLS = ["ach_last_error"] + list(_SIGNATURES)
+
+_lib = None
+
+
+class AchelousKernelError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise AchelousKernelError(
+            f"{LIB_PATH} not found: build it with `python -m achelous_b200.build` "
+            "(achelous_b200 has no CPU / ATen fallback by design)")
+    lib = C.CDLL(LIB_PATH)
+    lib.ach_last_error.argtypes = []
+    lib.ach_last_error.restype = C.c_char_p
+    for name, (argtypes, restype) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().ach_last_error().decode(errors="replace")
+        raise AchelousKernelError(f"{what or 'achelous_b200 kernel'} failed (status {status}): {msg}")

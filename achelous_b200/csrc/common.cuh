@@ -1,0 +1,75 @@
+// Shared device/host helpers for the achelous_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+#include "../../include/achelous_b200.h"
+
+namespace ach {
+
+// ---- error plumbing: the C ABI never throws; it returns a status and keeps a thread-local message
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define ACH_REQUIRE(cond, ...)                  \
+    do {                                        \
+        if (!(cond)) {                          \
+            ::ach::set_error(__VA_ARGS__);      \
+            return ACH_ERR_INVALID;             \
+        }                                       \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- activations (exact forms used by the reference; no fast-math)
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GELU = 3, ACT_SIGMOID = 4 };
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.0f);
+        case ACT_SILU: return v * sigmoidf_(v);
+        case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        case ACT_SIGMOID: return sigmoidf_(v);
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide sum for blockDim.x == 256 (8 warps); `red` is >= 8 floats of shared memory
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+// float atomic max that is correct for any sign (memory must be initialised, e.g. to -inf)
+__device__ __forceinline__ void atomic_max_float(float* addr, float val) {
+    if (val >= 0.f)
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(val));
+    else
+        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(val));
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace ach

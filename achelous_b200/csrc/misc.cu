@@ -1,0 +1,367 @@
+// Small HBM-bound kernels of the neck / fusion / PointNet path plus the error plumbing of the C ABI.
+// All are single-pass, coalesced along the contiguous pixel axis; reductions use warp shuffles.
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace ach {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+        return ACH_ERR_CUDA;
+    }
+    return ACH_OK;
+}
+
+// ------------------------------------------------------------------ channels-first LayerNorm
+__global__ void __launch_bounds__(256) layernorm_cf_kernel(const float* __restrict__ x, long long x_bs,
+                                                           const float* __restrict__ w, const float* __restrict__ bb,
+                                                           float* __restrict__ out, long long out_bs, int C, int P, float eps) {
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= P) return;
+    const float* xb = x + (long long)blockIdx.y * x_bs + p;
+    float* ob = out + (long long)blockIdx.y * out_bs + p;
+    float mean = 0.f;
+    for (int c = 0; c < C; ++c) mean += xb[(long long)c * P];
+    mean /= (float)C;
+    float var = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float d = xb[(long long)c * P] - mean;
+        var = fmaf(d, d, var);
+    }
+    const float rstd = 1.0f / sqrtf(var / (float)C + eps);
+    for (int c = 0; c < C; ++c) ob[(long long)c * P] = w[c] * ((xb[(long long)c * P] - mean) * rstd) + bb[c];
+}
+
+// ------------------------------------------------------------------ bilinear x2, align_corners=True
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                         long long out_bs, int C, int H, int W) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    const long long n = (long long)C * Ho * Wo;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int ox = (int)(i % Wo);
+    const int oy = (int)((i / Wo) % Ho);
+    const int c = (int)(i / ((long long)Wo * Ho));
+    // ATen upsample_bilinear2d, align_corners: src = dst * (in - 1) / (out - 1)
+    const float sy = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+    const float sx = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+    const float fy = sy * (float)oy, fx = sx * (float)ox;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* xp = x + (long long)blockIdx.y * x_bs + (long long)c * H * W;
+    const float v = hy * (hx * xp[y0 * W + x0] + lx * xp[y0 * W + x1]) + ly * (hx * xp[y1 * W + x0] + lx * xp[y1 * W + x1]);
+    out[(long long)blockIdx.y * out_bs + i] = v;
+}
+
+// ------------------------------------------------------------------ SPP max pools 5 / 9 / 13
+__global__ void __launch_bounds__(256) spp_maxpool_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ o5,
+                                                          float* __restrict__ o9, float* __restrict__ o13, long long out_bs,
+                                                          int C, int H, int W) {
+    extern __shared__ float plane[];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int P = H * W;
+    const float* xp = x + (long long)b * x_bs + (long long)c * P;
+    for (int i = threadIdx.x; i < P; i += 256) plane[i] = xp[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += 256) {
+        const int y = i / W, xx = i - y * W;
+        float m5 = -INFINITY, m9 = -INFINITY, m13 = -INFINITY;
+        for (int dy = -6; dy <= 6; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = -6; dx <= 6; ++dx) {
+                const int xc = xx + dx;
+                if (xc < 0 || xc >= W) continue;
+                const float v = plane[yy * W + xc];
+                m13 = fmaxf(m13, v);
+                if (dy >= -4 && dy <= 4 && dx >= -4 && dx <= 4) m9 = fmaxf(m9, v);
+                if (dy >= -2 && dy <= 2 && dx >= -2 && dx <= 2) m5 = fmaxf(m5, v);
+            }
+        }
+        const long long off = (long long)b * out_bs + (long long)c * P + i;
+        o5[off] = m5;
+        o9[off] = m9;
+        o13[off] = m13;
+    }
+}
+
+// ------------------------------------------------------------------ ShuffleAttention
+// One CTA per (b, source channel).  Source channel ch = g * cg + j (cg = C / G); j < cg/2 -> channel
+// gate x * sigmoid(cweight * mean + cbias); else spatial gate x * sigmoid(sweight * GN(x) + sbias) with
+// one-channel groups.  Destination channel after channel_shuffle(., 2): (ch % (C/2)) * 2 + ch / (C/2).
+__global__ void __launch_bounds__(256) shuffle_attention_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                                long long out_bs, const float* __restrict__ cweight,
+                                                                const float* __restrict__ cbias, const float* __restrict__ sweight,
+                                                                const float* __restrict__ sbias, const float* __restrict__ gn_w,
+                                                                const float* __restrict__ gn_b, int C, int P, int G, float eps) {
+    __shared__ float red[8];
+    const int ch = blockIdx.x, b = blockIdx.y;
+    const int cg = C / G, half = cg / 2;
+    const int j = ch % cg;
+    const float* xp = x + (long long)b * x_bs + (long long)ch * P;
+    const int dst = (ch % (C / 2)) * 2 + ch / (C / 2);
+    float* op = out + (long long)b * out_bs + (long long)dst * P;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < P; i += 256) s += xp[i];
+    const float mean = block_sum_256(s, red) / (float)P;
+    if (j < half) {
+        const float gate = sigmoidf_(fmaf(cweight[j], mean, cbias[j]));
+        for (int i = threadIdx.x; i < P; i += 256) op[i] = xp[i] * gate;
+    } else {
+        const int q = j - half;
+        float v = 0.f;
+        for (int i = threadIdx.x; i < P; i += 256) {
+            const float d = xp[i] - mean;
+            v = fmaf(d, d, v);
+        }
+        const float rstd = 1.0f / sqrtf(block_sum_256(v, red) / (float)P + eps);
+        const float gw = gn_w[q], gb = gn_b[q], sw = sweight[q], sb = sbias[q];
+        for (int i = threadIdx.x; i < P; i += 256) {
+            const float xv = xp[i];
+            const float n = fmaf((xv - mean) * rstd, gw, gb);
+            op[i] = xv * sigmoidf_(fmaf(sw, n, sb));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ plane mean, ECA fuse
+__global__ void __launch_bounds__(256) plane_mean_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ x2,
+                                                         long long x2_bs, float* __restrict__ out, int C, int P) {
+    __shared__ float red[8];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const float* xp = x + (long long)b * x_bs + (long long)c * P;
+    const float* yp = x2 ? x2 + (long long)b * x2_bs + (long long)c * P : nullptr;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < P; i += 256) s += yp ? xp[i] + yp[i] : xp[i];
+    const float t = block_sum_256(s, red);
+    if (threadIdx.x == 0) out[(long long)b * C + c] = t / (float)P;
+}
+
+__global__ void __launch_bounds__(256) eca_fuse_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ x2,
+                                                       long long x2_bs, const float* __restrict__ mean, const float* __restrict__ w1d,
+                                                       int k1d, const float* __restrict__ scale, const float* __restrict__ bias,
+                                                       float* __restrict__ out, long long out_bs, int C, int P) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    float a = 0.f;
+    const int r = (k1d - 1) / 2;
+    for (int t = 0; t < k1d; ++t) {
+        const int cc = c + t - r;
+        if (cc >= 0 && cc < C) a = fmaf(w1d[t], mean[(long long)b * C + cc], a);
+    }
+    const float gate = sigmoidf_(a);
+    const float s = scale[c], bi = bias[c];
+    const float* xp = x + (long long)b * x_bs + (long long)c * P;
+    const float* yp = x2 ? x2 + (long long)b * x2_bs + (long long)c * P : nullptr;
+    float* op = out + (long long)b * out_bs + (long long)c * P;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < P; i += gridDim.x * 256) {
+        const float v = yp ? xp[i] + yp[i] : xp[i];
+        op[i] = fmaxf(fmaf(s, v * gate, bi), 0.f);
+    }
+}
+
+// ------------------------------------------------------------------ avgpool 3x3 (count_include_pad)
+__global__ void __launch_bounds__(256) avgpool3_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                       long long out_bs, int C, int H, int W) {
+    const long long n = (long long)C * H * W;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int xx = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const long long cbase = i - (long long)y * W - xx;
+    const float* xp = x + (long long)blockIdx.y * x_bs + cbase;
+    float s = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int xc = xx + dx;
+            if (xc < 0 || xc >= W) continue;
+            s += xp[yy * W + xc];
+        }
+    }
+    out[(long long)blockIdx.y * out_bs + i] = s / 9.0f;
+}
+
+// ------------------------------------------------------------------ fully connected on (B, K) rows
+__global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ w,
+                                                 const float* __restrict__ scale, const float* __restrict__ bias,
+                                                 float* __restrict__ out, long long out_bs, int K, int O, int act) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int o = blockIdx.x * 8 + warp;
+    const int b = blockIdx.y;
+    if (o >= O) return;
+    const float* xr = x + (long long)b * x_bs;
+    const float* wr = w + (long long)o * K;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(wr[k], xr[k], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float sc = scale ? scale[o] : 1.f;
+        const float bi = bias ? bias[o] : 0.f;
+        out[(long long)b * out_bs + o] = apply_act(fmaf(sc, s, bi), act);
+    }
+}
+
+// ------------------------------------------------------------------ log_softmax over K, transposed output
+__global__ void __launch_bounds__(256) logsoftmax_t_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                           long long out_bs, int K, int N) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    if (n >= N) return;
+    const float* xp = x + (long long)b * x_bs + n;
+    float v[32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < K) {
+            v[k] = xp[(long long)k * N];
+            m = fmaxf(m, v[k]);
+        }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < K) s += expf(v[k] - m);
+    const float lse = logf(s);
+    float* op = out + (long long)b * out_bs + (long long)n * K;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < K) op[k] = (v[k] - m) - lse;
+}
+
+// ------------------------------------------------------------------ copy (+ broadcast add), add, fill
+__global__ void __launch_bounds__(256) copy_add_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ post,
+                                                       float* __restrict__ out, long long out_bs, long long n) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float v = x[(long long)blockIdx.y * x_bs + i];
+    if (post) v += post[i];
+    out[(long long)blockIdx.y * out_bs + i] = v;
+}
+
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, long long a_bs, const float* __restrict__ b2,
+                                                  long long b_bs, float* __restrict__ out, long long out_bs, long long n) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    out[(long long)blockIdx.y * out_bs + i] = a[(long long)blockIdx.y * a_bs + i] + b2[(long long)blockIdx.y * b_bs + i];
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ x, long long n, float v) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) x[i] = v;
+}
+
+}  // namespace ach
+
+using namespace ach;
+
+extern "C" const char* ach_last_error(void) { return g_err; }
+extern "C" int ach_version(void) { return 100; }
+
+extern "C" int ach_layernorm_cf(const float* x, long long x_bs, const float* w, const float* b, float* out, long long out_bs,
+                                int B, int C, int P, float eps, void* stream) {
+    ACH_REQUIRE(x && w && b && out && B > 0 && C > 0 && P > 0 && B <= 65535, "ach_layernorm_cf: bad args");
+    layernorm_cf_kernel<<<dim3(cdiv(P, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, w, b, out, out_bs, C, P, eps);
+    return check_launch("ach_layernorm_cf");
+}
+
+extern "C" int ach_upsample2x(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
+                              void* stream) {
+    ACH_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "ach_upsample2x: bad args");
+    const long long n = (long long)C * 4 * H * W;
+    upsample2x_kernel<<<dim3(cdiv(n, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, C, H, W);
+    return check_launch("ach_upsample2x");
+}
+
+extern "C" int ach_spp_maxpool(const float* x, long long x_bs, float* out5, float* out9, float* out13, long long out_bs,
+                               int B, int C, int H, int W, void* stream) {
+    ACH_REQUIRE(x && out5 && out9 && out13 && B > 0 && C > 0 && B <= 65535, "ach_spp_maxpool: bad args");
+    ACH_REQUIRE((size_t)H * W * 4 <= 48 * 1024, "ach_spp_maxpool: plane %dx%d too large for the shared-memory path", H, W);
+    spp_maxpool_kernel<<<dim3(C, B), 256, (size_t)H * W * 4, (cudaStream_t)stream>>>(x, x_bs, out5, out9, out13, out_bs, C, H, W);
+    return check_launch("ach_spp_maxpool");
+}
+
+extern "C" int ach_shuffle_attention(const float* x, long long x_bs, float* out, long long out_bs, const float* cweight,
+                                     const float* cbias, const float* sweight, const float* sbias, const float* gn_w,
+                                     const float* gn_b, int B, int C, int P, int G, float eps, void* stream) {
+    ACH_REQUIRE(x && out && cweight && cbias && sweight && sbias && gn_w && gn_b, "ach_shuffle_attention: null arg");
+    ACH_REQUIRE(B > 0 && B <= 65535 && G > 0 && C % (2 * G) == 0, "ach_shuffle_attention: C=%d must be divisible by 2G=%d", C, 2 * G);
+    shuffle_attention_kernel<<<dim3(C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, cweight, cbias, sweight, sbias,
+                                                                          gn_w, gn_b, C, P, G, eps);
+    return check_launch("ach_shuffle_attention");
+}
+
+extern "C" int ach_plane_mean(const float* x, long long x_bs, const float* x2, long long x2_bs, float* out, int B, int C,
+                              int P, void* stream) {
+    ACH_REQUIRE(x && out && B > 0 && C > 0 && P > 0 && B <= 65535, "ach_plane_mean: bad args");
+    plane_mean_kernel<<<dim3(C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, x2, x2_bs, out, C, P);
+    return check_launch("ach_plane_mean");
+}
+
+extern "C" int ach_eca_fuse(const float* x, long long x_bs, const float* x2, long long x2_bs, const float* mean,
+                            const float* w1d, int k1d, const float* scale, const float* bias, float* out, long long out_bs,
+                            int B, int C, int P, void* stream) {
+    ACH_REQUIRE(x && mean && w1d && scale && bias && out && B > 0 && C > 0 && P > 0, "ach_eca_fuse: bad args");
+    ACH_REQUIRE(k1d % 2 == 1 && C <= 65535 && B <= 65535, "ach_eca_fuse: bad k/C/B");
+    eca_fuse_kernel<<<dim3(min(cdiv(P, 256), 64), C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, x2, x2_bs, mean, w1d, k1d, scale,
+                                                                                        bias, out, out_bs, C, P);
+    return check_launch("ach_eca_fuse");
+}
+
+extern "C" int ach_avgpool3(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
+                            void* stream) {
+    ACH_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "ach_avgpool3: bad args");
+    const long long n = (long long)C * H * W;
+    avgpool3_kernel<<<dim3(cdiv(n, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, C, H, W);
+    return check_launch("ach_avgpool3");
+}
+
+extern "C" int ach_fc(const float* x, long long x_bs, const float* w, const float* scale, const float* bias, float* out,
+                      long long out_bs, int B, int K, int O, int act, void* stream) {
+    ACH_REQUIRE(x && w && out && B > 0 && K > 0 && O > 0 && B <= 65535, "ach_fc: bad args");
+    fc_kernel<<<dim3(cdiv(O, 8), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, w, scale, bias, out, out_bs, K, O, act);
+    return check_launch("ach_fc");
+}
+
+extern "C" int ach_logsoftmax_t(const float* x, long long x_bs, float* out, long long out_bs, int B, int K, int N, void* stream) {
+    ACH_REQUIRE(x && out && B > 0 && K > 0 && K <= 32 && N > 0 && B <= 65535, "ach_logsoftmax_t: bad args (K=%d must be <= 32)", K);
+    logsoftmax_t_kernel<<<dim3(cdiv(N, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, K, N);
+    return check_launch("ach_logsoftmax_t");
+}
+
+extern "C" int ach_copy_add(const float* x, long long x_bs, const float* post, float* out, long long out_bs, int B, int C,
+                            int P, void* stream) {
+    ACH_REQUIRE(x && out && B > 0 && C > 0 && P > 0 && B <= 65535, "ach_copy_add: bad args");
+    const long long n = (long long)C * P;
+    copy_add_kernel<<<dim3(cdiv(n, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, post, out, out_bs, n);
+    return check_launch("ach_copy_add");
+}
+
+extern "C" int ach_add(const float* a, long long a_bs, const float* b2, long long b_bs, float* out, long long out_bs, int B,
+                       int C, int P, void* stream) {
+    ACH_REQUIRE(a && b2 && out && B > 0 && C > 0 && P > 0 && B <= 65535, "ach_add: bad args");
+    const long long n = (long long)C * P;
+    add_kernel<<<dim3(cdiv(n, 256), B), 256, 0, (cudaStream_t)stream>>>(a, a_bs, b2, b_bs, out, out_bs, n);
+    return check_launch("ach_add");
+}
+
+extern "C" int ach_fill(float* x, long long n, float value, void* stream) {
+    ACH_REQUIRE(x && n > 0, "ach_fill: bad args");
+    fill_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, value);
+    return check_launch("ach_fill");
+}

@@ -1,0 +1,256 @@
+// Detection post-process on device: YOLOX box decode (utils/utils_bbox.py:33-85) and class-aware
+// greedy NMS (utils/utils_bbox.py:87-130 -> torchvision batched_nms, coordinate-trick branch).
+//
+// ach_nms runs one CTA per image and is a single launch for the whole batch - the reference loops over
+// images in Python and calls torchvision per image.  Inside the CTA:
+//   A. class max / first-argmax, score = obj * cls, threshold, ORDER-PRESERVING compaction (ballot scan)
+//   B. max coordinate over the candidates -> per-class box shift (the "coordinate trick")
+//   C. stable descending rank by counting (ties -> lower candidate index first, = torch stable sort)
+//   D. greedy sweep in rank order; every surviving box suppresses in parallel, one barrier per KEPT box
+//   E. order-preserving compaction of the survivors into (x1,y1,x2,y2,obj,cls_conf,cls) rows.
+// IoU arithmetic uses explicit round-to-nearest intrinsics (no FMA contraction) so kept indices are
+// bit-identical to the fp32 CPU oracle.
+#include "common.cuh"
+
+namespace ach {
+
+struct DecodeLevels {
+    const float* ptr[4];
+    long long bs[4];
+    int h[4], w[4], a0[4];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) decode_kernel(DecodeLevels L, float* __restrict__ out, int A, int CH, float input_h,
+                                                     float input_w) {
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
+    if (a >= A) return;
+    int l = 0;
+    while (l + 1 < L.n && a >= L.a0[l + 1]) ++l;
+    const int cell = a - L.a0[l];
+    const int h = L.h[l], w = L.w[l];
+    const int gy = cell / w, gx = cell - gy * w;
+    const long long plane = (long long)h * w;
+    const float* src = L.ptr[l] + (long long)b * L.bs[l] + cell;
+    float* dst = out + ((long long)b * A + a) * CH;
+    const float stride = input_h / (float)h;  // Python float input_shape[0] / h, then cast to fp32
+    // xy = (v + grid) * stride ; wh = exp(v) * stride ; then / input size.  No FMA contraction possible here.
+    dst[0] = __fdiv_rn(__fmul_rn(__fadd_rn(src[0], (float)gx), stride), input_w);
+    dst[1] = __fdiv_rn(__fmul_rn(__fadd_rn(src[plane], (float)gy), stride), input_h);
+    dst[2] = __fdiv_rn(__fmul_rn(expf(src[2 * plane]), stride), input_w);
+    dst[3] = __fdiv_rn(__fmul_rn(expf(src[3 * plane]), stride), input_h);
+    for (int c = 4; c < CH; ++c) dst[c] = sigmoidf_(src[(long long)c * plane]);
+}
+
+constexpr int NMS_T = 512;
+constexpr int NMS_MAX_A = 16384;  // shared `removed` bytes
+
+// exclusive block scan of a 0/1 flag (ballot based); returns position, adds the block total to *running
+__device__ __forceinline__ int block_scan_flag(bool flag, int* warp_tot, int* running) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    const int pre = __popc(m & ((1u << lane) - 1u));
+    __syncthreads();  // previous use of warp_tot / running is complete
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int base = *running;
+    for (int i = 0; i < warp; ++i) base += warp_tot[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < NMS_T / 32; ++i) t += warp_tot[i];
+        *running += t;
+    }
+    return base + pre;
+}
+
+__global__ void __launch_bounds__(NMS_T) nms_kernel(const float* __restrict__ decoded, int A, int K, float conf_thres,
+                                                    float nms_thres, float* __restrict__ kept, int* __restrict__ kept_idx,
+                                                    int* __restrict__ counts, char* __restrict__ workspace, long long ws_per_img) {
+    extern __shared__ unsigned char removed[];  // [A]
+    __shared__ int warp_tot[NMS_T / 32];
+    __shared__ int running;
+    __shared__ float red[NMS_T / 32];
+    __shared__ float s_maxc;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int CH = 5 + K;
+    const float* pred = decoded + (long long)b * A * CH;
+    char* ws = workspace + (long long)b * ws_per_img;
+    const int Ap = (A + 3) & ~3;
+    float4* c_box = reinterpret_cast<float4*>(ws);            // [Ap] unshifted boxes, candidate (anchor) order
+    float4* s_box = c_box + Ap;                               // [Ap] class-shifted boxes, rank order
+    float* c_score = reinterpret_cast<float*>(s_box + Ap);    // [Ap] candidate scores
+    float* s_area = c_score + Ap;                             // [Ap] areas, rank order
+    int* c_anchor = reinterpret_cast<int*>(s_area + Ap);      // [Ap]
+    int* c_cls = c_anchor + Ap;                               // [Ap]
+    int* order = c_cls + Ap;                                  // [Ap] rank -> candidate slot
+
+    if (tid == 0) running = 0;
+    __syncthreads();
+
+    // ---- A. candidates
+    float local_max = -INFINITY;
+    for (int a0 = 0; a0 < A; a0 += NMS_T) {
+        const int a = a0 + tid;
+        bool flag = false;
+        float score = 0.f;
+        int cls = 0;
+        float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
+        if (a < A) {
+            const float* r = pred + (long long)a * CH;
+            float conf = r[5];
+            for (int c = 1; c < K; ++c) {
+                const float v = r[5 + c];
+                if (v > conf) {
+                    conf = v;
+                    cls = c;
+                }
+            }
+            score = __fmul_rn(r[4], conf);
+            flag = score >= conf_thres;
+            if (flag) {
+                const float hw = __fmul_rn(r[2], 0.5f), hh = __fmul_rn(r[3], 0.5f);
+                x1 = __fsub_rn(r[0], hw);
+                y1 = __fsub_rn(r[1], hh);
+                x2 = __fadd_rn(r[0], hw);
+                y2 = __fadd_rn(r[1], hh);
+                local_max = fmaxf(local_max, fmaxf(fmaxf(x1, y1), fmaxf(x2, y2)));
+            }
+        }
+        const int pos = block_scan_flag(flag, warp_tot, &running);
+        if (flag) {
+            c_score[pos] = score;
+            c_anchor[pos] = a;
+            c_cls[pos] = cls;
+            c_box[pos] = make_float4(x1, y1, x2, y2);
+        }
+    }
+    __syncthreads();
+    const int n = running;
+    local_max = warp_max(local_max);
+    if ((tid & 31) == 0) red[tid >> 5] = local_max;
+    __syncthreads();
+    if (tid == 0) {
+        float m = -INFINITY;
+        for (int i = 0; i < NMS_T / 32; ++i) m = fmaxf(m, red[i]);
+        s_maxc = m;
+    }
+    __syncthreads();
+    if (n == 0) {
+        if (tid == 0) counts[b] = 0;
+        return;
+    }
+    const float shift = __fadd_rn(s_maxc, 1.0f);
+
+    // ---- C. stable descending rank
+    for (int s = tid; s < n; s += NMS_T) {
+        const float sc = c_score[s];
+        int rank = 0;
+        for (int t = 0; t < n; ++t) {
+            const float st = c_score[t];
+            rank += (st > sc) || (st == sc && t < s);
+        }
+        order[rank] = s;
+    }
+    __syncthreads();
+    // ---- B. class-shifted boxes + areas in rank order
+    for (int r = tid; r < n; r += NMS_T) {
+        const int s = order[r];
+        const float off = __fmul_rn((float)c_cls[s], shift);
+        const float4 u = c_box[s];
+        const float4 v = make_float4(__fadd_rn(u.x, off), __fadd_rn(u.y, off), __fadd_rn(u.z, off), __fadd_rn(u.w, off));
+        s_box[r] = v;
+        s_area[r] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
+        removed[r] = 0;
+    }
+    __syncthreads();
+
+    // ---- D. greedy sweep
+    for (int i = 0; i < n; ++i) {
+        if (removed[i]) continue;  // uniform: shared memory, written before the last barrier
+        const float4 bi = s_box[i];
+        const float ai = s_area[i];
+        for (int j = i + 1 + tid; j < n; j += NMS_T) {
+            if (removed[j]) continue;
+            const float4 bj = s_box[j];
+            const float w = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
+            const float h = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
+            const float inter = __fmul_rn(w, h);
+            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, s_area[j]), inter));
+            if (iou > nms_thres) removed[j] = 1;
+        }
+        __syncthreads();
+    }
+
+    // ---- E. survivors, rank order
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < n; r0 += NMS_T) {
+        const int r = r0 + tid;
+        const bool flag = (r < n) && !removed[r];
+        const int pos = block_scan_flag(flag, warp_tot, &running);
+        if (flag) {
+            const int s = order[r];
+            const int a = c_anchor[s];
+            const float* row = pred + (long long)a * CH;
+            const float hw = __fmul_rn(row[2], 0.5f), hh = __fmul_rn(row[3], 0.5f);
+            float* o = kept + ((long long)b * A + pos) * 7;
+            o[0] = __fsub_rn(row[0], hw);
+            o[1] = __fsub_rn(row[1], hh);
+            o[2] = __fadd_rn(row[0], hw);
+            o[3] = __fadd_rn(row[1], hh);
+            o[4] = row[4];
+            o[5] = row[5 + c_cls[s]];
+            o[6] = (float)c_cls[s];
+            kept_idx[(long long)b * A + pos] = a;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) counts[b] = running;
+}
+
+static long long nms_ws_per_img(int A) {
+    const long long Ap = (A + 3) & ~3LL;
+    return Ap * (16 + 16 + 4 + 4 + 4 + 4 + 4);
+}
+
+}  // namespace ach
+
+extern "C" int ach_decode_outputs(const float* const* levels, const long long* level_bs, const int* hs, const int* ws,
+                                  int n_levels, float* out, int B, int K, float input_h, float input_w, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(levels && level_bs && hs && ws && out, "ach_decode_outputs: null arg");
+    ACH_REQUIRE(n_levels >= 1 && n_levels <= 4 && B > 0 && B <= 65535 && K >= 1, "ach_decode_outputs: bad dims");
+    DecodeLevels L;
+    int A = 0;
+    for (int i = 0; i < n_levels; ++i) {
+        ACH_REQUIRE(levels[i] && hs[i] > 0 && ws[i] > 0, "ach_decode_outputs: bad level %d", i);
+        L.ptr[i] = levels[i];
+        L.bs[i] = level_bs[i];
+        L.h[i] = hs[i];
+        L.w[i] = ws[i];
+        L.a0[i] = A;
+        A += hs[i] * ws[i];
+    }
+    L.n = n_levels;
+    decode_kernel<<<dim3(cdiv(A, 256), B), 256, 0, (cudaStream_t)stream>>>(L, out, A, 5 + K, input_h, input_w);
+    return check_launch("ach_decode_outputs");
+}
+
+extern "C" long long ach_nms_workspace_bytes(int B, int A) { return (long long)B * ach::nms_ws_per_img(A); }
+
+extern "C" int ach_nms(const float* decoded, int B, int A, int K, float conf_thres, float nms_thres, float* kept,
+                       int* kept_idx, int* counts, void* workspace, long long workspace_bytes, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(decoded && kept && kept_idx && counts && workspace, "ach_nms: null arg");
+    ACH_REQUIRE(B > 0 && A > 0 && K >= 1, "ach_nms: bad dims");
+    ACH_REQUIRE(A <= NMS_MAX_A, "ach_nms: A=%d anchors per image exceeds the supported %d", A, NMS_MAX_A);
+    ACH_REQUIRE(workspace_bytes >= ach_nms_workspace_bytes(B, A), "ach_nms: workspace too small");
+    ACH_REQUIRE(aligned16(workspace), "ach_nms: workspace must be 16-byte aligned");
+    nms_kernel<<<B, NMS_T, (size_t)((A + 15) & ~15), (cudaStream_t)stream>>>(decoded, A, K, conf_thres, nms_thres, kept, kept_idx,
+                                                                           counts, static_cast<char*>(workspace), nms_ws_per_img(A));
+    return check_launch("ach_nms");
+}

@@ -1,0 +1,684 @@
+"""Execution engine: turns an :class:`achelous_b200.nets.Achelous.Achelous` parameter tree into
+(a) packed device weights (BN / LayerNorm folding, K-major GEMM layouts) and (b) a static launch
+plan of C-ABI kernel calls over pre-allocated HBM buffers, replayed per forward (optionally as one
+CUDA graph).  PyTorch is used only for device memory, streams and the weight folding arithmetic;
+every activation of the forward pass is produced by the sm_100a kernels in ``csrc/``.
+
+Data layout in HBM: fp32, channel-major planes exactly as torch NCHW / (B, C, N); a "view" is
+(pointer, batch stride), so channel slices and concatenations cost nothing.  All six outputs of a
+frame live in ONE packed buffer ``[det40 | det20 | det10 | se_seg | lane_seg | pc_seg]``
+(4 622 784 B / frame) so that the multi-GPU path is a single all-gather.
+"""
+import ctypes as C
+import math
+from collections import namedtuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConvDense, AchDwConv, AchPwConv, AchRcDeform
+from .nets import holders as Hd
+
+View = namedtuple("View", "ptr bs C H W")
+
+
+def _ceil4(n):
+    return (n + 3) // 4 * 4
+
+
+class Engine:
+    def __init__(self, model, batch, device, use_graph=True, dry_run=False):
+        """dry_run=True builds the plan and packs the weights without a GPU (host-logic tests only):
+        nothing can be launched from such an engine."""
+        self.lib = _lib.load()
+        self.model = model
+        self.B = int(batch)
+        self.device = torch.device(device)
+        self.dry_run = dry_run
+        if self.device.type != "cuda" and not dry_run:
+            raise _lib.AchelousKernelError("achelous_b200 runs on CUDA devices only (no CPU fallback)")
+        self.use_graph = use_graph
+        self.res = model.resolution
+        self.n_points = model.n_points
+        self.ops = []          # (cfunc, args) - stream appended at call time
+        self.op_names = []
+        self._keep = []        # ctypes structs / tensors that must outlive the plan
+        self._bufs = {}
+        self._weights = {}
+        self.graph = None
+        self._sig = None
+        if dry_run:
+            self._build()
+        else:
+            with torch.cuda.device(self.device):
+                self._build()
+
+    # ------------------------------------------------------------------ parameter access / packing
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self._params.values())
+
+    def _p(self, name):
+        return self._params[name].detach().to(torch.float64)
+
+    def _dev(self, t):
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _w(self, key, fn):
+        """Packed-weight slot: allocated once, refilled in place by repack()."""
+        val = fn()
+        val = val.to(device=self.device, dtype=torch.float32).contiguous()
+        if key in self._weights:
+            self._weights[key][0].copy_(val)
+        else:
+            self._weights[key] = (val, fn)
+        return self._weights[key][0]
+
+    def repack(self):
+        for key, (t, fn) in self._weights.items():
+            t.copy_(fn().to(device=self.device, dtype=torch.float32))
+        self._sig = self._signature()
+
+    def _bn_fold(self, prefix, eps, conv_bias=None):
+        """eval BatchNorm(conv + conv_bias) == scale * conv + bias"""
+        s = self._p(prefix + ".weight") / torch.sqrt(self._p(prefix + ".running_var") + eps)
+        b = self._p(prefix + ".bias") - self._p(prefix + ".running_mean") * s
+        if conv_bias is not None:
+            b = b + conv_bias * s
+        return s, b
+
+    @staticmethod
+    def _kmajor(w2d):
+        """(O, K) -> K-major (K, ceil4(O)) zero padded"""
+        O, K = w2d.shape
+        out = torch.zeros(K, _ceil4(O), dtype=w2d.dtype, device=w2d.device)
+        out[:, :O] = w2d.t()
+        return out
+
+    # ------------------------------------------------------------------ buffers / views
+    def buf(self, name, C_, H, W=1, fill=None):
+        t = torch.empty(self.B, C_, H, W, device=self.device, dtype=torch.float32)
+        if fill is not None:
+            t.fill_(fill)
+        assert name not in self._bufs, name
+        self._bufs[name] = t
+        return View(t.data_ptr(), t.stride(0), C_, H, W)
+
+    @staticmethod
+    def sl(v, c0, c1):
+        return View(v.ptr + c0 * v.H * v.W * 4, v.bs, c1 - c0, v.H, v.W)
+
+    def _ptr(self, t):
+        return None if t is None else t.data_ptr()
+
+    def _add(self, name, fn, *args):
+        self.ops.append((fn, args))
+        self.op_names.append(name)
+
+    # ------------------------------------------------------------------ op recorders
+    def pw(self, name, x0, out, wt, O, x1=None, scale=None, bias=None, pbias=None, res=None, gamma=None, ln=False,
+           ln_eps=1e-6, act=ACT_NONE, wt_bs=0, ldw=None, reduce_max=False, out_bs=None):
+        P = x0.H * x0.W
+        s = AchPwConv()
+        s.x0, s.x0_bs, s.c0 = x0.ptr, x0.bs, x0.C
+        s.x1, s.x1_bs, s.c1 = (x1.ptr, x1.bs, x1.C) if x1 is not None else (None, 0, 0)
+        if isinstance(wt, torch.Tensor):
+            s.ldw = wt.shape[-1] if ldw is None else ldw
+            s.wt = wt.data_ptr()
+        else:
+            s.wt, s.ldw = wt, ldw
+        s.wt_bs = wt_bs
+        s.scale, s.bias, s.pbias, s.gamma = self._ptr(scale), self._ptr(bias), self._ptr(pbias), self._ptr(gamma)
+        s.res, s.res_bs = (res.ptr, res.bs) if res is not None else (None, 0)
+        if reduce_max:
+            s.out, s.out_bs = out.data_ptr(), out.stride(0)
+        else:
+            assert out.C == O and out.H * out.W == P, (name, out, O, P)
+            s.out, s.out_bs = out.ptr, out.bs
+        s.B, s.O, s.P = self.B, O, P
+        s.ln, s.ln_eps, s.act, s.reduce_max = int(ln), ln_eps, act, int(reduce_max)
+        self._keep.append(s)
+        self._add(name, self.lib.ach_pw_conv, C.byref(s))
+
+    def dw(self, name, x, out, w, k, stride=1, scale=None, bias=None, act=ACT_NONE, xadd=None, post=None):
+        s = AchDwConv()
+        s.x, s.x_bs = x.ptr, x.bs
+        s.xadd, s.xadd_bs = (xadd.ptr, xadd.bs) if xadd is not None else (None, 0)
+        s.w, s.scale, s.bias, s.post = w.data_ptr(), self._ptr(scale), self._ptr(bias), post
+        s.out, s.out_bs = out.ptr, out.bs
+        s.B, s.C, s.H, s.W, s.Ho, s.Wo, s.k, s.stride, s.act = self.B, x.C, x.H, x.W, out.H, out.W, k, stride, act
+        assert out.C == x.C, (name, x, out)
+        self._keep.append(s)
+        self._add(name, self.lib.ach_dw_conv, C.byref(s))
+
+    def conv(self, name, x, out, w, k, stride, pad, scale=None, bias=None, act=ACT_NONE, ln_w=None, ln_b=None, ln_eps=1e-6):
+        s = AchConvDense()
+        s.x, s.x_bs, s.w = x.ptr, x.bs, w.data_ptr()
+        s.scale, s.bias, s.ln_w, s.ln_b = self._ptr(scale), self._ptr(bias), self._ptr(ln_w), self._ptr(ln_b)
+        s.out, s.out_bs = out.ptr, out.bs
+        s.B, s.Cin, s.H, s.W, s.O, s.ldo = self.B, x.C, x.H, x.W, out.C, w.shape[-1]
+        s.Ho, s.Wo, s.k, s.stride, s.pad, s.act = out.H, out.W, k, stride, pad, act
+        s.ln_out, s.ln_eps = int(ln_w is not None), ln_eps
+        self._keep.append(s)
+        self._add(name, self.lib.ach_conv_dense, C.byref(s))
+
+    def _pack_conv(self, key, wname):
+        """(O, Cin, k, k) -> [Cin][k*k][ceil4(O)]"""
+        def f():
+            w = self._p(wname)
+            O, Cin, kh, kw = w.shape
+            out = torch.zeros(Cin, kh * kw, _ceil4(O), dtype=w.dtype, device=w.device)
+            out[:, :, :O] = w.permute(1, 2, 3, 0).reshape(Cin, kh * kw, O)
+            return out
+        return self._w(key, f)
+
+    def _vec(self, key, fn):
+        return self._w(key, fn)
+
+    # ------------------------------------------------------------------ composite blocks
+    def pw_bn_act(self, name, prefix_conv, prefix_bn, eps, x0, out, act, x1=None, conv_bias=False, res=None, O=None):
+        """1x1 conv (+bias) + BN + act"""
+        wt = self._w(name + ".wt", lambda: self._kmajor(self._p(prefix_conv + ".weight").flatten(1)))
+        sc = self._vec(name + ".s", lambda: self._bn_fold(prefix_bn, eps, self._p(prefix_conv + ".bias") if conv_bias else None)[0])
+        bi = self._vec(name + ".b", lambda: self._bn_fold(prefix_bn, eps, self._p(prefix_conv + ".bias") if conv_bias else None)[1])
+        self.pw(name, x0, out, wt, out.C if O is None else O, x1=x1, scale=sc, bias=bi, act=act, res=res)
+
+    def pw_bias(self, name, prefix, x0, out, act=ACT_NONE):
+        wt = self._w(name + ".wt", lambda: self._kmajor(self._p(prefix + ".weight").flatten(1)))
+        bi = self._vec(name + ".b", lambda: self._p(prefix + ".bias"))
+        self.pw(name, x0, out, wt, out.C, bias=bi, act=act)
+
+    def dw_bn_act(self, name, prefix_conv, prefix_bn, eps, x, out, k, act, c0=0, c1=None, stride=1):
+        """depthwise conv (channel slice [c0, c1) of the parameter tensors) + BN + act"""
+        c1 = x.C + c0 if c1 is None else c1
+        w = self._w(name + ".w", lambda: self._p(prefix_conv + ".weight")[c0:c1].flatten(1))
+        sc = self._vec(name + ".s", lambda: self._bn_fold(prefix_bn, eps)[0][c0:c1])
+        bi = self._vec(name + ".b", lambda: self._bn_fold(prefix_bn, eps)[1][c0:c1])
+        self.dw(name, x, out, w, k, stride=stride, scale=sc, bias=bi, act=act)
+
+    def ghost(self, name, prefix, x0, out, relu, x1=None):
+        """GhostModule writing straight into `out` (oup = out.C channels)"""
+        oup = out.C
+        init = math.ceil(oup / 2)
+        act = ACT_RELU if relu else ACT_NONE
+        prim = self.sl(out, 0, init)
+        self.pw_bn_act(name + ".primary", prefix + ".primary_conv.0", prefix + ".primary_conv.1", 1e-5, x0, prim, act, x1=x1)
+        if oup > init:
+            src = self.sl(out, 0, oup - init)
+            self.dw_bn_act(name + ".cheap", prefix + ".cheap_operation.0", prefix + ".cheap_operation.1", 1e-5, src,
+                           self.sl(out, init, oup), 3, act, c0=0, c1=oup - init)
+
+    def upsample_block(self, name, prefix, x, out):
+        """Upsample: BaseConv 1x1 relu -> bilinear x2 into `out`"""
+        t = self.buf(name + ".pw", out.C, x.H, x.W)
+        self.pw_bn_act(name + ".conv", prefix + ".upsample.0.conv", prefix + ".upsample.0.bn", 1e-3, x, t, ACT_RELU)
+        self._add(name + ".up", self.lib.ach_upsample2x, t.ptr, t.bs, out.ptr, out.bs, self.B, t.C, t.H, t.W)
+
+    def ghost_bottleneck(self, name, prefix, xa, xb, mid, outc):
+        g1 = self.buf(name + ".g1", mid, xa.H, xa.W)
+        self.ghost(name + ".ghost1", prefix + ".ghost1", xa, g1, True, x1=xb)
+        g2 = self.buf(name + ".g2", outc, xa.H, xa.W)
+        self.ghost(name + ".ghost2", prefix + ".ghost2", g1, g2, False)
+        cin = xa.C + xb.C
+        sc = self.buf(name + ".sc", cin, xa.H, xa.W)
+        self.dw_bn_act(name + ".sc_dw_a", prefix + ".shortcut.0", prefix + ".shortcut.1", 1e-5, xa, self.sl(sc, 0, xa.C), 3,
+                       ACT_NONE, c0=0, c1=xa.C)
+        self.dw_bn_act(name + ".sc_dw_b", prefix + ".shortcut.0", prefix + ".shortcut.1", 1e-5, xb, self.sl(sc, xa.C, cin), 3,
+                       ACT_NONE, c0=xa.C, c1=cin)
+        out = self.buf(name + ".out", outc, xa.H, xa.W)
+        self.pw_bn_act(name + ".sc_pw", prefix + ".shortcut.2", prefix + ".shortcut.3", 1e-5, sc, out, ACT_NONE, res=g2)
+        return out
+
+    # ---- EdgeNeXt
+    def _ln_fold_linear(self, name, lin, ln):
+        """Linear(LayerNorm_affine(x)) == (W * ln_w) x_hat + (b + W ln_b)"""
+        wt = self._w(name + ".wt", lambda: self._kmajor(self._p(lin + ".weight") * self._p(ln + ".weight")[None, :]))
+        bi = self._vec(name + ".b", lambda: self._p(lin + ".bias") + self._p(lin + ".weight") @ self._p(ln + ".bias"))
+        return wt, bi
+
+    def mlp_res(self, name, prefix, x_ln_src, res, out):
+        """LN -> Linear(4C) -> GELU -> Linear(C) -> gamma -> + res   (conv_encoder.py:23-31, sdta_encoder.py:64-73)"""
+        Cc = x_ln_src.C
+        h = self.buf(name + ".h", 4 * Cc, x_ln_src.H, x_ln_src.W)
+        wt1, b1 = self._ln_fold_linear(name + ".pw1", prefix + ".pwconv1", prefix + ".norm")
+        self.pw(name + ".pw1", x_ln_src, h, wt1, 4 * Cc, bias=b1, ln=True, ln_eps=1e-6, act=ACT_GELU)
+        wt2 = self._w(name + ".pw2.wt", lambda: self._kmajor(self._p(prefix + ".pwconv2.weight")))
+        b2 = self._vec(name + ".pw2.b", lambda: self._p(prefix + ".pwconv2.bias"))
+        gm = self._vec(name + ".gamma", lambda: self._p(prefix + ".gamma"))
+        self.pw(name + ".pw2", h, out, wt2, Cc, bias=b2, res=res, gamma=gm)
+
+    def conv_encoder(self, name, prefix, x, k):
+        d = self.buf(name + ".dw", x.C, x.H, x.W)
+        w = self._w(name + ".dw.w", lambda: self._p(prefix + ".dwconv.weight").flatten(1))
+        b = self._vec(name + ".dw.b", lambda: self._p(prefix + ".dwconv.bias"))
+        self.dw(name + ".dw", x, d, w, k, bias=b)
+        out = self.buf(name + ".out", x.C, x.H, x.W)
+        self.mlp_res(name, prefix, d, x, out)
+        return out
+
+    def _fourier_pos(self, prefix, dim, H, W, hidden=32, temperature=10000.0):
+        """PositionalEncodingFourier features (layers.py:47-58) -> constant (64, H*W); the learned 1x1
+        token_projection is applied by the pw kernel at pack time."""
+        scale = 2 * math.pi
+        y = torch.arange(1, H + 1, dtype=torch.float32).view(H, 1).expand(H, W) / (float(H) + 1e-6) * scale
+        x = torch.arange(1, W + 1, dtype=torch.float32).view(1, W).expand(H, W) / (float(W) + 1e-6) * scale
+        dim_t = torch.arange(hidden, dtype=torch.float32)
+        dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / hidden)
+        px, py = x[:, :, None] / dim_t, y[:, :, None] / dim_t
+        px = torch.stack((px[:, :, 0::2].sin(), px[:, :, 1::2].cos()), dim=3).flatten(2)
+        py = torch.stack((py[:, :, 0::2].sin(), py[:, :, 1::2].cos()), dim=3).flatten(2)
+        return torch.cat((py, px), dim=2).permute(2, 0, 1).reshape(2 * hidden, H * W).contiguous()
+
+    def sdta(self, name, prefix, x, scales, heads, use_pos):
+        Cc, H, W = x.C, x.H, x.W
+        N = H * W
+        width = max(int(math.ceil(Cc / scales)), int(math.floor(Cc // scales)))
+        nums = 1 if scales == 1 else scales - 1
+        y = self.buf(name + ".y", Cc, H, W)
+        pos_ptr = None
+        if use_pos:
+            # pos = token_projection(fourier(H, W)) is input independent: evaluated by the pw kernel when
+            # weights are (re)packed, into a (C, N) constant that is added to every frame.
+            feat = self._dev(self._fourier_pos(prefix, Cc, H, W))
+            pos = torch.empty(1, Cc, H, W, device=self.device, dtype=torch.float32)
+            self._keep.append(pos)
+            wt = self._w(name + ".pos.wt", lambda: self._kmajor(self._p(prefix + ".pos_embd.token_projection.weight").flatten(1)))
+            bi = self._vec(name + ".pos.b", lambda: self._p(prefix + ".pos_embd.token_projection.bias"))
+            s = AchPwConv()
+            s.x0, s.x0_bs, s.c0, s.c1 = feat.data_ptr(), 0, feat.shape[0], 0
+            s.wt, s.ldw, s.bias = wt.data_ptr(), wt.shape[-1], bi.data_ptr()
+            s.out, s.out_bs, s.B, s.O, s.P = pos.data_ptr(), 0, 1, Cc, N
+            self._keep.append(s)
+            self.pack_ops.append((self.lib.ach_pw_conv, (C.byref(s),)))
+            pos_ptr = pos.data_ptr()
+        fuse_pos = use_pos and nums == 1
+        for i in range(nums):
+            w = self._w(f"{name}.convs{i}.w", (lambda i=i: self._p(f"{prefix}.convs.{i}.weight").flatten(1)))
+            b = self._vec(f"{name}.convs{i}.b", (lambda i=i: self._p(f"{prefix}.convs.{i}.bias")))
+            self.dw(f"{name}.convs{i}", self.sl(x, i * width, (i + 1) * width), self.sl(y, i * width, (i + 1) * width), w, 3, bias=b,
+                    xadd=self.sl(y, (i - 1) * width, i * width) if i > 0 else None,
+                    post=(pos_ptr + i * width * N * 4) if fuse_pos else None)
+        rest0 = nums * width
+        self._add(name + ".copy", self.lib.ach_copy_add, x.ptr + rest0 * N * 4, x.bs, (pos_ptr + rest0 * N * 4) if fuse_pos else None,
+                  y.ptr + rest0 * N * 4, y.bs, self.B, Cc - rest0, N)
+        if use_pos and not fuse_pos:
+            self._add(name + ".pos", self.lib.ach_copy_add, y.ptr, y.bs, pos_ptr, y.ptr, y.bs, self.B, Cc, N)
+        # XCA
+        qkv = self.buf(name + ".qkv", 3 * Cc, H, W)
+        wtq, bq = self._ln_fold_linear(name + ".qkv", prefix + ".xca.qkv", prefix + ".norm_xca")
+        self.pw(name + ".qkv", y, qkv, wtq, 3 * Cc, bias=bq, ln=True, ln_eps=1e-6)
+        ldw = _ceil4(Cc)
+        pwt = self._w(name + ".proj.wt", lambda: self._kmajor(self._p(prefix + ".xca.proj.weight")))
+        temp = self._vec(name + ".temp", lambda: self._p(prefix + ".xca.temperature").flatten())
+        weff = torch.zeros(self.B, Cc, ldw, device=self.device, dtype=torch.float32)
+        self._keep.append(weff)
+        self._add(name + ".xca_fold", self.lib.ach_xca_fold, qkv.ptr, qkv.bs, temp.data_ptr(), pwt.data_ptr(), ldw, weff.data_ptr(),
+                  Cc * ldw, self.B, Cc, heads, N)
+        t = self.buf(name + ".t", Cc, H, W)
+        pb = self._vec(name + ".proj.b", lambda: self._p(prefix + ".xca.proj.bias"))
+        gx = self._vec(name + ".gamma_xca", lambda: self._p(prefix + ".gamma_xca"))
+        self.pw(name + ".xca_apply", self.sl(qkv, 2 * Cc, 3 * Cc), t, weff.data_ptr(), Cc, bias=pb, res=y, gamma=gx, wt_bs=Cc * ldw, ldw=ldw)
+        out = self.buf(name + ".out", Cc, H, W)
+        self.mlp_res(name, prefix, t, x, out)
+        return out
+
+    def edgenext(self, x, prefix, phi):
+        cfg = Hd.EDGENEXT_CFG[phi]
+        dims, depths, heads = cfg["dims"], cfg["depths"], cfg["heads"]
+        H = self.res // 4
+        cur = self.buf("bb.stem", dims[0], H, H)
+        ds0 = prefix + ".downsample_layers.0"
+        self.conv("bb.stem", x, cur, self._pack_conv("bb.stem.w", ds0 + ".0.weight"), 4, 4, 0,
+                  bias=self._vec("bb.stem.b", lambda: self._p(ds0 + ".0.bias")),
+                  ln_w=self._vec("bb.stem.lnw", lambda: self._p(ds0 + ".1.weight")),
+                  ln_b=self._vec("bb.stem.lnb", lambda: self._p(ds0 + ".1.bias")), ln_eps=1e-6)
+        feats = []
+        for i in range(4):
+            if i > 0:
+                ds = f"{prefix}.downsample_layers.{i}"
+                ln = self.buf(f"bb.ds{i}.ln", dims[i - 1], H, H)
+                lw = self._vec(f"bb.ds{i}.lnw", (lambda ds=ds: self._p(ds + ".0.weight")))
+                lb = self._vec(f"bb.ds{i}.lnb", (lambda ds=ds: self._p(ds + ".0.bias")))
+                self._add(f"bb.ds{i}.ln", self.lib.ach_layernorm_cf, cur.ptr, cur.bs, lw.data_ptr(), lb.data_ptr(), ln.ptr, ln.bs,
+                          self.B, dims[i - 1], H * H, 1e-6)
+                H //= 2
+                nxt = self.buf(f"bb.ds{i}", dims[i], H, H)
+                self.conv(f"bb.ds{i}.conv", ln, nxt, self._pack_conv(f"bb.ds{i}.w", ds + ".1.weight"), 2, 2, 0,
+                          bias=self._vec(f"bb.ds{i}.b", (lambda ds=ds: self._p(ds + ".1.bias"))))
+                cur = nxt
+            for j in range(depths[i]):
+                bp = f"{prefix}.stages.{i}.{j}"
+                if i > 0 and j == depths[i] - 1:
+                    cur = self.sdta(f"bb.s{i}.{j}", bp, cur, Hd.EN_SCALES[i], heads[i], Hd.EN_POS[i])
+                else:
+                    cur = self.conv_encoder(f"bb.s{i}.{j}", bp, cur, Hd.EN_KERNELS[i])
+                self.taps[f"backbone.stage{i}.{j}"] = cur
+            feats.append(cur)
+        return feats
+
+    # ---- neck
+    def spp(self, x, prefix):
+        c_ = x.C // 2
+        cat = self.buf("spp.cat", 4 * c_, x.H, x.W)
+        self.pw_bn_act("spp.cv1", prefix + ".cv1.conv", prefix + ".cv1.bn", 1e-3, x, self.sl(cat, 0, c_), ACT_SILU)
+        P4 = c_ * x.H * x.W * 4
+        self._add("spp.pool", self.lib.ach_spp_maxpool, cat.ptr, cat.bs, cat.ptr + P4, cat.ptr + 2 * P4, cat.ptr + 3 * P4, cat.bs,
+                  self.B, c_, x.H, x.W)
+        out = self.buf("spp.out", x.C, x.H, x.W)
+        self.pw_bn_act("spp.cv2", prefix + ".cv2.conv", prefix + ".cv2.bn", 1e-3, cat, out, ACT_SILU)
+        return out
+
+    def shuffle_attention(self, name, prefix, x):
+        out = self.buf(name, x.C, x.H, x.W)
+        ps = [self._vec(f"{name}.{n}", (lambda n=n: self._p(f"{prefix}.{n}").flatten()))
+              for n in ("cweight", "cbias", "sweight", "sbias", "gn.weight", "gn.bias")]
+        self._add(name, self.lib.ach_shuffle_attention, x.ptr, x.bs, out.ptr, out.bs, *[p.data_ptr() for p in ps], self.B, x.C,
+                  x.H * x.W, 4, 1e-5)
+        return out
+
+    def seg_decoder(self, name, prefix, x, widths, out):
+        chans = [widths[1], widths[0], widths[0]]
+        cur = x
+        for stage, c in zip(("3_to_2", "2_to_1", "1_to_0"), chans):
+            up = self.buf(f"{name}.{stage}.up", c, cur.H * 2, cur.W * 2)
+            self.upsample_block(f"{name}.{stage}", f"{prefix}.{name}_seg_{stage}", cur, up)
+            g = self.buf(f"{name}.{stage}.ghost", c, up.H, up.W)
+            self.ghost(f"{name}.{stage}.ghost", f"{prefix}.{name}_seg_ghost_{stage}", up, g, True)
+            self.taps[f"neck.{name}_{stage}"] = g
+            cur = g
+        self.ghost(f"{name}.head", f"{prefix}.{name}_seg_head", cur, out, True)
+
+    def gdf_neck(self, feats, prefix, phi, out_se, out_lane):
+        w = Hd.WIDTHS[phi]
+        m2, m3, m4, m5 = feats
+        f5 = self.spp(m5, prefix + ".spp")
+        up4 = self.buf("fpn.up4", w[2], m4.H, m4.W)
+        self.upsample_block("fpn.up54", prefix + ".upsample_5_to_4", f5, up4)
+        f4 = self.ghost_bottleneck("fpn.g54", prefix + ".ghost_5_to_4", up4, m4, w[2] * 2, w[2])
+        up3 = self.buf("fpn.up3", w[1], m3.H, m3.W)
+        self.upsample_block("fpn.up43", prefix + ".upsample_4_to_3", f4, up3)
+        f3 = self.ghost_bottleneck("fpn.g43", prefix + ".ghost_4_to_3", up3, m3, w[1] * 2, w[1])
+        sa_lane = self.shuffle_attention("fpn.sa_lane", prefix + ".stage_3_lane_seg", f3)
+        sa_se = self.shuffle_attention("fpn.sa_se", prefix + ".stage_3_semantic_seg", f3)
+        self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
+        self.seg_decoder("lane", prefix, sa_lane, w, out_lane)
+        self.seg_decoder("se", prefix, sa_se, w, out_se)
+        return (f5, m5), (f4, m4), (f3, m3)
+
+    # ---- radar encoder
+    def rcnet(self, x, prefix, phi):
+        w = [c // 4 for c in Hd.WIDTHS[phi]]
+        spec = [(x.C, w[0], True), (w[0], w[0], True)]
+        for i in range(1, 4):
+            spec += [(w[i - 1], w[i - 1], False), (w[i - 1], w[i], True)]
+        feats = []
+        cur = x
+        for i, (cin, cout, down) in enumerate(spec):
+            bp = f"{prefix}.rc_blocks.{i}"
+            d = bp + ".radar_conv.deformable_conv"
+            pooled = self.buf(f"rc{i}.pool", cin, cur.H, cur.W)
+            self._add(f"rc{i}.pool", self.lib.ach_avgpool3, cur.ptr, cur.bs, pooled.ptr, pooled.bs, self.B, cin, cur.H, cur.W)
+
+            def w_om(d=d, cin=cin):
+                wo = torch.cat([self._p(d + ".offset_conv.weight"), self._p(d + ".modulator_conv.weight")], 0)  # (27, C, 3, 3)
+                out = torch.zeros(cin * 9, 28, dtype=wo.dtype, device=wo.device)
+                out[:, :27] = wo.reshape(27, cin * 9).t()
+                return out
+            s = AchRcDeform()
+            s.x, s.x_bs, s.pooled, s.pooled_bs = cur.ptr, cur.bs, pooled.ptr, pooled.bs
+            s.w_om = self._w(f"rc{i}.w_om", w_om).data_ptr()
+            s.b_om = self._vec(f"rc{i}.b_om", (lambda d=d: torch.cat([self._p(d + ".offset_conv.bias"), self._p(d + ".modulator_conv.bias")]))).data_ptr()
+            s.w_reg = self._w(f"rc{i}.w_reg", (lambda d=d, cin=cin: self._p(d + ".regular_conv.weight").reshape(cin, cin * 9).t())).data_ptr()
+            s.w1 = self._w(f"rc{i}.w1", (lambda bp=bp, cin=cin: self._p(bp + ".weight_conv1.weight").reshape(cin, cin).t())).data_ptr()
+            s.scale = self._vec(f"rc{i}.s", (lambda bp=bp: self._bn_fold(bp + ".norm", 1e-5, self._p(bp + ".weight_conv1.bias"))[0])).data_ptr()
+            s.bias = self._vec(f"rc{i}.b", (lambda bp=bp: self._bn_fold(bp + ".norm", 1e-5, self._p(bp + ".weight_conv1.bias"))[1])).data_ptr()
+            y = self.buf(f"rc{i}.y", cin, cur.H, cur.W)
+            s.out, s.out_bs, s.B, s.C, s.H, s.W = y.ptr, y.bs, self.B, cin, cur.H, cur.W
+            self._keep.append(s)
+            self._add(f"rc{i}.deform", self.lib.ach_rc_deform, C.byref(s))
+            if down:
+                out = self.buf(f"rc{i}.out", cout, cur.H // 2, cur.W // 2)
+                self.conv(f"rc{i}.down", y, out, self._pack_conv(f"rc{i}.w2", bp + ".weight_conv2.weight"), 3, 2, 1,
+                          bias=self._vec(f"rc{i}.b2", (lambda bp=bp: self._p(bp + ".weight_conv2.bias"))))
+            else:
+                out = self.buf(f"rc{i}.out", cout, cur.H, cur.W)
+                self.pw_bias(f"rc{i}.pw2", bp + ".weight_conv2", y, out)
+            self.taps[f"radar.block{i}"] = out
+            cur = out
+            if i > 1 and i % 2 == 1:
+                feats.append(out)
+        return feats
+
+    # ---- image-radar fusion (IREncoder.py:79-89)
+    def fuse_stage(self, s, prefix, fpn_map, radar):
+        (fa, fb) = fpn_map
+        Ci, Cr = fa.C, radar.C
+        P = fa.H * fa.W
+        out = self.buf(f"fuse{s}", Ci + Cr, fa.H, fa.W)
+        sc = self._vec(f"fuse{s}.s", lambda: self._bn_fold(f"{prefix}.norm_stage{s}", 1e-5)[0])
+        bi = self._vec(f"fuse{s}.b", lambda: self._bn_fold(f"{prefix}.norm_stage{s}", 1e-5)[1])
+        for j, (xa, xb, Cc, off) in enumerate(((fa, fb, Ci, 0), (radar, None, Cr, Ci))):
+            mean = torch.empty(self.B, Cc, device=self.device, dtype=torch.float32)
+            self._keep.append(mean)
+            w1d = self._vec(f"fuse{s}.eca{j}", (lambda j=j: self._p(f"{prefix}.channel_attn_stage{s}.{j}.conv.weight").flatten()))
+            self._add(f"fuse{s}.mean{j}", self.lib.ach_plane_mean, xa.ptr, xa.bs, xb.ptr if xb else None, xb.bs if xb else 0,
+                      mean.data_ptr(), self.B, Cc, P)
+            self._add(f"fuse{s}.eca{j}", self.lib.ach_eca_fuse, xa.ptr, xa.bs, xb.ptr if xb else None, xb.bs if xb else 0,
+                      mean.data_ptr(), w1d.data_ptr(), w1d.numel(), sc.data_ptr() + off * 4, bi.data_ptr() + off * 4,
+                      out.ptr + off * P * 4, out.bs, self.B, Cc, P)
+        self.taps[f"fuse.p{s}"] = out
+        return out
+
+    # ---- detection head
+    def det_level(self, k, prefix, x, out, num_det):
+        stem = self.buf(f"det{k}.stem", 64 if self.model.nano_head else 256, x.H, x.W)
+        self.pw_bn_act(f"det{k}.stem", f"{prefix}.stems.{k}.conv", f"{prefix}.stems.{k}.bn", 1e-3, x, stem, ACT_RELU)
+        feats = {}
+        for br in ("cls", "reg"):
+            cur = stem
+            for j in range(2):
+                bp = f"{prefix}.{br}_convs.{k}.{j}"
+                d = self.buf(f"det{k}.{br}{j}.dw", cur.C, x.H, x.W)
+                w = self._w(f"det{k}.{br}{j}.dw.w", (lambda bp=bp: self._p(bp + ".conv.dconv.weight").flatten(1)))
+                has_bias = (bp + ".conv.dconv.bias") in self._params
+                b = self._vec(f"det{k}.{br}{j}.dw.b", (lambda bp=bp: self._p(bp + ".conv.dconv.bias"))) if has_bias else None
+                self.dw(f"det{k}.{br}{j}.dw", cur, d, w, 5, bias=b)
+                nxt = self.buf(f"det{k}.{br}{j}.pw", cur.C, x.H, x.W)
+                self.pw_bn_act(f"det{k}.{br}{j}.pw", bp + ".conv.pconv", bp + ".bn", 1e-3, d, nxt, ACT_RELU, conv_bias=has_bias)
+                cur = nxt
+            feats[br] = cur
+        # preds: [reg(4), obj(1)] from reg_feat, cls(K) from cls_feat, written into the level's output planes
+        wt_ro = self._w(f"det{k}.ro.wt", lambda: self._kmajor(torch.cat([self._p(f"{prefix}.reg_preds.{k}.weight").flatten(1),
+                                                                        self._p(f"{prefix}.obj_preds.{k}.weight").flatten(1)], 0)))
+        b_ro = self._vec(f"det{k}.ro.b", lambda: torch.cat([self._p(f"{prefix}.reg_preds.{k}.bias"), self._p(f"{prefix}.obj_preds.{k}.bias")]))
+        self.pw(f"det{k}.regobj", feats["reg"], self.sl(out, 0, 5), wt_ro, 5, bias=b_ro)
+        self.pw_bias(f"det{k}.cls", f"{prefix}.cls_preds.{k}", feats["cls"], self.sl(out, 5, 5 + num_det))
+
+    # ---- PointNet
+    def _fc(self, name, x, xk, w, O, scale=None, bias=None, act=ACT_NONE):
+        out = torch.empty(self.B, O, device=self.device, dtype=torch.float32)
+        self._keep.append(out)
+        self._add(name, self.lib.ach_fc, x.data_ptr(), x.stride(0), w.data_ptr(), self._ptr(scale), self._ptr(bias), out.data_ptr(),
+                  out.stride(0), self.B, xk, O, act)
+        return out
+
+    def _c1_bn(self, name, conv, bnp, x, O, act, **kw):
+        out = self.buf(name, O, x.H, x.W)
+        self.pw_bn_act(name, conv, bnp, 1e-5, x, out, act, conv_bias=True)
+        return out
+
+    def stn(self, name, prefix, x, k, kpad, ldw):
+        """STN3d / STNkd -> per-frame K-major transform (B, kpad, ldw): rows k < `k` hold T (+I), the
+        remaining rows are identity (feature channels pass through, pointnet_utils.py:107-112)."""
+        a1 = self._c1_bn(name + ".c1", prefix + ".conv1", prefix + ".bn1", x, 64, ACT_RELU)
+        a2 = self._c1_bn(name + ".c2", prefix + ".conv2", prefix + ".bn2", a1, 128, ACT_RELU)
+        g = torch.empty(self.B, 1024, device=self.device, dtype=torch.float32)
+        self._keep.append(g)
+        self._add(name + ".fill", self.lib.ach_fill, g.data_ptr(), g.numel(), float("-inf"))
+        wt = self._w(name + ".c3.wt", lambda: self._kmajor(self._p(prefix + ".conv3.weight").flatten(1)))
+        sc = self._vec(name + ".c3.s", lambda: self._bn_fold(prefix + ".bn3", 1e-5, self._p(prefix + ".conv3.bias"))[0])
+        bi = self._vec(name + ".c3.b", lambda: self._bn_fold(prefix + ".bn3", 1e-5, self._p(prefix + ".conv3.bias"))[1])
+        self.pw(name + ".c3max", a2, g, wt, 1024, scale=sc, bias=bi, act=ACT_RELU, reduce_max=True)
+        f = g
+        for j, (fc, bnp, kin, kout) in enumerate(((".fc1", ".bn4", 1024, 512), (".fc2", ".bn5", 512, 256))):
+            w = self._w(f"{name}{fc}.w", (lambda fc=fc: self._p(prefix + fc + ".weight")))
+            s_ = self._vec(f"{name}{fc}.s", (lambda fc=fc, bnp=bnp: self._bn_fold(prefix + bnp, 1e-5, self._p(prefix + fc + ".bias"))[0]))
+            b_ = self._vec(f"{name}{fc}.b", (lambda fc=fc, bnp=bnp: self._bn_fold(prefix + bnp, 1e-5, self._p(prefix + fc + ".bias"))[1]))
+            f = self._fc(f"{name}{fc}", f, kin, w, kout, s_, b_, ACT_RELU)
+
+        def w3():
+            w = self._p(prefix + ".fc3.weight")  # (k*k, 256)
+            out = torch.zeros(kpad, ldw, 256, dtype=w.dtype, device=w.device)
+            out[:k, :k] = w.reshape(k, k, 256)
+            return out.reshape(kpad * ldw, 256)
+
+        def b3():
+            b = self._p(prefix + ".fc3.bias")
+            out = torch.zeros(kpad, ldw, dtype=b.dtype, device=b.device)
+            out[:k, :k] = b.reshape(k, k)
+            out[:kpad, :kpad] += torch.eye(kpad, dtype=b.dtype, device=b.device)
+            return out.flatten()
+        return self._fc(name + ".fc3", f, 256, self._w(name + ".fc3.w", w3), kpad * ldw, None, self._vec(name + ".fc3.b", b3))
+
+    def pointnet(self, x, prefix, out_pc, num_class):
+        D, N = x.C, x.H * x.W
+        f = prefix + ".feat"
+        ldw5 = _ceil4(D)
+        t3 = self.stn("pn.stn", f + ".stn", x, 3, D, ldw5)
+        xt = self.buf("pn.xt", D, N)
+        self.pw("pn.apply_t3", x, xt, t3.data_ptr(), D, wt_bs=D * ldw5, ldw=ldw5)
+        p1 = self._c1_bn("pn.c1", f + ".conv1", f + ".bn1", xt, 32, ACT_RELU)
+        tf = self.stn("pn.fstn", f + ".fstn", p1, 32, 32, 32)
+        pointfeat = self.buf("pn.pointfeat", 32, N)
+        self.pw("pn.apply_tf", p1, pointfeat, tf.data_ptr(), 32, wt_bs=32 * 32, ldw=32)
+        p2 = self._c1_bn("pn.c2", f + ".conv2", f + ".bn2", pointfeat, 64, ACT_RELU)
+        g = torch.empty(self.B, 128, device=self.device, dtype=torch.float32)
+        self._keep.append(g)
+        self._add("pn.gfill", self.lib.ach_fill, g.data_ptr(), g.numel(), float("-inf"))
+        wt = self._w("pn.c3.wt", lambda: self._kmajor(self._p(f + ".conv3.weight").flatten(1)))
+        sc = self._vec("pn.c3.s", lambda: self._bn_fold(f + ".bn3", 1e-5, self._p(f + ".conv3.bias"))[0])
+        bi = self._vec("pn.c3.b", lambda: self._bn_fold(f + ".bn3", 1e-5, self._p(f + ".conv3.bias"))[1])
+        self.pw("pn.c3max", p2, g, wt, 128, scale=sc, bias=bi, reduce_max=True)
+        # head conv1 over cat(global(128) repeated, pointfeat(32)): the global half is a per-frame bias
+        wg = self._w("pn.h1.wg", lambda: self._p(prefix + ".conv1.weight")[:, :128, 0])
+        pb = self._fc("pn.h1.gbias", g, 128, wg, 128)
+        wp = self._w("pn.h1.wt", lambda: self._kmajor(self._p(prefix + ".conv1.weight")[:, 128:, 0]))
+        s1 = self._vec("pn.h1.s", lambda: self._bn_fold(prefix + ".bn1", 1e-5, self._p(prefix + ".conv1.bias"))[0])
+        b1 = self._vec("pn.h1.b", lambda: self._bn_fold(prefix + ".bn1", 1e-5, self._p(prefix + ".conv1.bias"))[1])
+        h1 = self.buf("pn.h1", 128, N)
+        self.pw("pn.h1", pointfeat, h1, wp, 128, scale=s1, bias=b1, pbias=pb, act=ACT_RELU)
+        h2 = self._c1_bn("pn.h2", prefix + ".conv2", prefix + ".bn2", h1, 100, ACT_RELU)
+        h3 = self._c1_bn("pn.h3", prefix + ".conv3", prefix + ".bn3", h2, 64, ACT_RELU)
+        h4 = self.buf("pn.h4", num_class, N)
+        self.pw_bias("pn.h4", prefix + ".conv4", h3, h4)
+        self._add("pn.logsoftmax", self.lib.ach_logsoftmax_t, h4.ptr, h4.bs, out_pc, self.packed_out.stride(0), self.B, num_class, N)
+        self.taps_raw = {"pc.trans": t3, "pc.trans_feat": tf, "pc.global": g}
+        self.taps["pc.pointfeat"] = pointfeat
+
+    # ------------------------------------------------------------------ plan
+    def _build(self):
+        m = self.model
+        B, R, N = self.B, self.res, self.n_points
+        self._params = {k: v for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+        self.taps = {}
+        self.pack_ops = []
+        K, S, PC = m.num_det, m.num_seg, m.pc_classes
+        h3, h4, h5 = R // 8, R // 16, R // 32
+        sizes = [(5 + K) * h3 * h3, (5 + K) * h4 * h4, (5 + K) * h5 * h5, S * R * R, 2 * R * R]
+        if m.has_pc:
+            sizes.append(N * PC)
+        self.out_offsets = [0]
+        for s_ in sizes:
+            self.out_offsets.append(self.out_offsets[-1] + s_)
+        self.frame_elems = self.out_offsets[-1]
+        self.packed_out = torch.empty(B, self.frame_elems, device=self.device, dtype=torch.float32)
+        self.x_in = self.buf("in.x", m.image_channels, R, R)
+        self.r_in = self.buf("in.radar", m.radar_channels, R, R)
+        base, bs = self.packed_out.data_ptr(), self.packed_out.stride(0)
+
+        def oview(i, C_, H, W):
+            return View(base + self.out_offsets[i] * 4, bs, C_, H, W)
+        det_views = [oview(0, 5 + K, h3, h3), oview(1, 5 + K, h4, h4), oview(2, 5 + K, h5, h5)]
+        out_se, out_lane = oview(3, S, R, R), oview(4, 2, R, R)
+
+        if m.has_pc:
+            self.pc_in = self.buf("in.pc", m.pc_channels, N, 1)
+            if m.pc_seg == "pn":
+                self.pointnet(self.pc_in, "pc_seg_model", base + self.out_offsets[5] * 4, PC)
+            else:
+                raise NotImplementedError(f"pc_seg={m.pc_seg!r}")
+        ire = "image_radar_encoder"
+        if m.backbone == "en":
+            feats = self.edgenext(self.x_in, ire + ".fpn.backbone", m.phi)
+        else:
+            raise NotImplementedError("MobileViT engine path not built yet")
+        maps = self.gdf_neck(feats, ire + ".fpn", m.phi, out_se, out_lane)
+        radar = self.rcnet(self.r_in, ire + ".radar_encoder", m.phi)
+        fused = [self.fuse_stage(s, ire, maps[2 - i], radar[i]) for i, s in enumerate((3, 4, 5))]
+        for k in range(3):
+            self.det_level(k, "det_head", fused[k], det_views[k], K)
+        self.repack()
+        self._sig = self._signature()
+
+    # ------------------------------------------------------------------ execution
+    def _launch_all(self, stream):
+        if self.dry_run:
+            raise _lib.AchelousKernelError("dry-run engine cannot launch kernels")
+        check = _lib.check
+        for (fn, args), name in zip(self.ops, self.op_names):
+            st = fn(*args, stream)
+            if st:
+                check(st, name)
+
+    def run_packs(self, stream):
+        for fn, args in self.pack_ops:
+            _lib.check(fn(*args, stream), "pack op")
+
+    def ensure_packed(self):
+        if self._signature() != self._sig:
+            self.repack()
+            self._packs_done = False
+        if not getattr(self, "_packs_done", False):
+            self.run_packs(torch.cuda.current_stream(self.device).cuda_stream)
+            self._packs_done = True
+
+    def forward_static(self):
+        """Runs the plan on the static input buffers; results land in self.packed_out."""
+        self.ensure_packed()
+        if self.use_graph:
+            if self.graph is None:
+                self._launch_all(torch.cuda.current_stream(self.device).cuda_stream)  # warm-up: module loading, attributes
+                torch.cuda.current_stream(self.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_all(torch.cuda.current_stream(self.device).cuda_stream)
+                self.graph = g
+            self.graph.replay()
+        else:
+            self._launch_all(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def input_tensors(self):
+        t = [self._bufs["in.x"], self._bufs["in.radar"]]
+        if self.model.has_pc:
+            t.append(self._bufs["in.pc"].view(self.B, self.model.pc_channels, self.n_points))
+        return t
+
+    def output_views(self):
+        m = self.model
+        K, S, R = m.num_det, m.num_seg, self.res
+        o = self.out_offsets
+        po = self.packed_out
+        det = [po[:, o[i]:o[i + 1]].unflatten(1, (5 + K, R // s, R // s)) for i, s in enumerate((8, 16, 32))]
+        se = po[:, o[3]:o[4]].unflatten(1, (S, R, R))
+        lane = po[:, o[4]:o[5]].unflatten(1, (2, R, R))
+        pc = po[:, o[5]:o[6]].unflatten(1, (self.n_points, m.pc_classes)) if m.has_pc else None
+        return det, se, lane, pc
+
+    def tap(self, name):
+        """Intermediate activation by oracle tap name (tests only)."""
+        v = self.taps[name]
+        for t in self._bufs.values():
+            if t.data_ptr() == v.ptr:
+                return t
+        raise KeyError(name)

@@ -1,0 +1,143 @@
+"""Drop-in replacement of the reference's ``nets/Achelous.py`` module surface
+(``Achelous`` :26-53, ``Achelous3T`` :56-76): same constructor keywords, same parameter / buffer
+names (strict ``load_state_dict`` with reference checkpoints), same ``forward`` signature and return
+nesting - with the forward pass executed by the hand-written sm_100a kernels (no ATen compute, no CPU
+or eager fallback: a missing CUDA library or a non-CUDA input raises).
+
+    from achelous_b200.nets.Achelous import Achelous       # instead of `from nets.Achelous import *`
+    net = Achelous(num_det=7, num_seg=9, phi='S0', resolution=320, backbone='en', neck='gdf',
+                   pc_seg='pn', pc_channels=5, pc_classes=8, nano_head=True, spp=True).eval().cuda()
+    det, se_seg, lane_seg, pc_seg = net(x, x_radar, x_point_clouds)
+"""
+import torch
+import torch.nn as nn
+
+from . import holders as Hd
+
+image_encoder_width = Hd.WIDTHS  # nets/Achelous.py:18-23
+
+
+class _AchelousBase(nn.Module):
+    has_pc = True
+
+    def _init_common(self, num_det, num_seg, phi, image_channels, radar_channels, resolution, backbone, neck, pc_seg,
+                     pc_channels, pc_classes, nano_head, spp):
+        if phi not in ("S0", "S1", "S2"):
+            raise NotImplementedError(f"phi={phi!r}: achelous_b200 implements S0/S1/S2")
+        if not spp:
+            raise NotImplementedError("spp=False (SPPF) is outside the accelerated path")
+        if resolution % 32 != 0:
+            raise ValueError("resolution must be a multiple of 32")
+        self.num_det, self.num_seg, self.resolution = num_det, num_seg, resolution
+        self.phi, self.image_channels, self.radar_channels = phi, image_channels, radar_channels
+        self.backbone, self.neck, self.pc_seg = backbone, neck, pc_seg
+        self.pc_channels, self.pc_classes, self.nano_head = pc_channels, pc_classes, nano_head
+        self.n_points = 512
+        self.use_cuda_graph = True
+        self._engines = {}
+
+    # ---- engine cache: one plan per (device, batch); weights are re-packed when parameters change
+    def _engine(self, device, batch, n_points):
+        from ..engine import Engine
+        key = (device.index if device.index is not None else torch.cuda.current_device(), batch, n_points)
+        eng = self._engines.get(key)
+        if eng is None:
+            self.n_points = n_points
+            eng = Engine(self, batch, torch.device("cuda", key[0]), use_graph=self.use_cuda_graph)
+            self._engines[key] = eng
+        return eng
+
+    def _apply(self, fn, *a, **k):
+        self._engines = {}  # .to() / .cuda() / .float(): parameter storage moves, plans are rebuilt lazily
+        return super()._apply(fn, *a, **k)
+
+    def __deepcopy__(self, memo):  # ModelEMA deep-copies the model (detection_loss.py:441)
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_engines" else copy.deepcopy(v, memo)
+        return new
+
+    def _check(self, t, name, shape_tail):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+        if tuple(t.shape[1:]) != tuple(shape_tail):
+            raise RuntimeError(f"{name}: expected shape (B, {', '.join(map(str, shape_tail))}), got {tuple(t.shape)}")
+
+    def _run(self, x, x_radar, x_pc):
+        if self.training:
+            raise NotImplementedError("achelous_b200 is inference-only: call .eval() first (no autograd kernels)")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("achelous_b200 has no CPU path: move the module to a CUDA device")
+        R = self.resolution
+        self._check(x, "x", (self.image_channels, R, R))
+        self._check(x_radar, "x_radar", (self.radar_channels, R, R))
+        B = x.shape[0]
+        n_points = self.n_points
+        if self.has_pc:
+            if x_pc.dim() != 3 or x_pc.shape[1] != self.pc_channels:
+                raise RuntimeError(f"x_point_clouds: expected (B, {self.pc_channels}, N), got {tuple(x_pc.shape)}")
+            n_points = x_pc.shape[2]
+            self._check(x_pc, "x_point_clouds", (self.pc_channels, n_points))
+            if n_points % 4:
+                raise RuntimeError("x_point_clouds: N must be a multiple of 4")
+        if x_radar.shape[0] != B or (self.has_pc and x_pc.shape[0] != B):
+            raise RuntimeError("batch sizes of x / x_radar / x_point_clouds differ")
+        with torch.cuda.device(dev), torch.no_grad():
+            eng = self._engine(dev, B, n_points)
+            ins = eng.input_tensors()
+            # inputs may still be on the host (achelous.py:212 never moves x_radar): copy_ handles both
+            ins[0].copy_(x, non_blocking=True)
+            ins[1].copy_(x_radar, non_blocking=True)
+            if self.has_pc:
+                ins[2].copy_(x_pc, non_blocking=True)
+            eng.forward_static()
+            det, se, lane, pc = eng.output_views()
+            det = [d.contiguous() for d in det]  # fresh tensors owned by the caller
+            se, lane = se.contiguous(), lane.contiguous()
+            pc = pc.contiguous() if pc is not None else None
+        return det, se, lane, pc
+
+
+class Achelous(_AchelousBase):
+    """nets/Achelous.py:26-53"""
+
+    def __init__(self, num_det, num_seg, phi='S0', image_channels=3, radar_channels=3, resolution=416,
+                 backbone='ef', neck='gdf', pc_seg='pn', pc_channels=6, pc_classes=9, nano_head=False, spp=True):
+        super().__init__()
+        self._init_common(num_det, num_seg, phi, image_channels, radar_channels, resolution, backbone, neck, pc_seg,
+                          pc_channels, pc_classes, nano_head, spp)
+        if pc_seg == 'pn':
+            self.pc_seg_model = Hd.PointNet_SEG(num_class=pc_classes, point_cloud_channels=pc_channels)
+        else:
+            raise NotImplementedError(f"pc_seg={pc_seg!r}: implemented: 'pn'")
+        self.image_radar_encoder = Hd.IREncoder(num_class_seg=num_seg, phi=phi, backbone=backbone, neck=neck,
+                                                radar_channels=radar_channels)
+        self.det_head = Hd.DecoupleHead(num_classes=num_det, phi=phi, nano_head=nano_head)
+
+    def forward(self, x, x_radar, x_point_clouds):
+        det, se, lane, pc = self._run(x, x_radar, x_point_clouds)
+        return det, se, lane, pc
+
+
+class Achelous3T(_AchelousBase):
+    """nets/Achelous.py:56-76 (no point-cloud branch)"""
+    has_pc = False
+
+    def __init__(self, num_det, num_seg, phi='S0', image_channels=3, radar_channels=3, resolution=320,
+                 backbone='en', neck='gdf', pc_seg='pn', pc_channels=6, pc_classes=9, nano_head=True, spp=True):
+        super().__init__()
+        self._init_common(num_det, num_seg, phi, image_channels, radar_channels, resolution, backbone, neck, pc_seg,
+                          pc_channels, pc_classes, nano_head, spp)
+        self.image_radar_encoder = Hd.IREncoder(num_class_seg=num_seg, phi=phi, backbone=backbone, neck=neck,
+                                                radar_channels=radar_channels)
+        self.det_head = Hd.DecoupleHead(num_classes=num_det, phi=phi, nano_head=nano_head)
+
+    def forward(self, x, x_radar):
+        det, se, lane, _ = self._run(x, x_radar, None)
+        return det, se, lane

@@ -1,0 +1,213 @@
+/*
+ * achelous_b200 - C ABI of the sm_100a kernels behind the Achelous 5-task forward.
+ *
+ * The reference (GuanRunwei/Achelous) has no FFI: its hot path is a torch.nn.Module
+ * (nets/Achelous.py:49-53) whose native work is done by ATen/cuDNN/cuBLAS and
+ * torchvision._C.  This header is the boundary a maintainer binds instead of those
+ * library calls (ctypes stub in INTEGRATION.md; achelous_b200/_lib.py is that stub).
+ *
+ * Conventions
+ *   - every tensor is fp32; activations are "views" (pointer, batch stride in elements) over
+ *     channel-major planes: element (b, c, p) lives at ptr[b * bs + c * P + p], P = H * W
+ *     (exactly torch NCHW / (B, C, N) layout, so channel slices and concatenations are free);
+ *   - every entry point is stream-ordered on `stream` (a cudaStream_t), allocates nothing,
+ *     is re-entrant and CUDA-graph capturable;
+ *   - return value: 0 = ok, otherwise an ACH_ERR_* code; ach_last_error() returns the
+ *     thread-local message.  Nothing throws across this boundary.
+ *   - "folded" scale/bias: eval-mode BatchNorm (and conv bias) folded by the host into
+ *     y = scale[o] * acc + bias[o]; NULL scale means 1, NULL bias means 0.
+ */
+#ifndef ACHELOUS_B200_H
+#define ACHELOUS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ACH_API __attribute__((visibility("default")))
+#else
+#define ACH_API
+#endif
+
+#define ACH_OK 0
+#define ACH_ERR_INVALID 1
+#define ACH_ERR_CUDA 2
+
+#define ACH_ACT_NONE 0
+#define ACH_ACT_RELU 1
+#define ACH_ACT_SILU 2
+#define ACH_ACT_GELU 3
+#define ACH_ACT_SIGMOID 4
+
+ACH_API const char* ach_last_error(void);
+ACH_API int ach_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pointwise (1x1) convolution / Linear / Conv1d(k=1) / bmm as one GEMM per frame:
+ *   out[b, o, p] = res[b, o, p] + gamma[o] * act(scale[o] * (sum_k wt[b][k, o] * xn[b, k, p] + pbias[b, o]) + bias[o])
+ * x = concat(x0 (c0 channels), x1 (c1 channels)) along channels (x1 may be NULL);
+ * xn = x, or LayerNorm over channels without affine when ln != 0 (affine folded into wt/bias by the host).
+ * wt is K-major [K][ldw] (ldw % 4 == 0, zero padded); wt_bs != 0 selects per-frame weights.
+ * reduce_max != 0: out is (B, O) = max over p (must be pre-filled with -inf; res/gamma unused).
+ * Replaces: nn.Conv2d 1x1 (+BN+act) ghost_conv.py:13-17, normal_conv.py:36-49, spp.py:27-35,
+ *   decouplehead.py:37-57; nn.Linear in conv_encoder.py:11-13, sdta_encoder.py:25,33,155-159
+ *   (with F.layer_norm layers.py:20); Conv1d in pointnet_utils.py:13-15,92-94 and
+ *   pointnet_sem_seg.py:18-21; torch.bmm pointnet_utils.py:110,119; torch.max(x, 2) :36,76,127.
+ * Requires P % 4 == 0 and 16-byte aligned views.
+ */
+typedef struct AchPwConv {
+    const float* x0;
+    const float* x1;
+    const float* wt;
+    const float* scale;
+    const float* bias;
+    const float* pbias;   /* (B, O) added before scale, or NULL */
+    const float* res;     /* residual view (B, O, P) or NULL */
+    const float* gamma;   /* per-output layer-scale applied before the residual add, or NULL */
+    float* out;
+    long long x0_bs, x1_bs, wt_bs, res_bs, out_bs;
+    int c0, c1, ldw;
+    int B, O, P;
+    int ln;
+    float ln_eps;
+    int act;
+    int reduce_max;
+} AchPwConv;
+ACH_API int ach_pw_conv(const AchPwConv* p, void* stream);
+
+/* Depthwise k x k convolution (k in {3,5,7,9}, stride 1 or 2, pad k/2):
+ *   out[b,c] = act(scale[c] * dw(x[b,c] + xadd[b,c]) + bias[c]) + post[c]      (post broadcast over b)
+ * w is [C][k*k].  Replaces nn.Conv2d(groups=C): conv_encoder.py:10, sdta_encoder.py:23 (cascade
+ * `sp = conv(sp + spx[i])` :46-50), ghost_conv.py:19-23,48-61, normal_conv.py:26-27, mobilevit.py:104,117. */
+typedef struct AchDwConv {
+    const float* x;
+    const float* xadd;
+    const float* w;
+    const float* scale;
+    const float* bias;
+    const float* post;    /* (C, Ho*Wo) or NULL */
+    float* out;
+    long long x_bs, xadd_bs, out_bs;
+    int B, C, H, W, Ho, Wo, k, stride, act;
+} AchDwConv;
+ACH_API int ach_dw_conv(const AchDwConv* p, void* stream);
+
+/* Dense spatial convolution for the small-channel layers (patchify stem / downsample, RCNet
+ * 3x3 stride-2, MobileViT 3x3): w packed [Cin][k*k][ldo] (ldo % 4 == 0, zero padded).
+ *   y = act(scale * conv(x) + bias);  ln_out != 0: channels-first LayerNorm over the O outputs
+ *   (biased variance, affine ln_w/ln_b) applied after bias - requires O <= 32.
+ * Replaces nn.Conv2d in edgenext.py:24-34 (+LayerNorm layers.py:21-26), RadarEncoder.py:63,
+ * mobilevit.py:15-21. */
+typedef struct AchConvDense {
+    const float* x;
+    const float* w;
+    const float* scale;
+    const float* bias;
+    const float* ln_w;
+    const float* ln_b;
+    float* out;
+    long long x_bs, out_bs;
+    int B, Cin, H, W, O, ldo, Ho, Wo, k, stride, pad, act, ln_out;
+    float ln_eps;
+} AchConvDense;
+ACH_API int ach_conv_dense(const AchConvDense* p, void* stream);
+
+/* Channels-first LayerNorm over C for every (b, p): layers.py:21-26 (biased variance). */
+ACH_API int ach_layernorm_cf(const float* x, long long x_bs, const float* w, const float* b, float* out, long long out_bs,
+                     int B, int C, int P, float eps, void* stream);
+
+/* Bilinear x2 upsampling, align_corners=True (nn.Upsample, ghostdualfpn.py:34). */
+ACH_API int ach_upsample2x(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
+                   void* stream);
+
+/* SPP max-pools (kernel 5, 9, 13, stride 1, same padding; spp.py:47,52): writes the three pooled
+ * copies of x (B, C, H, W) to out5/out9/out13 views. */
+ACH_API int ach_spp_maxpool(const float* x, long long x_bs, float* out5, float* out9, float* out13, long long out_bs,
+                    int B, int C, int H, int W, void* stream);
+
+/* ShuffleAttention (G groups): shuffle_attention.py:48-72.  params: cweight,cbias,sweight,sbias,
+ * gn_w,gn_b each (C / 2G). */
+ACH_API int ach_shuffle_attention(const float* x, long long x_bs, float* out, long long out_bs, const float* cweight,
+                          const float* cbias, const float* sweight, const float* sbias, const float* gn_w,
+                          const float* gn_b, int B, int C, int P, int G, float eps, void* stream);
+
+/* Plane means: out[b, c] = mean_p (x[b,c,p] + x2[b,c,p])  (x2 may be NULL).  eca.py:12,17. */
+ACH_API int ach_plane_mean(const float* x, long long x_bs, const float* x2, long long x2_bs, float* out, int B, int C,
+                   int P, void* stream);
+
+/* ECA gate + concat slot + BN + ReLU of IREncoder.forward (IREncoder.py:79-89, eca.py:16-22):
+ *   out[b, c, p] = relu(scale[c] * ((x + x2)[b,c,p] * sigmoid(conv1d_k(mean[b, :])[c])) + bias[c]) */
+ACH_API int ach_eca_fuse(const float* x, long long x_bs, const float* x2, long long x2_bs, const float* mean,
+                 const float* w1d, int k1d, const float* scale, const float* bias, float* out, long long out_bs,
+                 int B, int C, int P, void* stream);
+
+/* AvgPool2d(3, stride 1, pad 1, count_include_pad) - RadarEncoder.py:33. */
+ACH_API int ach_avgpool3(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
+                 void* stream);
+
+/* RCBlock body after the pool (RadarEncoder.py:65-72, dcn.py:49-63, torchvision deform_conv2d):
+ *   offset/modulator 3x3 convs on `pooled`, modulated deformable 3x3 conv of `pooled`,
+ *   1x1 conv + BN + ReLU, + x.  Weights packed K-major:
+ *   w_om [C*9][28] (18 offset + 9 modulator outputs, 1 pad), b_om [27], w_reg [C*9][C], w1 [C][C].
+ * C must be one of {3, 8, 12, 16, 24, 30, 36}. */
+typedef struct AchRcDeform {
+    const float* x;
+    const float* pooled;
+    const float* w_om;
+    const float* b_om;
+    const float* w_reg;
+    const float* w1;
+    const float* scale;
+    const float* bias;
+    float* out;
+    long long x_bs, pooled_bs, out_bs;
+    int B, C, H, W;
+} AchRcDeform;
+ACH_API int ach_rc_deform(const AchRcDeform* p, void* stream);
+
+/* XCA attention core (sdta_encoder.py:162-185): from qkv (B, 3C, N) computes per (b, head) the
+ * softmax(temperature * normalize(q) normalize(k)^T) (d x d) and folds it into the output projection:
+ *   wt_eff[b][h*d + j][o] = sum_i proj_wt[h*d + i][o] * attn[b,h][i][j]
+ * so that proj(attn @ v) == ach_pw_conv(x0 = v, wt = wt_eff (per frame)).  proj_wt is [C][ldw]. */
+ACH_API int ach_xca_fold(const float* qkv, long long qkv_bs, const float* temperature, const float* proj_wt, int ldw,
+                 float* wt_eff, long long wt_eff_bs, int B, int C, int heads, int N, void* stream);
+
+/* Fully connected on (B, K) rows: out[b, o] = act(scale[o] * (w[o, :] . x[b, :]) + bias[o]).
+ * pointnet_utils.py:16-18,38-40 (fc + BN1d + ReLU), and the global-feature half of
+ * pointnet_sem_seg.py:18 (Conv1d over a point-wise constant). */
+ACH_API int ach_fc(const float* x, long long x_bs, const float* w, const float* scale, const float* bias, float* out,
+           long long out_bs, int B, int K, int O, int act, void* stream);
+
+/* (B, K, N) logits -> (B, N, K) log_softmax over K (frame b at out + b * out_bs): pointnet_sem_seg.py:34-36.  K <= 32. */
+ACH_API int ach_logsoftmax_t(const float* x, long long x_bs, float* out, long long out_bs, int B, int K, int N, void* stream);
+
+/* out[b, c, p] = x[b, c, p] + post[c, p]  (post may be NULL: plain strided copy). */
+ACH_API int ach_copy_add(const float* x, long long x_bs, const float* post, float* out, long long out_bs, int B, int C,
+                 int P, void* stream);
+
+/* out[b, c, p] = a[b, c, p] + b2[b, c, p]   (fpn + map sums, ghostdualfpn.py:200) */
+ACH_API int ach_add(const float* a, long long a_bs, const float* b2, long long b_bs, float* out, long long out_bs, int B,
+            int C, int P, void* stream);
+
+ACH_API int ach_fill(float* x, long long n, float value, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Detection post-process (second boundary: utils/utils_bbox.py).
+ * ach_decode_outputs: decode_outputs (:33-85) for up to 3 levels of (B, 5+K, H_l, W_l) raw logits
+ *   -> out (B, A, 5+K), xywh normalised by input_w/input_h.
+ * ach_nms: non_max_suppression (:87-130) up to (not including) the host-side letterbox un-warp:
+ *   per image keeps rows [x1,y1,x2,y2,obj,cls_conf,cls_idx] in score-descending order using the
+ *   torchvision batched_nms coordinate trick; kept (B, A, 7), kept_idx (B, A) anchor indices,
+ *   counts (B).  workspace: ach_nms_workspace_bytes(B, A).
+ */
+ACH_API int ach_decode_outputs(const float* const* levels, const long long* level_bs, const int* hs, const int* ws,
+                       int n_levels, float* out, int B, int K, float input_h, float input_w, void* stream);
+ACH_API long long ach_nms_workspace_bytes(int B, int A);
+ACH_API int ach_nms(const float* decoded, int B, int A, int K, float conf_thres, float nms_thres, float* kept,
+            int* kept_idx, int* counts, void* workspace, long long workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACHELOUS_B200_H */

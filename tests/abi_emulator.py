@@ -1,0 +1,251 @@
+"""CPU emulator of the C ABI in include/achelous_b200.h - TEST INFRASTRUCTURE ONLY.
+
+Each ``ach_*`` entry point is restated with plain PyTorch CPU ops acting on raw host pointers, with
+exactly the argument meaning of the header.  Two uses:
+
+* ``-m "not gpu"``: a dry-run :class:`achelous_b200.engine.Engine` (buffers in host memory) is executed
+  through this emulator and compared with the oracle - this pins the HOST logic (weight folding,
+  K-major packing, channel-slice views, concat-free wiring, output packing) without a GPU;
+* ``-m gpu``: every kernel is run on the device and compared with the emulator on copies of the same
+  buffers (tests/test_kernels_gpu.py), so a kernel bug and a host bug can be told apart.
+
+It is never imported by the product.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle.functional import deform_conv2d_3x3
+
+
+def fview(ptr, shape, strides):
+    """float32 torch view over raw host memory at `ptr` with element strides."""
+    if ptr is None or ptr == 0:
+        return None
+    extent = 1 + sum((s - 1) * st for s, st in zip(shape, strides))
+    arr = np.ctypeslib.as_array((C.c_float * extent).from_address(ptr))
+    v = np.lib.stride_tricks.as_strided(arr, shape, [st * 4 for st in strides])
+    return torch.from_numpy(v)
+
+
+def _act(y, act):
+    if act == 1:
+        return F.relu(y)
+    if act == 2:
+        return y * torch.sigmoid(y)
+    if act == 3:
+        return F.gelu(y)
+    if act == 4:
+        return torch.sigmoid(y)
+    return y
+
+
+def _vec(ptr, n):
+    return fview(ptr, (n,), (1,))
+
+
+def ach_pw_conv(s):
+    B, O, P, K = s.B, s.O, s.P, s.c0 + s.c1
+    x = fview(s.x0, (B, s.c0, P), (s.x0_bs, P, 1))
+    if s.c1:
+        x = torch.cat([x, fview(s.x1, (B, s.c1, P), (s.x1_bs, P, 1))], 1)
+    x = x.double()
+    if s.ln:
+        u = x.mean(1, keepdim=True)
+        v = (x - u).pow(2).mean(1, keepdim=True)
+        x = (x - u) / torch.sqrt(v + s.ln_eps)
+    wt = fview(s.wt, (B, K, O), (s.wt_bs, s.ldw, 1)).double()
+    y = torch.einsum("bko,bkp->bop", wt, x)
+    if s.pbias:
+        y = y + fview(s.pbias, (B, O), (O, 1)).double()[:, :, None]
+    if s.scale:
+        y = y * _vec(s.scale, O).double()[None, :, None]
+    if s.bias:
+        y = y + _vec(s.bias, O).double()[None, :, None]
+    y = _act(y.float(), s.act)
+    if s.reduce_max:
+        out = fview(s.out, (B, O), (s.out_bs, 1))
+        out.copy_(torch.maximum(out, y.max(2)[0]))
+        return
+    if s.res:
+        g = _vec(s.gamma, O)[None, :, None] if s.gamma else 1.0
+        y = fview(s.res, (B, O, P), (s.res_bs, P, 1)) + g * y
+    fview(s.out, (B, O, P), (s.out_bs, P, 1)).copy_(y)
+
+
+def ach_dw_conv(s):
+    B, Cc, H, W, Ho, Wo, k = s.B, s.C, s.H, s.W, s.Ho, s.Wo, s.k
+    x = fview(s.x, (B, Cc, H, W), (s.x_bs, H * W, W, 1)).clone()
+    if s.xadd:
+        x = x + fview(s.xadd, (B, Cc, H, W), (s.xadd_bs, H * W, W, 1))
+    w = fview(s.w, (Cc, 1, k, k), (k * k, k * k, k, 1))
+    y = F.conv2d(x, w, None, s.stride, k // 2, 1, Cc)
+    if s.scale:
+        y = y * _vec(s.scale, Cc)[None, :, None, None]
+    if s.bias:
+        y = y + _vec(s.bias, Cc)[None, :, None, None]
+    y = _act(y, s.act)
+    if s.post:
+        y = y + fview(s.post, (1, Cc, Ho, Wo), (0, Ho * Wo, Wo, 1))
+    fview(s.out, (B, Cc, Ho, Wo), (s.out_bs, Ho * Wo, Wo, 1)).copy_(y)
+
+
+def ach_conv_dense(s):
+    B, Cin, H, W, O, k = s.B, s.Cin, s.H, s.W, s.O, s.k
+    x = fview(s.x, (B, Cin, H, W), (s.x_bs, H * W, W, 1))
+    w = fview(s.w, (Cin, k * k, O), (k * k * s.ldo, s.ldo, 1)).permute(2, 0, 1).reshape(O, Cin, k, k)
+    y = F.conv2d(x, w, None, s.stride, s.pad)
+    if s.scale:
+        y = y * _vec(s.scale, O)[None, :, None, None]
+    if s.bias:
+        y = y + _vec(s.bias, O)[None, :, None, None]
+    y = _act(y, s.act)
+    if s.ln_out:
+        u = y.mean(1, keepdim=True)
+        v = (y - u).pow(2).mean(1, keepdim=True)
+        y = (y - u) / torch.sqrt(v + s.ln_eps)
+        y = y * _vec(s.ln_w, O)[None, :, None, None] + _vec(s.ln_b, O)[None, :, None, None]
+    fview(s.out, (B, O, s.Ho, s.Wo), (s.out_bs, s.Ho * s.Wo, s.Wo, 1)).copy_(y)
+
+
+def ach_layernorm_cf(x, x_bs, w, b, out, out_bs, B, Cc, P, eps):
+    xv = fview(x, (B, Cc, P), (x_bs, P, 1))
+    u = xv.mean(1, keepdim=True)
+    v = (xv - u).pow(2).mean(1, keepdim=True)
+    y = (xv - u) / torch.sqrt(v + eps) * _vec(w, Cc)[None, :, None] + _vec(b, Cc)[None, :, None]
+    fview(out, (B, Cc, P), (out_bs, P, 1)).copy_(y)
+
+
+def ach_upsample2x(x, x_bs, out, out_bs, B, Cc, H, W):
+    xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))
+    y = F.interpolate(xv, scale_factor=2, mode="bilinear", align_corners=True)
+    fview(out, (B, Cc, 2 * H, 2 * W), (out_bs, 4 * H * W, 2 * W, 1)).copy_(y)
+
+
+def ach_spp_maxpool(x, x_bs, o5, o9, o13, out_bs, B, Cc, H, W):
+    xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1)).clone()
+    for o, k in ((o5, 5), (o9, 9), (o13, 13)):
+        fview(o, (B, Cc, H, W), (out_bs, H * W, W, 1)).copy_(F.max_pool2d(xv, k, 1, k // 2))
+
+
+def ach_shuffle_attention(x, x_bs, out, out_bs, cw, cb, sw, sb, gw, gb, B, Cc, P, G, eps):
+    xv = fview(x, (B, Cc, P), (x_bs, P, 1)).clone()
+    c = Cc // (2 * G)
+    xg = xv.reshape(B * G, 2 * c, P)
+    x0, x1 = xg[:, :c], xg[:, c:]
+    pv = lambda p: _vec(p, c)[None, :, None]
+    xc = x0 * torch.sigmoid(pv(cw) * x0.mean(2, keepdim=True) + pv(cb))
+    u = x1.mean(2, keepdim=True)
+    v = (x1 - u).pow(2).mean(2, keepdim=True)
+    xs = (x1 - u) / torch.sqrt(v + eps) * pv(gw) + pv(gb)
+    xs = x1 * torch.sigmoid(pv(sw) * xs + pv(sb))
+    o = torch.cat([xc, xs], 1).reshape(B, Cc, P)
+    o = o.reshape(B, 2, Cc // 2, P).permute(0, 2, 1, 3).reshape(B, Cc, P)
+    fview(out, (B, Cc, P), (out_bs, P, 1)).copy_(o)
+
+
+def ach_plane_mean(x, x_bs, x2, x2_bs, out, B, Cc, P):
+    xv = fview(x, (B, Cc, P), (x_bs, P, 1))
+    if x2:
+        xv = xv + fview(x2, (B, Cc, P), (x2_bs, P, 1))
+    fview(out, (B, Cc), (Cc, 1)).copy_(xv.mean(2))
+
+
+def ach_eca_fuse(x, x_bs, x2, x2_bs, mean, w1d, k1d, scale, bias, out, out_bs, B, Cc, P):
+    xv = fview(x, (B, Cc, P), (x_bs, P, 1))
+    if x2:
+        xv = xv + fview(x2, (B, Cc, P), (x2_bs, P, 1))
+    m = fview(mean, (B, Cc), (Cc, 1))
+    a = F.conv1d(m.unsqueeze(1), _vec(w1d, k1d).view(1, 1, k1d), None, 1, (k1d - 1) // 2).squeeze(1)
+    y = xv * torch.sigmoid(a)[:, :, None]
+    y = F.relu(y * _vec(scale, Cc)[None, :, None] + _vec(bias, Cc)[None, :, None])
+    fview(out, (B, Cc, P), (out_bs, P, 1)).copy_(y)
+
+
+def ach_avgpool3(x, x_bs, out, out_bs, B, Cc, H, W):
+    xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))
+    fview(out, (B, Cc, H, W), (out_bs, H * W, W, 1)).copy_(F.avg_pool2d(xv, 3, 1, 1))
+
+
+def ach_rc_deform(s):
+    B, Cc, H, W = s.B, s.C, s.H, s.W
+    P = H * W
+    x = fview(s.x, (B, Cc, H, W), (s.x_bs, P, W, 1))
+    pooled = fview(s.pooled, (B, Cc, H, W), (s.pooled_bs, P, W, 1)).clone()
+    w_om = fview(s.w_om, (Cc * 9, 27), (28, 1)).t().reshape(27, Cc, 3, 3)
+    om = F.conv2d(pooled, w_om, _vec(s.b_om, 27), 1, 1)
+    offset, mask = om[:, :18], 2.0 * torch.sigmoid(om[:, 18:])
+    w_reg = fview(s.w_reg, (Cc * 9, Cc), (Cc, 1)).t().reshape(Cc, Cc, 3, 3)
+    y = deform_conv2d_3x3(pooled, offset, mask, w_reg)
+    w1 = fview(s.w1, (Cc, Cc), (Cc, 1)).t().reshape(Cc, Cc, 1, 1)
+    y = F.conv2d(y, w1)
+    y = F.relu(y * _vec(s.scale, Cc)[None, :, None, None] + _vec(s.bias, Cc)[None, :, None, None])
+    fview(s.out, (B, Cc, H, W), (s.out_bs, P, W, 1)).copy_(x + y)
+
+
+def ach_xca_fold(qkv, qkv_bs, temperature, proj_wt, ldw, wt_eff, wt_eff_bs, B, Cc, heads, N):
+    d = Cc // heads
+    q = fview(qkv, (B, heads, d, N), (qkv_bs, d * N, N, 1))
+    k = fview(qkv + Cc * N * 4, (B, heads, d, N), (qkv_bs, d * N, N, 1))
+    q, k = F.normalize(q, dim=-1), F.normalize(k, dim=-1)
+    attn = (q @ k.transpose(-2, -1)) * _vec(temperature, heads)[None, :, None, None]
+    attn = attn.softmax(-1)  # (B, h, i, j)
+    pw = fview(proj_wt, (heads, d, Cc), (d * ldw, ldw, 1))  # [h][i][o]
+    eff = torch.einsum("hio,bhij->bhjo", pw, attn).reshape(B, Cc, Cc)
+    out = fview(wt_eff, (B, Cc, ldw), (wt_eff_bs, ldw, 1))
+    out.zero_()
+    out[:, :, :Cc] = eff
+
+
+def ach_fc(x, x_bs, w, scale, bias, out, out_bs, B, K, O, act):
+    xv = fview(x, (B, K), (x_bs, 1))
+    y = xv @ fview(w, (O, K), (K, 1)).t()
+    if scale:
+        y = y * _vec(scale, O)
+    if bias:
+        y = y + _vec(bias, O)
+    fview(out, (B, O), (out_bs, 1)).copy_(_act(y, act))
+
+
+def ach_logsoftmax_t(x, x_bs, out, out_bs, B, K, N):
+    xv = fview(x, (B, K, N), (x_bs, N, 1))
+    fview(out, (B, N, K), (out_bs, K, 1)).copy_(F.log_softmax(xv.transpose(1, 2), dim=-1))
+
+
+def ach_copy_add(x, x_bs, post, out, out_bs, B, Cc, P):
+    y = fview(x, (B, Cc * P), (x_bs, 1)).clone()
+    if post:
+        y = y + fview(post, (1, Cc * P), (0, 1))
+    fview(out, (B, Cc * P), (out_bs, 1)).copy_(y)
+
+
+def ach_add(a, a_bs, b2, b_bs, out, out_bs, B, Cc, P):
+    fview(out, (B, Cc * P), (out_bs, 1)).copy_(fview(a, (B, Cc * P), (a_bs, 1)) + fview(b2, (B, Cc * P), (b_bs, 1)))
+
+
+def ach_fill(x, n, value):
+    fview(x, (n,), (1,)).fill_(value)
+
+
+EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
+                                     ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
+                                     ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill)}
+
+
+def _unwrap(a):
+    return a._obj if hasattr(a, "_obj") else a
+
+
+def emulate_op(fn, args):
+    EMULATORS[fn.__name__](*[_unwrap(a) for a in args])
+
+
+def emulate_engine(engine):
+    """Executes a dry-run engine's pack ops and launch plan on the host."""
+    with torch.no_grad():
+        for fn, args in engine.pack_ops:
+            emulate_op(fn, args)
+        for fn, args in engine.ops:
+            emulate_op(fn, args)

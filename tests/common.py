@@ -35,6 +35,7 @@ def load_keys(name):
 def rel_err(a, b):
     a = torch.as_tensor(a).float().cpu()
     b = torch.as_tensor(b).float().cpu()
+    a = a.reshape(b.shape)
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 

@@ -1,0 +1,53 @@
+"""CPU: the engine's host logic (weight folding/packing, views, wiring, output packing) executed through
+the C-ABI emulator (tests/abi_emulator.py) on a dry-run plan, compared with the oracle."""
+import pytest
+import torch
+
+from achelous_b200.engine import Engine
+from achelous_b200.nets.Achelous import Achelous
+from achelous_b200.synthetic import make_inputs
+from achelous_b200.weights import fill_state_dict
+from oracle import functional as OF
+from tests.abi_emulator import emulate_engine
+from tests.common import MODEL_KW, argmax_mismatch, rel_err
+
+TOL = 5e-5
+
+
+@pytest.mark.parametrize("phi,backbone,seed", [("S0", "en", 2), ("S2", "en", 0)])
+def test_plan_matches_oracle(phi, backbone, seed):
+    torch.set_num_threads(4)
+    model = Achelous(phi=phi, backbone=backbone, **MODEL_KW).eval()
+    sd = fill_state_dict(model.state_dict(), seed=seed)
+    model.load_state_dict(sd, strict=True)
+    B = 2
+    x, xr, pc = make_inputs(B, seed=21)
+    eng = Engine(model, B, "cpu", dry_run=True)
+    ins = eng.input_tensors()
+    ins[0].copy_(x), ins[1].copy_(xr), ins[2].copy_(pc)
+    emulate_engine(eng)
+    det, se, lane, pcs = eng.output_views()
+    taps = {}
+    o_det, o_se, o_lane, o_pc = OF.achelous_forward(sd, x, xr, pc, phi=phi, backbone=backbone, taps=taps)
+    for name in eng.taps:
+        assert rel_err(eng.tap(name), taps[name]) < TOL, name
+    for i in range(3):
+        assert rel_err(det[i], o_det[i]) < TOL
+    assert rel_err(se, o_se) < TOL and rel_err(lane, o_lane) < TOL and rel_err(pcs, o_pc) < TOL
+    for logits, ref in ((se, o_se), (lane, o_lane)):
+        _, n_safe_diff, _ = argmax_mismatch(logits, ref.argmax(1))
+        assert n_safe_diff == 0
+
+
+def test_repack_tracks_parameter_updates():
+    model = Achelous(phi="S0", backbone="en", **MODEL_KW).eval()
+    model.load_state_dict(fill_state_dict(model.state_dict(), seed=1))
+    eng = Engine(model, 1, "cpu", dry_run=True)
+    sig = eng._sig
+    key = "det0.stem.wt"
+    before = eng._weights[key][0].clone()
+    with torch.no_grad():
+        model.det_head.stems[0].conv.weight.mul_(2.0)
+    assert eng._signature() != sig
+    eng.repack()
+    assert torch.allclose(eng._weights[key][0], before * 2.0)
