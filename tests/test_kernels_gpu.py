@@ -1,0 +1,380 @@
+"""GPU: every C-ABI kernel against the CPU emulator of the same entry point on identical seeded
+buffers (tests/abi_emulator.py).  Tolerance: fp32 kernels vs an fp32/fp64 CPU evaluation with a
+different summation order -> max|a-b| <= 2e-5 * max|b| (+1e-6 abs)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from achelous_b200 import _lib
+from achelous_b200._lib import AchConvDense, AchDwConv, AchPwConv, AchRcDeform
+from tests import abi_emulator as emu
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-5
+
+
+class Arena:
+    """Allocates the same named tensors on the host or on the device."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.t = {}
+
+    def new(self, name, tensor):
+        t = tensor.detach().to(torch.float32).clone().to(self.device).contiguous()
+        self.t[name] = t
+        return t
+
+    def ptr(self, name, offset_elems=0):
+        return self.t[name].data_ptr() + 4 * offset_elems
+
+
+def run_both(fn_name, make, outs, seed=0, rtol=RTOL):
+    """make(arena) -> args tuple for the C function (without the stream)."""
+    lib = _lib.load()
+    results = {}
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(seed)
+        A = Arena(dev)
+        args = make(A)
+        if dev == "cpu":
+            emu.EMULATORS[fn_name](*args)
+        else:
+            cargs = [C.byref(a) if isinstance(a, C.Structure) else a for a in args]
+            st = getattr(lib, fn_name)(*cargs, torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, fn_name)
+            torch.cuda.synchronize()
+        results[dev] = {o: A.t[o].cpu() for o in outs}
+    for o in outs:
+        a, b = results["cuda"][o], results["cpu"][o]
+        assert torch.isfinite(a).all() or not torch.isfinite(b).all(), f"{fn_name}:{o} non-finite"
+        fin = torch.isfinite(b)
+        err = (a[fin] - b[fin]).abs().max().item() if fin.any() else 0.0
+        scale = b[fin].abs().max().item() if fin.any() else 0.0
+        assert err <= rtol * scale + 1e-6, f"{fn_name}:{o} max err {err:.3e} vs scale {scale:.3e}"
+        assert torch.equal(torch.isfinite(a), fin), f"{fn_name}:{o} finite mask differs"
+
+
+R = torch.randn
+
+
+# ------------------------------------------------------------------ pw_conv
+PW_CASES = [
+    # B, c0, c1, O, P, ln, act, res, gamma, pbias, per_batch_w, reduce_max, scale
+    dict(B=2, c0=32, c1=0, O=128, P=6400, ln=1, act=3),
+    dict(B=2, c0=128, c1=0, O=32, P=6400, res=1, gamma=1),
+    dict(B=3, c0=96, c1=96, O=96, P=400, act=1, scale=1),
+    dict(B=2, c0=176, c1=0, O=704, P=100, ln=1, act=3),
+    dict(B=2, c0=704, c1=0, O=176, P=100, res=1, gamma=1),
+    dict(B=2, c0=32, c1=0, O=16, P=25600, act=1, scale=1),
+    dict(B=2, c0=32, c1=0, O=5, P=1024, act=1, scale=1),
+    dict(B=2, c0=32, c1=0, O=1, P=1024, act=1, scale=1),
+    dict(B=2, c0=5, c1=0, O=5, P=512, per_batch_w=1),
+    dict(B=2, c0=5, c1=0, O=64, P=512, act=1, scale=1),
+    dict(B=2, c0=128, c1=0, O=1024, P=512, act=1, scale=1, reduce_max=1),
+    dict(B=2, c0=64, c1=0, O=128, P=512, scale=1, reduce_max=1),
+    dict(B=2, c0=32, c1=0, O=128, P=512, act=1, scale=1, pbias=1),
+    dict(B=2, c0=100, c1=0, O=64, P=512, act=1, scale=1),
+    dict(B=2, c0=48, c1=0, O=48, P=1600, per_batch_w=1, res=1, gamma=1),
+    dict(B=2, c0=48, c1=0, O=144, P=1600, ln=1),
+    dict(B=2, c0=64, c1=0, O=7, P=100),
+    dict(B=1, c0=288, c1=0, O=1152, P=100, ln=1, act=3),
+    dict(B=2, c0=60, c1=0, O=64, P=1600, act=1, scale=1),
+    dict(B=2, c0=352, c1=0, O=176, P=100, act=2, scale=1),
+]
+
+
+@pytest.mark.parametrize("case", PW_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_pw_conv(case):
+    c = dict(c1=0, ln=0, act=0, res=0, gamma=0, pbias=0, per_batch_w=0, reduce_max=0, scale=0)
+    c.update(case)
+    B, c0, c1, O, P = c["B"], c["c0"], c["c1"], c["O"], c["P"]
+    K = c0 + c1
+    ldw = (O + 3) // 4 * 4
+
+    def make(A):
+        # activations live inside wider buffers so that batch strides != C*P are exercised
+        A.new("x0", R(B, c0 + 3, P))
+        if c1:
+            A.new("x1", R(B, c1, P) * 2 + 1)
+        wt = torch.zeros(B if c["per_batch_w"] else 1, K, ldw)
+        wt[:, :, :O] = R(wt.shape[0], K, O) / K ** 0.5
+        A.new("wt", wt)
+        s = AchPwConv()
+        s.x0, s.x0_bs, s.c0 = A.ptr("x0", P), (c0 + 3) * P, c0
+        if c1:
+            s.x1, s.x1_bs, s.c1 = A.ptr("x1"), c1 * P, c1
+        s.wt, s.ldw, s.wt_bs = A.ptr("wt"), ldw, (K * ldw if c["per_batch_w"] else 0)
+        A.new("bias", R(O))
+        s.bias = A.ptr("bias")
+        if c["scale"]:
+            A.new("scale", torch.rand(O) + 0.5)
+            s.scale = A.ptr("scale")
+        if c["pbias"]:
+            A.new("pbias", R(B, O))
+            s.pbias = A.ptr("pbias")
+        if c["res"]:
+            A.new("res", R(B, O, P))
+            s.res, s.res_bs = A.ptr("res"), O * P
+        if c["gamma"]:
+            A.new("gamma", torch.rand(O) + 0.5)
+            s.gamma = A.ptr("gamma")
+        if c["reduce_max"]:
+            A.new("out", torch.full((B, O), float("-inf")))
+            s.out, s.out_bs = A.ptr("out"), O
+        else:
+            A.new("out", torch.zeros(B, O + 2, P))
+            s.out, s.out_bs = A.ptr("out", P), (O + 2) * P
+        s.B, s.O, s.P = B, O, P
+        s.ln, s.ln_eps, s.act, s.reduce_max = c["ln"], 1e-6, c["act"], c["reduce_max"]
+        return (s,)
+
+    run_both("ach_pw_conv", make, ["out"])
+
+
+# ------------------------------------------------------------------ dw_conv
+DW_CASES = [
+    dict(B=2, C=32, H=80, W=80, k=3, s=1, act=0),
+    dict(B=2, C=48, H=40, W=40, k=5, s=1, act=1, scale=1),
+    dict(B=2, C=96, H=20, W=20, k=7, s=1),
+    dict(B=2, C=176, H=10, W=10, k=9, s=1),
+    dict(B=1, C=16, H=320, W=320, k=3, s=1, act=1, scale=1),
+    dict(B=2, C=24, H=40, W=40, k=3, s=1, xadd=1, post=1),
+    dict(B=2, C=64, H=40, W=40, k=3, s=2, act=2, scale=1),
+    dict(B=2, C=5, H=33, W=47, k=3, s=1, act=1, scale=1),
+    dict(B=2, C=7, H=33, W=47, k=3, s=2),
+    dict(B=2, C=64, H=20, W=20, k=5, s=1),
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_dw_conv(case):
+    c = dict(act=0, scale=0, xadd=0, post=0)
+    c.update(case)
+    B, Cc, H, W, k, st = c["B"], c["C"], c["H"], c["W"], c["k"], c["s"]
+    Ho, Wo = (H + 2 * (k // 2) - k) // st + 1, (W + 2 * (k // 2) - k) // st + 1
+
+    def make(A):
+        A.new("x", R(B, Cc + 2, H, W))
+        A.new("w", R(Cc, k * k) / k)
+        A.new("bias", R(Cc))
+        A.new("out", torch.zeros(B, Cc + 1, Ho, Wo))
+        s = AchDwConv()
+        s.x, s.x_bs = A.ptr("x", H * W), (Cc + 2) * H * W
+        s.w, s.bias = A.ptr("w"), A.ptr("bias")
+        if c["scale"]:
+            A.new("scale", torch.rand(Cc) + 0.5)
+            s.scale = A.ptr("scale")
+        if c["xadd"]:
+            A.new("xadd", R(B, Cc, H, W))
+            s.xadd, s.xadd_bs = A.ptr("xadd"), Cc * H * W
+        if c["post"]:
+            A.new("post", R(Cc, Ho * Wo))
+            s.post = A.ptr("post")
+        s.out, s.out_bs = A.ptr("out", Ho * Wo), (Cc + 1) * Ho * Wo
+        s.B, s.C, s.H, s.W, s.Ho, s.Wo, s.k, s.stride, s.act = B, Cc, H, W, Ho, Wo, k, st, c["act"]
+        return (s,)
+
+    run_both("ach_dw_conv", make, ["out"])
+
+
+# ------------------------------------------------------------------ conv_dense
+CD_CASES = [
+    dict(B=2, Cin=3, H=320, W=320, O=32, k=4, s=4, p=0, ln=1),
+    dict(B=2, Cin=32, H=80, W=80, O=48, k=2, s=2, p=0),
+    dict(B=2, Cin=96, H=20, W=20, O=176, k=2, s=2, p=0),
+    dict(B=2, Cin=3, H=320, W=320, O=8, k=3, s=2, p=1),
+    dict(B=2, Cin=24, H=20, W=20, O=44, k=3, s=2, p=1),
+    dict(B=2, Cin=36, H=20, W=20, O=72, k=3, s=2, p=1),
+    dict(B=2, Cin=48, H=40, W=40, O=48, k=3, s=1, p=1, act=2, scale=1),
+    dict(B=2, Cin=3, H=64, W=64, O=16, k=3, s=2, p=1, act=2, scale=1),
+    dict(B=1, Cin=7, H=37, W=29, O=13, k=3, s=1, p=1),
+]
+
+
+@pytest.mark.parametrize("case", CD_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_dense(case):
+    c = dict(act=0, scale=0, ln=0)
+    c.update(case)
+    B, Cin, H, W, O, k, st, p = c["B"], c["Cin"], c["H"], c["W"], c["O"], c["k"], c["s"], c["p"]
+    Ho, Wo = (H + 2 * p - k) // st + 1, (W + 2 * p - k) // st + 1
+    ldo = (O + 3) // 4 * 4
+
+    def make(A):
+        A.new("x", R(B, Cin, H, W))
+        w = torch.zeros(Cin, k * k, ldo)
+        w[:, :, :O] = R(Cin, k * k, O) / (Cin * k * k) ** 0.5
+        A.new("w", w)
+        A.new("bias", R(O))
+        A.new("out", torch.zeros(B, O, Ho, Wo))
+        s = AchConvDense()
+        s.x, s.x_bs, s.w, s.bias = A.ptr("x"), Cin * H * W, A.ptr("w"), A.ptr("bias")
+        if c["scale"]:
+            A.new("scale", torch.rand(O) + 0.5)
+            s.scale = A.ptr("scale")
+        if c["ln"]:
+            A.new("ln_w", torch.rand(O) + 0.5)
+            A.new("ln_b", R(O))
+            s.ln_w, s.ln_b, s.ln_out, s.ln_eps = A.ptr("ln_w"), A.ptr("ln_b"), 1, 1e-6
+        s.out, s.out_bs = A.ptr("out"), O * Ho * Wo
+        s.B, s.Cin, s.H, s.W, s.O, s.ldo, s.Ho, s.Wo, s.k, s.stride, s.pad, s.act = B, Cin, H, W, O, ldo, Ho, Wo, k, st, p, c["act"]
+        return (s,)
+
+    run_both("ach_conv_dense", make, ["out"])
+
+
+# ------------------------------------------------------------------ small ops
+def test_layernorm_cf():
+    B, Cc, P = 2, 48, 1600
+
+    def make(A):
+        A.new("x", R(B, Cc, P) * 2 + 0.5), A.new("w", torch.rand(Cc) + 0.5), A.new("b", R(Cc)), A.new("out", torch.zeros(B, Cc, P))
+        return (A.ptr("x"), Cc * P, A.ptr("w"), A.ptr("b"), A.ptr("out"), Cc * P, B, Cc, P, 1e-6)
+    run_both("ach_layernorm_cf", make, ["out"])
+
+
+@pytest.mark.parametrize("Cc,H,W", [(96, 10, 10), (48, 40, 40), (32, 160, 160), (3, 7, 5)])
+def test_upsample2x(Cc, H, W):
+    B = 2
+
+    def make(A):
+        A.new("x", R(B, Cc, H, W)), A.new("out", torch.zeros(B, Cc + 1, 2 * H, 2 * W))
+        return (A.ptr("x"), Cc * H * W, A.ptr("out", 4 * H * W), (Cc + 1) * 4 * H * W, B, Cc, H, W)
+    run_both("ach_upsample2x", make, ["out"])
+
+
+def test_spp_maxpool():
+    B, Cc, H, W = 2, 88, 10, 10
+
+    def make(A):
+        A.new("cat", R(B, 4 * Cc, H, W))
+        P4 = Cc * H * W
+        return (A.ptr("cat"), 4 * P4, A.ptr("cat", P4), A.ptr("cat", 2 * P4), A.ptr("cat", 3 * P4), 4 * P4, B, Cc, H, W)
+    run_both("ach_spp_maxpool", make, ["cat"])
+
+
+@pytest.mark.parametrize("Cc", [48, 64])
+def test_shuffle_attention(Cc):
+    B, P, G = 2, 1600, 4
+    c = Cc // (2 * G)
+
+    def make(A):
+        A.new("x", R(B, Cc, P) * 2 + 0.3), A.new("out", torch.zeros(B, Cc, P))
+        for n in ("cw", "cb", "sw", "sb", "gw", "gb"):
+            A.new(n, R(c))
+        return (A.ptr("x"), Cc * P, A.ptr("out"), Cc * P, *[A.ptr(n) for n in ("cw", "cb", "sw", "sb", "gw", "gb")], B, Cc, P, G, 1e-5)
+    run_both("ach_shuffle_attention", make, ["out"])
+
+
+@pytest.mark.parametrize("two", [0, 1])
+def test_plane_mean_and_eca(two):
+    B, Cc, P, k = 2, 48, 1600, 3
+
+    def make_mean(A):
+        A.new("x", R(B, Cc, P) + 0.2), A.new("x2", R(B, Cc, P)), A.new("out", torch.zeros(B, Cc))
+        return (A.ptr("x"), Cc * P, A.ptr("x2") if two else None, Cc * P if two else 0, A.ptr("out"), B, Cc, P)
+    run_both("ach_plane_mean", make_mean, ["out"])
+
+    def make_eca(A):
+        A.new("x", R(B, Cc, P)), A.new("x2", R(B, Cc, P)), A.new("mean", R(B, Cc)), A.new("w", R(k))
+        A.new("s", torch.rand(Cc + 4) + 0.5), A.new("b", R(Cc + 4)), A.new("out", torch.zeros(B, Cc + 4, P))
+        return (A.ptr("x"), Cc * P, A.ptr("x2") if two else None, Cc * P if two else 0, A.ptr("mean"), A.ptr("w"), k,
+                A.ptr("s", 4), A.ptr("b", 4), A.ptr("out", 4 * P), (Cc + 4) * P, B, Cc, P)
+    run_both("ach_eca_fuse", make_eca, ["out"])
+
+
+def test_eca_k5():
+    B, Cc, P, k = 2, 176, 100, 5
+
+    def make_eca(A):
+        A.new("x", R(B, Cc, P)), A.new("mean", R(B, Cc)), A.new("w", R(k))
+        A.new("s", torch.rand(Cc) + 0.5), A.new("b", R(Cc)), A.new("out", torch.zeros(B, Cc, P))
+        return (A.ptr("x"), Cc * P, None, 0, A.ptr("mean"), A.ptr("w"), k, A.ptr("s"), A.ptr("b"), A.ptr("out"), Cc * P, B, Cc, P)
+    run_both("ach_eca_fuse", make_eca, ["out"])
+
+
+@pytest.mark.parametrize("Cc,H,W", [(3, 320, 320), (12, 40, 40), (5, 9, 13)])
+def test_avgpool3(Cc, H, W):
+    B = 2
+
+    def make(A):
+        A.new("x", R(B, Cc, H, W)), A.new("out", torch.zeros(B, Cc, H, W))
+        return (A.ptr("x"), Cc * H * W, A.ptr("out"), Cc * H * W, B, Cc, H, W)
+    run_both("ach_avgpool3", make, ["out"])
+
+
+@pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (8, 40, 40), (12, 40, 40), (16, 24, 20), (24, 20, 20), (30, 12, 12), (36, 20, 20)])
+def test_rc_deform(Cc, H, W):
+    B = 2
+
+    def make(A):
+        A.new("x", R(B, Cc, H, W)), A.new("pooled", R(B, Cc, H, W))
+        w_om = torch.zeros(Cc * 9, 28)
+        w_om[:, :27] = R(Cc * 9, 27) / (Cc * 9) ** 0.5
+        w_om[:, :18] *= 3.0  # offsets of a few pixels: taps leave the image at the borders
+        A.new("w_om", w_om), A.new("b_om", torch.rand(27) * 2 - 1)
+        A.new("w_reg", R(Cc * 9, Cc) / (Cc * 9) ** 0.5), A.new("w1", R(Cc, Cc) / Cc ** 0.5)
+        A.new("scale", torch.rand(Cc) + 0.5), A.new("bias", R(Cc) * 0.1), A.new("out", torch.zeros(B, Cc, H, W))
+        s = AchRcDeform()
+        s.x, s.pooled, s.w_om, s.b_om, s.w_reg, s.w1 = (A.ptr(n) for n in ("x", "pooled", "w_om", "b_om", "w_reg", "w1"))
+        s.scale, s.bias, s.out = A.ptr("scale"), A.ptr("bias"), A.ptr("out")
+        s.x_bs = s.pooled_bs = s.out_bs = Cc * H * W
+        s.B, s.C, s.H, s.W = B, Cc, H, W
+        return (s,)
+    # bilinear taps sit next to floor() discontinuities: one ulp in an offset moves a tap across a pixel
+    # boundary only if it lands within 1e-6 of an integer, continuous in value there -> same tolerance
+    run_both("ach_rc_deform", make, ["out"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("Cc,heads,N", [(48, 4, 1600), (96, 4, 400), (176, 4, 100), (64, 8, 1600), (144, 8, 400), (288, 8, 100)])
+def test_xca_fold(Cc, heads, N):
+    B = 2
+    ldw = (Cc + 3) // 4 * 4
+
+    def make(A):
+        A.new("qkv", R(B, 3 * Cc, N)), A.new("temp", torch.rand(heads) * 1.5 + 0.5)
+        pw = torch.zeros(Cc, ldw)
+        pw[:, :Cc] = R(Cc, Cc) / Cc ** 0.5
+        A.new("pw", pw), A.new("weff", torch.zeros(B, Cc, ldw))
+        return (A.ptr("qkv"), 3 * Cc * N, A.ptr("temp"), A.ptr("pw"), ldw, A.ptr("weff"), Cc * ldw, B, Cc, heads, N)
+    run_both("ach_xca_fold", make, ["weff"])
+
+
+@pytest.mark.parametrize("K,O,act", [(1024, 512, 1), (256, 40, 0), (256, 1024, 0), (128, 128, 0)])
+def test_fc(K, O, act):
+    B = 3
+
+    def make(A):
+        A.new("x", R(B, K)), A.new("w", R(O, K) / K ** 0.5), A.new("s", torch.rand(O) + 0.5), A.new("b", R(O)), A.new("out", torch.zeros(B, O))
+        return (A.ptr("x"), K, A.ptr("w"), A.ptr("s"), A.ptr("b"), A.ptr("out"), O, B, K, O, act)
+    run_both("ach_fc", make, ["out"])
+
+
+def test_logsoftmax_t():
+    B, K, N = 2, 8, 512
+
+    def make(A):
+        A.new("x", R(B, K, N) * 3), A.new("out", torch.zeros(B, N * K + 16))
+        return (A.ptr("x"), K * N, A.ptr("out"), N * K + 16, B, K, N)
+    run_both("ach_logsoftmax_t", make, ["out"])
+
+
+def test_copy_add_fill():
+    B, Cc, P = 2, 24, 1600
+
+    def make(A):
+        A.new("x", R(B, 2 * Cc, P)), A.new("post", R(Cc, P)), A.new("out", torch.zeros(B, 2 * Cc, P))
+        return (A.ptr("x", Cc * P), 2 * Cc * P, A.ptr("post"), A.ptr("out", Cc * P), 2 * Cc * P, B, Cc, P)
+    run_both("ach_copy_add", make, ["out"])
+
+    def make_add(A):
+        A.new("a", R(B, Cc, P)), A.new("b", R(B, Cc, P)), A.new("out", torch.zeros(B, Cc, P))
+        return (A.ptr("a"), Cc * P, A.ptr("b"), Cc * P, A.ptr("out"), Cc * P, B, Cc, P)
+    run_both("ach_add", make_add, ["out"])
+
+    def make_fill(A):
+        A.new("x", torch.zeros(1000))
+        return (A.ptr("x", 7), 900, float("-inf"))
+    run_both("ach_fill", make_fill, ["x"])

@@ -1,0 +1,58 @@
+"""GPU: decode + NMS kernels (achelous_b200.utils.utils_bbox) against the CPU oracle and the golden
+fixtures of the reference's own decode_outputs / non_max_suppression.  Kept indices: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from achelous_b200.utils import utils_bbox as UB
+from oracle import postprocess as OP
+from tests.common import GOLDEN_CONFIGS, WH_BIAS, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CONFIGS))
+def test_decode_and_nms_vs_golden(name):
+    g = load_golden(name)
+    det = [torch.from_numpy(g[f"det{i}"]).clone() for i in range(3)]
+    for d in det:
+        d[:, 4] += float(g["obj_bias"])
+        d[:, 2:4] += WH_BIAS
+    decoded = UB.decode_outputs([d.cuda() for d in det], (320, 320), 0)
+    # exp/sigmoid come from different libm implementations on host and device: 2 ulp
+    np.testing.assert_allclose(decoded.cpu().numpy(), g["decoded"], rtol=3e-7, atol=1e-7)
+    gold_dec = torch.from_numpy(g["decoded"]).cuda()
+    for tag, conf, iou, shape, lb in (("a", 0.35, 0.35, (320, 320), False), ("b", 0.25, 0.5, (1080, 1920), True)):
+        kept, kept_idx, counts = UB.nms_device(gold_dec.clone(), 7, conf, iou)
+        o_res, o_idx = OP.non_max_suppression(gold_dec.cpu(), 7, (320, 320), np.array(shape), lb, conf, iou, return_indices=True)
+        res = UB.non_max_suppression(gold_dec.clone(), 7, (320, 320), np.array(shape), lb, conf, iou)
+        for b in range(gold_dec.shape[0]):
+            n = int(counts[b])
+            assert np.array_equal(kept_idx[b, :n].cpu().numpy(), o_idx[b]), (tag, b)   # bit-exact kept indices vs oracle
+            np.testing.assert_allclose(res[b], o_res[b], rtol=1e-6, atol=1e-6)
+            gold = g[f"nms_{tag}_{b}"]
+            n_cand = int(((g["decoded"][b, :, 4] * g["decoded"][b, :, 5:].max(-1)) >= conf).sum())
+            if n_cand <= 1000:  # above that the reference's CPU torchvision takes the per-class branch
+                assert res[b].shape == gold.shape
+                np.testing.assert_allclose(res[b], gold, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n_boxes,seed", [(0, 0), (1, 1), (37, 2), (700, 3), (2100, 4)])
+def test_nms_random_dense(n_boxes, seed):
+    """Heavily overlapping random boxes incl. exact score ties; compares kept anchor indices bit-exactly."""
+    rng = np.random.default_rng(seed)
+    B, A, K = 3, 2100, 7
+    pred = np.zeros((B, A, 5 + K), np.float32)
+    pred[..., 0:2] = rng.uniform(0.2, 0.8, (B, A, 2))
+    pred[..., 2:4] = rng.uniform(0.05, 0.4, (B, A, 2))
+    pred[..., 4] = 0.01
+    for b in range(B):
+        idx = rng.choice(A, n_boxes, replace=False)
+        pred[b, idx, 4] = np.round(rng.uniform(0.5, 1.0, n_boxes), 2)  # rounded -> many exact ties
+    pred[..., 5:] = np.round(rng.uniform(0.5, 1.0, (B, A, K)), 1)
+    t = torch.from_numpy(pred)
+    kept, kept_idx, counts = UB.nms_device(t.cuda(), K, 0.2, 0.45)
+    _, o_idx = OP.non_max_suppression(t, K, (320, 320), np.array((320, 320)), False, 0.2, 0.45, return_indices=True)
+    for b in range(B):
+        n = int(counts[b])
+        assert np.array_equal(kept_idx[b, :n].cpu().numpy(), o_idx[b])
