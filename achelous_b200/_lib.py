@@ -46,6 +46,16 @@ class AchRcDeform(C.Structure):
                 ("B", I), ("C", I), ("H", I), ("W", I)]
 
 
+class AchUpGhost(C.Structure):
+    _fields_ = [("v", VP), ("b1", VP), ("w2", VP), ("s2", VP), ("b2", VP), ("out", VP), ("v_bs", LL), ("out_bs", LL),
+                ("B", I), ("Ci", I), ("Cn", I), ("h", I), ("w", I)]
+
+
+class AchUpGhostHead(C.Structure):
+    _fields_ = [("v", VP), ("out", VP), ("b1", VP), ("w2", VP), ("s2", VP), ("b2", VP), ("w3", VP), ("b3", VP), ("w4", VP),
+                ("s4", VP), ("b4", VP), ("v_bs", LL), ("out_bs", LL), ("B", I), ("C", I), ("init", I), ("K", I), ("h", I), ("w", I)]
+
+
 _SIGNATURES = {
     "ach_version": ([], I),
     "ach_pw_conv": ([C.POINTER(AchPwConv), VP], I),
@@ -65,6 +75,9 @@ _SIGNATURES = {
     "ach_copy_add": ([VP, LL, VP, VP, LL, I, I, I, VP], I),
     "ach_add": ([VP, LL, VP, LL, VP, LL, I, I, I, VP], I),
     "ach_fill": ([VP, LL, F, VP], I),
+    "ach_up_ghost": ([C.POINTER(AchUpGhost), VP], I),
+    "ach_up_ghost_head_supported": ([I, I, I], I),
+    "ach_up_ghost_head": ([C.POINTER(AchUpGhostHead), VP], I),
     "ach_decode_outputs": ([C.POINTER(VP), C.POINTER(LL), C.POINTER(I), C.POINTER(I), I, VP, I, I, F, F, VP], I),
     "ach_nms_workspace_bytes": ([I, I], LL),
     "ach_nms": ([VP, I, I, I, F, F, VP, VP, VP, VP, LL, VP], I),

@@ -1,0 +1,296 @@
+// Fused segmentation-decoder stages of the Ghost-Dual-FPN (ghostdualfpn.py:175-197).
+//
+// The decoder is the byte-dominant part of the network (85 % of block-level traffic):
+// each stage is  1x1 conv+BN+ReLU -> bilinear x2 (align_corners) -> GhostModule(1x1+BN+ReLU | dw3x3+BN+ReLU).
+// Bilinear interpolation and the Ghost "primary" 1x1 conv + BN affine are both linear and act on
+// different axes (space vs channels), so they commute:  primary(up(t)) == up(primary_linear(t)) + b.
+// The host therefore runs the primary conv at LOW resolution (4x fewer MACs, half the channels) and
+// these kernels do everything that happens at HIGH resolution in one pass over shared memory:
+//
+//   ach_up_ghost       v (B,Ci,h,w) -> out (B,Ci+Cn,2h,2w):  x1 = relu(up(v) + b1);  x2 = relu(s2*dw3x3(x1) + b2)
+//   ach_up_ghost_head  v (B,16,h,w) -> logits (B,K,2h,2w): the same stage, immediately followed by the head
+//                      GhostModule (1x1 32->INIT +BN+ReLU | dw3x3 +BN+ReLU, slice to K) WITHOUT ever writing
+//                      the 32-channel full-resolution tensor (13 MB/frame in the reference) to HBM.
+//
+// Tiles: the halo of each stage is recomputed (cheap ALU) instead of exchanged through memory.  All
+// per-channel weights of ach_up_ghost_head travel as kernel parameters (constant bank) so the inner FMAs
+// take them as immediate constant operands - no load instructions for weights at all.
+#include "common.cuh"
+
+namespace ach {
+
+// ATen upsample_bilinear2d (align_corners=True) source coordinate for destination index d
+__device__ __forceinline__ void bilin_src(int d, float scale, int in_size, int& i0, int& i1, float& l1) {
+    const float f = scale * (float)d;
+    i0 = (int)f;
+    i1 = i0 + (i0 < in_size - 1);
+    l1 = f - (float)i0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ach_up_ghost: per channel, 32x32 output tile.
+constexpr int UG_T = 32;                 // output tile edge
+constexpr int UG_X1 = UG_T + 2;          // x1 tile edge (halo 1 for the dw3x3)
+constexpr int UG_V = UG_X1 / 2 + 3;      // low-res tile edge (ceil(34 * 0.5) + interpolation neighbour + slack)
+constexpr int UG_CPB = 4;                // channels per CTA
+
+__global__ void __launch_bounds__(256) up_ghost_kernel(const AchUpGhost p) {
+    __shared__ float vs[UG_V][UG_V + 1];
+    __shared__ float x1s[UG_X1][UG_X1 + 1];
+    const int H = 2 * p.h, W = 2 * p.w;
+    const int tiles_x = (W + UG_T - 1) / UG_T;
+    const int ty0 = (blockIdx.x / tiles_x) * UG_T, tx0 = (blockIdx.x % tiles_x) * UG_T;
+    const int b = blockIdx.z;
+    const float sy = (float)(p.h - 1) / (float)(H - 1), sx = (float)(p.w - 1) / (float)(W - 1);
+    // low-res origin of this tile: source row/col of the first x1 row/col (clamped to the image)
+    const int vy0 = (int)(sy * (float)max(ty0 - 1, 0)), vx0 = (int)(sx * (float)max(tx0 - 1, 0));
+    const long long plane_lo = (long long)p.h * p.w, plane_hi = (long long)H * W;
+
+    for (int cc = 0; cc < UG_CPB; ++cc) {
+        const int c = blockIdx.y * UG_CPB + cc;
+        if (c >= p.Ci) break;
+        const float* vp = p.v + (long long)b * p.v_bs + (long long)c * plane_lo;
+        __syncthreads();
+        for (int i = threadIdx.x; i < UG_V * UG_V; i += 256) {
+            const int yy = i / UG_V, xx = i - yy * UG_V;
+            const int gy = min(vy0 + yy, p.h - 1), gx = min(vx0 + xx, p.w - 1);
+            vs[yy][xx] = vp[gy * p.w + gx];
+        }
+        __syncthreads();
+        const float b1 = p.b1[c];
+        float* o1 = p.out + (long long)b * p.out_bs + (long long)c * plane_hi;
+        for (int i = threadIdx.x; i < UG_X1 * UG_X1; i += 256) {
+            const int yy = i / UG_X1, xx = i - yy * UG_X1;
+            const int gy = ty0 - 1 + yy, gx = tx0 - 1 + xx;
+            float val = 0.f;  // zero padding of the dw3x3 outside the image
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                int y0, y1, x0, x1;
+                float ly, lx;
+                bilin_src(gy, sy, p.h, y0, y1, ly);
+                bilin_src(gx, sx, p.w, x0, x1, lx);
+                const float hy = 1.f - ly, hx = 1.f - lx;
+                y0 -= vy0; y1 -= vy0; x0 -= vx0; x1 -= vx0;
+                val = hy * (hx * vs[y0][x0] + lx * vs[y0][x1]) + ly * (hx * vs[y1][x0] + lx * vs[y1][x1]);
+                val = fmaxf(val + b1, 0.f);
+                if (yy >= 1 && yy <= UG_T && xx >= 1 && xx <= UG_T) o1[(long long)gy * W + gx] = val;
+            }
+            x1s[yy][xx] = val;
+        }
+        __syncthreads();
+        if (c < p.Cn) {
+            float wk[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wk[t] = p.w2[c * 9 + t];
+            const float s2 = p.s2[c], b2 = p.b2[c];
+            float* o2 = p.out + (long long)b * p.out_bs + (long long)(p.Ci + c) * plane_hi;
+            for (int i = threadIdx.x; i < UG_T * UG_T; i += 256) {
+                const int yy = i / UG_T, xx = i - yy * UG_T;
+                const int gy = ty0 + yy, gx = tx0 + xx;
+                if (gy >= H || gx >= W) continue;
+                float acc = 0.f;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) acc = fmaf(x1s[yy + ky][xx + kx], wk[ky * 3 + kx], acc);
+                o2[(long long)gy * W + gx] = fmaxf(fmaf(s2, acc, b2), 0.f);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ach_up_ghost_head: 30x30 output tile; x1 on 34x34 (16 channels, shared memory), x2 recomputed on the fly,
+// head primary p on 32x32 (one 1x4 column strip per thread = exactly 256 work items), then the head's
+// cheap dw3x3 from shared p.  p aliases the low-res tile (dead after x1 is built).
+constexpr int UH_T = 30;
+constexpr int UH_P = UH_T + 2;           // 32
+constexpr int UH_X1 = UH_T + 4;          // 34
+constexpr int UH_V = UH_X1 / 2 + 3;      // 20
+constexpr int UH_C = 16;                 // channels of v / x1 / x2
+constexpr int UH_X1P = UH_X1 + 1;        // row pitch
+
+template <int INIT, int KOUT>
+struct UpGhostHeadParams {
+    // stage ghost module
+    float b1[UH_C];
+    float w2[UH_C * 9];
+    float s2[UH_C];
+    float b2[UH_C];
+    // head ghost module: primary (BN scale folded into w3), cheap dw
+    float w3[2 * UH_C * INIT];  // [c][i]
+    float b3[INIT];
+    float w4[(KOUT - INIT) * 9];
+    float s4[KOUT - INIT];
+    float b4[KOUT - INIT];
+};
+
+template <int INIT, int KOUT>
+__global__ void __launch_bounds__(256, 2) up_ghost_head_kernel(const float* __restrict__ v, long long v_bs, float* __restrict__ out,
+                                                               long long out_bs, int h, int w,
+                                                               const __grid_constant__ UpGhostHeadParams<INIT, KOUT> P) {
+    extern __shared__ __align__(16) float smem[];
+    float* x1s = smem;                                  // [16][34][35]
+    float* vs = smem + UH_C * UH_X1 * UH_X1P;           // [16][20][21]
+    float* ps = vs;                                     // [INIT][32][33]  (aliases vs)
+    constexpr int VP = UH_V + 1, PP = UH_P + 1;
+    static_assert(INIT * UH_P * PP <= UH_C * UH_V * VP, "p tile must fit in the low-res tile");
+
+    const int H = 2 * h, W = 2 * w;
+    const int tiles_x = (W + UH_T - 1) / UH_T;
+    const int ty0 = (blockIdx.x / tiles_x) * UH_T, tx0 = (blockIdx.x % tiles_x) * UH_T;
+    const int b = blockIdx.y;
+    const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
+    const int vy0 = (int)(sy * (float)max(ty0 - 2, 0)), vx0 = (int)(sx * (float)max(tx0 - 2, 0));
+    const long long plane_lo = (long long)h * w, plane_hi = (long long)H * W;
+    const float* vb = v + (long long)b * v_bs;
+
+    // ---- low-res tile, all 16 channels
+    for (int i = threadIdx.x; i < UH_C * UH_V * UH_V; i += 256) {
+        const int c = i / (UH_V * UH_V);
+        const int r = i - c * (UH_V * UH_V);
+        const int yy = r / UH_V, xx = r - yy * UH_V;
+        const int gy = min(vy0 + yy, h - 1), gx = min(vx0 + xx, w - 1);
+        vs[(c * UH_V + yy) * VP + xx] = __ldg(vb + (long long)c * plane_lo + gy * w + gx);
+    }
+    __syncthreads();
+
+    // ---- x1 = relu(up(v) + b1) on the 34x34 halo tile (0 outside the image = dw zero padding)
+    for (int i = threadIdx.x; i < UH_X1 * UH_X1; i += 256) {
+        const int yy = i / UH_X1, xx = i - yy * UH_X1;
+        const int gy = ty0 - 2 + yy, gx = tx0 - 2 + xx;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+        float ly = 0.f, lx = 0.f;
+        if (in) {
+            bilin_src(gy, sy, h, y0, y1, ly);
+            bilin_src(gx, sx, w, x0, x1, lx);
+            y0 -= vy0; y1 -= vy0; x0 -= vx0; x1 -= vx0;
+        }
+        const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+        for (int c = 0; c < UH_C; ++c) {
+            const float* vc = vs + c * UH_V * VP;
+            float val = hy * (hx * vc[y0 * VP + x0] + lx * vc[y0 * VP + x1]) + ly * (hx * vc[y1 * VP + x0] + lx * vc[y1 * VP + x1]);
+            val = in ? fmaxf(val + P.b1[c], 0.f) : 0.f;
+            x1s[(c * UH_X1 + yy) * UH_X1P + xx] = val;
+        }
+    }
+    __syncthreads();  // vs is dead from here on; ps (alias) may be written
+
+    // ---- head primary p = relu(w3 . [x1, x2] + b3) on the 32x32 tile, x2 = relu(s2*dw3x3(x1)+b2) on the fly.
+    // thread -> column `col` (0..31), strip of 4 rows starting at 4*strip (0..7): 6x3 x1 values serve 4 pixels.
+    {
+        const int col = threadIdx.x & 31, strip = threadIdx.x >> 5;
+        float acc[4][INIT];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < INIT; ++i) acc[r][i] = P.b3[i];
+#pragma unroll
+        for (int c = 0; c < UH_C; ++c) {
+            const float* xc = x1s + (c * UH_X1 + 4 * strip) * UH_X1P + col;  // x1 row (4*strip), col: p pixel (r, col) centre = x1[r+1][col+1]
+            float win[6][3];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) win[r][k] = xc[r * UH_X1P + k];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float d = 0.f;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) d = fmaf(win[r + ky][kx], P.w2[c * 9 + ky * 3 + kx], d);
+                const float x2 = fmaxf(fmaf(P.s2[c], d, P.b2[c]), 0.f);
+                const float x1c = win[r + 1][1];
+#pragma unroll
+                for (int i = 0; i < INIT; ++i) {
+                    acc[r][i] = fmaf(x1c, P.w3[c * INIT + i], acc[r][i]);
+                    acc[r][i] = fmaf(x2, P.w3[(UH_C + c) * INIT + i], acc[r][i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int py = 4 * strip + r;
+            const int gy = ty0 - 1 + py, gx = tx0 - 1 + col;
+            const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+#pragma unroll
+            for (int i = 0; i < INIT; ++i) ps[(i * UH_P + py) * PP + col] = in ? fmaxf(acc[r][i], 0.f) : 0.f;
+        }
+    }
+    __syncthreads();
+
+    // ---- outputs: channels [0, INIT) = p, [INIT, KOUT) = relu(s4 * dw3x3(p) + b4)
+    float* ob = out + (long long)b * out_bs;
+    for (int i = threadIdx.x; i < UH_T * UH_T; i += 256) {
+        const int yy = i / UH_T, xx = i - yy * UH_T;
+        const int gy = ty0 + yy, gx = tx0 + xx;
+        if (gy >= H || gx >= W) continue;
+        const long long o = (long long)gy * W + gx;
+#pragma unroll
+        for (int k = 0; k < INIT; ++k) ob[k * plane_hi + o] = ps[(k * UH_P + yy + 1) * PP + xx + 1];
+#pragma unroll
+        for (int k = 0; k < KOUT - INIT; ++k) {
+            float d = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) d = fmaf(ps[(k * UH_P + yy + ky) * PP + xx + kx], P.w4[k * 9 + ky * 3 + kx], d);
+            ob[(INIT + k) * plane_hi + o] = fmaxf(fmaf(P.s4[k], d, P.b4[k]), 0.f);
+        }
+    }
+}
+
+template <int INIT, int KOUT>
+static int launch_head(const AchUpGhostHead& a, cudaStream_t st) {
+    UpGhostHeadParams<INIT, KOUT> P;
+    memcpy(P.b1, a.b1, sizeof(P.b1));
+    memcpy(P.w2, a.w2, sizeof(P.w2));
+    memcpy(P.s2, a.s2, sizeof(P.s2));
+    memcpy(P.b2, a.b2, sizeof(P.b2));
+    memcpy(P.w3, a.w3, sizeof(P.w3));
+    memcpy(P.b3, a.b3, sizeof(P.b3));
+    memcpy(P.w4, a.w4, sizeof(P.w4));
+    memcpy(P.s4, a.s4, sizeof(P.s4));
+    memcpy(P.b4, a.b4, sizeof(P.b4));
+    constexpr size_t smem = (size_t)(UH_C * UH_X1 * UH_X1P + UH_C * UH_V * (UH_V + 1)) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(up_ghost_head_kernel<INIT, KOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int H = 2 * a.h, W = 2 * a.w;
+    dim3 grid(cdiv(W, UH_T) * cdiv(H, UH_T), a.B);
+    up_ghost_head_kernel<INIT, KOUT><<<grid, 256, smem, st>>>(a.v, a.v_bs, a.out, a.out_bs, a.h, a.w, P);
+    return check_launch("ach_up_ghost_head");
+}
+
+}  // namespace ach
+
+extern "C" int ach_up_ghost(const AchUpGhost* pp, void* stream) {
+    using namespace ach;
+    const AchUpGhost& p = *pp;
+    ACH_REQUIRE(p.v && p.b1 && p.out, "ach_up_ghost: null arg");
+    ACH_REQUIRE(p.Cn == 0 || (p.w2 && p.s2 && p.b2), "ach_up_ghost: null cheap-op weights");
+    ACH_REQUIRE(p.B > 0 && p.B <= 65535 && p.Ci > 0 && p.Cn >= 0 && p.Cn <= p.Ci && p.h > 1 && p.w > 1, "ach_up_ghost: bad dims");
+    const int H = 2 * p.h, W = 2 * p.w;
+    dim3 grid(cdiv(W, UG_T) * cdiv(H, UG_T), cdiv(p.Ci, UG_CPB), p.B);
+    up_ghost_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("ach_up_ghost");
+}
+
+extern "C" int ach_up_ghost_head_supported(int c_in, int init, int k_out) {
+    return c_in == ach::UH_C && ((init == 1 && k_out == 2) || (init == 5 && k_out == 9));
+}
+
+extern "C" int ach_up_ghost_head(const AchUpGhostHead* pp, void* stream) {
+    using namespace ach;
+    const AchUpGhostHead& a = *pp;
+    ACH_REQUIRE(a.v && a.out && a.b1 && a.w2 && a.s2 && a.b2 && a.w3 && a.b3 && a.w4 && a.s4 && a.b4, "ach_up_ghost_head: null arg");
+    ACH_REQUIRE(a.B > 0 && a.B <= 65535 && a.h > 1 && a.w > 1, "ach_up_ghost_head: bad dims");
+    ACH_REQUIRE(ach_up_ghost_head_supported(a.C, a.init, a.K), "ach_up_ghost_head: (C=%d, init=%d, K=%d) not instantiated", a.C, a.init, a.K);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (a.init == 1) return launch_head<1, 2>(a, st);
+    return launch_head<5, 9>(a, st);
+}

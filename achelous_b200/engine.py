@@ -16,7 +16,8 @@ from collections import namedtuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConvDense, AchDwConv, AchPwConv, AchRcDeform
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost,
+                   AchUpGhostHead)
 from .nets import holders as Hd
 
 View = namedtuple("View", "ptr bs C H W")
@@ -42,9 +43,11 @@ class Engine:
         self.n_points = model.n_points
         self.ops = []          # (cfunc, args) - stream appended at call time
         self.op_names = []
+        self.op_bytes = []
         self._keep = []        # ctypes structs / tensors that must outlive the plan
         self._bufs = {}
         self._weights = {}
+        self._host = {}        # host-side weight arrays that travel as kernel parameters
         self.graph = None
         self._sig = None
         if dry_run:
@@ -75,9 +78,22 @@ class Engine:
             self._weights[key] = (val, fn)
         return self._weights[key][0]
 
+    def _h(self, key, fn):
+        """Host float array slot (for weights passed as kernel parameters); refreshed by repack()."""
+        val = fn().to(dtype=torch.float32, device="cpu").contiguous().flatten()
+        arr = (C.c_float * val.numel())()
+        C.memmove(arr, val.data_ptr(), val.numel() * 4)
+        self._host[key] = (arr, fn)
+        return C.addressof(arr)
+
     def repack(self):
         for key, (t, fn) in self._weights.items():
             t.copy_(fn().to(device=self.device, dtype=torch.float32))
+        for key, (arr, fn) in self._host.items():
+            val = fn().to(dtype=torch.float32, device="cpu").contiguous().flatten()
+            C.memmove(arr, val.data_ptr(), val.numel() * 4)
+        if self._host:
+            self.graph = None  # kernel-parameter weights are baked into a captured graph: re-capture
         self._sig = self._signature()
 
     def _bn_fold(self, prefix, eps, conv_bias=None):
@@ -112,9 +128,14 @@ class Engine:
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
 
-    def _add(self, name, fn, *args):
+    def _add(self, name, fn, *args, nbytes=None):
         self.ops.append((fn, args))
         self.op_names.append(name)
+        self.op_bytes.append(nbytes)
+
+    def algorithmic_bytes(self, i):
+        """Unique input + output + weight bytes of launch i (fp32 storage), or None when not modelled."""
+        return self.op_bytes[i]
 
     # ------------------------------------------------------------------ op recorders
     def pw(self, name, x0, out, wt, O, x1=None, scale=None, bias=None, pbias=None, res=None, gamma=None, ln=False,
@@ -139,7 +160,10 @@ class Engine:
         s.B, s.O, s.P = self.B, O, P
         s.ln, s.ln_eps, s.act, s.reduce_max = int(ln), ln_eps, act, int(reduce_max)
         self._keep.append(s)
-        self._add(name, self.lib.ach_pw_conv, C.byref(s))
+        K_ = s.c0 + s.c1
+        nb = 4 * (self.B * K_ * P + (self.B * O if reduce_max else self.B * O * P) + (self.B * O * P if res is not None else 0)
+                  + K_ * s.ldw * (self.B if wt_bs else 1))
+        self._add(name, self.lib.ach_pw_conv, C.byref(s), nbytes=nb)
 
     def dw(self, name, x, out, w, k, stride=1, scale=None, bias=None, act=ACT_NONE, xadd=None, post=None):
         s = AchDwConv()
@@ -150,7 +174,8 @@ class Engine:
         s.B, s.C, s.H, s.W, s.Ho, s.Wo, s.k, s.stride, s.act = self.B, x.C, x.H, x.W, out.H, out.W, k, stride, act
         assert out.C == x.C, (name, x, out)
         self._keep.append(s)
-        self._add(name, self.lib.ach_dw_conv, C.byref(s))
+        nb = 4 * self.B * x.C * (x.H * x.W * (2 if xadd is not None else 1) + out.H * out.W)
+        self._add(name, self.lib.ach_dw_conv, C.byref(s), nbytes=nb)
 
     def conv(self, name, x, out, w, k, stride, pad, scale=None, bias=None, act=ACT_NONE, ln_w=None, ln_b=None, ln_eps=1e-6):
         s = AchConvDense()
@@ -161,7 +186,8 @@ class Engine:
         s.Ho, s.Wo, s.k, s.stride, s.pad, s.act = out.H, out.W, k, stride, pad, act
         s.ln_out, s.ln_eps = int(ln_w is not None), ln_eps
         self._keep.append(s)
-        self._add(name, self.lib.ach_conv_dense, C.byref(s))
+        nb = 4 * (self.B * (x.C * x.H * x.W + out.C * out.H * out.W) + w.numel())
+        self._add(name, self.lib.ach_conv_dense, C.byref(s), nbytes=nb)
 
     def _pack_conv(self, key, wname):
         """(O, Cin, k, k) -> [Cin][k*k][ceil4(O)]"""
@@ -213,7 +239,8 @@ class Engine:
         """Upsample: BaseConv 1x1 relu -> bilinear x2 into `out`"""
         t = self.buf(name + ".pw", out.C, x.H, x.W)
         self.pw_bn_act(name + ".conv", prefix + ".upsample.0.conv", prefix + ".upsample.0.bn", 1e-3, x, t, ACT_RELU)
-        self._add(name + ".up", self.lib.ach_upsample2x, t.ptr, t.bs, out.ptr, out.bs, self.B, t.C, t.H, t.W)
+        self._add(name + ".up", self.lib.ach_upsample2x, t.ptr, t.bs, out.ptr, out.bs, self.B, t.C, t.H, t.W,
+                  nbytes=4 * self.B * t.C * t.H * t.W * 5)
 
     def ghost_bottleneck(self, name, prefix, xa, xb, mid, outc):
         g1 = self.buf(name + ".g1", mid, xa.H, xa.W)
@@ -389,6 +416,58 @@ class Engine:
             cur = g
         self.ghost(f"{name}.head", f"{prefix}.{name}_seg_head", cur, out, True)
 
+    def seg_decoder_fused(self, name, prefix, x, widths, out):
+        """Same decoder with the Ghost primary conv hoisted below the upsampling (it commutes with the
+        bilinear interpolation) and the full-resolution work in the fused ach_up_ghost[_head] kernels."""
+        chans = [widths[1], widths[0], widths[0]]
+        cur = x
+        for si, (stage, c) in enumerate(zip(("3_to_2", "2_to_1", "1_to_0"), chans)):
+            up_p, g_p = f"{prefix}.{name}_seg_{stage}", f"{prefix}.{name}_seg_ghost_{stage}"
+            n = f"{name}.{stage}"
+            t = self.buf(n + ".t", c, cur.H, cur.W)
+            self.pw_bn_act(n + ".conv", up_p + ".upsample.0.conv", up_p + ".upsample.0.bn", 1e-3, cur, t, ACT_RELU)
+            init = math.ceil(c / 2)
+            cn = c - init
+            v = self.buf(n + ".v", init, cur.H, cur.W)
+            wt = self._w(n + ".prim.wt", (lambda g_p=g_p: self._kmajor(
+                self._bn_fold(g_p + ".primary_conv.1", 1e-5)[0][:, None] * self._p(g_p + ".primary_conv.0.weight").flatten(1))))
+            self.pw(n + ".prim", t, v, wt, init)
+            b1f = (lambda g_p=g_p: self._bn_fold(g_p + ".primary_conv.1", 1e-5)[1])
+            w2f = (lambda g_p=g_p, cn=cn: self._p(g_p + ".cheap_operation.0.weight")[:cn].flatten(1))
+            s2f = (lambda g_p=g_p, cn=cn: self._bn_fold(g_p + ".cheap_operation.1", 1e-5)[0][:cn])
+            b2f = (lambda g_p=g_p, cn=cn: self._bn_fold(g_p + ".cheap_operation.1", 1e-5)[1][:cn])
+            K = out.C
+            hinit = math.ceil(K / 2)
+            if si == 2 and self.lib.ach_up_ghost_head_supported(init, hinit, K) and cn == init:
+                h_p = f"{prefix}.{name}_seg_head"
+                a = AchUpGhostHead()
+                a.v, a.v_bs, a.out, a.out_bs = v.ptr, v.bs, out.ptr, out.bs
+                a.b1, a.w2, a.s2, a.b2 = self._h(n + ".b1", b1f), self._h(n + ".w2", w2f), self._h(n + ".s2", s2f), self._h(n + ".b2", b2f)
+                a.w3 = self._h(n + ".w3", lambda: (self._bn_fold(h_p + ".primary_conv.1", 1e-5)[0][:, None]
+                                                   * self._p(h_p + ".primary_conv.0.weight").flatten(1)).t())
+                a.b3 = self._h(n + ".b3", lambda: self._bn_fold(h_p + ".primary_conv.1", 1e-5)[1])
+                a.w4 = self._h(n + ".w4", lambda: self._p(h_p + ".cheap_operation.0.weight")[:K - hinit].flatten(1))
+                a.s4 = self._h(n + ".s4", lambda: self._bn_fold(h_p + ".cheap_operation.1", 1e-5)[0][:K - hinit])
+                a.b4 = self._h(n + ".b4", lambda: self._bn_fold(h_p + ".cheap_operation.1", 1e-5)[1][:K - hinit])
+                a.B, a.C, a.init, a.K, a.h, a.w = self.B, init, hinit, K, cur.H, cur.W
+                self._keep.append(a)
+                self._add(n + ".up_ghost_head", self.lib.ach_up_ghost_head, C.byref(a),
+                          nbytes=4 * self.B * (init * cur.H * cur.W + K * 4 * cur.H * cur.W))
+                return
+            g = self.buf(n + ".ghost", c, cur.H * 2, cur.W * 2)
+            u = AchUpGhost()
+            u.v, u.v_bs, u.out, u.out_bs = v.ptr, v.bs, g.ptr, g.bs
+            u.b1 = self._vec(n + ".b1", b1f).data_ptr()
+            if cn:
+                u.w2, u.s2, u.b2 = (self._w(n + ".w2", w2f).data_ptr(), self._vec(n + ".s2", s2f).data_ptr(),
+                                    self._vec(n + ".b2", b2f).data_ptr())
+            u.B, u.Ci, u.Cn, u.h, u.w = self.B, init, cn, cur.H, cur.W
+            self._keep.append(u)
+            self._add(n + ".up_ghost", self.lib.ach_up_ghost, C.byref(u), nbytes=4 * self.B * cur.H * cur.W * (init + 4 * c))
+            self.taps[f"neck.{name}_{stage}"] = g
+            cur = g
+        self.ghost(f"{name}.head", f"{prefix}.{name}_seg_head", cur, out, True)
+
     def gdf_neck(self, feats, prefix, phi, out_se, out_lane):
         w = Hd.WIDTHS[phi]
         m2, m3, m4, m5 = feats
@@ -402,8 +481,9 @@ class Engine:
         sa_lane = self.shuffle_attention("fpn.sa_lane", prefix + ".stage_3_lane_seg", f3)
         sa_se = self.shuffle_attention("fpn.sa_se", prefix + ".stage_3_semantic_seg", f3)
         self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
-        self.seg_decoder("lane", prefix, sa_lane, w, out_lane)
-        self.seg_decoder("se", prefix, sa_se, w, out_se)
+        dec = self.seg_decoder_fused if self.model.fuse_seg_decoder else self.seg_decoder
+        dec("lane", prefix, sa_lane, w, out_lane)
+        dec("se", prefix, sa_se, w, out_se)
         return (f5, m5), (f4, m4), (f3, m3)
 
     # ---- radar encoder
@@ -436,7 +516,7 @@ class Engine:
             y = self.buf(f"rc{i}.y", cin, cur.H, cur.W)
             s.out, s.out_bs, s.B, s.C, s.H, s.W = y.ptr, y.bs, self.B, cin, cur.H, cur.W
             self._keep.append(s)
-            self._add(f"rc{i}.deform", self.lib.ach_rc_deform, C.byref(s))
+            self._add(f"rc{i}.deform", self.lib.ach_rc_deform, C.byref(s), nbytes=4 * self.B * cin * cur.H * cur.W * 3)
             if down:
                 out = self.buf(f"rc{i}.out", cout, cur.H // 2, cur.W // 2)
                 self.conv(f"rc{i}.down", y, out, self._pack_conv(f"rc{i}.w2", bp + ".weight_conv2.weight"), 3, 2, 1,

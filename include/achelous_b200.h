@@ -193,6 +193,50 @@ ACH_API int ach_add(const float* a, long long a_bs, const float* b2, long long b
 ACH_API int ach_fill(float* x, long long n, float value, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused segmentation-decoder stages (ghostdualfpn.py:28-39 Upsample + ghost_conv.py:25-29 GhostModule,
+ * called from ghostdualfpn.py:175-197).  The Ghost primary 1x1 conv (+BN scale) is linear and commutes
+ * with the bilinear x2 upsampling, so the host evaluates it at LOW resolution into `v`; these kernels do
+ * the full-resolution part:
+ *   ach_up_ghost:       out[:, :Ci]      = x1 = relu(up2x(v) + b1)
+ *                       out[:, Ci:Ci+Cn] = relu(s2 * dw3x3(x1[:, :Cn]) + b2)          (w2 [Cn][9])
+ *   ach_up_ghost_head:  the same stage with Ci = Cn = 16 followed by the head GhostModule
+ *                       p = relu(w3^T [x1, x2] + b3) (w3 [32][init], BN scale folded), out[:, :init] = p,
+ *                       out[:, init:K] = relu(s4 * dw3x3(p[:, :K-init]) + b4), never materialising the
+ *                       32-channel full-resolution tensor.  Its weight arrays are HOST pointers: they are
+ *                       copied into kernel parameters (constant bank) at launch.
+ *                       Instantiated for (init, K) in {(1, 2), (5, 9)}: see ach_up_ghost_head_supported.
+ */
+typedef struct AchUpGhost {
+    const float* v;
+    const float* b1;
+    const float* w2;
+    const float* s2;
+    const float* b2;
+    float* out;
+    long long v_bs, out_bs;
+    int B, Ci, Cn, h, w;
+} AchUpGhost;
+ACH_API int ach_up_ghost(const AchUpGhost* p, void* stream);
+
+typedef struct AchUpGhostHead {
+    const float* v;       /* device (B, 16, h, w) */
+    float* out;           /* device (B, K, 2h, 2w) */
+    const float* b1;      /* host [16]      */
+    const float* w2;      /* host [16][9]   */
+    const float* s2;      /* host [16]      */
+    const float* b2;      /* host [16]      */
+    const float* w3;      /* host [32][init]*/
+    const float* b3;      /* host [init]    */
+    const float* w4;      /* host [K-init][9] */
+    const float* s4;      /* host [K-init]  */
+    const float* b4;      /* host [K-init]  */
+    long long v_bs, out_bs;
+    int B, C, init, K, h, w;
+} AchUpGhostHead;
+ACH_API int ach_up_ghost_head_supported(int c_in, int init, int k_out);
+ACH_API int ach_up_ghost_head(const AchUpGhostHead* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Detection post-process (second boundary: utils/utils_bbox.py).
  * ach_decode_outputs: decode_outputs (:33-85) for up to 3 levels of (B, 5+K, H_l, W_l) raw logits
  *   -> out (B, A, 5+K), xywh normalised by input_w/input_h.

@@ -229,9 +229,37 @@ def ach_fill(x, n, value):
     fview(x, (n,), (1,)).fill_(value)
 
 
+def _up_ghost(v, b1, w2, s2, b2, Cn):
+    x1 = F.relu(F.interpolate(v, scale_factor=2, mode="bilinear", align_corners=True) + b1[None, :, None, None])
+    x2 = F.conv2d(x1[:, :Cn], w2.reshape(Cn, 1, 3, 3), None, 1, 1, 1, Cn)
+    x2 = F.relu(x2 * s2[None, :, None, None] + b2[None, :, None, None])
+    return torch.cat([x1, x2], 1)
+
+
+def ach_up_ghost(s):
+    B, Ci, Cn, h, w = s.B, s.Ci, s.Cn, s.h, s.w
+    v = fview(s.v, (B, Ci, h, w), (s.v_bs, h * w, w, 1))
+    y = _up_ghost(v, _vec(s.b1, Ci), _vec(s.w2, Cn * 9) if Cn else None, _vec(s.s2, Cn) if Cn else None,
+                  _vec(s.b2, Cn) if Cn else None, Cn) if Cn else F.relu(
+        F.interpolate(v, scale_factor=2, mode="bilinear", align_corners=True) + _vec(s.b1, Ci)[None, :, None, None])
+    fview(s.out, (B, Ci + Cn, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(y)
+
+
+def ach_up_ghost_head(s):
+    B, Cc, init, K, h, w = s.B, s.C, s.init, s.K, s.h, s.w
+    v = fview(s.v, (B, Cc, h, w), (s.v_bs, h * w, w, 1))
+    g = _up_ghost(v, _vec(s.b1, Cc), _vec(s.w2, Cc * 9), _vec(s.s2, Cc), _vec(s.b2, Cc), Cc)  # (B, 2C, H, W)
+    w3 = fview(s.w3, (2 * Cc, init), (init, 1))
+    p = F.relu(torch.einsum("ci,bchw->bihw", w3, g) + _vec(s.b3, init)[None, :, None, None])
+    n = K - init
+    q = F.conv2d(p[:, :n], _vec(s.w4, n * 9).reshape(n, 1, 3, 3), None, 1, 1, 1, n)
+    q = F.relu(q * _vec(s.s4, n)[None, :, None, None] + _vec(s.b4, n)[None, :, None, None])
+    fview(s.out, (B, K, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(torch.cat([p, q], 1))
+
+
 EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
-                                     ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill)}
+                                     ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head)}
 
 
 def _unwrap(a):

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from achelous_b200 import _lib
-from achelous_b200._lib import AchConvDense, AchDwConv, AchPwConv, AchRcDeform
+from achelous_b200._lib import AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost, AchUpGhostHead
 from tests import abi_emulator as emu
 
 pytestmark = pytest.mark.gpu
@@ -22,8 +22,8 @@ class Arena:
         self.device = torch.device(device)
         self.t = {}
 
-    def new(self, name, tensor):
-        t = tensor.detach().to(torch.float32).clone().to(self.device).contiguous()
+    def new(self, name, tensor, host=False):
+        t = tensor.detach().to(torch.float32).clone().to("cpu" if host else self.device).contiguous()
         self.t[name] = t
         return t
 
@@ -378,3 +378,39 @@ def test_copy_add_fill():
         A.new("x", torch.zeros(1000))
         return (A.ptr("x", 7), 900, float("-inf"))
     run_both("ach_fill", make_fill, ["x"])
+
+
+# ------------------------------------------------------------------ fused seg-decoder stages
+@pytest.mark.parametrize("Ci,Cn,h,w", [(24, 24, 40, 40), (16, 16, 80, 80), (16, 16, 160, 160), (5, 4, 17, 23), (3, 0, 9, 9)])
+def test_up_ghost(Ci, Cn, h, w):
+    B = 2
+
+    def make(A):
+        A.new("v", R(B, Ci + 1, h, w)), A.new("b1", R(Ci) * 0.3), A.new("out", torch.zeros(B, Ci + Cn + 1, 2 * h, 2 * w))
+        s = AchUpGhost()
+        s.v, s.v_bs, s.b1 = A.ptr("v", h * w), (Ci + 1) * h * w, A.ptr("b1")
+        if Cn:
+            A.new("w2", R(Cn, 9) / 3), A.new("s2", torch.rand(Cn) + 0.5), A.new("b2", R(Cn) * 0.3)
+            s.w2, s.s2, s.b2 = A.ptr("w2"), A.ptr("s2"), A.ptr("b2")
+        s.out, s.out_bs = A.ptr("out", 4 * h * w), (Ci + Cn + 1) * 4 * h * w
+        s.B, s.Ci, s.Cn, s.h, s.w = B, Ci, Cn, h, w
+        return (s,)
+    run_both("ach_up_ghost", make, ["out"])
+
+
+@pytest.mark.parametrize("init,K,h,w", [(5, 9, 160, 160), (1, 2, 160, 160), (5, 9, 23, 31), (1, 2, 16, 15)])
+def test_up_ghost_head(init, K, h, w):
+    B, Cc = 2, 16
+
+    def make(A):
+        A.new("v", R(B, Cc, h, w)), A.new("out", torch.zeros(B, K, 2 * h, 2 * w))
+        A.new("b1", R(Cc) * 0.3, host=True), A.new("w2", R(Cc, 9) / 3, host=True), A.new("s2", torch.rand(Cc) + 0.5, host=True)
+        A.new("b2", R(Cc) * 0.3, host=True), A.new("w3", R(2 * Cc, init) / 4, host=True), A.new("b3", R(init) * 0.3, host=True)
+        A.new("w4", R(K - init, 9) / 3, host=True), A.new("s4", torch.rand(K - init) + 0.5, host=True), A.new("b4", R(K - init) * 0.3, host=True)
+        s = AchUpGhostHead()
+        s.v, s.v_bs, s.out, s.out_bs = A.ptr("v"), Cc * h * w, A.ptr("out"), K * 4 * h * w
+        for n in ("b1", "w2", "s2", "b2", "w3", "b3", "w4", "s4", "b4"):
+            setattr(s, n, A.ptr(n))
+        s.B, s.C, s.init, s.K, s.h, s.w = B, Cc, init, K, h, w
+        return (s,)
+    run_both("ach_up_ghost_head", make, ["out"])
