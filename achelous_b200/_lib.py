@@ -59,6 +59,9 @@ class AchUpGhostHead(C.Structure):
 _SIGNATURES = {
     "ach_version": ([], I),
     "ach_pw_conv": ([C.POINTER(AchPwConv), VP], I),
+    "ach_pack_pw_tc_elems": ([I, I], LL),
+    "ach_pack_pw_tc": ([VP, I, I, I, VP, VP, VP], I),
+    "ach_pw_conv_tc": ([C.POINTER(AchPwConv), VP, VP, VP, VP], I),
     "ach_dw_conv": ([C.POINTER(AchDwConv), VP], I),
     "ach_conv_dense": ([C.POINTER(AchConvDense), VP], I),
     "ach_layernorm_cf": ([VP, LL, VP, VP, VP, LL, I, I, I, F, VP], I),

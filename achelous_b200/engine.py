@@ -44,6 +44,13 @@ class Engine:
         self.ops = []          # (cfunc, args) - stream appended at call time
         self.op_names = []
         self.op_bytes = []
+        self.op_lane = []      # stream lane of every launch (0 = caller's stream)
+        self.sync_before = {}  # op index -> [(waiter_lane, waited_lane)] cross-lane dependencies
+        self.sync_end = []
+        self.cur_lane = 0
+        self.in_pack = False
+        self.multi_stream = True
+        self._side_streams = {}
         self._keep = []        # ctypes structs / tensors that must outlive the plan
         self._bufs = {}
         self._weights = {}
@@ -132,6 +139,11 @@ class Engine:
         self.ops.append((fn, args))
         self.op_names.append(name)
         self.op_bytes.append(nbytes)
+        self.op_lane.append(self.cur_lane)
+
+    def wait(self, waiter, waited):
+        """Lane `waiter` waits for everything recorded so far on lane `waited` (before the next launch)."""
+        self.sync_before.setdefault(len(self.ops), []).append((waiter, waited))
 
     def algorithmic_bytes(self, i):
         """Unique input + output + weight bytes of launch i (fp32 storage), or None when not modelled."""
@@ -163,6 +175,20 @@ class Engine:
         K_ = s.c0 + s.c1
         nb = 4 * (self.B * K_ * P + (self.B * O if reduce_max else self.B * O * P) + (self.B * O * P if res is not None else 0)
                   + K_ * s.ldw * (self.B if wt_bs else 1))
+        tc_mode = self.model.use_tensor_cores
+        # measured on B200 (profiles/r1_tc_vs_simt.md): the single-stage tcgen05 kernel beats the SIMT GEMM for wide
+        # outputs over a short K (the LN -> 4C expansion and qkv layers); "all" forces it wherever it is legal
+        tc_ok = (tc_mode == "all" and O >= 16) or (tc_mode is True and O >= 128 and K_ <= 192)
+        if tc_ok and not reduce_max and wt_bs == 0 and isinstance(wt, torch.Tensor) and not self.in_pack:
+            # tcgen05 path: weights re-packed on the device into hi/lo UMMA tile images whenever they change
+            n = self.lib.ach_pack_pw_tc_elems(K_, O)
+            hi = torch.zeros(n, device=self.device, dtype=torch.float32)
+            lo = torch.zeros(n, device=self.device, dtype=torch.float32)
+            self._keep += [hi, lo]
+            self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt.data_ptr(), K_, O, s.ldw, hi.data_ptr(), lo.data_ptr())))
+            wsum = self._w(name + ".wsum", lambda wt=wt, O=O: wt[:, :O].double().sum(0)) if ln else None
+            self._add(name, self.lib.ach_pw_conv_tc, C.byref(s), hi.data_ptr(), lo.data_ptr(), self._ptr(wsum), nbytes=nb)
+            return
         self._add(name, self.lib.ach_pw_conv, C.byref(s), nbytes=nb)
 
     def dw(self, name, x, out, w, k, stride=1, scale=None, bias=None, act=ACT_NONE, xadd=None, post=None):
@@ -482,7 +508,10 @@ class Engine:
         sa_se = self.shuffle_attention("fpn.sa_se", prefix + ".stage_3_semantic_seg", f3)
         self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
         dec = self.seg_decoder_fused if self.model.fuse_seg_decoder else self.seg_decoder
+        self.cur_lane = 3                  # the two decoders are independent of each other
+        self.wait(3, 0)
         dec("lane", prefix, sa_lane, w, out_lane)
+        self.cur_lane = 0
         dec("se", prefix, sa_se, w, out_se)
         return (f5, m5), (f4, m4), (f3, m3)
 
@@ -685,7 +714,10 @@ class Engine:
         if m.has_pc:
             self.pc_in = self.buf("in.pc", m.pc_channels, N, 1)
             if m.pc_seg == "pn":
+                self.cur_lane = 1          # the point-cloud branch is independent of the image/radar graph
+                self.wait(1, 0)
                 self.pointnet(self.pc_in, "pc_seg_model", base + self.out_offsets[5] * 4, PC)
+                self.cur_lane = 0
             else:
                 raise NotImplementedError(f"pc_seg={m.pc_seg!r}")
         ire = "image_radar_encoder"
@@ -694,22 +726,55 @@ class Engine:
         else:
             raise NotImplementedError("MobileViT engine path not built yet")
         maps = self.gdf_neck(feats, ire + ".fpn", m.phi, out_se, out_lane)
+        self.cur_lane = 2                  # radar encoder: independent until the fusion stages
+        self.wait(2, 0)
         radar = self.rcnet(self.r_in, ire + ".radar_encoder", m.phi)
+        self.cur_lane = 0
+        self.wait(0, 2)
         fused = [self.fuse_stage(s, ire, maps[2 - i], radar[i]) for i, s in enumerate((3, 4, 5))]
-        for k in range(3):
+        for k, lane in enumerate((0, 4, 5)):   # the three detection levels are independent
+            if lane:
+                self.cur_lane = lane
+                self.wait(lane, 0)
             self.det_level(k, "det_head", fused[k], det_views[k], K)
+        self.cur_lane = 0
+        self.sync_end = [(0, l) for l in sorted(set(self.op_lane)) if l]
         self.repack()
         self._sig = self._signature()
 
     # ------------------------------------------------------------------ execution
-    def _launch_all(self, stream):
+    def _launch_all(self, stream=None):
+        """Issues the whole plan.  Lane 0 is the caller's current stream; with multi_stream the independent
+        sub-graphs (point cloud, radar, lane decoder, detection levels) go to side streams joined by events,
+        which a CUDA-graph capture turns into parallel branches of the graph."""
         if self.dry_run:
             raise _lib.AchelousKernelError("dry-run engine cannot launch kernels")
         check = _lib.check
-        for (fn, args), name in zip(self.ops, self.op_names):
-            st = fn(*args, stream)
+        main = torch.cuda.current_stream(self.device)
+        if not self.multi_stream:
+            sp = main.cuda_stream
+            for (fn, args), name in zip(self.ops, self.op_names):
+                st = fn(*args, sp)
+                if st:
+                    check(st, name)
+            return
+        streams = {0: main}
+        for l in set(self.op_lane):
+            if l:
+                if l not in self._side_streams:
+                    self._side_streams[l] = torch.cuda.Stream(self.device)
+                streams[l] = self._side_streams[l]
+        ptrs = {l: s_.cuda_stream for l, s_ in streams.items()}
+        sync = self.sync_before
+        for i, (fn, args) in enumerate(self.ops):
+            if i in sync:
+                for waiter, waited in sync[i]:
+                    streams[waiter].wait_stream(streams[waited])
+            st = fn(*args, ptrs[self.op_lane[i]])
             if st:
-                check(st, name)
+                check(st, self.op_names[i])
+        for waiter, waited in self.sync_end:
+            streams[waiter].wait_stream(streams[waited])
 
     def run_packs(self, stream):
         for fn, args in self.pack_ops:
@@ -728,15 +793,15 @@ class Engine:
         self.ensure_packed()
         if self.use_graph:
             if self.graph is None:
-                self._launch_all(torch.cuda.current_stream(self.device).cuda_stream)  # warm-up: module loading, attributes
-                torch.cuda.current_stream(self.device).synchronize()
+                self._launch_all()  # warm-up: module loading, function attributes
+                torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._launch_all(torch.cuda.current_stream(self.device).cuda_stream)
+                    self._launch_all()
                 self.graph = g
             self.graph.replay()
         else:
-            self._launch_all(torch.cuda.current_stream(self.device).cuda_stream)
+            self._launch_all()
 
     def input_tensors(self):
         t = [self._bufs["in.x"], self._bufs["in.radar"]]

@@ -34,6 +34,7 @@ class _AchelousBase(nn.Module):
         self.pc_channels, self.pc_classes, self.nano_head = pc_channels, pc_classes, nano_head
         self.n_points = 512
         self.use_cuda_graph = True
+        self.use_tensor_cores = True   # 1x1 convs / Linears on tcgen05 (3xTF32, fp32-accurate); False: fp32 CUDA-core GEMM
         self.fuse_seg_decoder = True   # False: block-by-block decoder (keeps every reference intermediate)
         self._engines = {}
 

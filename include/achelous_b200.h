@@ -76,6 +76,16 @@ typedef struct AchPwConv {
 } AchPwConv;
 ACH_API int ach_pw_conv(const AchPwConv* p, void* stream);
 
+/* Tensor-core (tcgen05 + TMEM, 3xTF32 split = fp32-accurate) version of ach_pw_conv for shared weights
+ * (wt_bs == 0) without reduce_max.  Same AchPwConv contract except that the weights come pre-packed:
+ * ach_pack_pw_tc converts K-major wt [K][ldw] into two UMMA shared-memory tile images (tf32 "hi" part and
+ * fp32 residual "lo" part), each ach_pack_pw_tc_elems(K, O) floats.  AchPwConv.wt / ldw are ignored.
+ * With the LayerNorm prologue (ln != 0) the kernel multiplies the RAW activations and applies
+ * LN(x).w = rstd * (x.w - mean * wsum[o]) in the epilogue: wsum (O floats) = sum_k wt[k][o], else NULL. */
+ACH_API long long ach_pack_pw_tc_elems(int K, int O);
+ACH_API int ach_pack_pw_tc(const float* wt, int K, int O, int ldw, float* w_hi, float* w_lo, void* stream);
+ACH_API int ach_pw_conv_tc(const AchPwConv* p, const float* w_hi, const float* w_lo, const float* wsum, void* stream);
+
 /* Depthwise k x k convolution (k in {3,5,7,9}, stride 1 or 2, pad k/2):
  *   out[b,c] = act(scale[c] * dw(x[b,c] + xadd[b,c]) + bias[c]) + post[c]      (post broadcast over b)
  * w is [C][k*k].  Replaces nn.Conv2d(groups=C): conv_encoder.py:10, sdta_encoder.py:23 (cascade

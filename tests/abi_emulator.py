@@ -75,6 +75,63 @@ def ach_pw_conv(s):
     fview(s.out, (B, O, P), (s.out_bs, P, 1)).copy_(y)
 
 
+def _tc_tile_n(O):
+    return 32 if O <= 32 else (64 if O <= 64 else 128)
+
+
+def _tc_index(K, O):
+    """(o, k) of every element of the UMMA tile image written by ach_pack_pw_tc."""
+    NT, KC = _tc_tile_n(O), 16
+    n_ot, n_kc = -(-O // NT), -(-K // KC)
+    i = torch.arange(n_ot * n_kc * NT * KC)
+    blk, r = i // (NT * KC), i % (NT * KC)
+    e, row = r % 4, (r // 4) % 8
+    r2 = r // 32  # 8 rows x 4 k per core matrix
+    ncore, kcore = r2 % (NT // 8), r2 // (NT // 8)
+    o = (blk // n_kc) * NT + ncore * 8 + row
+    k = (blk % n_kc) * KC + kcore * 4 + e
+    return o, k
+
+
+def ach_pack_pw_tc(wt, K, O, ldw, w_hi, w_lo):
+    w = fview(wt, (K, O), (ldw, 1))
+    o, k = _tc_index(K, O)
+    ok = (o < O) & (k < K)
+    vals = torch.zeros(o.numel())
+    vals[ok] = w[k[ok], o[ok]]
+    hi = (vals.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)  # cvt.rna.tf32: round-to-nearest, ties away
+    fview(w_hi, (o.numel(),), (1,)).copy_(hi)
+    fview(w_lo, (o.numel(),), (1,)).copy_(vals - hi)
+
+
+def ach_pw_conv_tc(s, w_hi, w_lo, wsum):
+    K, O = s.c0 + s.c1, s.O
+    o, k = _tc_index(K, O)
+    n = o.numel()
+    tiles = fview(w_hi, (n,), (1,)) + fview(w_lo, (n,), (1,))
+    ok = (o < O) & (k < K)
+    ldw = (O + 3) // 4 * 4
+    wt = torch.zeros(K, ldw)
+    wt[k[ok], o[ok]] = tiles[ok]
+    if s.ln:  # the kernel relies on the host-provided row sums
+        assert torch.allclose(_vec(wsum, O), wt[:, :O].sum(0), rtol=1e-5, atol=1e-6)
+    t = AchPwConvShim(s, wt)
+    ach_pw_conv(t)
+    t.keep = None
+
+
+class AchPwConvShim:
+    """AchPwConv view with the weight pointer replaced by a host K-major matrix."""
+
+    def __init__(self, s, wt):
+        self.__dict__["s"], self.__dict__["keep"] = s, wt
+        self.__dict__["ov"] = {"wt": wt.data_ptr(), "ldw": wt.shape[1], "wt_bs": 0}
+
+    def __getattr__(self, name):
+        ov = self.__dict__["ov"]
+        return ov[name] if name in ov else getattr(self.__dict__["s"], name)
+
+
 def ach_dw_conv(s):
     B, Cc, H, W, Ho, Wo, k = s.B, s.C, s.H, s.W, s.Ho, s.Wo, s.k
     x = fview(s.x, (B, Cc, H, W), (s.x_bs, H * W, W, 1)).clone()
@@ -259,7 +316,8 @@ def ach_up_ghost_head(s):
 
 EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
-                                     ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head)}
+                                     ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
+                                     ach_pack_pw_tc, ach_pw_conv_tc)}
 
 
 def _unwrap(a):

@@ -14,11 +14,12 @@ from tests.common import MODEL_KW, argmax_mismatch, rel_err
 TOL = 5e-5
 
 
-@pytest.mark.parametrize("phi,backbone,seed,fuse", [("S0", "en", 2, True), ("S0", "en", 2, False), ("S2", "en", 0, True)])
-def test_plan_matches_oracle(phi, backbone, seed, fuse):
+@pytest.mark.parametrize("phi,backbone,seed,fuse,tc", [("S0", "en", 2, True, "all"), ("S0", "en", 2, False, False), ("S2", "en", 0, True, True)])
+def test_plan_matches_oracle(phi, backbone, seed, fuse, tc):
     torch.set_num_threads(4)
     model = Achelous(phi=phi, backbone=backbone, **MODEL_KW).eval()
     model.fuse_seg_decoder = fuse
+    model.use_tensor_cores = tc
     sd = fill_state_dict(model.state_dict(), seed=seed)
     model.load_state_dict(sd, strict=True)
     B = 2

@@ -24,20 +24,21 @@ TIGHT = 2e-4
 SUPPORTED = [n for n in GOLDEN_CONFIGS if GOLDEN_CONFIGS[n][1] == "en"]
 
 
-def build(phi, bb, wseed, graph=True, fuse=True):
+def build(phi, bb, wseed, graph=True, fuse=True, tc=True):
     model = Achelous(phi=phi, backbone=bb, **MODEL_KW).eval()
     model.fuse_seg_decoder = fuse
+    model.use_tensor_cores = tc
     sd = fill_state_dict(model.state_dict(), seed=wseed)
     model.load_state_dict(sd, strict=True)
     model.use_cuda_graph = graph
     return model.cuda(), sd
 
 
-@pytest.mark.parametrize("fuse", [True, False], ids=["fused_seg", "blockwise_seg"])
+@pytest.mark.parametrize("fuse,tc", [(True, True), (False, "all"), (True, False)], ids=["fused_seg-tcgen05", "blockwise_seg-tcgen05_everywhere", "fused_seg-simt"])
 @pytest.mark.parametrize("name", SUPPORTED)
-def test_forward_vs_golden_and_oracle(name, fuse):
+def test_forward_vs_golden_and_oracle(name, fuse, tc):
     phi, bb, wseed, iseed = GOLDEN_CONFIGS[name]
-    model, sd = build(phi, bb, wseed, fuse=fuse)
+    model, sd = build(phi, bb, wseed, fuse=fuse, tc=tc)
     x, xr, pc = make_inputs(2, seed=iseed)
     det, se, lane, pcs = model(x.cuda(), xr.cuda(), pc.cuda())
     torch.cuda.synchronize()

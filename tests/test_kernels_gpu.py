@@ -57,6 +57,29 @@ def run_both(fn_name, make, outs, seed=0, rtol=RTOL):
         assert torch.equal(torch.isfinite(a), fin), f"{fn_name}:{o} finite mask differs"
 
 
+def run_seq(make, outs, seed=0, rtol=RTOL):
+    """make(arena) -> list of (fn_name, args); executed in order on both sides."""
+    lib = _lib.load()
+    results = {}
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(seed)
+        A = Arena(dev)
+        for fn_name, args in make(A):
+            if dev == "cpu":
+                emu.EMULATORS[fn_name](*args)
+            else:
+                cargs = [C.byref(a) if isinstance(a, C.Structure) else a for a in args]
+                _lib.check(getattr(lib, fn_name)(*cargs, torch.cuda.current_stream().cuda_stream), fn_name)
+        if dev == "cuda":
+            torch.cuda.synchronize()
+        results[dev] = {o: A.t[o].cpu() for o in outs}
+    for o in outs:
+        a, b = results["cuda"][o], results["cpu"][o]
+        err = (a - b).abs().max().item()
+        scale = b.abs().max().item()
+        assert err <= rtol * scale + 1e-6, f"{o} max err {err:.3e} vs scale {scale:.3e}"
+
+
 R = torch.randn
 
 
@@ -414,3 +437,58 @@ def test_up_ghost_head(init, K, h, w):
         s.B, s.C, s.init, s.K, s.h, s.w = B, Cc, init, K, h, w
         return (s,)
     run_both("ach_up_ghost_head", make, ["out"])
+
+
+# ------------------------------------------------------------------ tcgen05 pointwise GEMM
+TC_CASES = [c for c in PW_CASES if not c.get("reduce_max") and not c.get("per_batch_w") and c["O"] >= 16] + [
+    dict(B=2, c0=32, c1=0, O=32, P=25600, act=1, scale=1),
+    dict(B=1, c0=8, c1=0, O=16, P=128),
+    dict(B=2, c0=40, c1=0, O=200, P=132, act=2, scale=1, res=1),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_pw_conv_tc(case):
+    c = dict(c1=0, ln=0, act=0, res=0, gamma=0, pbias=0, scale=0)
+    c.update(case)
+    B, c0, c1, O, P = c["B"], c["c0"], c["c1"], c["O"], c["P"]
+    K = c0 + c1
+    ldw = (O + 3) // 4 * 4
+    lib = _lib.load()
+    n_tiles = lib.ach_pack_pw_tc_elems(K, O)
+
+    def make(A):
+        A.new("x0", R(B, c0 + 3, P))
+        if c1:
+            A.new("x1", R(B, c1, P) * 2 + 1)
+        wt = torch.zeros(K, ldw)
+        wt[:, :O] = R(K, O) / K ** 0.5
+        A.new("wt", wt), A.new("hi", torch.zeros(n_tiles)), A.new("lo", torch.zeros(n_tiles))
+        s = AchPwConv()
+        s.x0, s.x0_bs, s.c0 = A.ptr("x0", P), (c0 + 3) * P, c0
+        if c1:
+            s.x1, s.x1_bs, s.c1 = A.ptr("x1"), c1 * P, c1
+        s.wt, s.ldw = A.ptr("wt"), ldw
+        A.new("bias", R(O))
+        s.bias = A.ptr("bias")
+        if c["scale"]:
+            A.new("scale", torch.rand(O) + 0.5)
+            s.scale = A.ptr("scale")
+        if c["pbias"]:
+            A.new("pbias", R(B, O))
+            s.pbias = A.ptr("pbias")
+        if c["res"]:
+            A.new("res", R(B, O, P))
+            s.res, s.res_bs = A.ptr("res"), O * P
+        if c["gamma"]:
+            A.new("gamma", torch.rand(O) + 0.5)
+            s.gamma = A.ptr("gamma")
+        A.new("out", torch.zeros(B, O + 2, P))
+        s.out, s.out_bs = A.ptr("out", P), (O + 2) * P
+        s.B, s.O, s.P = B, O, P
+        s.ln, s.ln_eps, s.act = c["ln"], 1e-6, c["act"]
+        A.new("wsum", wt[:, :O].sum(0))
+        return [("ach_pack_pw_tc", (A.ptr("wt"), K, O, ldw, A.ptr("hi"), A.ptr("lo"))),
+                ("ach_pw_conv_tc", (s, A.ptr("hi"), A.ptr("lo"), A.ptr("wsum") if c["ln"] else None))]
+
+    run_seq(make, ["hi", "lo", "out"])
