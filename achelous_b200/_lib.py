@@ -73,6 +73,7 @@ _SIGNATURES = {
     "ach_avgpool3": ([VP, LL, VP, LL, I, I, I, I, VP], I),
     "ach_rc_deform": ([C.POINTER(AchRcDeform), VP], I),
     "ach_xca_fold": ([VP, LL, VP, VP, I, VP, LL, I, I, I, I, VP], I),
+    "ach_mvit_attention": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
     "ach_fc": ([VP, LL, VP, VP, VP, VP, LL, I, I, I, I, VP], I),
     "ach_logsoftmax_t": ([VP, LL, VP, LL, I, I, I, VP], I),
     "ach_copy_add": ([VP, LL, VP, VP, LL, I, I, I, VP], I),

@@ -410,6 +410,102 @@ class Engine:
             feats.append(cur)
         return feats
 
+    # ---- MobileViT (mobilevit_modules/mobilevit.py)
+    def conv_bn_silu(self, name, prefix, x, out, k, stride=1):
+        """conv_nxn_bn / conv_1x1_bn: conv (no bias) + BN(1e-5) + SiLU  (mobilevit.py:7-21)"""
+        if k == 1:
+            self.pw_bn_act(name, prefix + ".0", prefix + ".1", 1e-5, x, out, ACT_SILU)
+        else:
+            sc = self._vec(name + ".s", lambda: self._bn_fold(prefix + ".1", 1e-5)[0])
+            bi = self._vec(name + ".b", lambda: self._bn_fold(prefix + ".1", 1e-5)[1])
+            self.conv(name, x, out, self._pack_conv(name + ".w", prefix + ".0.weight"), k, stride, 1, scale=sc, bias=bi, act=ACT_SILU)
+
+    def mv2(self, name, prefix, x, out, stride, expansion):
+        """MV2Block: pw+BN+SiLU -> dw3x3(stride)+BN+SiLU -> pw+BN (+x)  (mobilevit.py:93-131)"""
+        c = prefix + ".conv"
+        inp, oup = x.C, out.C
+        hidden = int(inp * expansion)
+        assert expansion != 1
+        h1 = self.buf(name + ".h1", hidden, x.H, x.W)
+        self.pw_bn_act(name + ".pw1", c + ".0", c + ".1", 1e-5, x, h1, ACT_SILU)
+        h2 = self.buf(name + ".h2", hidden, out.H, out.W)
+        self.dw_bn_act(name + ".dw", c + ".3", c + ".4", 1e-5, h1, h2, 3, ACT_SILU, stride=stride)
+        res = x if (stride == 1 and inp == oup) else None
+        self.pw_bn_act(name + ".pw2", c + ".6", c + ".7", 1e-5, h2, out, ACT_NONE, res=res)
+
+    def mvit_block(self, name, prefix, cat, depth, dim, mlp_dim):
+        """MobileViTBlock (mobilevit.py:134-165).  `cat` is the (B, 2*channel, H, W) buffer whose second half
+        already holds the block input y (written there by the producer), so torch.cat((x, y)) is free."""
+        ch = cat.C // 2
+        H, W = cat.H, cat.W
+        y = self.sl(cat, ch, 2 * ch)
+        c1 = self.buf(name + ".c1", ch, H, W)
+        self.conv_bn_silu(name + ".conv1", prefix + ".conv1", y, c1, 3)
+        t = self.buf(name + ".t0", dim, H, W)
+        self.conv_bn_silu(name + ".conv2", prefix + ".conv2", c1, t, 1)
+        heads, dh = 4, 8
+        inner = heads * dh
+        for l in range(depth):
+            lp = f"{prefix}.transformer.layers.{l}"
+            n = f"{name}.l{l}"
+            # attention: LN -> qkv (no bias) -> softmax(QK^T/sqrt(d))V per patch-position group -> out proj + residual
+            qkv = self.buf(n + ".qkv", 3 * inner, H, W)
+            wq = self._w(n + ".qkv.wt", (lambda lp=lp: self._kmajor(self._p(lp + ".0.fn.to_qkv.weight") * self._p(lp + ".0.norm.weight")[None, :])))
+            bq = self._vec(n + ".qkv.b", (lambda lp=lp: self._p(lp + ".0.fn.to_qkv.weight") @ self._p(lp + ".0.norm.bias")))
+            self.pw(n + ".qkv", t, qkv, wq, 3 * inner, bias=bq, ln=True, ln_eps=1e-5)
+            ao = self.buf(n + ".attn", inner, H, W)
+            self._add(n + ".attn", self.lib.ach_mvit_attention, qkv.ptr, qkv.bs, ao.ptr, ao.bs, self.B, heads, dh, H, W)
+            t1 = self.buf(n + ".t1", dim, H, W)
+            wo = self._w(n + ".out.wt", (lambda lp=lp: self._kmajor(self._p(lp + ".0.fn.to_out.0.weight"))))
+            bo = self._vec(n + ".out.b", (lambda lp=lp: self._p(lp + ".0.fn.to_out.0.bias")))
+            self.pw(n + ".out", ao, t1, wo, dim, bias=bo, res=t)
+            # feed-forward: LN -> Linear -> SiLU -> Linear + residual
+            hbuf = self.buf(n + ".ffh", mlp_dim, H, W)
+            w1 = self._w(n + ".ff1.wt", (lambda lp=lp: self._kmajor(self._p(lp + ".1.fn.net.0.weight") * self._p(lp + ".1.norm.weight")[None, :])))
+            b1 = self._vec(n + ".ff1.b", (lambda lp=lp: self._p(lp + ".1.fn.net.0.bias") + self._p(lp + ".1.fn.net.0.weight") @ self._p(lp + ".1.norm.bias")))
+            self.pw(n + ".ff1", t1, hbuf, w1, mlp_dim, bias=b1, ln=True, ln_eps=1e-5, act=ACT_SILU)
+            t2 = self.buf(n + ".t2", dim, H, W)
+            w2 = self._w(n + ".ff2.wt", (lambda lp=lp: self._kmajor(self._p(lp + ".1.fn.net.3.weight"))))
+            b2 = self._vec(n + ".ff2.b", (lambda lp=lp: self._p(lp + ".1.fn.net.3.bias")))
+            self.pw(n + ".ff2", hbuf, t2, w2, dim, bias=b2, res=t1)
+            t = t2
+        self.conv_bn_silu(name + ".conv3", prefix + ".conv3", t, self.sl(cat, 0, ch), 1)
+        out = self.buf(name + ".out", ch, H, W)
+        self.conv_bn_silu(name + ".conv4", prefix + ".conv4", cat, out, 3)
+        return out
+
+    def mobilevit(self, x, prefix, phi):
+        cfg = Hd.MOBILEVIT_CFG[phi]
+        dims, ch, e = cfg["dims"], cfg["channels"], cfg["expansion"]
+        L = [2, 4, 3]
+        R = self.res
+        c0 = self.buf("mv.conv1", ch[0], R // 2, R // 2)
+        self.conv_bn_silu("mv.conv1", prefix + ".conv1", x, c0, 3, stride=2)
+        m0 = self.buf("mv.mv2_0", ch[1], R // 2, R // 2)
+        self.mv2("mv.mv2_0", prefix + ".mv2.0", c0, m0, 1, e)
+        m1 = self.buf("mv.mv2_1", ch[2], R // 4, R // 4)
+        self.mv2("mv.mv2_1", prefix + ".mv2.1", m0, m1, 2, e)
+        m2 = self.buf("mv.mv2_2", ch[3], R // 4, R // 4)
+        self.mv2("mv.mv2_2", prefix + ".mv2.2", m1, m2, 1, e)
+        f2 = self.buf("mv.mv2_3", ch[3], R // 4, R // 4)
+        self.mv2("mv.mv2_3", prefix + ".mv2.3", m2, f2, 1, e)
+        feats = [f2]
+        cur = f2
+        for i, (mi, cidx) in enumerate(((4, 5), (5, 7), (6, 9))):
+            Hs = R // (8 << i)
+            cat = self.buf(f"mv.cat{i}", 2 * ch[cidx], Hs, Hs)
+            self.mv2(f"mv.mv2_{mi}", f"{prefix}.mv2.{mi}", cur, self.sl(cat, ch[cidx], 2 * ch[cidx]), 2, e)
+            mlp = int(dims[i] * 2) if i == 0 else int(dims[i] * 4)
+            cur = self.mvit_block(f"mv.mvit{i}", f"{prefix}.mvit.{i}", cat, L[i], dims[i], mlp)
+            if i < 2:
+                feats.append(cur)
+        f5 = self.buf("mv.conv2", ch[-1], R // 32, R // 32)
+        self.conv_bn_silu("mv.conv2", prefix + ".conv2", cur, f5, 1)
+        feats.append(f5)
+        for n_, f in zip("2345", feats):
+            self.taps[f"backbone.feat{n_}"] = f
+        return feats
+
     # ---- neck
     def spp(self, x, prefix):
         c_ = x.C // 2
@@ -724,7 +820,7 @@ class Engine:
         if m.backbone == "en":
             feats = self.edgenext(self.x_in, ire + ".fpn.backbone", m.phi)
         else:
-            raise NotImplementedError("MobileViT engine path not built yet")
+            feats = self.mobilevit(self.x_in, ire + ".fpn.backbone", m.phi)
         maps = self.gdf_neck(feats, ire + ".fpn", m.phi, out_se, out_lane)
         self.cur_lane = 2                  # radar encoder: independent until the fusion stages
         self.wait(2, 0)

@@ -183,6 +183,12 @@ ACH_API int ach_rc_deform(const AchRcDeform* p, void* stream);
 ACH_API int ach_xca_fold(const float* qkv, long long qkv_bs, const float* temperature, const float* proj_wt, int ldw,
                  float* wt_eff, long long wt_eff_bs, int B, int C, int heads, int N, void* stream);
 
+/* MobileViT token self-attention (mobilevit.py:48-73,156-158): qkv (B, 3*heads*d, H*W) channel-major
+ * [q | k | v], each (heads d) ordered; tokens are pixels grouped by 2x2 patch position (y&1, x&1);
+ * out (B, heads*d, H*W) = softmax(q k^T / sqrt(d)) v per (group, head).  dim_head must be 8. */
+ACH_API int ach_mvit_attention(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head,
+                               int H, int W, void* stream);
+
 /* Fully connected on (B, K) rows: out[b, o] = act(scale[o] * (w[o, :] . x[b, :]) + bias[o]).
  * pointnet_utils.py:16-18,38-40 (fc + BN1d + ReLU), and the global-feature half of
  * pointnet_sem_seg.py:18 (Conv1d over a point-wise constant). */

@@ -256,6 +256,18 @@ def ach_xca_fold(qkv, qkv_bs, temperature, proj_wt, ldw, wt_eff, wt_eff_bs, B, C
     out[:, :, :Cc] = eff
 
 
+def ach_mvit_attention(qkv, qkv_bs, out, out_bs, B, heads, d, H, W):
+    inner, P = heads * d, H * W
+    t = fview(qkv, (B, 3, heads, d, H // 2, 2, W // 2, 2), (qkv_bs, inner * P, d * P, P, 2 * W, W, 2, 1))
+    # -> (B, ph, pw, head, N, d)
+    t = t.permute(1, 0, 5, 7, 2, 4, 6, 3).reshape(3, B, 2, 2, heads, (H // 2) * (W // 2), d)
+    q, k, v = t[0], t[1], t[2]
+    attn = torch.softmax((q @ k.transpose(-1, -2)) * d ** -0.5, dim=-1)
+    o = attn @ v  # (B, ph, pw, head, N, d)
+    o = o.reshape(B, 2, 2, heads, H // 2, W // 2, d).permute(0, 3, 6, 4, 1, 5, 2).reshape(B, inner, H, W)
+    fview(out, (B, inner, H, W), (out_bs, P, W, 1)).copy_(o)
+
+
 def ach_fc(x, x_bs, w, scale, bias, out, out_bs, B, K, O, act):
     xv = fview(x, (B, K), (x_bs, 1))
     y = xv @ fview(w, (O, K), (K, 1)).t()
@@ -317,7 +329,7 @@ def ach_up_ghost_head(s):
 EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
-                                     ach_pack_pw_tc, ach_pw_conv_tc)}
+                                     ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention)}
 
 
 def _unwrap(a):

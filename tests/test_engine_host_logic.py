@@ -14,7 +14,7 @@ from tests.common import MODEL_KW, argmax_mismatch, rel_err
 TOL = 5e-5
 
 
-@pytest.mark.parametrize("phi,backbone,seed,fuse,tc", [("S0", "en", 2, True, "all"), ("S0", "en", 2, False, False), ("S2", "en", 0, True, True)])
+@pytest.mark.parametrize("phi,backbone,seed,fuse,tc", [("S0", "en", 2, True, "all"), ("S0", "en", 2, False, False), ("S2", "en", 0, True, True), ("S0", "mv", 0, True, True)])
 def test_plan_matches_oracle(phi, backbone, seed, fuse, tc):
     torch.set_num_threads(4)
     model = Achelous(phi=phi, backbone=backbone, **MODEL_KW).eval()

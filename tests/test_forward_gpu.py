@@ -21,7 +21,7 @@ from tests.common import (GOLDEN_CONFIGS, MODEL_KW, REL_TOL, argmax_mismatch, lo
 pytestmark = pytest.mark.gpu
 
 TIGHT = 2e-4
-SUPPORTED = [n for n in GOLDEN_CONFIGS if GOLDEN_CONFIGS[n][1] == "en"]
+SUPPORTED = list(GOLDEN_CONFIGS)
 
 
 def build(phi, bb, wseed, graph=True, fuse=True, tc=True):

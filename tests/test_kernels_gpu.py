@@ -492,3 +492,14 @@ def test_pw_conv_tc(case):
                 ("ach_pw_conv_tc", (s, A.ptr("hi"), A.ptr("lo"), A.ptr("wsum") if c["ln"] else None))]
 
     run_seq(make, ["hi", "lo", "out"])
+
+
+@pytest.mark.parametrize("H,W", [(40, 40), (20, 20), (10, 10), (6, 14)])
+def test_mvit_attention(H, W):
+    B, heads, d = 2, 4, 8
+    P = H * W
+
+    def make(A):
+        A.new("qkv", R(B, 3 * heads * d + 5, P) * 1.5), A.new("out", torch.zeros(B, heads * d, P))
+        return (A.ptr("qkv", 5 * P), (3 * heads * d + 5) * P, A.ptr("out"), heads * d * P, B, heads, d, H, W)
+    run_both("ach_mvit_attention", make, ["out"])
