@@ -65,6 +65,7 @@ _SIGNATURES = {
     "ach_dw_conv": ([C.POINTER(AchDwConv), VP], I),
     "ach_conv_dense": ([C.POINTER(AchConvDense), VP], I),
     "ach_layernorm_cf": ([VP, LL, VP, VP, VP, LL, I, I, I, F, VP], I),
+    "ach_ln_s2d": ([VP, LL, VP, VP, VP, LL, I, I, I, I, F, VP], I),
     "ach_upsample2x": ([VP, LL, VP, LL, I, I, I, I, VP], I),
     "ach_spp_maxpool": ([VP, LL, VP, VP, VP, LL, I, I, I, I, VP], I),
     "ach_shuffle_attention": ([VP, LL, VP, LL, VP, VP, VP, VP, VP, VP, I, I, I, I, F, VP], I),

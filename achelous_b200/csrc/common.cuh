@@ -29,11 +29,25 @@ enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GELU = 3, ACT_SIGMOID = 4 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): 1 rcp + 1 ex2 + 7 fma instead of the ~40-instruction
+// branchy libdevice erff; GELU inherits an absolute error <= 0.75e-7 * |x| - below fp32 rounding of the GEMM feeding it.
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float e = exp2f(-ax * ax * 1.4426950408889634f);
+    return copysignf(fmaf(-poly, e, 1.0f), x);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
         case ACT_RELU: return fmaxf(v, 0.0f);
         case ACT_SILU: return v * sigmoidf_(v);
-        case ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        case ACT_GELU: return 0.5f * v * (1.0f + erf_as(v * 0.70710678118654752440f));
         case ACT_SIGMOID: return sigmoidf_(v);
         default: return v;
     }

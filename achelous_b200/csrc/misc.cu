@@ -44,6 +44,33 @@ __global__ void __launch_bounds__(256) layernorm_cf_kernel(const float* __restri
     for (int c = 0; c < C; ++c) ob[(long long)c * P] = w[c] * ((xb[(long long)c * P] - mean) * rstd) + bb[c];
 }
 
+// ------------------------------------------------------------------ channels-first LayerNorm + 2x2 space-to-depth
+// EdgeNeXt downsample layers are LayerNorm -> Conv2d(k=2, s=2) (edgenext.py:29-34): a patchify conv is a GEMM
+// over K = 4C once the 2x2 patch is moved into the channel axis.  One thread normalises one input pixel over its
+// C channels (coalesced across the warp) and scatters it to channel c*4 + (y&1)*2 + (x&1) of the half-resolution
+// map - exactly the flatten order of the conv weight (O, C, 2, 2) - so the conv itself runs on the GEMM kernels.
+__global__ void __launch_bounds__(256) ln_s2d_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ w,
+                                                     const float* __restrict__ bb, float* __restrict__ out, long long out_bs, int C,
+                                                     int H, int W, float eps) {
+    const int P = H * W;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= P) return;
+    const int y = p / W, xx = p - y * W;
+    const float* xb = x + (long long)blockIdx.y * x_bs + p;
+    float mean = 0.f;
+    for (int c = 0; c < C; ++c) mean += xb[(long long)c * P];
+    mean /= (float)C;
+    float var = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float d = xb[(long long)c * P] - mean;
+        var = fmaf(d, d, var);
+    }
+    const float rstd = 1.0f / sqrtf(var / (float)C + eps);
+    const int Po = (H / 2) * (W / 2);
+    float* ob = out + (long long)blockIdx.y * out_bs + (long long)(((y & 1) << 1) | (xx & 1)) * Po + (y >> 1) * (W / 2) + (xx >> 1);
+    for (int c = 0; c < C; ++c) ob[(long long)c * 4 * Po] = w[c] * ((xb[(long long)c * P] - mean) * rstd) + bb[c];
+}
+
 // ------------------------------------------------------------------ bilinear x2, align_corners=True
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
                                                          long long out_bs, int C, int H, int W) {
@@ -176,26 +203,35 @@ __global__ void __launch_bounds__(256) eca_fuse_kernel(const float* __restrict__
 // ------------------------------------------------------------------ avgpool 3x3 (count_include_pad)
 __global__ void __launch_bounds__(256) avgpool3_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
                                                        long long out_bs, int C, int H, int W) {
-    const long long n = (long long)C * H * W;
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    // one thread = 4 horizontally adjacent outputs of one row (32-bit index math; rows reused from registers)
+    const int W4 = (W + 3) >> 2;
+    const int n = C * H * W4;
+    const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    const int xx = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const long long cbase = i - (long long)y * W - xx;
-    const float* xp = x + (long long)blockIdx.y * x_bs + cbase;
-    float s = 0.f;
+    const int x4 = i % W4;
+    const int row = i / W4;          // c * H + y
+    const int y = row % H;
+    const int x0 = x4 * 4;
+    const float* xp = x + (long long)blockIdx.y * x_bs + (long long)(row - y) * W;   // plane base
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int dy = -1; dy <= 1; ++dy) {
         const int yy = y + dy;
         if (yy < 0 || yy >= H) continue;
+        const float* r = xp + yy * W;
+        float v[6];
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int xc = xx + dx;
-            if (xc < 0 || xc >= W) continue;
-            s += xp[yy * W + xc];
+        for (int j = 0; j < 6; ++j) {
+            const int xc = x0 - 1 + j;
+            v[j] = (xc >= 0 && xc < W) ? r[xc] : 0.f;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += v[j] + v[j + 1] + v[j + 2];
     }
-    out[(long long)blockIdx.y * out_bs + i] = s / 9.0f;
+    float* op = out + (long long)blockIdx.y * out_bs + (long long)row * W + x0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (x0 + j < W) op[j] = acc[j] / 9.0f;
 }
 
 // ------------------------------------------------------------------ fully connected on (B, K) rows
@@ -280,6 +316,14 @@ extern "C" int ach_layernorm_cf(const float* x, long long x_bs, const float* w, 
     return check_launch("ach_layernorm_cf");
 }
 
+extern "C" int ach_ln_s2d(const float* x, long long x_bs, const float* w, const float* b, float* out, long long out_bs, int B,
+                          int C, int H, int W, float eps, void* stream) {
+    ACH_REQUIRE(x && w && b && out && B > 0 && C > 0 && B <= 65535, "ach_ln_s2d: bad args");
+    ACH_REQUIRE(H % 2 == 0 && W % 2 == 0, "ach_ln_s2d: H, W must be even");
+    ln_s2d_kernel<<<dim3(cdiv((long long)H * W, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, w, b, out, out_bs, C, H, W, eps);
+    return check_launch("ach_ln_s2d");
+}
+
 extern "C" int ach_upsample2x(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
                               void* stream) {
     ACH_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "ach_upsample2x: bad args");
@@ -326,7 +370,8 @@ extern "C" int ach_eca_fuse(const float* x, long long x_bs, const float* x2, lon
 extern "C" int ach_avgpool3(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
                             void* stream) {
     ACH_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "ach_avgpool3: bad args");
-    const long long n = (long long)C * H * W;
+    const long long n = (long long)C * H * ((W + 3) / 4);
+    ACH_REQUIRE(n < (1LL << 31), "ach_avgpool3: plane too large for 32-bit indexing");
     avgpool3_kernel<<<dim3(cdiv(n, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, C, H, W);
     return check_launch("ach_avgpool3");
 }

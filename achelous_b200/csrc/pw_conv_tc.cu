@@ -20,16 +20,18 @@
 //   B = W tile [NT outputs][32 k], pre-packed on the device by ach_pack_pw_tc into exactly the shared-memory
 //       image [k-core][n-core][8 rows][4 k] so the kernel copies it linearly
 //       (descriptor: LBO = NT/8 * 128 B between k cores, SBO = 128 B between n cores).
-// One CTA = 256 threads = one 128-pixel x NT-output tile.  Thread t owns pixel t % 128; the two thread
-// halves split the k-cores of every 16-wide K chunk on the way in and the TMEM columns on the way out.
-// K is consumed in chunks of 16 through a single shared-memory stage (33 KB): all threads load + split +
-// store the chunk, one thread issues the 6 MMAs and commits them to an mbarrier, everybody waits for the
-// commit before refilling; 4-6 CTAs are resident per SM so loads of one CTA overlap MMAs/epilogues of others.
+// Persistent CTAs of 256 threads walk a list of (frame, 128-pixel tile, NT-output tile) work items, so TMEM
+// allocation, mbarrier setup and descriptor construction are paid once per CTA, not once per tile.  Thread t
+// owns pixel t % 128; the two thread halves split the k-cores of every 16-wide K chunk on the way in and the
+// TMEM columns on the way out.  K chunks go through a 2-stage shared-memory ring: all threads load + split +
+// store chunk c into stage c & 1, one thread issues its 6 MMAs and commits them to that stage's mbarrier;
+// the global loads of chunk c+1 therefore overlap the MMAs of chunk c, and a stage is only refilled after its
+// previous MMAs have signalled completion.  3 CTAs are resident per SM (64 KB smem, 128 TMEM columns each).
 // LayerNorm prologue: because thread = pixel, the (shifted) sum / sum of squares of the pixel's channels
 // accumulate in registers while the chunks stream by; the MMA runs on the raw x and the epilogue applies
 //   LN(x) . w = rstd * (x . w - mean * sum_k w)      (wsum = row sums of the folded weights, from the host)
 // so the activations are read exactly once.
-// Epilogue: rolled loop of tcgen05.ld 32x32b.x8 (thread = pixel, registers = outputs; kept small on purpose:
+// Epilogue: rolled loop of tcgen05.ld 32x32b.x16 (thread = pixel, registers = outputs; kept small on purpose:
 // a fully unrolled 128-output epilogue with erf-GELU thrashed the instruction cache - ncu stall_no_instruction
 // 6.4 per issue), folded scale/bias, activation, layer-scale + residual, coalesced 128-byte stores.
 #include "common.cuh"
@@ -80,29 +82,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         : "memory");
 }
 
-template <int NT>
+template <int NT, int STAGES, int ACT>
 __global__ void __launch_bounds__(256) pw_conv_tc_kernel(const AchPwConv p, const float* __restrict__ w_hi,
                                                          const float* __restrict__ w_lo, const float* __restrict__ wsum,
-                                                         int n_kchunks) {
+                                                         int n_kchunks, int n_pt, int n_ot, int total_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float* a_hi = reinterpret_cast<float*>(smem_raw);                   // [4 k-cores][128 px][4]  8 KB
-    float* a_lo = a_hi + TC_KC * TC_M;                                  // 8 KB
-    float* b_hi = a_lo + TC_KC * TC_M;                                  // [4 k-cores][NT][4]
-    float* b_lo = b_hi + NT * TC_KC;
-    __shared__ __align__(8) uint64_t mbar;
+    constexpr int A_ELEMS = TC_KC * TC_M;     // per hi / lo matrix
+    constexpr int B_ELEMS = NT * TC_KC;
+    constexpr int STAGE = 2 * A_ELEMS + 2 * B_ELEMS;
+    float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2 stages][a_hi | a_lo | b_hi | b_lo]
+    __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_ln[2][TC_M][2];
+    __shared__ __align__(16) float4 s_ep[NT];   // per output of the current tile: {scale, scale*wsum, bias + scale*pbias, gamma}
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int px = tid & (TC_M - 1), half = tid >> 7;   // half is warp-uniform
-    const int b = blockIdx.z;
-    const int p_base = blockIdx.x * TC_M;
-    const int o_tile = blockIdx.y;
-    const int o_base = o_tile * NT;
     const int K = p.c0 + p.c1;
     const int P = p.P;
-    const float* __restrict__ x0 = p.x0 + (long long)b * p.x0_bs;
-    const float* __restrict__ x1 = p.x1 ? p.x1 + (long long)b * p.x1_bs : nullptr;
 
     // ---- one-time setup: TMEM allocation (warp 0), mbarrier init (thread 0)
     if (warp == 0) {
@@ -110,15 +107,10 @@ __global__ void __launch_bounds__(256) pw_conv_tc_kernel(const AchPwConv p, cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const int pp = p_base + px;
-    const bool p_ok = pp < P;
-    // LayerNorm running sums, shifted by the pixel's first channel to avoid cancellation
-    const float shift = (p.ln && p_ok) ? x0[pp] : 0.f;
-    float s1 = 0.f, s2 = 0.f;
-
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -127,114 +119,180 @@ __global__ void __launch_bounds__(256) pw_conv_tc_kernel(const AchPwConv p, cons
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N=NT, M=128
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(NT >> 3) << 17) |
                                ((uint32_t)(TC_M >> 4) << 24);
-    const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo), b_hi_s = smem_u32(b_hi), b_lo_s = smem_u32(b_lo);
-    const uint32_t mbar_s = smem_u32(&mbar);
     constexpr uint32_t B_LBO = (NT / 8) * 128, B_SBO = 128;   // K-major, no swizzle
     constexpr uint32_t A_LBO = (TC_M / 8) * 128, A_SBO = 128; // K-major, no swizzle
+    const uint32_t stage_s = smem_u32(stage_base);
+    const uint32_t mbar_s0 = smem_u32(&mbar[0]), mbar_s1 = smem_u32(&mbar[1]);
+    uint32_t uses0 = 0u, uses1 = 0u;   // commits issued so far on each stage barrier (identical in every thread)
+    const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
 
-    uint32_t parity = 0;
-    for (int c = 0; c < n_kchunks; ++c) {
-        const int k0 = c * TC_KC;
-        // ---- A chunk: thread = pixel; this half's 2 of the 4 k-cores (4 channels each)
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int o_tile = item % n_ot;
+        const int pt = (item / n_ot) % n_pt;
+        const int b = item / (n_ot * n_pt);
+        const int p_base = pt * TC_M;
+        const int o_base = o_tile * NT;
+        const float* __restrict__ x0 = p.x0 + (long long)b * p.x0_bs;
+        const float* __restrict__ x1 = p.x1 ? p.x1 + (long long)b * p.x1_bs : nullptr;
+        const int pp = p_base + px;
+        const bool p_ok = pp < P;
+        // LayerNorm running sums, shifted by the pixel's first channel to avoid cancellation
+        const float shift = (p.ln && p_ok) ? x0[pp] : 0.f;
+        float s1 = 0.f, s2 = 0.f;
+
+        for (int c = 0; c < n_kchunks; ++c) {
+            const int k0 = c * TC_KC;
+            const int st = (STAGES == 2) ? (c & 1) : 0;
+            float* a_hi = stage_base + st * STAGE;
+            float* a_lo = a_hi + A_ELEMS;
+            float* b_hi = a_lo + A_ELEMS;
+            float* b_lo = b_hi + B_ELEMS;
+            // global loads first (they do not touch shared memory), so their latency overlaps the wait below
+            float v[2][4];
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int j = half + 2 * jj;
-            float v[4];
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = half + 2 * jj;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int kk = k0 + j * 4 + e;
-                float t = 0.f;
-                if (kk < K && p_ok) {
-                    t = (kk < p.c0) ? __ldg(x0 + (long long)kk * P + pp) : __ldg(x1 + (long long)(kk - p.c0) * P + pp);
-                    const float d = t - shift;
-                    s1 += d;
-                    s2 = fmaf(d, d, s2);
+                for (int e = 0; e < 4; ++e) {
+                    const int kk = k0 + j * 4 + e;
+                    float t = 0.f;
+                    if (kk < K && p_ok) t = (kk < p.c0) ? __ldg(x0 + (long long)kk * P + pp) : __ldg(x1 + (long long)(kk - p.c0) * P + pp);
+                    v[jj][e] = t;
                 }
-                v[e] = t;
             }
-            float4 h, l;
-            h.x = to_tf32(v[0]); h.y = to_tf32(v[1]); h.z = to_tf32(v[2]); h.w = to_tf32(v[3]);
-            l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
-            *reinterpret_cast<float4*>(a_hi + j * (TC_M * 4) + px * 4) = h;
-            *reinterpret_cast<float4*>(a_lo + j * (TC_M * 4) + px * 4) = l;
-        }
-        // ---- B chunk: linear copy of the pre-packed tile (NT*16 floats each for hi and lo)
-        {
-            const long long blk = ((long long)o_tile * n_kchunks + c) * (NT * TC_KC);
-            const float4* gh = reinterpret_cast<const float4*>(w_hi + blk);
-            const float4* gl = reinterpret_cast<const float4*>(w_lo + blk);
-            constexpr int N4 = NT * TC_KC / 4;   // 128 (NT=32) .. 512 (NT=128) float4 per matrix
+            constexpr int N4 = B_ELEMS / 4;   // float4 per weight matrix: 128 (NT=32) .. 512 (NT=128)
+            constexpr int NB = (N4 + 255) / 256;
+            float4 wh[NB], wl[NB];
+            {
+                const long long blk = ((long long)o_tile * n_kchunks + c) * B_ELEMS;
+                const float4* gh = reinterpret_cast<const float4*>(w_hi + blk);
+                const float4* gl = reinterpret_cast<const float4*>(w_lo + blk);
 #pragma unroll
-            for (int i = 0; i < (N4 + 255) / 256; ++i) {
+                for (int i = 0; i < NB; ++i) {
+                    const int idx = tid + 256 * i;
+                    if (idx < N4) {
+                        wh[i] = __ldg(gh + idx);
+                        wl[i] = __ldg(gl + idx);
+                    }
+                }
+            }
+            // the stage is free once the MMAs of its previous use have completed
+            const uint32_t mbar_st = st ? mbar_s1 : mbar_s0;
+            const uint32_t uses_st = st ? uses1 : uses0;
+            if (uses_st > 0) mbar_wait(mbar_st, (uses_st - 1) & 1);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = half + 2 * jj;
+                if (p.ln) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (k0 + j * 4 + e < K && p_ok) {
+                            const float d = v[jj][e] - shift;
+                            s1 += d;
+                            s2 = fmaf(d, d, s2);
+                        }
+                }
+                float4 h, l;
+                h.x = to_tf32(v[jj][0]); h.y = to_tf32(v[jj][1]); h.z = to_tf32(v[jj][2]); h.w = to_tf32(v[jj][3]);
+                l.x = v[jj][0] - h.x; l.y = v[jj][1] - h.y; l.z = v[jj][2] - h.z; l.w = v[jj][3] - h.w;
+                *reinterpret_cast<float4*>(a_hi + j * (TC_M * 4) + px * 4) = h;
+                *reinterpret_cast<float4*>(a_lo + j * (TC_M * 4) + px * 4) = l;
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
                 const int idx = tid + 256 * i;
                 if (idx < N4) {
-                    reinterpret_cast<float4*>(b_hi)[idx] = __ldg(gh + idx);
-                    reinterpret_cast<float4*>(b_lo)[idx] = __ldg(gl + idx);
+                    reinterpret_cast<float4*>(b_hi)[idx] = wh[i];
+                    reinterpret_cast<float4*>(b_lo)[idx] = wl[i];
                 }
             }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the MMA (async proxy)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // (first chunk) previous item's TMEM reads are ordered before the new MMAs
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi_s = stage_s + st * STAGE * 4, a_lo_s = a_hi_s + A_ELEMS * 4;
+                const uint32_t b_hi_s = a_lo_s + A_ELEMS * 4, b_lo_s = b_hi_s + B_ELEMS * 4;
 #pragma unroll
-            for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                const uint64_t ah = make_desc(a_hi_s + ks * 2 * A_LBO, A_LBO, A_SBO, 0);
-                const uint64_t al = make_desc(a_lo_s + ks * 2 * A_LBO, A_LBO, A_SBO, 0);
-                const uint64_t bh = make_desc(b_hi_s + ks * 2 * B_LBO, B_LBO, B_SBO, 0);
-                const uint64_t bl = make_desc(b_lo_s + ks * 2 * B_LBO, B_LBO, B_SBO, 0);
-                mma_tf32(tmem_d, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                mma_tf32(tmem_d, al, bh, idesc, 1u);
-                mma_tf32(tmem_d, ah, bl, idesc, 1u);
+                for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                    const uint64_t ah = make_desc(a_hi_s + ks * 2 * A_LBO, A_LBO, A_SBO, 0);
+                    const uint64_t al = make_desc(a_lo_s + ks * 2 * A_LBO, A_LBO, A_SBO, 0);
+                    const uint64_t bh = make_desc(b_hi_s + ks * 2 * B_LBO, B_LBO, B_SBO, 0);
+                    const uint64_t bl = make_desc(b_lo_s + ks * 2 * B_LBO, B_LBO, B_SBO, 0);
+                    mma_tf32(tmem_d, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32(tmem_d, al, bh, idesc, 1u);
+                    mma_tf32(tmem_d, ah, bl, idesc, 1u);
+                }
+                // arrives on the stage barrier when all MMAs issued so far have completed
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_st) : "memory");
             }
-            // arrives on the mbarrier when all MMAs issued so far have completed (implies fence::before_thread_sync)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_s) : "memory");
+            if (st) uses1 += 1; else uses0 += 1;
         }
-        mbar_wait(mbar_s, parity);
-        parity ^= 1;
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // all MMAs of this item are complete once the last commit has arrived
+        {
+            const int st = (STAGES == 2) ? ((n_kchunks - 1) & 1) : 0;
+            mbar_wait(st ? mbar_s1 : mbar_s0, ((st ? uses1 : uses0) - 1) & 1);
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- LayerNorm statistics: combine the two halves' partial sums
-    float mean = 0.f, rstd = 1.f;
-    if (p.ln) {
-        s_ln[half][px][0] = s1;
-        s_ln[half][px][1] = s2;
+        // ---- per-output epilogue constants of this (frame, output tile) + LayerNorm partial sums -> shared memory
+        if (tid < NT) {
+            const int o = o_base + tid;
+            float4 e = make_float4(0.f, 0.f, 0.f, 1.f);
+            if (o < p.O) {
+                e.x = p.scale ? p.scale[o] : 1.f;
+                e.y = p.ln ? e.x * wsum[o] : 0.f;
+                e.z = (p.bias ? p.bias[o] : 0.f) + (p.pbias ? e.x * p.pbias[(long long)b * p.O + o] : 0.f);
+                e.w = p.gamma ? p.gamma[o] : 1.f;
+            }
+            s_ep[tid] = e;
+        }
+        if (p.ln) {
+            s_ln[half][px][0] = s1;
+            s_ln[half][px][1] = s2;
+        }
         __syncthreads();
-        const float t1 = (s_ln[0][px][0] + s_ln[1][px][0]) / (float)K;
-        const float t2 = (s_ln[0][px][1] + s_ln[1][px][1]) / (float)K;
-        mean = shift + t1;
-        rstd = 1.0f / sqrtf(fmaxf(t2 - t1 * t1, 0.f) + p.ln_eps);
-    }
+        // y = act(rs * (scale*acc) - ms * (scale*wsum) + c)  with rs = rstd, ms = mean*rstd   (rs = 1, ms = 0 without LayerNorm)
+        float rs = 1.f, ms = 0.f;
+        if (p.ln) {
+            const float t1 = (s_ln[0][px][0] + s_ln[1][px][0]) / (float)K;
+            const float t2 = (s_ln[0][px][1] + s_ln[1][px][1]) / (float)K;
+            rs = 1.0f / sqrtf(fmaxf(t2 - t1 * t1, 0.f) + p.ln_eps);
+            ms = (shift + t1) * rs;
+        }
 
-    // ---- epilogue: thread = pixel (TMEM lane 32*(warp%4) + lane); this half's NT/2 columns, 8 at a time
-    const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
-    constexpr int NH = NT / 2;
+        // ---- epilogue: thread = pixel (TMEM lane 32*(warp%4) + lane); this half's NT/2 columns, 16 at a time
+        constexpr int NH = NT / 2;
+        float* optr = p.out + (long long)b * p.out_bs + (long long)(o_base + half * NH) * P + pp;
+        const float* rptr = p.res ? p.res + (long long)b * p.res_bs + (long long)(o_base + half * NH) * P + pp : nullptr;
+        const int o_lim = p.O - o_base;   // valid outputs in this tile
 #pragma unroll 1
-    for (int n0 = half * NH; n0 < (half + 1) * NH; n0 += 8) {
-        uint32_t r[8];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                     : "r"(t_lane + (uint32_t)n0)
-                     : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int n0 = half * NH; n0 < (half + 1) * NH; n0 += 16) {
+            uint32_t r[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(t_lane + (uint32_t)n0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (p_ok) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int o = o_base + n0 + j;
-            if (o < p.O && p_ok) {
-                float acc = __uint_as_float(r[j]);
-                if (p.ln) acc = rstd * fmaf(-mean, wsum[o], acc);
-                const float s = p.scale ? p.scale[o] : 1.f;
-                const float bi = p.bias ? p.bias[o] : 0.f;
-                const float pb = p.pbias ? p.pbias[(long long)b * p.O + o] : 0.f;
-                float y = apply_act(fmaf(s, acc + pb, bi), p.act);
-                if (p.res) {
-                    const float g = p.gamma ? p.gamma[o] : 1.f;
-                    y = fmaf(g, y, p.res[(long long)b * p.res_bs + (long long)o * P + pp]);
+                for (int j = 0; j < 16; ++j) {
+                    if (n0 + j < o_lim) {
+                        const float4 e = s_ep[n0 + j];
+                        float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
+                        y = apply_act(y, ACT);
+                        if (rptr) y = fmaf(e.w, y, rptr[(long long)j * P]);
+                        optr[(long long)j * P] = y;
+                    }
                 }
-                p.out[(long long)b * p.out_bs + (long long)o * P + pp] = y;
             }
+            optr += (long long)16 * P;
+            if (rptr) rptr += (long long)16 * P;
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // s_ep / s_ln are rewritten and the accumulator is overwritten by the next item
     }
 
     // ---- teardown
@@ -269,19 +327,44 @@ __global__ void __launch_bounds__(256) pack_pw_tc_kernel(const float* __restrict
 
 static int tc_tile_n(int O) { return O <= 32 ? 32 : (O <= 64 ? 64 : 128); }
 
-template <int NT>
+template <int NT, int STAGES, int ACT>
 static int launch_tc(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
     const int K = p.c0 + p.c1;
     const int n_kchunks = cdiv(K, TC_KC);
-    constexpr size_t smem = 2 * TC_KC * TC_M * 4 + 2 * (size_t)NT * TC_KC * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(pw_conv_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    constexpr size_t smem = STAGES * (2 * TC_KC * TC_M * 4 + 2 * (size_t)NT * TC_KC * 4);
+    static int ctas_per_wave = 0;
+    if (!ctas_per_wave) {
+        cudaFuncSetAttribute(pw_conv_tc_kernel<NT, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int per_sm = (int)((227 * 1024) / (smem + 4096));          // shared memory
+        per_sm = per_sm < 512 / (NT < 32 ? 32 : NT) ? per_sm : 512 / (NT < 32 ? 32 : NT);   // TMEM columns
+        per_sm = per_sm < 4 ? per_sm : 4;                           // registers (<= 64 x 256 threads)
+        ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
     }
-    dim3 grid(cdiv(p.P, TC_M), cdiv(p.O, NT), p.B);
-    pw_conv_tc_kernel<NT><<<grid, 256, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks);
+    const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);
+    const long long total = (long long)n_pt * n_ot * p.B;
+    ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
+    const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
+    pw_conv_tc_kernel<NT, STAGES, ACT><<<grid, 256, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
     return check_launch("ach_pw_conv_tc");
+}
+
+template <int NT>
+static int launch_tc_nt(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
+    // long K: a second shared-memory stage lets chunk c+1 load while chunk c multiplies; short K: keep the
+    // footprint small so that more CTAs (each at a different phase of load / MMA / epilogue) share the SM
+    const bool two = p.c0 + p.c1 > 3 * TC_KC;
+    switch (p.act) {
+        case ACT_NONE: return two ? launch_tc<NT, 2, ACT_NONE>(p, w_hi, w_lo, wsum, st) : launch_tc<NT, 1, ACT_NONE>(p, w_hi, w_lo, wsum, st);
+        case ACT_RELU: return two ? launch_tc<NT, 2, ACT_RELU>(p, w_hi, w_lo, wsum, st) : launch_tc<NT, 1, ACT_RELU>(p, w_hi, w_lo, wsum, st);
+        case ACT_SILU: return two ? launch_tc<NT, 2, ACT_SILU>(p, w_hi, w_lo, wsum, st) : launch_tc<NT, 1, ACT_SILU>(p, w_hi, w_lo, wsum, st);
+        case ACT_GELU: return two ? launch_tc<NT, 2, ACT_GELU>(p, w_hi, w_lo, wsum, st) : launch_tc<NT, 1, ACT_GELU>(p, w_hi, w_lo, wsum, st);
+        default: break;
+    }
+    set_error("ach_pw_conv_tc: activation %d not instantiated", p.act);
+    return ACH_ERR_INVALID;
 }
 
 }  // namespace ach
@@ -315,8 +398,8 @@ extern "C" int ach_pw_conv_tc(const AchPwConv* pp, const float* w_hi, const floa
     ACH_REQUIRE(!p.ln || wsum, "ach_pw_conv_tc: the LayerNorm prologue needs wsum (row sums of the folded weights)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (tc_tile_n(p.O)) {
-        case 32: return launch_tc<32>(p, w_hi, w_lo, wsum, st);
-        case 64: return launch_tc<64>(p, w_hi, w_lo, wsum, st);
-        default: return launch_tc<128>(p, w_hi, w_lo, wsum, st);
+        case 32: return launch_tc_nt<32>(p, w_hi, w_lo, wsum, st);
+        case 64: return launch_tc_nt<64>(p, w_hi, w_lo, wsum, st);
+        default: return launch_tc_nt<128>(p, w_hi, w_lo, wsum, st);
     }
 }

@@ -176,9 +176,9 @@ class Engine:
         nb = 4 * (self.B * K_ * P + (self.B * O if reduce_max else self.B * O * P) + (self.B * O * P if res is not None else 0)
                   + K_ * s.ldw * (self.B if wt_bs else 1))
         tc_mode = self.model.use_tensor_cores
-        # measured on B200 (profiles/r1_tc_vs_simt.md): the single-stage tcgen05 kernel beats the SIMT GEMM for wide
-        # outputs over a short K (the LN -> 4C expansion and qkv layers); "all" forces it wherever it is legal
-        tc_ok = (tc_mode == "all" and O >= 16) or (tc_mode is True and O >= 128 and K_ <= 192)
+        # measured on B200 (profiles/r1_tc_vs_simt.md): the persistent tcgen05 kernel beats the SIMT GEMM on every
+        # shared-weight layer with >= 24 outputs; narrower outputs waste most of a 32-column MMA tile
+        tc_ok = (tc_mode == "all" and O >= 16) or (tc_mode is True and O >= 24)
         if tc_ok and not reduce_max and wt_bs == 0 and isinstance(wt, torch.Tensor) and not self.in_pack:
             # tcgen05 path: weights re-packed on the device into hi/lo UMMA tile images whenever they change
             n = self.lib.ach_pack_pw_tc_elems(K_, O)
@@ -390,15 +390,15 @@ class Engine:
         for i in range(4):
             if i > 0:
                 ds = f"{prefix}.downsample_layers.{i}"
-                ln = self.buf(f"bb.ds{i}.ln", dims[i - 1], H, H)
+                # LayerNorm + 2x2 space-to-depth, then the k=2,s=2 conv as a pointwise GEMM over K = 4C
+                s2d = self.buf(f"bb.ds{i}.s2d", 4 * dims[i - 1], H // 2, H // 2)
                 lw = self._vec(f"bb.ds{i}.lnw", (lambda ds=ds: self._p(ds + ".0.weight")))
                 lb = self._vec(f"bb.ds{i}.lnb", (lambda ds=ds: self._p(ds + ".0.bias")))
-                self._add(f"bb.ds{i}.ln", self.lib.ach_layernorm_cf, cur.ptr, cur.bs, lw.data_ptr(), lb.data_ptr(), ln.ptr, ln.bs,
-                          self.B, dims[i - 1], H * H, 1e-6)
+                self._add(f"bb.ds{i}.ln_s2d", self.lib.ach_ln_s2d, cur.ptr, cur.bs, lw.data_ptr(), lb.data_ptr(), s2d.ptr, s2d.bs,
+                          self.B, dims[i - 1], H, H, 1e-6, nbytes=4 * self.B * dims[i - 1] * H * H * 2)
                 H //= 2
                 nxt = self.buf(f"bb.ds{i}", dims[i], H, H)
-                self.conv(f"bb.ds{i}.conv", ln, nxt, self._pack_conv(f"bb.ds{i}.w", ds + ".1.weight"), 2, 2, 0,
-                          bias=self._vec(f"bb.ds{i}.b", (lambda ds=ds: self._p(ds + ".1.bias"))))
+                self.pw_bias(f"bb.ds{i}.conv", ds + ".1", s2d, nxt)
                 cur = nxt
             for j in range(depths[i]):
                 bp = f"{prefix}.stages.{i}.{j}"

@@ -127,6 +127,12 @@ ACH_API int ach_conv_dense(const AchConvDense* p, void* stream);
 ACH_API int ach_layernorm_cf(const float* x, long long x_bs, const float* w, const float* b, float* out, long long out_bs,
                      int B, int C, int P, float eps, void* stream);
 
+/* Channels-first LayerNorm (layers.py:21-26) fused with a 2x2 space-to-depth: out (B, 4C, H/2, W/2) with
+ * out[b, c*4 + (y&1)*2 + (x&1), y/2, x/2] = LN(x)[b, c, y, x] - the im2col of the k=2, s=2 downsample conv
+ * (edgenext.py:29-34), which then runs as a pointwise GEMM over K = 4C. */
+ACH_API int ach_ln_s2d(const float* x, long long x_bs, const float* w, const float* b, float* out, long long out_bs, int B,
+                       int C, int H, int W, float eps, void* stream);
+
 /* Bilinear x2 upsampling, align_corners=True (nn.Upsample, ghostdualfpn.py:34). */
 ACH_API int ach_upsample2x(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
                    void* stream);

@@ -175,6 +175,15 @@ def ach_layernorm_cf(x, x_bs, w, b, out, out_bs, B, Cc, P, eps):
     fview(out, (B, Cc, P), (out_bs, P, 1)).copy_(y)
 
 
+def ach_ln_s2d(x, x_bs, w, b, out, out_bs, B, Cc, H, W, eps):
+    xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))
+    u = xv.mean(1, keepdim=True)
+    v = (xv - u).pow(2).mean(1, keepdim=True)
+    y = (xv - u) / torch.sqrt(v + eps) * _vec(w, Cc)[None, :, None, None] + _vec(b, Cc)[None, :, None, None]
+    y = y.reshape(B, Cc, H // 2, 2, W // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, Cc * 4, H // 2, W // 2)
+    fview(out, (B, Cc * 4, H // 2, W // 2), (out_bs, (H // 2) * (W // 2), W // 2, 1)).copy_(y)
+
+
 def ach_upsample2x(x, x_bs, out, out_bs, B, Cc, H, W):
     xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))
     y = F.interpolate(xv, scale_factor=2, mode="bilinear", align_corners=True)
@@ -329,7 +338,7 @@ def ach_up_ghost_head(s):
 EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
-                                     ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention)}
+                                     ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d)}
 
 
 def _unwrap(a):

@@ -503,3 +503,13 @@ def test_mvit_attention(H, W):
         A.new("qkv", R(B, 3 * heads * d + 5, P) * 1.5), A.new("out", torch.zeros(B, heads * d, P))
         return (A.ptr("qkv", 5 * P), (3 * heads * d + 5) * P, A.ptr("out"), heads * d * P, B, heads, d, H, W)
     run_both("ach_mvit_attention", make, ["out"])
+
+
+@pytest.mark.parametrize("Cc,H,W", [(32, 80, 80), (96, 20, 20), (5, 6, 10)])
+def test_ln_s2d(Cc, H, W):
+    B = 2
+
+    def make(A):
+        A.new("x", R(B, Cc + 1, H, W) * 2 + 0.3), A.new("w", torch.rand(Cc) + 0.5), A.new("b", R(Cc)), A.new("out", torch.zeros(B, 4 * Cc, H // 2, W // 2))
+        return (A.ptr("x", H * W), (Cc + 1) * H * W, A.ptr("w"), A.ptr("b"), A.ptr("out"), Cc * H * W, B, Cc, H, W, 1e-6)
+    run_both("ach_ln_s2d", make, ["out"])

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--phi", default="S0")
     ap.add_argument("--backbone", default="en")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--tc", default="default", help="default | all | off")
     ap.add_argument("--out", default="gpurun_out/op_times.json")
     a = ap.parse_args()
     kw = dict(num_det=7, num_seg=9, phi=a.phi, resolution=320, backbone=a.backbone, neck="gdf", pc_seg="pn", pc_channels=5,
@@ -28,6 +29,8 @@ def main():
     model = Achelous(**kw).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=0))
     model.use_cuda_graph = False
+    if a.tc != "default":
+        model.use_tensor_cores = "all" if a.tc == "all" else False
     model = model.cuda()
     x, xr, pc = [t.cuda() for t in make_inputs(a.batch, seed=1)]
     model(x, xr, pc)
