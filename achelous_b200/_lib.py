@@ -83,6 +83,10 @@ _SIGNATURES = {
     "ach_up_ghost": ([C.POINTER(AchUpGhost), VP], I),
     "ach_up_ghost_head_supported": ([I, I, I], I),
     "ach_up_ghost_head": ([C.POINTER(AchUpGhostHead), VP], I),
+    "ach_pn2_fps": ([VP, LL, I, I, I, VP, VP, LL, VP], I),
+    "ach_pn2_group": ([VP, LL, VP, LL, I, VP, LL, I, I, I, I, F, VP, LL, VP, VP], I),
+    "ach_pn2_group_max": ([VP, LL, VP, LL, I, I, I, I, VP], I),
+    "ach_pn2_interp3": ([VP, LL, VP, LL, VP, LL, I, I, I, I, VP, LL, VP], I),
     "ach_decode_outputs": ([C.POINTER(VP), C.POINTER(LL), C.POINTER(I), C.POINTER(I), I, VP, I, I, F, F, VP], I),
     "ach_nms_workspace_bytes": ([I, I], LL),
     "ach_nms": ([VP, I, I, I, F, F, VP, VP, VP, VP, LL, VP], I),

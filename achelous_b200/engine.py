@@ -781,6 +781,59 @@ class Engine:
         self.taps_raw = {"pc.trans": t3, "pc.trans_feat": tf, "pc.global": g}
         self.taps["pc.pointfeat"] = pointfeat
 
+    # ---- PointNet++ (builder-defined, oracle/pn2.py)
+    def pointnet2(self, x, prefix, out_pc, num_class):
+        D, N = x.C, x.H * x.W
+        ibuf = lambda name, *shape: self._keep.append(torch.zeros(*shape, device=self.device, dtype=torch.int32)) or self._keep[-1]
+        xyz = [self.sl(x, 0, 3)]
+        pts = [x]
+        n_prev = N
+        for li, cfg in enumerate(Hd.PN2_SA, 1):
+            S, ns = cfg["npoint"], cfg["nsample"]
+            sp = f"{prefix}.sa{li}"
+            fps_idx = ibuf(f"pn2.sa{li}.fps", self.B, S)
+            nxyz = self.buf(f"pn2.sa{li}.xyz", 3, S)
+            self._add(f"pn2.sa{li}.fps", self.lib.ach_pn2_fps, xyz[-1].ptr, xyz[-1].bs, self.B, n_prev, S, fps_idx.data_ptr(), nxyz.ptr, nxyz.bs)
+            Cin = pts[-1].C
+            g = self.buf(f"pn2.sa{li}.group", 3 + Cin, S * ns)
+            gidx = ibuf(f"pn2.sa{li}.idx", self.B, S, ns)
+            self._add(f"pn2.sa{li}.group", self.lib.ach_pn2_group, xyz[-1].ptr, xyz[-1].bs, pts[-1].ptr, pts[-1].bs, Cin, nxyz.ptr, nxyz.bs,
+                      self.B, n_prev, S, ns, float(cfg["radius"]), g.ptr, g.bs, gidx.data_ptr())
+            cur = g
+            for i, c in enumerate(cfg["mlp"]):
+                nxt = self.buf(f"pn2.sa{li}.mlp{i}", c, S * ns)
+                self.pw_bn_act(f"pn2.sa{li}.mlp{i}", f"{sp}.mlp_convs.{i}", f"{sp}.mlp_bns.{i}", 1e-5, cur, nxt, ACT_RELU, conv_bias=True)
+                cur = nxt
+            o = self.buf(f"pn2.sa{li}.out", cfg["mlp"][-1], S)
+            self._add(f"pn2.sa{li}.max", self.lib.ach_pn2_group_max, cur.ptr, cur.bs, o.ptr, o.bs, self.B, cur.C, S, ns)
+            self.taps[f"pc.sa{li}.out"] = o
+            self.taps_int = getattr(self, "taps_int", {})
+            self.taps_int[f"pc.sa{li}.fps"], self.taps_int[f"pc.sa{li}.idx"] = fps_idx, gidx
+            xyz.append(nxyz)
+            pts.append(o)
+            n_prev = S
+
+        def fp(name, pfx, xyz1, xyz2, p1, p2, mlp):
+            n1, S = xyz1.H * xyz1.W, xyz2.H * xyz2.W
+            it = self.buf(name + ".interp", p2.C, n1)
+            self._add(name + ".interp", self.lib.ach_pn2_interp3, xyz1.ptr, xyz1.bs, xyz2.ptr, xyz2.bs, p2.ptr, p2.bs, self.B, p2.C, n1, S,
+                      it.ptr, it.bs)
+            cur, x1 = p1, it
+            for i, c in enumerate(mlp):
+                nxt = self.buf(f"{name}.mlp{i}", c, n1)
+                self.pw_bn_act(f"{name}.mlp{i}", f"{pfx}.mlp_convs.{i}", f"{pfx}.mlp_bns.{i}", 1e-5, cur, nxt, ACT_RELU, x1=x1, conv_bias=True)
+                cur, x1 = nxt, None
+            return cur
+        f2 = fp("pn2.fp3", prefix + ".fp3", xyz[2], xyz[3], pts[2], pts[3], Hd.PN2_FP[3])
+        f1 = fp("pn2.fp2", prefix + ".fp2", xyz[1], xyz[2], pts[1], f2, Hd.PN2_FP[2])
+        f0 = fp("pn2.fp1", prefix + ".fp1", xyz[0], xyz[1], pts[0], f1, Hd.PN2_FP[1])
+        self.taps.update({"pc.fp3": f2, "pc.fp2": f1, "pc.fp1": f0})
+        h = self.buf("pn2.h1", 128, N)
+        self.pw_bn_act("pn2.h1", prefix + ".conv1", prefix + ".bn1", 1e-5, f0, h, ACT_RELU, conv_bias=True)
+        h2 = self.buf("pn2.h2", num_class, N)
+        self.pw_bias("pn2.h2", prefix + ".conv2", h, h2)
+        self._add("pn2.logsoftmax", self.lib.ach_logsoftmax_t, h2.ptr, h2.bs, out_pc, self.packed_out.stride(0), self.B, num_class, N)
+
     # ------------------------------------------------------------------ plan
     def _build(self):
         m = self.model
@@ -813,6 +866,11 @@ class Engine:
                 self.cur_lane = 1          # the point-cloud branch is independent of the image/radar graph
                 self.wait(1, 0)
                 self.pointnet(self.pc_in, "pc_seg_model", base + self.out_offsets[5] * 4, PC)
+                self.cur_lane = 0
+            elif m.pc_seg == "pn2":
+                self.cur_lane = 1
+                self.wait(1, 0)
+                self.pointnet2(self.pc_in, "pc_seg_model", base + self.out_offsets[5] * 4, PC)
                 self.cur_lane = 0
             else:
                 raise NotImplementedError(f"pc_seg={m.pc_seg!r}")

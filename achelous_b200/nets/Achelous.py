@@ -116,8 +116,11 @@ class Achelous(_AchelousBase):
                           pc_channels, pc_classes, nano_head, spp)
         if pc_seg == 'pn':
             self.pc_seg_model = Hd.PointNet_SEG(num_class=pc_classes, point_cloud_channels=pc_channels)
+        elif pc_seg == 'pn2':
+            # the reference advertises pn2 but ships no code for it: builder-defined network
+            self.pc_seg_model = Hd.PointNet2_SEG(num_class=pc_classes, point_cloud_channels=pc_channels)
         else:
-            raise NotImplementedError(f"pc_seg={pc_seg!r}: implemented: 'pn'")
+            raise NotImplementedError(f"pc_seg={pc_seg!r}: implemented: 'pn', 'pn2'")
         self.image_radar_encoder = Hd.IREncoder(num_class_seg=num_seg, phi=phi, backbone=backbone, neck=neck,
                                                 radar_channels=radar_channels)
         self.det_head = Hd.DecoupleHead(num_classes=num_det, phi=phi, nano_head=nano_head)

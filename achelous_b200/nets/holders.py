@@ -444,3 +444,52 @@ class PointNet_SEG(Holder):
         self.conv3 = nn.Conv1d(100, 64, 1)
         self.conv4 = nn.Conv1d(64, self.k, 1)
         self.bn1, self.bn2, self.bn3 = nn.BatchNorm1d(128), nn.BatchNorm1d(100), nn.BatchNorm1d(64)
+
+
+# ------------------------------------------------------------------ PointNet++ (builder-defined: the reference has no PN2 code)
+PN2_SA = [dict(npoint=128, radius=0.04, nsample=16, mlp=[32, 32, 64]),
+          dict(npoint=32, radius=0.08, nsample=16, mlp=[64, 64, 128]),
+          dict(npoint=8, radius=0.16, nsample=8, mlp=[128, 128, 256])]
+PN2_FP = {3: [256, 128], 2: [128, 128], 1: [128, 128]}
+
+
+class PN2SetAbstraction(Holder):
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for c in mlp:
+            self.mlp_convs.append(nn.Conv2d(last, c, 1))
+            self.mlp_bns.append(nn.BatchNorm2d(c))
+            last = c
+
+
+class PN2FeaturePropagation(Holder):
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        self.mlp_convs, self.mlp_bns = nn.ModuleList(), nn.ModuleList()
+        last = in_channel
+        for c in mlp:
+            self.mlp_convs.append(nn.Conv1d(last, c, 1))
+            self.mlp_bns.append(nn.BatchNorm1d(c))
+            last = c
+
+
+class PointNet2_SEG(Holder):
+    """Same I/O contract as PointNet_SEG; architecture defined in oracle/pn2.py (parity unpinned)."""
+
+    def __init__(self, num_class, point_cloud_channels):
+        super().__init__()
+        self.k, D = num_class, point_cloud_channels
+        cin = D
+        outs = []
+        for i, cfg in enumerate(PN2_SA, 1):
+            setattr(self, f"sa{i}", PN2SetAbstraction(cin + 3, cfg["mlp"]))
+            cin = cfg["mlp"][-1]
+            outs.append(cin)
+        self.fp3 = PN2FeaturePropagation(outs[2] + outs[1], PN2_FP[3])
+        self.fp2 = PN2FeaturePropagation(PN2_FP[3][-1] + outs[0], PN2_FP[2])
+        self.fp1 = PN2FeaturePropagation(PN2_FP[2][-1] + D, PN2_FP[1])
+        self.conv1 = nn.Conv1d(PN2_FP[1][-1], 128, 1)
+        self.bn1 = nn.BatchNorm1d(128)
+        self.conv2 = nn.Conv1d(128, num_class, 1)

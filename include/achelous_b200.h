@@ -259,6 +259,28 @@ ACH_API int ach_up_ghost_head_supported(int c_in, int init, int k_out);
 ACH_API int ach_up_ghost_head(const AchUpGhostHead* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * PointNet++ (pc_seg='pn2') building blocks.  The reference advertises PN2 (README.md:63) but contains no code
+ * for it (nets/Achelous.py:31-32 handles only 'pn'): these implement the builder-defined network of
+ * oracle/pn2.py.  xyz tensors are (B, 3, N) views, features (B, C, N); indices are int32.
+ *   ach_pn2_fps:       farthest-point sampling, start index 0, ties -> lowest index; writes idx (B, npoint) and
+ *                      the sampled coordinates new_xyz (B, 3, npoint).
+ *   ach_pn2_group:     ball query (first nsample indices with d2 <= radius^2, padded with the first hit) + grouping:
+ *                      out[b][ch][j*nsample + s] = ch < 3 ? xyz[ch][idx] - new_xyz[ch][j] : pts[ch-3][idx];
+ *                      idx_out (B, S, nsample) optional.
+ *   ach_pn2_group_max: (B, C, S*nsample) -> (B, C, S), max over each run of nsample.
+ *   ach_pn2_interp3:   3-NN inverse-squared-distance interpolation of pts2 (B, C2, S) at xyz1 (B, 3, N1).
+ */
+ACH_API int ach_pn2_fps(const float* xyz, long long xyz_bs, int B, int N, int npoint, int* idx_out, float* new_xyz,
+                        long long new_bs, void* stream);
+ACH_API int ach_pn2_group(const float* xyz, long long xyz_bs, const float* pts, long long pts_bs, int C, const float* new_xyz,
+                          long long new_bs, int B, int N, int S, int nsample, float radius, float* out, long long out_bs,
+                          int* idx_out, void* stream);
+ACH_API int ach_pn2_group_max(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int S, int nsample,
+                              void* stream);
+ACH_API int ach_pn2_interp3(const float* xyz1, long long xyz1_bs, const float* xyz2, long long xyz2_bs, const float* pts2,
+                            long long pts2_bs, int B, int C2, int N1, int S, float* out, long long out_bs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Detection post-process (second boundary: utils/utils_bbox.py).
  * ach_decode_outputs: decode_outputs (:33-85) for up to 3 levels of (B, 5+K, H_l, W_l) raw logits
  *   -> out (B, A, 5+K), xywh normalised by input_w/input_h.

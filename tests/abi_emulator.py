@@ -335,10 +335,58 @@ def ach_up_ghost_head(s):
     fview(s.out, (B, K, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(torch.cat([p, q], 1))
 
 
+def iview(ptr, shape):
+    n = 1
+    for d in shape:
+        n *= d
+    arr = np.ctypeslib.as_array((C.c_int32 * n).from_address(ptr))
+    return torch.from_numpy(arr).view(*shape)
+
+
+def ach_pn2_fps(xyz, xyz_bs, B, N, npoint, idx_out, new_xyz, new_bs):
+    from oracle.pn2 import farthest_point_sample
+    x = fview(xyz, (B, 3, N), (xyz_bs, N, 1)).permute(0, 2, 1).contiguous()
+    idx = farthest_point_sample(x, npoint)
+    iview(idx_out, (B, npoint)).copy_(idx.to(torch.int32))
+    fview(new_xyz, (B, 3, npoint), (new_bs, npoint, 1)).copy_(torch.gather(x, 1, idx[:, :, None].expand(-1, -1, 3)).permute(0, 2, 1))
+
+
+def ach_pn2_group(xyz, xyz_bs, pts, pts_bs, Cc, new_xyz, new_bs, B, N, S, nsample, radius, out, out_bs, idx_out):
+    from oracle.pn2 import _gather, ball_query
+    x = fview(xyz, (B, 3, N), (xyz_bs, N, 1)).permute(0, 2, 1).contiguous()
+    p = fview(pts, (B, Cc, N), (pts_bs, N, 1)).permute(0, 2, 1).contiguous()
+    nx = fview(new_xyz, (B, 3, S), (new_bs, S, 1)).permute(0, 2, 1).contiguous()
+    idx = ball_query(radius, nsample, x, nx)                          # (B, S, ns)
+    g = torch.cat([_gather(x, idx) - nx[:, :, None, :], _gather(p, idx)], -1)   # (B, S, ns, 3+C)
+    fview(out, (B, 3 + Cc, S, nsample), (out_bs, S * nsample, nsample, 1)).copy_(g.permute(0, 3, 1, 2))
+    if idx_out:
+        iview(idx_out, (B, S, nsample)).copy_(idx.to(torch.int32))
+
+
+def ach_pn2_group_max(x, x_bs, out, out_bs, B, Cc, S, nsample):
+    xv = fview(x, (B, Cc, S, nsample), (x_bs, S * nsample, nsample, 1))
+    fview(out, (B, Cc, S), (out_bs, S, 1)).copy_(xv.max(3)[0])
+
+
+def ach_pn2_interp3(xyz1, xyz1_bs, xyz2, xyz2_bs, pts2, pts2_bs, B, C2, N1, S, out, out_bs):
+    from oracle.pn2 import _gather, sqdist
+    x1 = fview(xyz1, (B, 3, N1), (xyz1_bs, N1, 1)).permute(0, 2, 1).contiguous()
+    x2 = fview(xyz2, (B, 3, S), (xyz2_bs, S, 1)).permute(0, 2, 1).contiguous()
+    p2 = fview(pts2, (B, C2, S), (pts2_bs, S, 1)).permute(0, 2, 1).contiguous()
+    d3, i3 = torch.sort(sqdist(x1, x2), dim=-1, stable=True)
+    d3, i3 = d3[:, :, :3], i3[:, :, :3]
+    rec = 1.0 / (d3 + 1e-8)
+    w = rec / ((rec[..., 0] + rec[..., 1]) + rec[..., 2])[..., None]
+    nb = _gather(p2, i3)
+    interp = (nb[:, :, 0] * w[:, :, 0:1] + nb[:, :, 1] * w[:, :, 1:2]) + nb[:, :, 2] * w[:, :, 2:3]
+    fview(out, (B, C2, N1), (out_bs, N1, 1)).copy_(interp.permute(0, 2, 1))
+
+
 EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
-                                     ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d)}
+                                     ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
+                                     ach_pn2_group_max, ach_pn2_interp3)}
 
 
 def _unwrap(a):

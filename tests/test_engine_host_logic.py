@@ -41,6 +41,29 @@ def test_plan_matches_oracle(phi, backbone, seed, fuse, tc):
         assert n_safe_diff == 0
 
 
+def test_pn2_plan_matches_builder_oracle():
+    """Config 4 (EN-GDF-PN2-S2): PointNet++ is builder-defined (oracle/pn2.py) - parity UNPINNED against the reference,
+    which ships no PN2 code.  FPS / ball-query indices must be bit-identical, features within tolerance."""
+    torch.set_num_threads(4)
+    kw = dict(MODEL_KW, pc_seg="pn2")
+    model = Achelous(phi="S2", backbone="en", **kw).eval()
+    sd = fill_state_dict(model.state_dict(), seed=3)
+    model.load_state_dict(sd, strict=True)
+    B = 2
+    x, xr, pc = make_inputs(B, seed=22)
+    eng = Engine(model, B, "cpu", dry_run=True)
+    ins = eng.input_tensors()
+    ins[0].copy_(x), ins[1].copy_(xr), ins[2].copy_(pc)
+    emulate_engine(eng)
+    taps = {}
+    o_det, o_se, o_lane, o_pc = OF.achelous_forward(sd, x, xr, pc, phi="S2", backbone="en", pc_seg="pn2", taps=taps)
+    for k, v in eng.taps_int.items():
+        assert torch.equal(v.long(), taps[k]), k
+    for name in ("pc.sa1.out", "pc.sa2.out", "pc.sa3.out", "pc.fp3", "pc.fp2", "pc.fp1"):
+        assert rel_err(eng.tap(name), taps[name]) < TOL, name
+    assert rel_err(eng.output_views()[3], o_pc) < TOL
+
+
 def test_repack_tracks_parameter_updates():
     model = Achelous(phi="S0", backbone="en", **MODEL_KW).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=1))

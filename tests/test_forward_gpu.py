@@ -7,6 +7,8 @@ kernels are fp32 end to end so the observed error is ~1e-5, asserted at 2e-4 to 
 Seg argmax: exact on every pixel whose top-2 margin exceeds 1e-4 of the logit range (ReLU-ed logits tie
 exactly at 0 - ties are resolved lowest-index-first like torch.argmax - and near-ties flip with any change
 of summation order); total mismatch additionally bounded at 0.1 % of pixels."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -123,3 +125,29 @@ def test_weight_update_invalidates_packs():
     out1 = model(x, xr, pc)[1]
     ref = OF.achelous_forward(sd2, x.cpu(), xr.cpu(), pc.cpu())[1]
     assert rel_err(out1, ref) < TIGHT and not torch.equal(out0, out1)
+
+
+def test_config4_pn2_s2_vs_builder_oracle():
+    """BASELINE config 4 (EN-GDF-PN2-S2).  The point-cloud branch is compared with the BUILDER-DEFINED oracle
+    (oracle/pn2.py; the reference has no PN2 implementation - parity unpinned); the image/radar branches are
+    the reference-pinned EN-S2 network.  FPS / ball-query indices must be bit-identical."""
+    kw = dict(MODEL_KW, pc_seg="pn2")
+    model = Achelous(phi="S2", backbone="en", **kw).eval()
+    sd = fill_state_dict(model.state_dict(), seed=3)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    x, xr, pc = make_inputs(3, seed=22)
+    det, se, lane, pcs = model(x.cuda(), xr.cuda(), pc.cuda())
+    taps = {}
+    o_det, o_se, o_lane, o_pc = OF.achelous_forward(sd, x, xr, pc, phi="S2", backbone="en", pc_seg="pn2", taps=taps)
+    eng = next(iter(model._engines.values()))
+    for k, v in eng.taps_int.items():
+        assert torch.equal(v.cpu().long(), taps[k]), k
+    for name in ("pc.sa1.out", "pc.sa2.out", "pc.sa3.out", "pc.fp3", "pc.fp2", "pc.fp1"):
+        assert rel_err(eng.tap(name), taps[name]) < TIGHT, name
+    assert rel_err(pcs, o_pc) < TIGHT
+    for i in range(3):
+        assert rel_err(det[i], o_det[i]) < TIGHT
+    assert rel_err(se, o_se) < TIGHT and rel_err(lane, o_lane) < TIGHT
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pn2_builder_defined.npz"))
+    assert rel_err(pcs[:2], g["pc"]) < TIGHT

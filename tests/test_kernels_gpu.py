@@ -513,3 +513,79 @@ def test_ln_s2d(Cc, H, W):
         A.new("x", R(B, Cc + 1, H, W) * 2 + 0.3), A.new("w", torch.rand(Cc) + 0.5), A.new("b", R(Cc)), A.new("out", torch.zeros(B, 4 * Cc, H // 2, W // 2))
         return (A.ptr("x", H * W), (Cc + 1) * H * W, A.ptr("w"), A.ptr("b"), A.ptr("out"), Cc * H * W, B, Cc, H, W, 1e-6)
     run_both("ach_ln_s2d", make, ["out"])
+
+
+# ------------------------------------------------------------------ PointNet++ blocks (indices must be bit-exact)
+def _cloud(B, N):
+    pts = R(B, N, 5)
+    pts = pts / pts.norm(dim=1, keepdim=True)
+    return pts.permute(0, 2, 1).contiguous()
+
+
+def run_both_int(fn_name, make, float_outs, int_outs, seed=0):
+    lib = _lib.load()
+    res = {}
+    for dev in ("cpu", "cuda"):
+        torch.manual_seed(seed)
+        A = Arena(dev)
+        args = make(A)
+        if dev == "cpu":
+            emu.EMULATORS[fn_name](*args)
+        else:
+            _lib.check(getattr(lib, fn_name)(*args, torch.cuda.current_stream().cuda_stream), fn_name)
+            torch.cuda.synchronize()
+        res[dev] = {o: A.t[o].cpu() for o in float_outs + int_outs}
+    for o in int_outs:
+        assert torch.equal(res["cuda"][o], res["cpu"][o]), f"{fn_name}:{o} indices differ"
+    for o in float_outs:
+        a, b = res["cuda"][o], res["cpu"][o]
+        assert (a - b).abs().max().item() <= RTOL * b.abs().max().item() + 1e-7, f"{fn_name}:{o}"
+
+
+class IArena(Arena):
+    def newi(self, name, shape):
+        self.t[name] = torch.zeros(*shape, dtype=torch.int32, device=self.device)
+        return self.t[name]
+
+    def iptr(self, name):
+        return self.t[name].data_ptr()
+
+
+@pytest.mark.parametrize("N,npoint", [(512, 128), (128, 32), (32, 8), (100, 17)])
+def test_pn2_fps(N, npoint):
+    B = 3
+
+    def make(A):
+        A.__class__ = IArena
+        A.new("x", _cloud(B, N)), A.newi("idx", (B, npoint)), A.new("nx", torch.zeros(B, 3, npoint))
+        return (A.ptr("x"), 5 * N, B, N, npoint, A.iptr("idx"), A.ptr("nx"), 3 * npoint)
+    run_both_int("ach_pn2_fps", make, ["nx"], ["idx"])
+
+
+@pytest.mark.parametrize("N,S,ns,r,Cf", [(512, 128, 16, 0.04, 5), (128, 32, 16, 0.08, 64), (32, 8, 8, 0.16, 128), (100, 20, 7, 0.05, 3)])
+def test_pn2_group_and_max(N, S, ns, r, Cf):
+    B = 2
+
+    def make(A):
+        A.__class__ = IArena
+        c = _cloud(B, N)
+        A.new("x", c), A.new("pts", R(B, Cf, N)), A.new("nx", c[:, :3, :S].contiguous())
+        A.new("out", torch.zeros(B, 3 + Cf, S * ns)), A.newi("idx", (B, S, ns))
+        return (A.ptr("x"), 5 * N, A.ptr("pts"), Cf * N, Cf, A.ptr("nx"), 3 * S, B, N, S, ns, r, A.ptr("out"), (3 + Cf) * S * ns, A.iptr("idx"))
+    run_both_int("ach_pn2_group", make, ["out"], ["idx"])
+
+    def make_max(A):
+        A.new("x", R(B, Cf, S * ns)), A.new("out", torch.zeros(B, Cf, S))
+        return (A.ptr("x"), Cf * S * ns, A.ptr("out"), Cf * S, B, Cf, S, ns)
+    run_both("ach_pn2_group_max", make_max, ["out"])
+
+
+@pytest.mark.parametrize("N1,S,C2", [(32, 8, 256), (128, 32, 128), (512, 128, 128), (50, 3, 7)])
+def test_pn2_interp3(N1, S, C2):
+    B = 2
+
+    def make(A):
+        c = _cloud(B, N1)
+        A.new("x1", c), A.new("x2", c[:, :3, :S].contiguous()), A.new("p2", R(B, C2, S)), A.new("out", torch.zeros(B, C2 + 2, N1))
+        return (A.ptr("x1"), 5 * N1, A.ptr("x2"), 3 * S, A.ptr("p2"), C2 * S, B, C2, N1, S, A.ptr("out", 2 * N1), (C2 + 2) * N1)
+    run_both("ach_pn2_interp3", make, ["out"])
