@@ -37,11 +37,12 @@ class _AchelousBase(nn.Module):
         self.use_tensor_cores = True   # 1x1 convs / Linears on tcgen05 (3xTF32, fp32-accurate); False: fp32 CUDA-core GEMM
         self.fuse_seg_decoder = True   # False: block-by-block decoder (keeps every reference intermediate)
         self._engines = {}
+        self._host_bufs = {}
 
     # ---- engine cache: one plan per (device, batch); weights are re-packed when parameters change
-    def _engine(self, device, batch, n_points):
+    def _engine(self, device, batch, n_points, slot=0):
         from ..engine import Engine
-        key = (device.index if device.index is not None else torch.cuda.current_device(), batch, n_points)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), batch, n_points, slot)
         eng = self._engines.get(key)
         if eng is None:
             self.n_points = n_points
@@ -59,7 +60,7 @@ class _AchelousBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == "_engines" else copy.deepcopy(v, memo)
+            new.__dict__[k] = {} if k in ("_engines", "_host_bufs") else copy.deepcopy(v, memo)
         return new
 
     def _check(self, t, name, shape_tail):
@@ -104,6 +105,86 @@ class _AchelousBase(nn.Module):
             se, lane = se.contiguous(), lane.contiguous()
             pc = pc.contiguous() if pc is not None else None
         return det, se, lane, pc
+
+
+    # ------------------------------------------------------------------ throughput API (host batches in, host results out)
+    def stream_forward(self, batches):
+        """Pipelined inference over an iterable of HOST batches ``(x, x_radar[, x_point_clouds])`` (pinned memory
+        recommended).  Yields, per batch and in order, ``(det[3], se_seg, lane_seg, pc_seg)`` as views of a pinned host
+        buffer that stays valid until two further batches have been requested.
+
+        Same results as ``forward`` (same kernels, same plan); what changes is the schedule: two plans (double
+        buffering) and three streams overlap the host->device copy of batch i+1 and the device->host copy of
+        batch i-1 with the kernels of batch i, so a PCIe-bound caller sees max(copy, compute) per batch instead of
+        their sum.  The reference has no equivalent (achelous.py:244-266 copies, runs and reads back serially)."""
+        if self.training:
+            raise NotImplementedError("achelous_b200 is inference-only: call .eval() first")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("achelous_b200 has no CPU path: move the module to a CUDA device")
+        with torch.cuda.device(dev), torch.no_grad():
+            main = torch.cuda.current_stream(dev)
+            h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            engines, host, ev = [None, None], [None, None], [dict(), dict()]
+            pending = []   # slots whose results have not been yielded yet, oldest first
+
+            def views(slot):
+                eng, hb = engines[slot], host[slot]
+                o = eng.out_offsets
+                K, S, R = self.num_det, self.num_seg, self.resolution
+                det = [hb[:, o[i]:o[i + 1]].unflatten(1, (5 + K, R // s_, R // s_)) for i, s_ in enumerate((8, 16, 32))]
+                se = hb[:, o[3]:o[4]].unflatten(1, (S, R, R))
+                lane = hb[:, o[4]:o[5]].unflatten(1, (2, R, R))
+                pc = hb[:, o[5]:o[6]].unflatten(1, (eng.n_points, self.pc_classes)) if self.has_pc else None
+                return det, se, lane, pc
+
+            for i, batch in enumerate(batches):
+                slot = i & 1
+                x, xr = batch[0], batch[1]
+                xp = batch[2] if self.has_pc else None
+                B = x.shape[0]
+                n_points = xp.shape[2] if self.has_pc else self.n_points
+                if engines[slot] is None or engines[slot].B != B:
+                    engines[slot] = self._engine(dev, B, n_points, slot=slot)
+                    engines[slot].ensure_packed()
+                    hk = (dev.index, B, n_points, slot)
+                    if hk not in self._host_bufs:       # pinning 300 MB costs ~100 ms: do it once per (device, batch, slot)
+                        self._host_bufs[hk] = torch.empty(B, engines[slot].frame_elems, dtype=torch.float32).pin_memory()
+                    host[slot] = self._host_bufs[hk]
+                eng = engines[slot]
+                # results of the batch that used this slot two iterations ago must be handed out before reuse
+                while pending and pending[0] == slot:
+                    ev[slot]["copied"].synchronize()
+                    pending.pop(0)
+                    yield views(slot)
+                ins = eng.input_tensors()
+                if "done" in ev[slot]:
+                    h2d.wait_event(ev[slot]["done"])      # the previous compute on this slot no longer reads its inputs
+                with torch.cuda.stream(h2d):
+                    ins[0].copy_(x, non_blocking=True)
+                    ins[1].copy_(xr, non_blocking=True)
+                    if self.has_pc:
+                        ins[2].copy_(xp, non_blocking=True)
+                    ev[slot]["in"] = h2d.record_event()
+                main.wait_event(ev[slot]["in"])
+                if "copied" in ev[slot]:
+                    main.wait_event(ev[slot]["copied"])   # the previous D2H of this slot's output buffer has finished
+                eng.forward_static()
+                ev[slot]["done"] = main.record_event()
+                d2h.wait_event(ev[slot]["done"])
+                with torch.cuda.stream(d2h):
+                    host[slot].copy_(eng.packed_out, non_blocking=True)
+                    ev[slot]["copied"] = d2h.record_event()
+                pending.append(slot)
+                # hand out the previous batch while this one is in flight
+                if len(pending) == 2:
+                    prev = pending.pop(0)
+                    ev[prev]["copied"].synchronize()
+                    yield views(prev)
+            while pending:
+                prev = pending.pop(0)
+                ev[prev]["copied"].synchronize()
+                yield views(prev)
 
 
 class Achelous(_AchelousBase):

@@ -151,3 +151,18 @@ def test_config4_pn2_s2_vs_builder_oracle():
     assert rel_err(se, o_se) < TIGHT and rel_err(lane, o_lane) < TIGHT
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pn2_builder_defined.npz"))
     assert rel_err(pcs[:2], g["pc"]) < TIGHT
+
+
+def test_stream_forward_matches_forward():
+    """The pipelined throughput API returns exactly what forward() returns, batch by batch, in order."""
+    model, _ = build("S0", "en", 2)
+    batches = [make_inputs(2, seed=100 + i) for i in range(5)]
+    ref = [model(*[t.cuda() for t in b]) for b in batches]
+    ref = [([d.cpu() for d in r[0]], r[1].cpu(), r[2].cpu(), r[3].cpu()) for r in ref]
+    pinned = [tuple(t.pin_memory() for t in b) for b in batches]
+    n = 0
+    for out, r in zip(model.stream_forward(iter(pinned)), ref):
+        for a, b_ in zip(list(out[0]) + [out[1], out[2], out[3]], list(r[0]) + [r[1], r[2], r[3]]):
+            assert torch.equal(a, b_)
+        n += 1
+    assert n == 5
