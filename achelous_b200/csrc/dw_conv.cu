@@ -114,10 +114,15 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const AchDwConv p, int TH,
 
 template <int KS, int S>
 static int launch_dw(const AchDwConv& p, cudaStream_t st) {
-    const int TW = min((p.Wo + 3) & ~3, 32);
-    const int TH = min(p.Ho, 32);
-    const int strips = (TW + DW_NX - 1) / DW_NX;
-    int CPB = max(1, 256 / (TH * strips));   // >= 1 strip per thread per pass
+    // tile = (TH x TW) outputs x CPB channels with TW a multiple of 4 that divides the (rounded) row evenly, so that
+    // e.g. 40-wide planes are one 40-wide tile instead of a 32-wide tile plus a mostly empty one
+    const int Wr = (p.Wo + 3) & ~3;
+    const int n_tx = cdiv(Wr, 64);
+    const int TW = (cdiv(Wr, n_tx) + 3) & ~3;
+    const int strips = TW / DW_NX;
+    int TH = min(p.Ho, max(1, 256 / strips));
+    TH = cdiv(p.Ho, cdiv(p.Ho, TH));           // balance the rows over the tiles
+    int CPB = max(1, 256 / (TH * strips));     // >= 1 strip per thread per pass
     CPB = min(CPB, p.C);
     const int IH = (TH - 1) * S + KS, IW = (TW - 1) * S + KS;
     const int IWp = ((IW + 3) & ~3) + 4;

@@ -276,7 +276,19 @@ __global__ void __launch_bounds__(256) pw_conv_tc_kernel(const AchPwConv p, cons
                 : "r"(t_lane + (uint32_t)n0)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (p_ok) {
+            if (p.reduce_max) {
+                // out (B, O) = max over pixels: warp-shuffle max over the warp's 32 pixels, one atomic per (warp, output)
+                const int lane = tid & 31;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 e = s_ep[n0 + j];
+                    float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
+                    y = p_ok ? apply_act(y, ACT) : -INFINITY;
+#pragma unroll
+                    for (int sft = 16; sft > 0; sft >>= 1) y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, sft));
+                    if (lane == 0 && n0 + j < o_lim) atomic_max_float(p.out + (long long)b * p.out_bs + o_base + n0 + j, y);
+                }
+            } else if (p_ok) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (n0 + j < o_lim) {
@@ -393,7 +405,8 @@ extern "C" int ach_pw_conv_tc(const AchPwConv* pp, const float* w_hi, const floa
     ACH_REQUIRE(p.P % 4 == 0, "ach_pw_conv_tc: P=%d must be a multiple of 4", p.P);
     ACH_REQUIRE(aligned16(p.x0) && aligned16(p.x1) && aligned16(w_hi) && aligned16(w_lo), "ach_pw_conv_tc: views must be 16-byte aligned");
     ACH_REQUIRE(p.x0_bs % 4 == 0 && p.x1_bs % 4 == 0, "ach_pw_conv_tc: batch strides must be multiples of 4 elements");
-    ACH_REQUIRE(!p.reduce_max && p.wt_bs == 0, "ach_pw_conv_tc: reduce_max / per-frame weights use ach_pw_conv");
+    ACH_REQUIRE(p.wt_bs == 0, "ach_pw_conv_tc: per-frame weights use ach_pw_conv");
+    ACH_REQUIRE(!(p.reduce_max && p.res), "ach_pw_conv_tc: reduce_max excludes a residual");
     ACH_REQUIRE(p.B <= 65535, "ach_pw_conv_tc: B too large");
     ACH_REQUIRE(!p.ln || wsum, "ach_pw_conv_tc: the LayerNorm prologue needs wsum (row sums of the folded weights)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

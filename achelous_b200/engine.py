@@ -179,7 +179,7 @@ class Engine:
         # measured on B200 (profiles/r1_tc_vs_simt.md): the persistent tcgen05 kernel beats the SIMT GEMM on every
         # shared-weight layer with >= 24 outputs; narrower outputs waste most of a 32-column MMA tile
         tc_ok = (tc_mode == "all" and O >= 16) or (tc_mode is True and O >= 24)
-        if tc_ok and not reduce_max and wt_bs == 0 and isinstance(wt, torch.Tensor) and not self.in_pack:
+        if tc_ok and wt_bs == 0 and isinstance(wt, torch.Tensor) and not self.in_pack:
             # tcgen05 path: weights re-packed on the device into hi/lo UMMA tile images whenever they change
             n = self.lib.ach_pack_pw_tc_elems(K_, O)
             hi = torch.zeros(n, device=self.device, dtype=torch.float32)

@@ -440,7 +440,7 @@ def test_up_ghost_head(init, K, h, w):
 
 
 # ------------------------------------------------------------------ tcgen05 pointwise GEMM
-TC_CASES = [c for c in PW_CASES if not c.get("reduce_max") and not c.get("per_batch_w") and c["O"] >= 16] + [
+TC_CASES = [c for c in PW_CASES if not c.get("per_batch_w") and c["O"] >= 16] + [
     dict(B=2, c0=32, c1=0, O=32, P=25600, act=1, scale=1),
     dict(B=1, c0=8, c1=0, O=16, P=128),
     dict(B=2, c0=40, c1=0, O=200, P=132, act=2, scale=1, res=1),
@@ -483,8 +483,12 @@ def test_pw_conv_tc(case):
         if c["gamma"]:
             A.new("gamma", torch.rand(O) + 0.5)
             s.gamma = A.ptr("gamma")
-        A.new("out", torch.zeros(B, O + 2, P))
-        s.out, s.out_bs = A.ptr("out", P), (O + 2) * P
+        if c.get("reduce_max"):
+            A.new("out", torch.full((B, O), float("-inf")))
+            s.out, s.out_bs, s.reduce_max = A.ptr("out"), O, 1
+        else:
+            A.new("out", torch.zeros(B, O + 2, P))
+            s.out, s.out_bs = A.ptr("out", P), (O + 2) * P
         s.B, s.O, s.P = B, O, P
         s.ln, s.ln_eps, s.act = c["ln"], 1e-6, c["act"]
         A.new("wsum", wt[:, :O].sum(0))
