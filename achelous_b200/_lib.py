@@ -73,6 +73,8 @@ _SIGNATURES = {
     "ach_eca_fuse": ([VP, LL, VP, LL, VP, VP, I, VP, VP, VP, LL, I, I, I, VP], I),
     "ach_avgpool3": ([VP, LL, VP, LL, I, I, I, I, VP], I),
     "ach_rc_deform": ([C.POINTER(AchRcDeform), VP], I),
+    "ach_rc_deform_tc_supported": ([I], I),
+    "ach_rc_deform_tc": ([C.POINTER(AchRcDeform), VP, VP, VP, VP, VP], I),
     "ach_xca_fold": ([VP, LL, VP, VP, I, VP, LL, I, I, I, I, VP], I),
     "ach_mvit_attention": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
     "ach_fc": ([VP, LL, VP, VP, VP, VP, LL, I, I, I, I, VP], I),

@@ -53,6 +53,16 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+// Blackwell packed fp32 FMA (FFMA2): two independent fp32 FMAs per issued instruction; bit-identical to two fmaf().
+// acc[0..3] += x * w[0..3] costs 2 issue slots instead of 4 in the issue-bound direct-convolution inner loops.
+__device__ __forceinline__ void fma4_bcast(float* acc, float x, const float4& w) {
+    const float2 xx = make_float2(x, x);
+    float2 a01 = make_float2(acc[0], acc[1]), a23 = make_float2(acc[2], acc[3]);
+    a01 = __ffma2_rn(xx, make_float2(w.x, w.y), a01);
+    a23 = __ffma2_rn(xx, make_float2(w.z, w.w), a23);
+    acc[0] = a01.x; acc[1] = a01.y; acc[2] = a23.x; acc[3] = a23.y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -63,13 +63,7 @@ __global__ void __launch_bounds__(256) conv_dense_kernel(const AchConvDense p, i
                     const float xv = t[ky * IWp + kx];
                     const float4* w4 = reinterpret_cast<const float4*>(w + (ky * k + kx) * OT);
 #pragma unroll
-                    for (int i = 0; i < OT / 4; ++i) {
-                        const float4 wv = w4[i];
-                        acc[4 * i + 0] = fmaf(xv, wv.x, acc[4 * i + 0]);
-                        acc[4 * i + 1] = fmaf(xv, wv.y, acc[4 * i + 1]);
-                        acc[4 * i + 2] = fmaf(xv, wv.z, acc[4 * i + 2]);
-                        acc[4 * i + 3] = fmaf(xv, wv.w, acc[4 * i + 3]);
-                    }
+                    for (int i = 0; i < OT / 4; ++i) fma4_bcast(acc + 4 * i, xv, w4[i]);
                 }
         }
     }

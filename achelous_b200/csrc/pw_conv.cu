@@ -140,12 +140,7 @@ __global__ void __launch_bounds__(256) pw_conv_kernel(const AchPwConv p) {
                 a[0] = a0.x; a[1] = a0.y;
             }
 #pragma unroll
-            for (int i = 0; i < TM; ++i) {
-                acc[i][0] = fmaf(a[i], bv.x, acc[i][0]);
-                acc[i][1] = fmaf(a[i], bv.y, acc[i][1]);
-                acc[i][2] = fmaf(a[i], bv.z, acc[i][2]);
-                acc[i][3] = fmaf(a[i], bv.w, acc[i][3]);
-            }
+            for (int i = 0; i < TM; ++i) fma4_bcast(acc[i], a[i], bv);   // FFMA2: 2 issue slots per 4 MACs
         }
         if (c + 1 < nk) store_chunk((c + 1) & 1);
         __syncthreads();

@@ -35,55 +35,12 @@
 // a fully unrolled 128-output epilogue with erf-GELU thrashed the instruction cache - ncu stall_no_instruction
 // 6.4 per issue), folded scale/bias, activation, layer-scale + residual, coalesced 128-byte stores.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ach {
 
-constexpr int TC_M = 128;   // pixels per tile
-constexpr int TC_KC = 16;   // K per shared-memory chunk (2 MMA K-steps of 8)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ float to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)(layout_type & 7) << 61; // 0 = no swizzle
-    return d;
-}
-
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}\n" ::"r"(mbar), "r"(parity)
-        : "memory");
-}
-
 template <int NT, int STAGES, int ACT>
-__global__ void __launch_bounds__(256) pw_conv_tc_kernel(const AchPwConv p, const float* __restrict__ w_hi,
+__global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, const float* __restrict__ w_hi,
                                                          const float* __restrict__ w_lo, const float* __restrict__ wsum,
                                                          int n_kchunks, int n_pt, int n_ot, int total_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -350,9 +307,7 @@ static int launch_tc(const AchPwConv& p, const float* w_hi, const float* w_lo, c
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int per_sm = (int)((227 * 1024) / (smem + 4096));          // shared memory
-        per_sm = per_sm < 512 / (NT < 32 ? 32 : NT) ? per_sm : 512 / (NT < 32 ? 32 : NT);   // TMEM columns
-        per_sm = per_sm < 4 ? per_sm : 4;                           // registers (<= 64 x 256 threads)
+        const int per_sm = tc_ctas_per_sm(pw_conv_tc_kernel<NT, STAGES, ACT>, 256, smem, NT < 32 ? 32 : NT);
         ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);

@@ -50,13 +50,7 @@ __global__ void __launch_bounds__(128) rc_deform_kernel(const AchRcDeform p) {
             if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(pc + yy * W + xx);
             const float4* w4 = reinterpret_cast<const float4*>(s_om + (c * 9 + t) * 28);
 #pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const float4 wv = w4[i];
-                om[4 * i + 0] = fmaf(v, wv.x, om[4 * i + 0]);
-                om[4 * i + 1] = fmaf(v, wv.y, om[4 * i + 1]);
-                om[4 * i + 2] = fmaf(v, wv.z, om[4 * i + 2]);
-                om[4 * i + 3] = fmaf(v, wv.w, om[4 * i + 3]);
-            }
+            for (int i = 0; i < 7; ++i) fma4_bcast(om + 4 * i, v, w4[i]);
         }
     }
 
@@ -88,13 +82,7 @@ __global__ void __launch_bounds__(128) rc_deform_kernel(const AchRcDeform p) {
             const float v = m * (w00 * __ldg(pc + i00) + w01 * __ldg(pc + i01) + w10 * __ldg(pc + i10) + w11 * __ldg(pc + i11));
             const float4* w4 = reinterpret_cast<const float4*>(s_reg + (c * 9 + t) * CP);
 #pragma unroll
-            for (int i = 0; i < CP / 4; ++i) {
-                const float4 wv = w4[i];
-                acc[4 * i + 0] = fmaf(v, wv.x, acc[4 * i + 0]);
-                acc[4 * i + 1] = fmaf(v, wv.y, acc[4 * i + 1]);
-                acc[4 * i + 2] = fmaf(v, wv.z, acc[4 * i + 2]);
-                acc[4 * i + 3] = fmaf(v, wv.w, acc[4 * i + 3]);
-            }
+            for (int i = 0; i < CP / 4; ++i) fma4_bcast(acc + 4 * i, v, w4[i]);
         }
     }
 
@@ -106,13 +94,7 @@ __global__ void __launch_bounds__(128) rc_deform_kernel(const AchRcDeform p) {
     for (int c = 0; c < C; ++c) {
         const float4* w4 = reinterpret_cast<const float4*>(s_w1 + c * CP);
 #pragma unroll
-        for (int i = 0; i < CP / 4; ++i) {
-            const float4 wv = w4[i];
-            z[4 * i + 0] = fmaf(acc[c], wv.x, z[4 * i + 0]);
-            z[4 * i + 1] = fmaf(acc[c], wv.y, z[4 * i + 1]);
-            z[4 * i + 2] = fmaf(acc[c], wv.z, z[4 * i + 2]);
-            z[4 * i + 3] = fmaf(acc[c], wv.w, z[4 * i + 3]);
-        }
+        for (int i = 0; i < CP / 4; ++i) fma4_bcast(z + 4 * i, acc[c], w4[i]);
     }
     const float* __restrict__ xr = p.x + (long long)b * p.x_bs + pix;
     float* __restrict__ orow = p.out + (long long)b * p.out_bs + pix;

@@ -641,7 +641,24 @@ class Engine:
             y = self.buf(f"rc{i}.y", cin, cur.H, cur.W)
             s.out, s.out_bs, s.B, s.C, s.H, s.W = y.ptr, y.bs, self.B, cin, cur.H, cur.W
             self._keep.append(s)
-            self._add(f"rc{i}.deform", self.lib.ach_rc_deform, C.byref(s), nbytes=4 * self.B * cin * cur.H * cur.W * 3)
+            nb_rc = 4 * self.B * cin * cur.H * cur.W * 3
+            # measured (profiles/r1_tc_vs_simt.md): the synchronous tensor-core RCBlock kernel only ties the SIMT one, so it is opt-in
+            if self.model.use_tensor_cores == "all" and self.lib.ach_rc_deform_tc_supported(cin):
+                # both contractions of the block as implicit GEMMs on tcgen05; weights packed on the device at (re)pack time
+                w_om_t = self._weights[f"rc{i}.w_om"][0]
+                w_reg_t = self._w(f"rc{i}.w_reg_tap", (lambda d=d, cin=cin: torch.nn.functional.pad(
+                    self._p(d + ".regular_conv.weight").reshape(cin, cin, 9).permute(2, 1, 0).reshape(9 * cin, cin), (0, _ceil4(cin) - cin))))
+                tiles = []
+                for wt_, K_, O_ in ((w_om_t, cin * 9, 27), (w_reg_t, 9 * cin, cin)):
+                    n_ = self.lib.ach_pack_pw_tc_elems(K_, O_)
+                    hi = torch.zeros(n_, device=self.device, dtype=torch.float32)
+                    lo = torch.zeros(n_, device=self.device, dtype=torch.float32)
+                    self._keep += [hi, lo]
+                    self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt_.data_ptr(), K_, O_, wt_.shape[-1], hi.data_ptr(), lo.data_ptr())))
+                    tiles += [hi.data_ptr(), lo.data_ptr()]
+                self._add(f"rc{i}.deform", self.lib.ach_rc_deform_tc, C.byref(s), *tiles, nbytes=nb_rc)
+            else:
+                self._add(f"rc{i}.deform", self.lib.ach_rc_deform, C.byref(s), nbytes=nb_rc)
             if down:
                 out = self.buf(f"rc{i}.out", cout, cur.H // 2, cur.W // 2)
                 self.conv(f"rc{i}.down", y, out, self._pack_conv(f"rc{i}.w2", bp + ".weight_conv2.weight"), 3, 2, 1,

@@ -182,6 +182,15 @@ typedef struct AchRcDeform {
 } AchRcDeform;
 ACH_API int ach_rc_deform(const AchRcDeform* p, void* stream);
 
+/* Tensor-core version of ach_rc_deform for C in {3, 8, 12} (the high-resolution RCNet blocks): both dense
+ * contractions run as implicit GEMMs on tcgen05 (3xTF32).  Weights pre-packed with ach_pack_pw_tc:
+ *   wom_hi/lo  <- K-major [C*9][28] (k = ch*9 + tap; 18 offset + 9 modulator outputs), O = 27
+ *   wreg_hi/lo <- K-major [9*C][ceil4(C)] with TAP-MAJOR k = tap*C + ch, O = C
+ * The AchRcDeform fields w_om / w_reg are ignored; x, pooled, b_om, w1, scale, bias, out as in ach_rc_deform. */
+ACH_API int ach_rc_deform_tc_supported(int C);
+ACH_API int ach_rc_deform_tc(const AchRcDeform* p, const float* wom_hi, const float* wom_lo, const float* wreg_hi,
+                             const float* wreg_lo, void* stream);
+
 /* XCA attention core (sdta_encoder.py:162-185): from qkv (B, 3C, N) computes per (b, head) the
  * softmax(temperature * normalize(q) normalize(k)^T) (d x d) and folds it into the output projection:
  *   wt_eff[b][h*d + j][o] = sum_i proj_wt[h*d + i][o] * attn[b,h][i][j]

@@ -251,6 +251,34 @@ def ach_rc_deform(s):
     fview(s.out, (B, Cc, H, W), (s.out_bs, P, W, 1)).copy_(x + y)
 
 
+def _tc_unpack(w_hi, w_lo, K, O):
+    o, k = _tc_index(K, O)
+    n = o.numel()
+    tiles = fview(w_hi, (n,), (1,)) + fview(w_lo, (n,), (1,))
+    ok = (o < O) & (k < K)
+    m = torch.zeros(K, O)
+    m[k[ok], o[ok]] = tiles[ok]
+    return m
+
+
+class _Shim:
+    def __init__(self, s, **ov):
+        self.__dict__["s"], self.__dict__["ov"] = s, ov
+
+    def __getattr__(self, name):
+        ov = self.__dict__["ov"]
+        return ov[name] if name in ov else getattr(self.__dict__["s"], name)
+
+
+def ach_rc_deform_tc(s, wom_hi, wom_lo, wreg_hi, wreg_lo):
+    Cc = s.C
+    wom = torch.zeros(Cc * 9, 28)
+    wom[:, :27] = _tc_unpack(wom_hi, wom_lo, Cc * 9, 27)
+    wreg_tap = _tc_unpack(wreg_hi, wreg_lo, 9 * Cc, Cc)                      # rows k = tap*C + ch
+    wreg = wreg_tap.reshape(9, Cc, Cc).permute(1, 0, 2).reshape(Cc * 9, Cc).contiguous()   # rows ch*9 + tap
+    ach_rc_deform(_Shim(s, w_om=wom.data_ptr(), w_reg=wreg.data_ptr()))
+
+
 def ach_xca_fold(qkv, qkv_bs, temperature, proj_wt, ldw, wt_eff, wt_eff_bs, B, Cc, heads, N):
     d = Cc // heads
     q = fview(qkv, (B, heads, d, N), (qkv_bs, d * N, N, 1))
@@ -386,7 +414,7 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc)}
 
 
 def _unwrap(a):
