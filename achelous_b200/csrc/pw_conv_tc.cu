@@ -39,8 +39,8 @@
 
 namespace ach {
 
-template <int NT, int STAGES, int ACT>
-__global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, const float* __restrict__ w_hi,
+template <int NT, int STAGES, int ACT, int HALVES>
+__global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(const AchPwConv p, const float* __restrict__ w_hi,
                                                          const float* __restrict__ w_lo, const float* __restrict__ wsum,
                                                          int n_kchunks, int n_pt, int n_ot, int total_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -50,10 +50,11 @@ __global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, c
     float* stage_base = reinterpret_cast<float*>(smem_raw);   // [2 stages][a_hi | a_lo | b_hi | b_lo]
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_ln[2][TC_M][2];
+    __shared__ float s_ln[HALVES][TC_M][2];
     __shared__ __align__(16) float4 s_ep[NT];   // per output of the current tile: {scale, scale*wsum, bias + scale*pbias, gamma}
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr int THREADS = 128 * HALVES;   // HALVES thread groups share the k-cores on the way in and the columns on the way out
     const int px = tid & (TC_M - 1), half = tid >> 7;   // half is warp-uniform
     const int K = p.c0 + p.c1;
     const int P = p.P;
@@ -105,10 +106,11 @@ __global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, c
             float* b_hi = a_lo + A_ELEMS;
             float* b_lo = b_hi + B_ELEMS;
             // global loads first (they do not touch shared memory), so their latency overlaps the wait below
-            float v[2][4];
+            constexpr int JJ = 4 / HALVES;   // k-cores of the chunk handled by this thread
+            float v[JJ][4];
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = half + 2 * jj;
+            for (int jj = 0; jj < JJ; ++jj) {
+                const int j = half + HALVES * jj;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int kk = k0 + j * 4 + e;
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, c
                 }
             }
             constexpr int N4 = B_ELEMS / 4;   // float4 per weight matrix: 128 (NT=32) .. 512 (NT=128)
-            constexpr int NB = (N4 + 255) / 256;
+            constexpr int NB = (N4 + THREADS - 1) / THREADS;
             float4 wh[NB], wl[NB];
             {
                 const long long blk = ((long long)o_tile * n_kchunks + c) * B_ELEMS;
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, c
                 const float4* gl = reinterpret_cast<const float4*>(w_lo + blk);
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
-                    const int idx = tid + 256 * i;
+                    const int idx = tid + THREADS * i;
                     if (idx < N4) {
                         wh[i] = __ldg(gh + idx);
                         wl[i] = __ldg(gl + idx);
@@ -138,8 +140,8 @@ __global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, c
             const uint32_t uses_st = st ? uses1 : uses0;
             if (uses_st > 0) mbar_wait(mbar_st, (uses_st - 1) & 1);
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = half + 2 * jj;
+            for (int jj = 0; jj < JJ; ++jj) {
+                const int j = half + HALVES * jj;
                 if (p.ln) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, c
             }
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
-                const int idx = tid + 256 * i;
+                const int idx = tid + THREADS * i;
                 if (idx < N4) {
                     reinterpret_cast<float4*>(b_hi)[idx] = wh[i];
                     reinterpret_cast<float4*>(b_lo)[idx] = wl[i];
@@ -212,14 +214,14 @@ __global__ void __launch_bounds__(256, 4) pw_conv_tc_kernel(const AchPwConv p, c
         // y = act(rs * (scale*acc) - ms * (scale*wsum) + c)  with rs = rstd, ms = mean*rstd   (rs = 1, ms = 0 without LayerNorm)
         float rs = 1.f, ms = 0.f;
         if (p.ln) {
-            const float t1 = (s_ln[0][px][0] + s_ln[1][px][0]) / (float)K;
-            const float t2 = (s_ln[0][px][1] + s_ln[1][px][1]) / (float)K;
+            const float t1 = (s_ln[0][px][0] + s_ln[HALVES - 1][px][0] * (HALVES - 1)) / (float)K;
+            const float t2 = (s_ln[0][px][1] + s_ln[HALVES - 1][px][1] * (HALVES - 1)) / (float)K;
             rs = 1.0f / sqrtf(fmaxf(t2 - t1 * t1, 0.f) + p.ln_eps);
             ms = (shift + t1) * rs;
         }
 
         // ---- epilogue: thread = pixel (TMEM lane 32*(warp%4) + lane); this half's NT/2 columns, 16 at a time
-        constexpr int NH = NT / 2;
+        constexpr int NH = NT / HALVES;
         float* optr = p.out + (long long)b * p.out_bs + (long long)(o_base + half * NH) * P + pp;
         const float* rptr = p.res ? p.res + (long long)b * p.res_bs + (long long)(o_base + half * NH) * P + pp : nullptr;
         const int o_lim = p.O - o_base;   // valid outputs in this tile
@@ -298,23 +300,27 @@ static int tc_tile_n(int O) { return O <= 32 ? 32 : (O <= 64 ? 64 : 128); }
 
 template <int NT, int STAGES, int ACT>
 static int launch_tc(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
+    // narrow tiles (<= 64 TMEM columns) run as 128-thread CTAs, 8 per SM: twice as many independent load / MMA /
+    // epilogue pipelines per SM to hide each other's barrier and mbarrier waits; 128-column tiles are capped at 4
+    // CTAs per SM by TMEM and keep 256 threads
+    constexpr int HALVES = (NT <= 64 && STAGES == 1) ? 1 : 2;   // measured: long-K narrow layers prefer 256 threads (half the loads per thread)
     const int K = p.c0 + p.c1;
     const int n_kchunks = cdiv(K, TC_KC);
     constexpr size_t smem = STAGES * (2 * TC_KC * TC_M * 4 + 2 * (size_t)NT * TC_KC * 4);
     static int ctas_per_wave = 0;
     if (!ctas_per_wave) {
-        cudaFuncSetAttribute(pw_conv_tc_kernel<NT, STAGES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(pw_conv_tc_kernel<NT, STAGES, ACT, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = tc_ctas_per_sm(pw_conv_tc_kernel<NT, STAGES, ACT>, 256, smem, NT < 32 ? 32 : NT);
+        const int per_sm = tc_ctas_per_sm(pw_conv_tc_kernel<NT, STAGES, ACT, HALVES>, 128 * HALVES, smem, NT < 32 ? 32 : NT);
         ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);
     const long long total = (long long)n_pt * n_ot * p.B;
     ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
-    pw_conv_tc_kernel<NT, STAGES, ACT><<<grid, 256, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
+    pw_conv_tc_kernel<NT, STAGES, ACT, HALVES><<<grid, 128 * HALVES, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
     return check_launch("ach_pw_conv_tc");
 }
 
