@@ -195,11 +195,16 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ncu_range = os.environ.get("ACH_NCU_RANGE") == "1"   # `ncu --profile-from-start off`: profile exactly the timed steps
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
     barrier()
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
@@ -323,8 +328,16 @@ def measure_dominant(eng, K, torch):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
+    traffic = None
+    try:   # dram__bytes_read+write of this launch from the committed `ncu --set full` capture (profiles/r1_traffic.json)
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            traffic = json.load(f).get(eng.op_names[top], {}).get("dram_bytes")
+    except Exception:
+        pass
     return {"bound": "hbm", "kernel": f"{eng.op_names[top]} ({fn.__name__})", "share_of_step": t[top] / total,
-            "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes": nbytes, "launch_ms": ms, "traffic": None}
+            "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes": nbytes, "launch_ms": ms, "traffic": traffic,
+            "note": "the top launch by time; every kernel on this path is HBM-bound by arithmetic intensity but the round-1 kernels are "
+                    "instruction-issue bound (profiles/r1_ncu_final_summary.txt)"}
 
 
 if __name__ == "__main__":
