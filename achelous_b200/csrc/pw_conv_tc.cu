@@ -108,15 +108,27 @@ __global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(co
             // global loads first (they do not touch shared memory), so their latency overlaps the wait below
             constexpr int JJ = 4 / HALVES;   // k-cores of the chunk handled by this thread
             float v[JJ][4];
+            if (k0 + TC_KC <= p.c0 || (k0 >= p.c0 && k0 + TC_KC <= K)) {
+                // fast path (the common case): the whole chunk lies inside one source -> one base pointer, constant strides,
+                // no per-element bounds / source selection
+                const float* __restrict__ src = (k0 < p.c0) ? x0 + (long long)k0 * P + pp : x1 + (long long)(k0 - p.c0) * P + pp;
 #pragma unroll
-            for (int jj = 0; jj < JJ; ++jj) {
-                const int j = half + HALVES * jj;
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int j = half + HALVES * jj;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int kk = k0 + j * 4 + e;
-                    float t = 0.f;
-                    if (kk < K && p_ok) t = (kk < p.c0) ? __ldg(x0 + (long long)kk * P + pp) : __ldg(x1 + (long long)(kk - p.c0) * P + pp);
-                    v[jj][e] = t;
+                    for (int e = 0; e < 4; ++e) v[jj][e] = p_ok ? __ldg(src + (long long)(j * 4 + e) * P) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int j = half + HALVES * jj;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int kk = k0 + j * 4 + e;
+                        float t = 0.f;
+                        if (kk < K && p_ok) t = (kk < p.c0) ? __ldg(x0 + (long long)kk * P + pp) : __ldg(x1 + (long long)(kk - p.c0) * P + pp);
+                        v[jj][e] = t;
+                    }
                 }
             }
             constexpr int N4 = B_ELEMS / 4;   // float4 per weight matrix: 128 (NT=32) .. 512 (NT=128)
@@ -144,12 +156,12 @@ __global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(co
                 const int j = half + HALVES * jj;
                 if (p.ln) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (k0 + j * 4 + e < K && p_ok) {
-                            const float d = v[jj][e] - shift;
-                            s1 += d;
-                            s2 = fmaf(d, d, s2);
-                        }
+                    for (int e = 0; e < 4; ++e) {
+                        // padded elements are exactly 0 and must not enter the statistics: predicate once per element
+                        const float d = (k0 + j * 4 + e < K && p_ok) ? v[jj][e] - shift : 0.f;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
+                    }
                 }
                 float4 h, l;
                 h.x = to_tf32(v[jj][0]); h.y = to_tf32(v[jj][1]); h.z = to_tf32(v[jj][2]); h.w = to_tf32(v[jj][3]);
