@@ -56,6 +56,11 @@ class AchUpGhostHead(C.Structure):
                 ("s4", VP), ("b4", VP), ("v_bs", LL), ("out_bs", LL), ("B", I), ("C", I), ("init", I), ("K", I), ("h", I), ("w", I)]
 
 
+class AchUpGhostPw2(C.Structure):
+    _fields_ = [("v", VP), ("out", VP), ("b1", VP), ("w2", VP), ("s2", VP), ("b2", VP), ("w1t", VP), ("c1", VP), ("w2t", VP),
+                ("v_bs", LL), ("out_bs", LL), ("B", I), ("Ci", I), ("C1", I), ("N2", I), ("h", I), ("w", I)]
+
+
 _SIGNATURES = {
     "ach_version": ([], I),
     "ach_pw_conv": ([C.POINTER(AchPwConv), VP], I),
@@ -83,6 +88,8 @@ _SIGNATURES = {
     "ach_add": ([VP, LL, VP, LL, VP, LL, I, I, I, VP], I),
     "ach_fill": ([VP, LL, F, VP], I),
     "ach_up_ghost": ([C.POINTER(AchUpGhost), VP], I),
+    "ach_up_ghost_pw2_supported": ([I, I, I], I),
+    "ach_up_ghost_pw2": ([C.POINTER(AchUpGhostPw2), VP], I),
     "ach_up_ghost_head_supported": ([I, I, I], I),
     "ach_up_ghost_head": ([C.POINTER(AchUpGhostHead), VP], I),
     "ach_pn2_fps": ([VP, LL, I, I, I, VP, VP, LL, VP], I),

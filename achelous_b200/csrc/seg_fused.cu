@@ -294,3 +294,174 @@ extern "C" int ach_up_ghost_head(const AchUpGhostHead* pp, void* stream) {
     if (a.init == 1) return launch_head<1, 2>(a, st);
     return launch_head<5, 9>(a, st);
 }
+
+// ------------------------------------------------------------------------------------------------
+// ach_up_ghost_pw2: one decoder stage END TO END at the output resolution of the stage:
+//   x1 = relu(up(v) + b1), x2 = relu(s2*dw3x3(x1) + b2)          (GhostModule of stage s, as ach_up_ghost)
+//   t  = relu(W1 [x1, x2] + c1)                                   (next stage's Upsample 1x1 conv + BN + ReLU, 32 ch)
+//   v' = W2 t                                                      (next stage's Ghost primary conv, BN scale folded, 16 ch)
+// so the stage's 2*Ci-channel output and the 32-channel t never touch HBM: the kernel reads Ci channels at (h, w)
+// and writes 16 channels at (2h, 2w) - what the next ach_up_ghost_pw2 / ach_up_ghost_head consumes.
+// Tile 16 x 32 outputs; x1 on the 18 x 34 halo tile in shared memory; every thread owns a vertical pixel pair,
+// keeps t[32][2] in registers and streams the weights from shared memory as float4 broadcasts into FFMA2s.
+namespace ach {
+
+constexpr int UP_TH = 16, UP_TW = 32;
+constexpr int UP_XH = UP_TH + 2, UP_XW = UP_TW + 2, UP_XP = UP_XW + 1;
+constexpr int UP_VH = UP_XH / 2 + 3, UP_VW = UP_XW / 2 + 3;
+constexpr int UP_C1 = 32, UP_N2 = 16;
+
+template <int CI>
+__global__ void __launch_bounds__(256, 2) up_ghost_pw2_kernel(const AchUpGhostPw2 p) {
+    extern __shared__ __align__(16) float smem[];
+    float* x1s = smem;                                   // [CI][18][35]
+    float* vs = x1s + CI * UP_XH * UP_XP;                // [CI][12][20+1]
+    float* w1s = vs + CI * UP_VH * (UP_VW + 1);          // [2*CI][32]
+    float* w2s = w1s + 2 * CI * UP_C1;                   // [32][16]
+    float* dws = w2s + UP_C1 * UP_N2;                    // [CI][12]: 9 taps, s2, b2, b1
+    float* c1s = dws + CI * 12;                          // [32]
+
+    const int h = p.h, w = p.w, H = 2 * h, W = 2 * w;
+    const int tiles_x = (W + UP_TW - 1) / UP_TW;
+    const int ty0 = (blockIdx.x / tiles_x) * UP_TH, tx0 = (blockIdx.x % tiles_x) * UP_TW;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
+    const int vy0 = (int)(sy * (float)max(ty0 - 1, 0)), vx0 = (int)(sx * (float)max(tx0 - 1, 0));
+    const long long plane_lo = (long long)h * w, plane_hi = (long long)H * W;
+    const float* vb = p.v + (long long)b * p.v_bs;
+
+    for (int i = tid; i < 2 * CI * UP_C1; i += 256) w1s[i] = p.w1t[i];
+    for (int i = tid; i < UP_C1 * UP_N2; i += 256) w2s[i] = p.w2t[i];
+    for (int i = tid; i < CI * 12; i += 256) {
+        const int c = i / 12, k = i - c * 12;
+        dws[i] = k < 9 ? p.w2[c * 9 + k] : (k == 9 ? p.s2[c] : (k == 10 ? p.b2[c] : p.b1[c]));
+    }
+    if (tid < UP_C1) c1s[tid] = p.c1[tid];
+    for (int i = tid; i < CI * UP_VH * UP_VW; i += 256) {
+        const int c = i / (UP_VH * UP_VW);
+        const int r = i - c * (UP_VH * UP_VW);
+        const int yy = r / UP_VW, xx = r - yy * UP_VW;
+        const int gy = min(vy0 + yy, h - 1), gx = min(vx0 + xx, w - 1);
+        vs[(c * UP_VH + yy) * (UP_VW + 1) + xx] = __ldg(vb + (long long)c * plane_lo + gy * w + gx);
+    }
+    __syncthreads();
+
+    // ---- x1 on the halo tile (0 outside the image: dw zero padding)
+    for (int i = tid; i < UP_XH * UP_XW; i += 256) {
+        const int yy = i / UP_XW, xx = i - yy * UP_XW;
+        const int gy = ty0 - 1 + yy, gx = tx0 - 1 + xx;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+        float ly = 0.f, lx = 0.f;
+        if (in) {
+            bilin_src(gy, sy, h, y0, y1, ly);
+            bilin_src(gx, sx, w, x0, x1, lx);
+            y0 -= vy0; y1 -= vy0; x0 -= vx0; x1 -= vx0;
+        }
+        const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll 4
+        for (int c = 0; c < CI; ++c) {
+            const float* vc = vs + c * UP_VH * (UP_VW + 1);
+            float val = hy * (hx * vc[y0 * (UP_VW + 1) + x0] + lx * vc[y0 * (UP_VW + 1) + x1]) +
+                        ly * (hx * vc[y1 * (UP_VW + 1) + x0] + lx * vc[y1 * (UP_VW + 1) + x1]);
+            x1s[(c * UP_XH + yy) * UP_XP + xx] = in ? fmaxf(val + dws[c * 12 + 11], 0.f) : 0.f;
+        }
+    }
+    __syncthreads();
+
+    // ---- per vertical pixel pair: t = relu(W1 [x1, x2] + c1)
+    const int col = tid & 31, rp = tid >> 5;          // output rows 2*rp, 2*rp+1; x1 tile rows 2*rp .. 2*rp+3
+    float t[2][UP_C1];
+#pragma unroll
+    for (int o = 0; o < UP_C1; ++o) t[0][o] = t[1][o] = c1s[o];
+#pragma unroll 2
+    for (int c = 0; c < CI; ++c) {
+        const float* xc = x1s + (c * UP_XH + 2 * rp) * UP_XP + col;
+        float win[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) win[r][k] = xc[r * UP_XP + k];
+        const float* dk = dws + c * 12;
+        float g1[2], g2[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float d = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) d = fmaf(win[r + ky][kx], dk[ky * 3 + kx], d);
+            g1[r] = win[r + 1][1];
+            g2[r] = fmaxf(fmaf(dk[9], d, dk[10]), 0.f);
+        }
+        const float4* wa = reinterpret_cast<const float4*>(w1s + c * UP_C1);
+        const float4* wb = reinterpret_cast<const float4*>(w1s + (CI + c) * UP_C1);
+#pragma unroll
+        for (int i = 0; i < UP_C1 / 4; ++i) {
+            const float4 a = wa[i], bq = wb[i];
+            fma4_bcast(t[0] + 4 * i, g1[0], a);
+            fma4_bcast(t[1] + 4 * i, g1[1], a);
+            fma4_bcast(t[0] + 4 * i, g2[0], bq);
+            fma4_bcast(t[1] + 4 * i, g2[1], bq);
+        }
+    }
+    // ---- v' = W2 relu(t)
+    float vo[2][UP_N2];
+#pragma unroll
+    for (int o = 0; o < UP_N2; ++o) vo[0][o] = vo[1][o] = 0.f;
+#pragma unroll
+    for (int k = 0; k < UP_C1; ++k) {
+        const float a0 = fmaxf(t[0][k], 0.f), a1 = fmaxf(t[1][k], 0.f);
+        const float4* w4 = reinterpret_cast<const float4*>(w2s + k * UP_N2);
+#pragma unroll
+        for (int i = 0; i < UP_N2 / 4; ++i) {
+            const float4 wv = w4[i];
+            fma4_bcast(vo[0] + 4 * i, a0, wv);
+            fma4_bcast(vo[1] + 4 * i, a1, wv);
+        }
+    }
+    float* ob = p.out + (long long)b * p.out_bs;
+    const int gx = tx0 + col;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int gy = ty0 + 2 * rp + r;
+        if (gy < H && gx < W) {
+#pragma unroll
+            for (int o = 0; o < UP_N2; ++o) ob[(long long)o * plane_hi + (long long)gy * W + gx] = vo[r][o];
+        }
+    }
+}
+
+template <int CI>
+static int launch_up_ghost_pw2(const AchUpGhostPw2& p, cudaStream_t st) {
+    const size_t smem = (size_t)(CI * UP_XH * UP_XP + CI * UP_VH * (UP_VW + 1) + 2 * CI * UP_C1 + UP_C1 * UP_N2 + CI * 12 + UP_C1) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(up_ghost_pw2_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int H = 2 * p.h, W = 2 * p.w;
+    dim3 grid(cdiv(W, UP_TW) * cdiv(H, UP_TH), p.B);
+    up_ghost_pw2_kernel<CI><<<grid, 256, smem, st>>>(p);
+    return check_launch("ach_up_ghost_pw2");
+}
+
+}  // namespace ach
+
+extern "C" int ach_up_ghost_pw2_supported(int ci, int c1, int n2) {
+    return (ci == 16 || ci == 24 || ci == 32) && c1 == ach::UP_C1 && n2 == ach::UP_N2;
+}
+
+extern "C" int ach_up_ghost_pw2(const AchUpGhostPw2* pp, void* stream) {
+    using namespace ach;
+    const AchUpGhostPw2& p = *pp;
+    ACH_REQUIRE(p.v && p.out && p.b1 && p.w2 && p.s2 && p.b2 && p.w1t && p.c1 && p.w2t, "ach_up_ghost_pw2: null arg");
+    ACH_REQUIRE(p.B > 0 && p.B <= 65535 && p.h > 1 && p.w > 1, "ach_up_ghost_pw2: bad dims");
+    ACH_REQUIRE(ach_up_ghost_pw2_supported(p.Ci, p.C1, p.N2), "ach_up_ghost_pw2: (Ci=%d, C1=%d, N2=%d) not instantiated", p.Ci, p.C1, p.N2);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p.Ci) {
+        case 16: return launch_up_ghost_pw2<16>(p, st);
+        case 24: return launch_up_ghost_pw2<24>(p, st);
+        default: return launch_up_ghost_pw2<32>(p, st);
+    }
+}

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost,
-                   AchUpGhostHead)
+                   AchUpGhostHead, AchUpGhostPw2)
 from .nets import holders as Hd
 
 View = namedtuple("View", "ptr bs C H W")
@@ -542,22 +542,52 @@ class Engine:
         """Same decoder with the Ghost primary conv hoisted below the upsampling (it commutes with the
         bilinear interpolation) and the full-resolution work in the fused ach_up_ghost[_head] kernels."""
         chans = [widths[1], widths[0], widths[0]]
+        stages = ("3_to_2", "2_to_1", "1_to_0")
         cur = x
-        for si, (stage, c) in enumerate(zip(("3_to_2", "2_to_1", "1_to_0"), chans)):
+        chained_v = None   # low-res Ghost-primary output handed over by the previous stage's ach_up_ghost_pw2
+        for si, (stage, c) in enumerate(zip(stages, chans)):
             up_p, g_p = f"{prefix}.{name}_seg_{stage}", f"{prefix}.{name}_seg_ghost_{stage}"
             n = f"{name}.{stage}"
-            t = self.buf(n + ".t", c, cur.H, cur.W)
-            self.pw_bn_act(n + ".conv", up_p + ".upsample.0.conv", up_p + ".upsample.0.bn", 1e-3, cur, t, ACT_RELU)
             init = math.ceil(c / 2)
             cn = c - init
-            v = self.buf(n + ".v", init, cur.H, cur.W)
-            wt = self._w(n + ".prim.wt", (lambda g_p=g_p: self._kmajor(
-                self._bn_fold(g_p + ".primary_conv.1", 1e-5)[0][:, None] * self._p(g_p + ".primary_conv.0.weight").flatten(1))))
-            self.pw(n + ".prim", t, v, wt, init)
+            if chained_v is not None:
+                v = chained_v
+            else:
+                t = self.buf(n + ".t", c, cur.H, cur.W)
+                self.pw_bn_act(n + ".conv", up_p + ".upsample.0.conv", up_p + ".upsample.0.bn", 1e-3, cur, t, ACT_RELU)
+                v = self.buf(n + ".v", init, cur.H, cur.W)
+                wt = self._w(n + ".prim.wt", (lambda g_p=g_p: self._kmajor(
+                    self._bn_fold(g_p + ".primary_conv.1", 1e-5)[0][:, None] * self._p(g_p + ".primary_conv.0.weight").flatten(1))))
+                self.pw(n + ".prim", t, v, wt, init)
             b1f = (lambda g_p=g_p: self._bn_fold(g_p + ".primary_conv.1", 1e-5)[1])
             w2f = (lambda g_p=g_p, cn=cn: self._p(g_p + ".cheap_operation.0.weight")[:cn].flatten(1))
             s2f = (lambda g_p=g_p, cn=cn: self._bn_fold(g_p + ".cheap_operation.1", 1e-5)[0][:cn])
             b2f = (lambda g_p=g_p, cn=cn: self._bn_fold(g_p + ".cheap_operation.1", 1e-5)[1][:cn])
+            if si < 2 and self.model.fuse_seg_chain and cn == init:
+                c_next = chans[si + 1]
+                init_next = math.ceil(c_next / 2)
+                if self.lib.ach_up_ghost_pw2_supported(init, c_next, init_next):
+                    # whole stage + next stage's 1x1 conv + next Ghost primary in one kernel: 2c-channel map never hits HBM
+                    up_n, g_n = f"{prefix}.{name}_seg_{stages[si + 1]}", f"{prefix}.{name}_seg_ghost_{stages[si + 1]}"
+                    vn = self.buf(n + ".vnext", init_next, v.H * 2, v.W * 2)
+                    u = AchUpGhostPw2()
+                    u.v, u.v_bs, u.out, u.out_bs = v.ptr, v.bs, vn.ptr, vn.bs
+                    u.b1 = self._vec(n + ".b1", b1f).data_ptr()
+                    u.w2, u.s2, u.b2 = (self._w(n + ".w2", w2f).data_ptr(), self._vec(n + ".s2", s2f).data_ptr(),
+                                        self._vec(n + ".b2", b2f).data_ptr())
+                    u.w1t = self._w(n + ".chain.w1t", (lambda up_n=up_n: (self._bn_fold(up_n + ".upsample.0.bn", 1e-3)[0][:, None]
+                                                                         * self._p(up_n + ".upsample.0.conv.weight").flatten(1)).t())).data_ptr()
+                    u.c1 = self._vec(n + ".chain.c1", (lambda up_n=up_n: self._bn_fold(up_n + ".upsample.0.bn", 1e-3)[1])).data_ptr()
+                    u.w2t = self._w(n + ".chain.w2t", (lambda g_n=g_n: (self._bn_fold(g_n + ".primary_conv.1", 1e-5)[0][:, None]
+                                                                       * self._p(g_n + ".primary_conv.0.weight").flatten(1)).t())).data_ptr()
+                    u.B, u.Ci, u.C1, u.N2, u.h, u.w = self.B, init, c_next, init_next, v.H, v.W
+                    self._keep.append(u)
+                    self._add(n + ".up_ghost_pw2", self.lib.ach_up_ghost_pw2, C.byref(u),
+                              nbytes=4 * self.B * v.H * v.W * (init + 4 * init_next))
+                    chained_v = vn
+                    cur = vn   # only its spatial size is used below
+                    continue
+            chained_v = None
             K = out.C
             hinit = math.ceil(K / 2)
             if si == 2 and self.lib.ach_up_ghost_head_supported(init, hinit, K) and cn == init:

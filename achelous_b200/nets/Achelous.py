@@ -36,6 +36,7 @@ class _AchelousBase(nn.Module):
         self.use_cuda_graph = True
         self.use_tensor_cores = True   # 1x1 convs / Linears on tcgen05 (3xTF32, fp32-accurate); False: fp32 CUDA-core GEMM
         self.fuse_seg_decoder = True   # False: block-by-block decoder (keeps every reference intermediate)
+        self.fuse_seg_chain = True     # decoder stages chained through ach_up_ghost_pw2 (no full-width maps in HBM)
         self._engines = {}
         self._host_bufs = {}
 

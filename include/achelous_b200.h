@@ -267,6 +267,27 @@ typedef struct AchUpGhostHead {
 ACH_API int ach_up_ghost_head_supported(int c_in, int init, int k_out);
 ACH_API int ach_up_ghost_head(const AchUpGhostHead* p, void* stream);
 
+/* One whole decoder stage at its output resolution: the GhostModule of stage s (as ach_up_ghost, Cn = Ci) followed by
+ * the NEXT stage's Upsample 1x1 conv + BN + ReLU (w1t K-major [2*Ci][32], BN scale folded; c1 bias [32]) and the next
+ * stage's Ghost primary conv (w2t K-major [32][16], BN scale folded, bias applied by the consumer):
+ *   out (B, 16, 2h, 2w) = w2t^T relu(w1t^T [x1, x2] + c1).   All pointers are device arrays.
+ * Replaces, per stage, ach_up_ghost + two ach_pw_conv launches and their HBM round trips (ghostdualfpn.py:175-197). */
+typedef struct AchUpGhostPw2 {
+    const float* v;
+    float* out;
+    const float* b1;
+    const float* w2;
+    const float* s2;
+    const float* b2;
+    const float* w1t;
+    const float* c1;
+    const float* w2t;
+    long long v_bs, out_bs;
+    int B, Ci, C1, N2, h, w;
+} AchUpGhostPw2;
+ACH_API int ach_up_ghost_pw2_supported(int ci, int c1, int n2);
+ACH_API int ach_up_ghost_pw2(const AchUpGhostPw2* p, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * PointNet++ (pc_seg='pn2') building blocks.  The reference advertises PN2 (README.md:63) but contains no code
  * for it (nets/Achelous.py:31-32 handles only 'pn'): these implement the builder-defined network of

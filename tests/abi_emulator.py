@@ -351,6 +351,15 @@ def ach_up_ghost(s):
     fview(s.out, (B, Ci + Cn, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(y)
 
 
+def ach_up_ghost_pw2(s):
+    B, Ci, C1, N2, h, w = s.B, s.Ci, s.C1, s.N2, s.h, s.w
+    v = fview(s.v, (B, Ci, h, w), (s.v_bs, h * w, w, 1))
+    g = _up_ghost(v, _vec(s.b1, Ci), _vec(s.w2, Ci * 9), _vec(s.s2, Ci), _vec(s.b2, Ci), Ci)       # (B, 2Ci, H, W)
+    t = F.relu(torch.einsum("ko,bkhw->bohw", fview(s.w1t, (2 * Ci, C1), (C1, 1)), g) + _vec(s.c1, C1)[None, :, None, None])
+    o = torch.einsum("ko,bkhw->bohw", fview(s.w2t, (C1, N2), (N2, 1)), t)
+    fview(s.out, (B, N2, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(o)
+
+
 def ach_up_ghost_head(s):
     B, Cc, init, K, h, w = s.B, s.C, s.init, s.K, s.h, s.w
     v = fview(s.v, (B, Cc, h, w), (s.v_bs, h * w, w, 1))
@@ -414,7 +423,7 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2)}
 
 
 def _unwrap(a):

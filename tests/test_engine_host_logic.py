@@ -19,6 +19,7 @@ def test_plan_matches_oracle(phi, backbone, seed, fuse, tc):
     torch.set_num_threads(4)
     model = Achelous(phi=phi, backbone=backbone, **MODEL_KW).eval()
     model.fuse_seg_decoder = fuse
+    model.fuse_seg_chain = fuse and phi == "S0" and backbone == "en" and tc == "all" or (phi == "S2")
     model.use_tensor_cores = tc
     sd = fill_state_dict(model.state_dict(), seed=seed)
     model.load_state_dict(sd, strict=True)

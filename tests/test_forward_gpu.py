@@ -26,9 +26,10 @@ TIGHT = 2e-4
 SUPPORTED = list(GOLDEN_CONFIGS)
 
 
-def build(phi, bb, wseed, graph=True, fuse=True, tc=True):
+def build(phi, bb, wseed, graph=True, fuse="chain", tc=True):
     model = Achelous(phi=phi, backbone=bb, **MODEL_KW).eval()
-    model.fuse_seg_decoder = fuse
+    model.fuse_seg_decoder = bool(fuse)
+    model.fuse_seg_chain = fuse == "chain"
     model.use_tensor_cores = tc
     sd = fill_state_dict(model.state_dict(), seed=wseed)
     model.load_state_dict(sd, strict=True)
@@ -36,7 +37,7 @@ def build(phi, bb, wseed, graph=True, fuse=True, tc=True):
     return model.cuda(), sd
 
 
-@pytest.mark.parametrize("fuse,tc", [(True, True), (False, "all"), (True, False)], ids=["fused_seg-tcgen05", "blockwise_seg-tcgen05_everywhere", "fused_seg-simt"])
+@pytest.mark.parametrize("fuse,tc", [("chain", True), (True, True), (False, "all"), (True, False)], ids=["chained_seg-tcgen05", "fused_seg-tcgen05", "blockwise_seg-tcgen05_everywhere", "fused_seg-simt"])
 @pytest.mark.parametrize("name", SUPPORTED)
 def test_forward_vs_golden_and_oracle(name, fuse, tc):
     phi, bb, wseed, iseed = GOLDEN_CONFIGS[name]

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from achelous_b200 import _lib
-from achelous_b200._lib import AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost, AchUpGhostHead
+from achelous_b200._lib import AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost, AchUpGhostHead, AchUpGhostPw2
 from tests import abi_emulator as emu
 
 pytestmark = pytest.mark.gpu
@@ -622,3 +622,20 @@ def test_rc_deform_tc(Cc, H, W):
                 ("ach_pack_pw_tc", (A.ptr("w_reg_tap"), 9 * Cc, Cc, ldr, A.ptr("rgh"), A.ptr("rgl"))),
                 ("ach_rc_deform_tc", (s, A.ptr("omh"), A.ptr("oml"), A.ptr("rgh"), A.ptr("rgl")))]
     run_seq(make, ["out"], rtol=1e-4)
+
+
+@pytest.mark.parametrize("Ci,h,w", [(16, 80, 80), (24, 40, 40), (32, 40, 40), (16, 23, 37)])
+def test_up_ghost_pw2(Ci, h, w):
+    B, C1, N2 = 2, 32, 16
+
+    def make(A):
+        A.new("v", R(B, Ci + 1, h, w)), A.new("out", torch.zeros(B, N2, 2 * h, 2 * w))
+        A.new("b1", R(Ci) * 0.3), A.new("w2", R(Ci, 9) / 3), A.new("s2", torch.rand(Ci) + 0.5), A.new("b2", R(Ci) * 0.3)
+        A.new("w1t", R(2 * Ci, C1) / (2 * Ci) ** 0.5), A.new("c1", R(C1) * 0.2), A.new("w2t", R(C1, N2) / C1 ** 0.5)
+        s = AchUpGhostPw2()
+        s.v, s.v_bs, s.out, s.out_bs = A.ptr("v", h * w), (Ci + 1) * h * w, A.ptr("out"), N2 * 4 * h * w
+        for n in ("b1", "w2", "s2", "b2", "w1t", "c1", "w2t"):
+            setattr(s, n, A.ptr(n))
+        s.B, s.Ci, s.C1, s.N2, s.h, s.w = B, Ci, C1, N2, h, w
+        return (s,)
+    run_both("ach_up_ghost_pw2", make, ["out"])
