@@ -98,16 +98,10 @@ __global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(co
         const float shift = (p.ln && p_ok) ? x0[pp] : 0.f;
         float s1 = 0.f, s2 = 0.f;
 
-        for (int c = 0; c < n_kchunks; ++c) {
+        constexpr int JJ = 4 / HALVES;   // k-cores of a chunk handled by this thread
+        // activation loads of chunk c (global -> registers only)
+        auto load_a = [&](int c, float (&v)[JJ][4]) {
             const int k0 = c * TC_KC;
-            const int st = (STAGES == 2) ? (c & 1) : 0;
-            float* a_hi = stage_base + st * STAGE;
-            float* a_lo = a_hi + A_ELEMS;
-            float* b_hi = a_lo + A_ELEMS;
-            float* b_lo = b_hi + B_ELEMS;
-            // global loads first (they do not touch shared memory), so their latency overlaps the wait below
-            constexpr int JJ = 4 / HALVES;   // k-cores of the chunk handled by this thread
-            float v[JJ][4];
             if (k0 + TC_KC <= p.c0 || (k0 >= p.c0 && k0 + TC_KC <= K)) {
                 // fast path (the common case): the whole chunk lies inside one source -> one base pointer, constant strides,
                 // no per-element bounds / source selection
@@ -131,6 +125,19 @@ __global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(co
                     }
                 }
             }
+        };
+        // software pipeline: the activation loads of chunk c+1 are issued before chunk c is split / stored / multiplied,
+        // so their HBM latency overlaps a whole iteration instead of stalling the shared-memory store that consumes them
+        float v[JJ][4], vn[JJ][4];
+        load_a(0, v);
+        for (int c = 0; c < n_kchunks; ++c) {
+            const int k0 = c * TC_KC;
+            const int st = (STAGES == 2) ? (c & 1) : 0;
+            float* a_hi = stage_base + st * STAGE;
+            float* a_lo = a_hi + A_ELEMS;
+            float* b_hi = a_lo + A_ELEMS;
+            float* b_lo = b_hi + B_ELEMS;
+            if (c + 1 < n_kchunks) load_a(c + 1, vn);
             constexpr int N4 = B_ELEMS / 4;   // float4 per weight matrix: 128 (NT=32) .. 512 (NT=128)
             constexpr int NB = (N4 + THREADS - 1) / THREADS;
             float4 wh[NB], wl[NB];
@@ -198,6 +205,10 @@ __global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(co
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_st) : "memory");
             }
             if (st) uses1 += 1; else uses0 += 1;
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[jj][e] = vn[jj][e];
         }
         // all MMAs of this item are complete once the last commit has arrived
         {
@@ -260,13 +271,20 @@ __global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(co
                     if (lane == 0 && n0 + j < o_lim) atomic_max_float(p.out + (long long)b * p.out_bs + o_base + n0 + j, y);
                 }
             } else if (p_ok) {
+                // residual values first, as 16 independent loads: interleaved with the stores below they would each
+                // stall for a full memory round trip (the compiler cannot hoist a load above a possibly aliasing store)
+                float rr[16];
+                if (rptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) rr[j] = (n0 + j < o_lim) ? rptr[(long long)j * P] : 0.f;
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     if (n0 + j < o_lim) {
                         const float4 e = s_ep[n0 + j];
                         float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
                         y = apply_act(y, ACT);
-                        if (rptr) y = fmaf(e.w, y, rptr[(long long)j * P]);
+                        if (rptr) y = fmaf(e.w, y, rr[j]);
                         optr[(long long)j * P] = y;
                     }
                 }
