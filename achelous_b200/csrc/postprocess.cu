@@ -254,3 +254,81 @@ extern "C" int ach_nms(const float* decoded, int B, int A, int K, float conf_thr
                                                                            counts, static_cast<char*>(workspace), nms_ws_per_img(A));
     return check_launch("ach_nms");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Segmentation post-process on device (reference achelous.py:283-318 does it on the host):
+//   softmax over classes -> letterbox crop -> cv2.resize(INTER_LINEAR) to the original image size -> argmax.
+// ach_seg_softmax writes class probabilities at network resolution; ach_seg_resize_argmax evaluates, per
+// destination pixel, OpenCV's half-pixel-centre bilinear rule (fx = (dx + 0.5) * scale - 0.5, indices clamped with
+// the weight forced to 0 at the borders, horizontal pass then vertical pass in fp32) on the cropped window and writes
+// the first-max class index as uint8: 1 byte per original pixel leaves the GPU instead of 4*K bytes per network pixel.
+namespace ach {
+
+__global__ void __launch_bounds__(256) seg_softmax_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                          long long out_bs, int K, int P) {
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= P) return;
+    const float* xp = x + (long long)blockIdx.y * x_bs + p;
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) m = fmaxf(m, xp[(long long)k * P]);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += expf(xp[(long long)k * P] - m);
+    float* op = out + (long long)blockIdx.y * out_bs + p;
+    for (int k = 0; k < K; ++k) op[(long long)k * P] = expf(xp[(long long)k * P] - m) / s;
+}
+
+__device__ __forceinline__ void cv_linear_coord(int d, double scale, int ssize, int& s0, int& s1, float& a0, float& a1) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+    s0 = s;
+    s1 = min(s + 1, ssize - 1);
+    a0 = 1.f - f;
+    a1 = f;
+}
+
+__global__ void __launch_bounds__(256) seg_resize_argmax_kernel(const float* __restrict__ prob, long long prob_bs, int K, int H, int W,
+                                                                int y_off, int x_off, int nh, int nw, unsigned char* __restrict__ out,
+                                                                int OH, int OW) {
+    const int ox = blockIdx.x * 256 + threadIdx.x;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    if (ox >= OW) return;
+    int sx0, sx1, sy0, sy1;
+    float ax0, ax1, ay0, ay1;
+    cv_linear_coord(ox, (double)nw / (double)OW, nw, sx0, sx1, ax0, ax1);
+    cv_linear_coord(oy, (double)nh / (double)OH, nh, sy0, sy1, ay0, ay1);
+    const long long P = (long long)H * W;
+    const float* pb = prob + (long long)b * prob_bs;
+    const long long r0 = (long long)(y_off + sy0) * W + x_off, r1 = (long long)(y_off + sy1) * W + x_off;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int k = 0; k < K; ++k) {
+        const float* pk = pb + (long long)k * P;
+        const float h0 = __fadd_rn(__fmul_rn(pk[r0 + sx0], ax0), __fmul_rn(pk[r0 + sx1], ax1));   // horizontal pass, row 0
+        const float h1 = __fadd_rn(__fmul_rn(pk[r1 + sx0], ax0), __fmul_rn(pk[r1 + sx1], ax1));   // horizontal pass, row 1
+        const float v = __fadd_rn(__fmul_rn(h0, ay0), __fmul_rn(h1, ay1));                         // vertical pass
+        if (v > best) { best = v; arg = k; }
+    }
+    out[((long long)b * OH + oy) * OW + ox] = (unsigned char)arg;
+}
+
+}  // namespace ach
+
+extern "C" int ach_seg_softmax(const float* x, long long x_bs, float* out, long long out_bs, int B, int K, int P, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(x && out && B > 0 && B <= 65535 && K > 0 && P > 0, "ach_seg_softmax: bad args");
+    seg_softmax_kernel<<<dim3(cdiv(P, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, K, P);
+    return check_launch("ach_seg_softmax");
+}
+
+extern "C" int ach_seg_resize_argmax(const float* prob, long long prob_bs, int B, int K, int H, int W, int y_off, int x_off, int nh,
+                                     int nw, unsigned char* out, int OH, int OW, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(prob && out && B > 0 && B <= 65535 && K > 0 && K <= 255, "ach_seg_resize_argmax: bad args");
+    ACH_REQUIRE(nh > 0 && nw > 0 && y_off >= 0 && x_off >= 0 && y_off + nh <= H && x_off + nw <= W, "ach_seg_resize_argmax: crop window outside the map");
+    ACH_REQUIRE(OH > 0 && OH <= 65535 && OW > 0, "ach_seg_resize_argmax: bad output size");
+    seg_resize_argmax_kernel<<<dim3(cdiv(OW, 256), OH, B), 256, 0, (cudaStream_t)stream>>>(prob, prob_bs, K, H, W, y_off, x_off, nh, nw, out, OH, OW);
+    return check_launch("ach_seg_resize_argmax");
+}

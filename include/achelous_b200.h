@@ -325,6 +325,14 @@ ACH_API long long ach_nms_workspace_bytes(int B, int A);
 ACH_API int ach_nms(const float* decoded, int B, int A, int K, float conf_thres, float nms_thres, float* kept,
             int* kept_idx, int* counts, void* workspace, long long workspace_bytes, void* stream);
 
+/* Segmentation post-process on device: the caller-side sequence of achelous.py:283-318
+ * (softmax over classes -> letterbox crop rows [y_off, y_off+nh) x cols [x_off, x_off+nw) -> cv2.resize INTER_LINEAR to
+ * (OH, OW) -> argmax).  ach_seg_softmax: (B, K, P) logits -> probabilities.  ach_seg_resize_argmax: probabilities
+ * (B, K, H, W) -> uint8 class map (B, OH, OW), first max on ties, OpenCV half-pixel bilinear rule in fp32. */
+ACH_API int ach_seg_softmax(const float* x, long long x_bs, float* out, long long out_bs, int B, int K, int P, void* stream);
+ACH_API int ach_seg_resize_argmax(const float* prob, long long prob_bs, int B, int K, int H, int W, int y_off, int x_off, int nh,
+                                  int nw, unsigned char* out, int OH, int OW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -115,3 +115,22 @@ def non_max_suppression(prediction, num_classes, input_shape, image_shape, lette
         det[:, :4] = yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
         output.append(det)
     return (output, kept) if return_indices else output
+
+
+def seg_postprocess(seg_logits, image_shape, letterbox_image=True):
+    """CPU oracle of the caller-side segmentation post-process, written with the reference's own calls
+    (achelous.py:283-296): softmax -> crop of the letterbox window -> cv2.resize(INTER_LINEAR) -> argmax.
+    seg_logits (K, H, W) torch tensor -> (prob (oh, ow, K) float32, argmax (oh, ow) int64)."""
+    import cv2
+    import torch.nn.functional as F
+    K, H, W = seg_logits.shape
+    oh, ow = int(image_shape[0]), int(image_shape[1])
+    if letterbox_image:
+        scale = min(W / ow, H / oh)
+        nw, nh = int(ow * scale), int(oh * scale)
+    else:
+        nw, nh = W, H
+    pr = F.softmax(seg_logits.permute(1, 2, 0), dim=-1).cpu().numpy()
+    pr = pr[int((H - nh) // 2): int((H - nh) // 2 + nh), int((W - nw) // 2): int((W - nw) // 2 + nw)]
+    pr = cv2.resize(pr, (ow, oh), interpolation=cv2.INTER_LINEAR)
+    return pr, pr.argmax(axis=-1)

@@ -56,3 +56,24 @@ def test_nms_random_dense(n_boxes, seed):
     for b in range(B):
         n = int(counts[b])
         assert np.array_equal(kept_idx[b, :n].cpu().numpy(), o_idx[b])
+
+
+@pytest.mark.parametrize("shape,lb", [((1080, 1920), True), ((480, 640), True), ((320, 320), False), ((97, 211), True)])
+def test_seg_postprocess_on_device(shape, lb):
+    """softmax -> letterbox crop -> cv2-style bilinear resize -> argmax on the GPU vs the reference's host sequence
+    (oracle/postprocess.py::seg_postprocess = torch softmax + cv2.resize).  Exact wherever the interpolated top-2
+    probabilities differ by more than 1e-5 (OpenCV's SIMD build may contract a*b+c differently by one ulp)."""
+    from achelous_b200.utils.seg_post import seg_argmax
+    torch.manual_seed(0)
+    B, K, H, W = 2, 9, 320, 320
+    logits = torch.relu(torch.randn(B, K, H, W) * 2)
+    # smooth the logits so that class regions exist (and ReLU zeros tie exactly, as in the real head)
+    logits = torch.nn.functional.avg_pool2d(logits, 9, 1, 4)
+    mine = seg_argmax(logits.cuda(), shape, lb).cpu().numpy()
+    for b in range(B):
+        pr, am = OP.seg_postprocess(logits[b], shape, lb)
+        top2 = np.sort(pr, axis=-1)[..., -2:]
+        safe = (top2[..., 1] - top2[..., 0]) > 1e-5
+        diff = mine[b] != am
+        assert (diff & safe).sum() == 0
+        assert diff.mean() < 2e-3
