@@ -43,7 +43,7 @@ class AchConvDense(C.Structure):
 class AchRcDeform(C.Structure):
     _fields_ = [("x", VP), ("pooled", VP), ("w_om", VP), ("b_om", VP), ("w_reg", VP), ("w1", VP), ("scale", VP),
                 ("bias", VP), ("out", VP), ("x_bs", LL), ("pooled_bs", LL), ("out_bs", LL),
-                ("B", I), ("C", I), ("H", I), ("W", I)]
+                ("B", I), ("C", I), ("H", I), ("W", I), ("pooled_cl", I)]
 
 
 class AchUpGhost(C.Structure):
@@ -77,6 +77,7 @@ _SIGNATURES = {
     "ach_plane_mean": ([VP, LL, VP, LL, VP, I, I, I, VP], I),
     "ach_eca_fuse": ([VP, LL, VP, LL, VP, VP, I, VP, VP, VP, LL, I, I, I, VP], I),
     "ach_avgpool3": ([VP, LL, VP, LL, I, I, I, I, VP], I),
+    "ach_avgpool3_cl": ([VP, LL, VP, LL, I, I, I, I, VP], I),
     "ach_rc_deform": ([C.POINTER(AchRcDeform), VP], I),
     "ach_rc_deform_tc_supported": ([I], I),
     "ach_rc_deform_tc": ([C.POINTER(AchRcDeform), VP, VP, VP, VP, VP], I),

@@ -1,6 +1,8 @@
 // Depthwise k x k convolution (k in {3,5,7,9}; stride 1/2; pad k/2), HBM-bound stencil.
+// Two kernels: dw_rows_kernel (stride 1, the hot one: register sliding window, see below) and the tiled
+// dw_conv_kernel (stride 2, MobileViT MV2 blocks).
 //
-// One CTA stages the halo tile of CPB channels of one frame in shared memory (warp-per-row coalesced
+// Tiled kernel: one CTA stages the halo tile of CPB channels of one frame in shared memory (warp-per-row coalesced
 // loads, optional fused pre-add of a second tensor - the SDTA cascade `conv(sp + spx[i])`), then every
 // thread produces a strip of 4 horizontally adjacent outputs: per kernel row it pulls the
 // (3*S + KS)-wide input segment with conflict-free 128-bit shared loads into registers and reuses it
@@ -8,6 +10,7 @@
 // channel held in registers.  Epilogue: folded BN/bias, activation, optional broadcast post-add
 // (positional encoding), 128-bit stores when the row pitch allows.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace ach {
 
@@ -112,6 +115,145 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const AchDwConv p, int TH,
     }
 }
 
+// ---- stride-1 path: register sliding window, no shared memory, no barrier.
+// Thread = (frame, channel, block of R output rows, strip of 4 output columns); consecutive threads take consecutive
+// strips, so every row access of a warp is a run of contiguous 16-byte loads.  The thread walks the R + KS - 1 input
+// rows of its block once; each row segment (4 + 2*pad values: the strip plus its halo, the halo coming from L1 where
+// the neighbouring thread's strip already is) feeds the up to KS output rows it overlaps while it is in registers.
+// Everything is unrolled at compile time: KS*KS taps and R*4 accumulators live in registers, the instruction stream
+// is KS*KS FMAs per output plus ~3 loads per 4*KS FMAs.  The tiled kernel above spends 5-10x that on staging
+// arithmetic (ncu: 160 instructions per output for a 3x3).  Summation order per output is (ky, kx) like the tiled kernel.
+template <int KS, int R, bool AL>
+__global__ void __launch_bounds__(128) dw_rows_kernel(const AchDwConv p, int strips, int nrb, long long total) {
+    constexpr int pad = KS / 2;
+    constexpr int SEG = 4 + 2 * pad;
+    const long long idx = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (idx >= total) return;
+    const int s = (int)(idx % strips);
+    long long t = idx / strips;
+    const int rb = (int)(t % nrb);
+    t /= nrb;
+    const int c = (int)(t % p.C);
+    const int b = (int)(t / p.C);
+    const int H = p.H, W = p.W;
+    const int x0 = 4 * s, r0 = rb * R;
+    const long long plane = (long long)H * W;
+    const float* __restrict__ xp = p.x + (long long)b * p.x_bs + (long long)c * plane;
+    const float* __restrict__ ap = p.xadd ? p.xadd + (long long)b * p.xadd_bs + (long long)c * plane : nullptr;
+
+    float wk[KS * KS];
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) wk[i] = __ldg(p.w + (long long)c * KS * KS + i);
+
+    float acc[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+
+    const bool has_l = s > 0, has_r = s < strips - 1;
+    auto load_seg = [&](const float* __restrict__ row, float (&seg)[SEG]) {
+        if constexpr (AL) {
+            const float4 cur = __ldg(reinterpret_cast<const float4*>(row + x0));
+            seg[pad + 0] = cur.x; seg[pad + 1] = cur.y; seg[pad + 2] = cur.z; seg[pad + 3] = cur.w;
+            if constexpr (pad == 1) {
+                seg[0] = has_l ? __ldg(row + x0 - 1) : 0.f;
+                seg[5] = has_r ? __ldg(row + x0 + 4) : 0.f;
+            } else if constexpr (pad == 2) {
+                const float2 l = has_l ? __ldg(reinterpret_cast<const float2*>(row + x0 - 2)) : make_float2(0.f, 0.f);
+                const float2 r = has_r ? __ldg(reinterpret_cast<const float2*>(row + x0 + 4)) : make_float2(0.f, 0.f);
+                seg[0] = l.x; seg[1] = l.y; seg[6] = r.x; seg[7] = r.y;
+            } else {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 l = has_l ? __ldg(reinterpret_cast<const float4*>(row + x0 - 4)) : z;
+                const float4 r = has_r ? __ldg(reinterpret_cast<const float4*>(row + x0 + 4)) : z;
+                const float lv[4] = {l.x, l.y, l.z, l.w}, rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int i = 0; i < pad; ++i) {
+                    seg[i] = lv[4 - pad + i];
+                    seg[pad + 4 + i] = rv[i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                const int xx = x0 - pad + i;
+                seg[i] = (xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
+            }
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < R + 2 * pad; ++i) {
+        const int y = r0 - pad + i;
+        float seg[SEG];
+#pragma unroll
+        for (int q = 0; q < SEG; ++q) seg[q] = 0.f;
+        if (y >= 0 && y < H) {
+            load_seg(xp + (long long)y * W, seg);
+            if (ap) {
+                float sa[SEG];
+                load_seg(ap + (long long)y * W, sa);
+#pragma unroll
+                for (int q = 0; q < SEG; ++q) seg[q] += sa[q];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int ky = i - r;   // input row y = (r0 + r) - pad + ky
+            if (ky >= 0 && ky < KS) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[r][j] = fmaf(seg[j + kx], wk[ky * KS + kx], acc[r][j]);
+            }
+        }
+    }
+
+    const float sc = p.scale ? p.scale[c] : 1.f;
+    const float bi = p.bias ? p.bias[c] : 0.f;
+    float* __restrict__ op = p.out + (long long)b * p.out_bs + (long long)c * plane;
+    const float* __restrict__ pp = p.post ? p.post + (long long)c * plane : nullptr;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int y = r0 + r;
+        if (y >= H) break;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = apply_act(fmaf(sc, acc[r][j], bi), p.act);
+        const long long po = (long long)y * W + x0;
+        if constexpr (AL) {
+            if (pp) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(pp + po));
+                v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+            }
+            *reinterpret_cast<float4*>(op + po) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x0 + j < W) op[po + j] = pp ? v[j] + pp[po + j] : v[j];
+        }
+    }
+}
+
+template <int KS, int R>
+static int launch_rows(const AchDwConv& p, cudaStream_t st) {
+    const bool al = (p.W % 4 == 0) && aligned16(p.x) && aligned16(p.xadd) && aligned16(p.out) && aligned16(p.post) &&
+                    p.x_bs % 4 == 0 && p.xadd_bs % 4 == 0 && p.out_bs % 4 == 0;
+    const int strips = cdiv(p.W, 4), nrb = cdiv(p.H, R);
+    const long long total = (long long)p.B * p.C * nrb * strips;
+    const unsigned grid = (unsigned)cdiv(total, 128);
+    if (al) dw_rows_kernel<KS, R, true><<<grid, 128, 0, st>>>(p, strips, nrb, total);
+    else dw_rows_kernel<KS, R, false><<<grid, 128, 0, st>>>(p, strips, nrb, total);
+    return check_launch("ach_dw_conv");
+}
+
+template <int KS>
+static int launch_rows_k(const AchDwConv& p, cudaStream_t st) {
+    // rows per thread: 8 on tall planes (halo re-reads (R + KS - 1) / R stay small), otherwise a divisor of H
+    if (p.H >= 40 && KS <= 5) return launch_rows<KS, 8>(p, st);
+    if (p.H % 5 == 0) return launch_rows<KS, 5>(p, st);
+    return launch_rows<KS, 4>(p, st);
+}
+
 template <int KS, int S>
 static int launch_dw(const AchDwConv& p, cudaStream_t st) {
     // tile = (TH x TW) outputs x CPB channels with TW a multiple of 4 that divides the (rounded) row evenly, so that
@@ -152,6 +294,16 @@ extern "C" int ach_dw_conv(const AchDwConv* pp, void* stream) {
                 "ach_dw_conv: output size (%d,%d) inconsistent with input (%d,%d) k=%d s=%d", p.Ho, p.Wo, p.H, p.W, p.k, p.stride);
     ACH_REQUIRE(p.B <= 65535 && p.C <= 65535, "ach_dw_conv: grid too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static const bool tiled_only = getenv("ACH_DW_TILED") != nullptr;   // A/B switch for tools/op_times.py
+    if (p.stride == 1 && !tiled_only) {
+        switch (p.k) {
+            case 3: return launch_rows_k<3>(p, st);
+            case 5: return launch_rows_k<5>(p, st);
+            case 7: return launch_rows_k<7>(p, st);
+            case 9: return launch_rows_k<9>(p, st);
+            default: break;
+        }
+    }
     const int key = p.k * 10 + p.stride;
     switch (key) {
         case 31: return launch_dw<3, 1>(p, st);

@@ -234,6 +234,41 @@ __global__ void __launch_bounds__(256) avgpool3_kernel(const float* __restrict__
         if (x0 + j < W) op[j] = acc[j] / 9.0f;
 }
 
+// channel-last variant: thread = pixel, all channels; writes ceil4(C) floats per pixel as 16-byte stores
+__global__ void __launch_bounds__(128) avgpool3_cl_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                          long long out_bs, int C, int H, int W) {
+    const int P = H * W;
+    const int pix = blockIdx.x * 128 + threadIdx.x;
+    if (pix >= P) return;
+    const int y = pix / W, xx = pix - y * W;
+    const float* xb = x + (long long)blockIdx.y * x_bs;
+    const int CP4 = (C + 3) >> 2;
+    float4* op = reinterpret_cast<float4*>(out + (long long)blockIdx.y * out_bs) + (long long)pix * CP4;
+    for (int q = 0; q < CP4; ++q) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = q * 4 + e;
+            float acc = 0.f;
+            if (c < C) {
+                const float* xp = xb + (long long)c * P;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = y + dy;
+                    if (yy < 0 || yy >= H) continue;
+                    const float* r = xp + yy * W;
+                    const float a = xx > 0 ? __ldg(r + xx - 1) : 0.f;
+                    const float m = __ldg(r + xx);
+                    const float z = xx + 1 < W ? __ldg(r + xx + 1) : 0.f;
+                    acc += a + m + z;   // same summation order as avgpool3_kernel
+                }
+            }
+            o[e] = acc / 9.0f;
+        }
+        op[q] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ------------------------------------------------------------------ fully connected on (B, K) rows
 __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ w,
                                                  const float* __restrict__ scale, const float* __restrict__ bias,
@@ -374,6 +409,15 @@ extern "C" int ach_avgpool3(const float* x, long long x_bs, float* out, long lon
     ACH_REQUIRE(n < (1LL << 31), "ach_avgpool3: plane too large for 32-bit indexing");
     avgpool3_kernel<<<dim3(cdiv(n, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, C, H, W);
     return check_launch("ach_avgpool3");
+}
+
+extern "C" int ach_avgpool3_cl(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
+                               void* stream) {
+    ACH_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "ach_avgpool3_cl: bad args");
+    ACH_REQUIRE(aligned16(out) && out_bs % 4 == 0, "ach_avgpool3_cl: out must be 16-byte aligned");
+    ACH_REQUIRE((long long)H * W < (1LL << 28), "ach_avgpool3_cl: plane too large for 32-bit indexing");
+    avgpool3_cl_kernel<<<dim3(cdiv((long long)H * W, 128), B), 128, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, C, H, W);
+    return check_launch("ach_avgpool3_cl");
 }
 
 extern "C" int ach_fc(const float* x, long long x_bs, const float* w, const float* scale, const float* bias, float* out,

@@ -236,6 +236,7 @@ extern "C" int ach_rc_deform_tc(const AchRcDeform* pp, const float* wom_hi, cons
     ACH_REQUIRE(p.x && p.pooled && p.b_om && p.w1 && p.scale && p.bias && p.out && wom_hi && wom_lo && wreg_hi && wreg_lo,
                 "ach_rc_deform_tc: null arg");
     ACH_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0 && (long long)p.B * p.H * p.W < (1LL << 31), "ach_rc_deform_tc: bad dims");
+    ACH_REQUIRE(!p.pooled_cl, "ach_rc_deform_tc: needs the channel-major pooled map (ach_avgpool3)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (p.C) {
         case 3: return launch_rc_tc<3>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);

@@ -652,8 +652,12 @@ class Engine:
         for i, (cin, cout, down) in enumerate(spec):
             bp = f"{prefix}.rc_blocks.{i}"
             d = bp + ".radar_conv.deformable_conv"
-            pooled = self.buf(f"rc{i}.pool", cin, cur.H, cur.W)
-            self._add(f"rc{i}.pool", self.lib.ach_avgpool3, cur.ptr, cur.bs, pooled.ptr, pooled.bs, self.B, cin, cur.H, cur.W)
+            # measured (profiles/r1_tc_vs_simt.md): the synchronous tensor-core RCBlock kernel only ties the SIMT one, so it is opt-in
+            use_tc = self.model.use_tensor_cores == "all" and bool(self.lib.ach_rc_deform_tc_supported(cin))
+            # channel-last pooled map [P][ceil4(C)] for the SIMT kernel's 16-byte gathers; the tensor-core kernel reads planes
+            pooled = self.buf(f"rc{i}.pool", _ceil4(cin), cur.H, cur.W)
+            self._add(f"rc{i}.pool", self.lib.ach_avgpool3 if use_tc else self.lib.ach_avgpool3_cl, cur.ptr, cur.bs, pooled.ptr,
+                      pooled.bs, self.B, cin, cur.H, cur.W, nbytes=4 * self.B * cur.H * cur.W * (cin + _ceil4(cin)))
 
             def w_om(d=d, cin=cin):
                 wo = torch.cat([self._p(d + ".offset_conv.weight"), self._p(d + ".modulator_conv.weight")], 0)  # (27, C, 3, 3)
@@ -670,10 +674,10 @@ class Engine:
             s.bias = self._vec(f"rc{i}.b", (lambda bp=bp: self._bn_fold(bp + ".norm", 1e-5, self._p(bp + ".weight_conv1.bias"))[1])).data_ptr()
             y = self.buf(f"rc{i}.y", cin, cur.H, cur.W)
             s.out, s.out_bs, s.B, s.C, s.H, s.W = y.ptr, y.bs, self.B, cin, cur.H, cur.W
+            s.pooled_cl = 0 if use_tc else 1
             self._keep.append(s)
             nb_rc = 4 * self.B * cin * cur.H * cur.W * 3
-            # measured (profiles/r1_tc_vs_simt.md): the synchronous tensor-core RCBlock kernel only ties the SIMT one, so it is opt-in
-            if self.model.use_tensor_cores == "all" and self.lib.ach_rc_deform_tc_supported(cin):
+            if use_tc:
                 # both contractions of the block as implicit GEMMs on tcgen05; weights packed on the device at (re)pack time
                 w_om_t = self._weights[f"rc{i}.w_om"][0]
                 w_reg_t = self._w(f"rc{i}.w_reg_tap", (lambda d=d, cin=cin: torch.nn.functional.pad(

@@ -161,12 +161,17 @@ ACH_API int ach_eca_fuse(const float* x, long long x_bs, const float* x2, long l
 /* AvgPool2d(3, stride 1, pad 1, count_include_pad) - RadarEncoder.py:33. */
 ACH_API int ach_avgpool3(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
                  void* stream);
+/* Same pool, output CHANNEL-LAST: out[b][pixel][ceil4(C)] (pad channels 0) - the layout ach_rc_deform gathers from
+ * (one 16-byte load per 4 channels of a bilinear corner instead of 4 scattered 4-byte loads). */
+ACH_API int ach_avgpool3_cl(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W,
+                 void* stream);
 
 /* RCBlock body after the pool (RadarEncoder.py:65-72, dcn.py:49-63, torchvision deform_conv2d):
  *   offset/modulator 3x3 convs on `pooled`, modulated deformable 3x3 conv of `pooled`,
  *   1x1 conv + BN + ReLU, + x.  Weights packed K-major:
  *   w_om [C*9][28] (18 offset + 9 modulator outputs, 1 pad), b_om [27], w_reg [C*9][C], w1 [C][C].
- * C must be one of {3, 8, 12, 16, 24, 30, 36}. */
+ * `pooled` is channel-major planes (pooled_cl = 0, from ach_avgpool3) or channel-last [H*W][ceil4(C)]
+ * (pooled_cl = 1, from ach_avgpool3_cl; the fast path).  C must be one of {3, 8, 12, 16, 24, 30, 36}. */
 typedef struct AchRcDeform {
     const float* x;
     const float* pooled;
@@ -179,6 +184,7 @@ typedef struct AchRcDeform {
     float* out;
     long long x_bs, pooled_bs, out_bs;
     int B, C, H, W;
+    int pooled_cl;
 } AchRcDeform;
 ACH_API int ach_rc_deform(const AchRcDeform* p, void* stream);
 
@@ -186,7 +192,8 @@ ACH_API int ach_rc_deform(const AchRcDeform* p, void* stream);
  * contractions run as implicit GEMMs on tcgen05 (3xTF32).  Weights pre-packed with ach_pack_pw_tc:
  *   wom_hi/lo  <- K-major [C*9][28] (k = ch*9 + tap; 18 offset + 9 modulator outputs), O = 27
  *   wreg_hi/lo <- K-major [9*C][ceil4(C)] with TAP-MAJOR k = tap*C + ch, O = C
- * The AchRcDeform fields w_om / w_reg are ignored; x, pooled, b_om, w1, scale, bias, out as in ach_rc_deform. */
+ * The AchRcDeform fields w_om / w_reg are ignored; x, pooled (pooled_cl must be 0), b_om, w1, scale, bias, out as in
+ * ach_rc_deform. */
 ACH_API int ach_rc_deform_tc_supported(int C);
 ACH_API int ach_rc_deform_tc(const AchRcDeform* p, const float* wom_hi, const float* wom_lo, const float* wreg_hi,
                              const float* wreg_lo, void* stream);

@@ -235,11 +235,23 @@ def ach_avgpool3(x, x_bs, out, out_bs, B, Cc, H, W):
     fview(out, (B, Cc, H, W), (out_bs, H * W, W, 1)).copy_(F.avg_pool2d(xv, 3, 1, 1))
 
 
+def ach_avgpool3_cl(x, x_bs, out, out_bs, B, Cc, H, W):
+    xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))
+    CP = (Cc + 3) // 4 * 4
+    o = fview(out, (B, H * W, CP), (out_bs, CP, 1))
+    o.zero_()
+    o[:, :, :Cc] = F.avg_pool2d(xv, 3, 1, 1).reshape(B, Cc, H * W).transpose(1, 2)
+
+
 def ach_rc_deform(s):
     B, Cc, H, W = s.B, s.C, s.H, s.W
     P = H * W
     x = fview(s.x, (B, Cc, H, W), (s.x_bs, P, W, 1))
-    pooled = fview(s.pooled, (B, Cc, H, W), (s.pooled_bs, P, W, 1)).clone()
+    if s.pooled_cl:
+        CP = (Cc + 3) // 4 * 4
+        pooled = fview(s.pooled, (B, P, CP), (s.pooled_bs, CP, 1))[:, :, :Cc].transpose(1, 2).reshape(B, Cc, H, W).clone()
+    else:
+        pooled = fview(s.pooled, (B, Cc, H, W), (s.pooled_bs, P, W, 1)).clone()
     w_om = fview(s.w_om, (Cc * 9, 27), (28, 1)).t().reshape(27, Cc, 3, 3)
     om = F.conv2d(pooled, w_om, _vec(s.b_om, 27), 1, 1)
     offset, mask = om[:, :18], 2.0 * torch.sigmoid(om[:, 18:])
@@ -420,7 +432,7 @@ def ach_pn2_interp3(xyz1, xyz1_bs, xyz2, xyz2_bs, pts2, pts2_bs, B, C2, N1, S, o
 
 
 EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
-                                     ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_rc_deform, ach_xca_fold,
+                                     ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
                                      ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2)}

@@ -328,12 +328,31 @@ def test_avgpool3(Cc, H, W):
     run_both("ach_avgpool3", make, ["out"])
 
 
-@pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (8, 40, 40), (12, 40, 40), (16, 24, 20), (24, 20, 20), (30, 12, 12), (36, 20, 20)])
-def test_rc_deform(Cc, H, W):
+@pytest.mark.parametrize("Cc,H,W", [(3, 320, 320), (12, 40, 40), (5, 9, 13), (36, 20, 20)])
+def test_avgpool3_cl(Cc, H, W):
     B = 2
+    CP = (Cc + 3) // 4 * 4
 
     def make(A):
-        A.new("x", R(B, Cc, H, W)), A.new("pooled", R(B, Cc, H, W))
+        A.new("x", R(B, Cc, H, W)), A.new("out", torch.full((B, H * W, CP), 7.0))
+        return (A.ptr("x"), Cc * H * W, A.ptr("out"), CP * H * W, B, Cc, H, W)
+    run_both("ach_avgpool3_cl", make, ["out"])
+
+
+@pytest.mark.parametrize("cl", [0, 1])
+@pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (16, 24, 20), (24, 20, 20), (30, 12, 12), (36, 20, 20)])
+def test_rc_deform(Cc, H, W, cl):
+    B = 2
+    CP = (Cc + 3) // 4 * 4
+
+    def make(A):
+        A.new("x", R(B, Cc, H, W))
+        if cl:
+            pc = torch.zeros(B, H * W, CP)
+            pc[:, :, :Cc] = R(B, H * W, Cc)
+            A.new("pooled", pc)
+        else:
+            A.new("pooled", R(B, Cc, H, W))
         w_om = torch.zeros(Cc * 9, 28)
         w_om[:, :27] = R(Cc * 9, 27) / (Cc * 9) ** 0.5
         w_om[:, :18] *= 3.0  # offsets of a few pixels: taps leave the image at the borders
@@ -345,6 +364,8 @@ def test_rc_deform(Cc, H, W):
         s.scale, s.bias, s.out = A.ptr("scale"), A.ptr("bias"), A.ptr("out")
         s.x_bs = s.pooled_bs = s.out_bs = Cc * H * W
         s.B, s.C, s.H, s.W = B, Cc, H, W
+        if cl:
+            s.pooled_cl, s.pooled_bs = 1, CP * H * W
         return (s,)
     # bilinear taps sit next to floor() discontinuities: one ulp in an offset moves a tap across a pixel
     # boundary only if it lands within 1e-6 of an integer, continuous in value there -> same tolerance
