@@ -29,17 +29,30 @@ enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GELU = 3, ACT_SIGMOID = 4 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// MUFU.RCP / MUFU.EX2 without the range-fixup code the C library wraps around them (9 and 6 instructions); callers
+// guarantee a normal-range argument (rcp) or accept flush-to-zero on underflow (ex2).  Relative error <= 2^-22.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): 1 rcp + 1 ex2 + 7 fma instead of the ~40-instruction
 // branchy libdevice erff; GELU inherits an absolute error <= 0.75e-7 * |x| - below fp32 rounding of the GEMM feeding it.
 __device__ __forceinline__ float erf_as(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));   // argument >= 1
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
     poly *= t;
-    const float e = exp2f(-ax * ax * 1.4426950408889634f);
+    const float e = ex2_approx(-ax * ax * 1.4426950408889634f);   // underflow -> 0 -> erf = +-1
     return copysignf(fmaf(-poly, e, 1.0f), x);
 }
 
@@ -47,7 +60,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     switch (act) {
         case ACT_RELU: return fmaxf(v, 0.0f);
         case ACT_SILU: return v * sigmoidf_(v);
-        case ACT_GELU: return 0.5f * v * (1.0f + erf_as(v * 0.70710678118654752440f));
+        case ACT_GELU: {
+            const float h = 0.5f * v;
+            return fmaf(h, erf_as(v * 0.70710678118654752440f), h);
+        }
         case ACT_SIGMOID: return sigmoidf_(v);
         default: return v;
     }

@@ -234,22 +234,24 @@ __global__ void __launch_bounds__(256) avgpool3_kernel(const float* __restrict__
         if (x0 + j < W) op[j] = acc[j] / 9.0f;
 }
 
-// channel-last variant: thread = pixel, all channels; writes ceil4(C) floats per pixel as 16-byte stores
+// channel-last variant: thread = 4 horizontally adjacent pixels of one row, all channels; per 4 channels it writes the
+// 4 pixels' 16-byte groups (contiguous 64 B per thread when ceil4(C) = 4)
 __global__ void __launch_bounds__(128) avgpool3_cl_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
                                                           long long out_bs, int C, int H, int W) {
+    const int W4 = (W + 3) >> 2;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= H * W4) return;
+    const int y = i / W4, x0 = (i - y * W4) * 4;
     const int P = H * W;
-    const int pix = blockIdx.x * 128 + threadIdx.x;
-    if (pix >= P) return;
-    const int y = pix / W, xx = pix - y * W;
     const float* xb = x + (long long)blockIdx.y * x_bs;
-    const int CP4 = (C + 3) >> 2;
-    float4* op = reinterpret_cast<float4*>(out + (long long)blockIdx.y * out_bs) + (long long)pix * CP4;
-    for (int q = 0; q < CP4; ++q) {
-        float o[4];
+    const int Q = (C + 3) >> 2;
+    float4* op = reinterpret_cast<float4*>(out + (long long)blockIdx.y * out_bs) + (long long)(y * W + x0) * Q;
+    for (int q = 0; q < Q; ++q) {
+        float o[4][4];   // [channel in quad][pixel]
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int c = q * 4 + e;
-            float acc = 0.f;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
             if (c < C) {
                 const float* xp = xb + (long long)c * P;
 #pragma unroll
@@ -257,15 +259,22 @@ __global__ void __launch_bounds__(128) avgpool3_cl_kernel(const float* __restric
                     const int yy = y + dy;
                     if (yy < 0 || yy >= H) continue;
                     const float* r = xp + yy * W;
-                    const float a = xx > 0 ? __ldg(r + xx - 1) : 0.f;
-                    const float m = __ldg(r + xx);
-                    const float z = xx + 1 < W ? __ldg(r + xx + 1) : 0.f;
-                    acc += a + m + z;   // same summation order as avgpool3_kernel
+                    float v[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int xc = x0 - 1 + j;
+                        v[j] = (xc >= 0 && xc < W) ? __ldg(r + xc) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] += v[j] + v[j + 1] + v[j + 2];   // same summation order as avgpool3_kernel
                 }
             }
-            o[e] = acc / 9.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[e][j] = acc[j] / 9.0f;
         }
-        op[q] = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x0 + j < W) op[(long long)j * Q + q] = make_float4(o[0][j], o[1][j], o[2][j], o[3][j]);
     }
 }
 
@@ -416,7 +425,7 @@ extern "C" int ach_avgpool3_cl(const float* x, long long x_bs, float* out, long 
     ACH_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "ach_avgpool3_cl: bad args");
     ACH_REQUIRE(aligned16(out) && out_bs % 4 == 0, "ach_avgpool3_cl: out must be 16-byte aligned");
     ACH_REQUIRE((long long)H * W < (1LL << 28), "ach_avgpool3_cl: plane too large for 32-bit indexing");
-    avgpool3_cl_kernel<<<dim3(cdiv((long long)H * W, 128), B), 128, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, C, H, W);
+    avgpool3_cl_kernel<<<dim3(cdiv((long long)H * ((W + 3) / 4), 128), B), 128, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, C, H, W);
     return check_launch("ach_avgpool3_cl");
 }
 

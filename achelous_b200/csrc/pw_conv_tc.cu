@@ -34,6 +34,8 @@
 // Epilogue: rolled loop of tcgen05.ld 32x32b.x16 (thread = pixel, registers = outputs; kept small on purpose:
 // a fully unrolled 128-output epilogue with erf-GELU thrashed the instruction cache - ncu stall_no_instruction
 // 6.4 per issue), folded scale/bias, activation, layer-scale + residual, coalesced 128-byte stores.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -273,18 +275,32 @@ __global__ void __launch_bounds__(128 * HALVES, 8 / HALVES) pw_conv_tc_kernel(co
             } else if (p_ok) {
                 // residual values first, as 16 independent loads: interleaved with the stores below they would each
                 // stall for a full memory round trip (the compiler cannot hoist a load above a possibly aliasing store)
-                float rr[16];
-                if (rptr) {
+                if (n0 + 16 <= o_lim) {
+                    // full block (all but the last block of a ragged tile): no per-output predicate
+                    float rr[16];
+                    if (rptr) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) rr[j] = (n0 + j < o_lim) ? rptr[(long long)j * P] : 0.f;
-                }
+                        for (int j = 0; j < 16; ++j) rr[j] = rptr[(long long)j * P];
+                    }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (n0 + j < o_lim) {
+                    for (int j = 0; j < 16; ++j) {
                         const float4 e = s_ep[n0 + j];
                         float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
                         y = apply_act(y, ACT);
                         if (rptr) y = fmaf(e.w, y, rr[j]);
+                        optr[(long long)j * P] = y;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < 16 && n0 + j < o_lim; ++j) {
+                        const float4 e = s_ep[n0 + j];
+                        // r[] must stay in registers: select with a compile-time unrolled chain instead of dynamic indexing
+                        uint32_t rv = r[0];
+#pragma unroll
+                        for (int q = 1; q < 16; ++q) rv = (j == q) ? r[q] : rv;
+                        float y = fmaf(rs * e.x, __uint_as_float(rv), fmaf(-ms, e.y, e.z));
+                        y = apply_act(y, ACT);
+                        if (rptr) y = fmaf(e.w, y, rptr[(long long)j * P]);
                         optr[(long long)j * P] = y;
                     }
                 }
@@ -370,6 +386,8 @@ static int launch_tc_nt(const AchPwConv& p, const float* w_hi, const float* w_lo
     return ACH_ERR_INVALID;
 }
 
+int pw_conv_tc_ws_launch(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st);   // pw_conv_tc_ws.cu
+
 }  // namespace ach
 
 extern "C" long long ach_pack_pw_tc_elems(int K, int O) {
@@ -401,6 +419,10 @@ extern "C" int ach_pw_conv_tc(const AchPwConv* pp, const float* w_hi, const floa
     ACH_REQUIRE(p.B <= 65535, "ach_pw_conv_tc: B too large");
     ACH_REQUIRE(!p.ln || wsum, "ach_pw_conv_tc: the LayerNorm prologue needs wsum (row sums of the folded weights)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // default: the warp-specialised asynchronous kernel (pw_conv_tc_ws.cu) for every layer; ACH_TC_WS_MINCHUNKS=n keeps the
+    // synchronous kernel below for layers with fewer than n K-chunks (A/B switch for tools/op_times.py; large n = all sync)
+    static const int ws_min_chunks = getenv("ACH_TC_WS_MINCHUNKS") ? atoi(getenv("ACH_TC_WS_MINCHUNKS")) : 0;
+    if (cdiv(p.c0 + p.c1, TC_KC) >= ws_min_chunks) return pw_conv_tc_ws_launch(p, w_hi, w_lo, wsum, st);
     switch (tc_tile_n(p.O)) {
         case 32: return launch_tc_nt<32>(p, w_hi, w_lo, wsum, st);
         case 64: return launch_tc_nt<64>(p, w_hi, w_lo, wsum, st);

@@ -1,0 +1,393 @@
+// Warp-specialised, asynchronous version of the tcgen05 pointwise-convolution GEMM (same contract, operand layouts and
+// 3xTF32 arithmetic as pw_conv_tc.cu; this is the default path, the synchronous kernel there is the A/B fallback).
+//
+// Why: in the synchronous kernel every 16-wide K chunk is a round trip  global load -> split -> st.shared -> fence ->
+// __syncthreads -> MMA -> commit  with the weight tile loaded by the same threads right before it is needed.  ncu
+// (profiles/r1_ncu_final_summary.txt, source page): on the long-K layers (K = 352, 22 chunks, only 200 work items on 148
+// SMs) 27 % of all stall samples sit on the first use of the loaded registers and on the barrier - 3.3 us per chunk for
+// 24 KB of operands.  Here the three jobs run decoupled, synchronised only through mbarriers:
+//   * warps 0-7 (256 threads, "producers"): activation chunk c+2 is requested from HBM while chunk c is split into
+//     tf32 hi/lo terms and written K-major into a 2-stage shared-memory ring; per-warp mbarrier arrive, no CTA barrier.
+//     After the last chunk they prefetch the first two chunks of the CTA's NEXT tile, then run the epilogue of the
+//     current one (TMEM -> registers -> LayerNorm / scale / bias / activation / residual -> coalesced stores).
+//   * warp 8, one elected thread ("MMA thread"): streams the pre-packed hi/lo weight tiles with 1-D bulk TMA copies
+//     (cp.async.bulk + mbarrier complete_tx) into a 4-stage ring, two chunks ahead and across tile boundaries; waits
+//     for "activations stored" + "weights landed", issues the 6 tcgen05.mma of the chunk and commits them to the
+//     stage's "MMA done" barrier, which is what lets producers and TMA reuse a stage.
+// The accumulator (NT TMEM columns) is handed back and forth with two more barriers (acc_full / acc_empty).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ach {
+
+constexpr int WS_SA = 2;        // activation ring stages
+constexpr int WS_SB = 4;        // weight ring stages
+constexpr int WS_PF = 2;        // weight chunks in flight ahead of the MMA
+constexpr int WS_PROD = 256;    // producer / epilogue threads (8 warps); warp 8 is the MMA warp
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WS_PROD) : "memory"); }
+
+template <int NT, int ACT>
+__global__ void __launch_bounds__(WS_PROD + 32, 2)
+    pw_conv_tc_ws_kernel(const AchPwConv p, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
+                         const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int A_ELEMS = TC_KC * TC_M;   // per hi / lo matrix
+    constexpr int B_ELEMS = NT * TC_KC;
+    float* a_ring = reinterpret_cast<float*>(smem_raw);                  // [SA][a_hi | a_lo]
+    float* b_ring = a_ring + WS_SA * 2 * A_ELEMS;                        // [SB][b_hi | b_lo]
+    __shared__ __align__(8) uint64_t bar_full_a[WS_SA], bar_full_b[WS_SB], bar_mma[WS_SA], bar_acc_full, bar_acc_empty;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_ln[2][TC_M][2];
+    __shared__ __align__(16) float4 s_ep[NT];   // per output of the current tile: {scale, scale*wsum, bias + scale*pbias, gamma}
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.c0 + p.c1, P = p.P;
+    constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < WS_SA; ++i) {
+            mbar_init(smem_u32(&bar_full_a[i]), WS_PROD / 32);
+            mbar_init(smem_u32(&bar_mma[i]), 1);
+        }
+        for (int i = 0; i < WS_SB; ++i) mbar_init(smem_u32(&bar_full_b[i]), 1);
+        mbar_init(smem_u32(&bar_acc_full), 1);
+        mbar_init(smem_u32(&bar_acc_empty), WS_PROD / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+    const uint32_t a_ring_s = smem_u32(a_ring), b_ring_s = smem_u32(b_ring);
+
+    if (warp == WS_PROD / 32) {
+        // ================================================================== MMA + weight-TMA thread
+        if (lane == 0) {
+            constexpr uint32_t idesc = tf32_idesc(NT);
+            constexpr uint32_t B_LBO = (NT / 8) * 128, A_LBO = (TC_M / 8) * 128;
+            int pit = 0, p_item = blockIdx.x, p_c = 0;   // weight prefetch cursor: chunk counter, (item, chunk)
+            auto issue_b = [&]() {
+                if (p_item >= total_items) return;
+                const int sb = pit % WS_SB;
+                const int prev = pit - WS_SB;            // the chunk whose MMAs last read this stage
+                if (prev >= 0) mbar_wait(smem_u32(&bar_mma[prev & 1]), (uint32_t)(prev >> 1) & 1u);
+                const long long blk = ((long long)(p_item % n_ot) * n_kchunks + p_c) * B_ELEMS;
+                const uint32_t full = smem_u32(&bar_full_b[sb]);
+                const uint32_t dst = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u;
+                mbar_expect_tx(full, 2u * B_ELEMS * 4u);
+                bulk_g2s(dst, w_hi + blk, B_ELEMS * 4u, full);
+                bulk_g2s(dst + B_ELEMS * 4u, w_lo + blk, B_ELEMS * 4u, full);
+                ++pit;
+                if (++p_c == n_kchunks) {
+                    p_c = 0;
+                    p_item += gridDim.x;
+                }
+            };
+#pragma unroll 1
+            for (int i = 0; i < WS_PF; ++i) issue_b();
+            int it = 0, tile_n = 0;
+#pragma unroll 1
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++tile_n) {
+                if (tile_n > 0) {   // the epilogue of the previous tile has drained the accumulator
+                    mbar_wait(smem_u32(&bar_acc_empty), (uint32_t)(tile_n - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+#pragma unroll 1
+                for (int c = 0; c < n_kchunks; ++c, ++it) {
+                    issue_b();   // chunk it + WS_PF
+                    const int sa = it & 1, sb = it % WS_SB;
+                    mbar_wait(smem_u32(&bar_full_b[sb]), (uint32_t)(it / WS_SB) & 1u);
+                    mbar_wait(smem_u32(&bar_full_a[sa]), (uint32_t)(it >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi_s = a_ring_s + (uint32_t)sa * 2u * A_ELEMS * 4u, a_lo_s = a_hi_s + A_ELEMS * 4u;
+                    const uint32_t b_hi_s = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
+#pragma unroll
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        const uint64_t ah = make_desc(a_hi_s + ks * 2 * A_LBO, A_LBO, 128u, 0);
+                        const uint64_t al = make_desc(a_lo_s + ks * 2 * A_LBO, A_LBO, 128u, 0);
+                        const uint64_t bh = make_desc(b_hi_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
+                        const uint64_t bl = make_desc(b_lo_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
+                        mma_tf32(tmem_d, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32(tmem_d, al, bh, idesc, 1u);
+                        mma_tf32(tmem_d, ah, bl, idesc, 1u);
+                    }
+                    tc_commit(smem_u32(&bar_mma[sa]));
+                    if (c == n_kchunks - 1) tc_commit(smem_u32(&bar_acc_full));
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================== producers + epilogue (256 threads)
+        const int px = tid & (TC_M - 1), half = tid >> 7;   // half is warp-uniform
+        const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+
+        struct Item {
+            const float* x0;
+            const float* x1;
+            int b, o_base, pp;
+            bool p_ok;
+        };
+        auto decode = [&](int item) {
+            Item t;
+            const int o_tile = item % n_ot;
+            const int pt = (item / n_ot) % n_pt;
+            t.b = item / (n_ot * n_pt);
+            t.o_base = o_tile * NT;
+            t.pp = pt * TC_M + px;
+            t.p_ok = t.pp < P;
+            t.x0 = p.x0 + (long long)t.b * p.x0_bs;
+            t.x1 = p.x1 ? p.x1 + (long long)t.b * p.x1_bs : nullptr;
+            return t;
+        };
+        // activation loads of chunk c (global -> registers only): this thread's 2 k-cores x 4 k
+        auto load_a = [&](const Item& t, int c, float (&v)[2][4]) {
+            const int k0 = c * TC_KC;
+            if (k0 + TC_KC <= p.c0 || (k0 >= p.c0 && k0 + TC_KC <= K)) {
+                const float* __restrict__ src = (k0 < p.c0) ? t.x0 + (long long)k0 * P + t.pp : t.x1 + (long long)(k0 - p.c0) * P + t.pp;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[jj][e] = t.p_ok ? __ldg(src + (long long)((half + 2 * jj) * 4 + e) * P) : 0.f;
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int kk = k0 + (half + 2 * jj) * 4 + e;
+                        float x = 0.f;
+                        if (kk < K && t.p_ok) x = (kk < p.c0) ? __ldg(t.x0 + (long long)kk * P + t.pp) : __ldg(t.x1 + (long long)(kk - p.c0) * P + t.pp);
+                        v[jj][e] = x;
+                    }
+            }
+        };
+
+        uint32_t it = 0;
+        int tile_n = 0;
+        int item = blockIdx.x;
+        Item cur = decode(item);
+        float v0[2][4], v1[2][4], v2[2][4];
+        load_a(cur, 0, v0);
+        if (n_kchunks > 1) load_a(cur, 1, v1);
+#pragma unroll 1
+        for (; item < total_items; ++tile_n) {
+            // LayerNorm running sums, shifted by the pixel's first channel to avoid cancellation
+            const float shift = (p.ln && cur.p_ok) ? __ldg(cur.x0 + cur.pp) : 0.f;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < n_kchunks; ++c, ++it) {
+                if (c + 2 < n_kchunks) load_a(cur, c + 2, v2);
+                const uint32_t sa = it & 1u;
+                if (it >= 2) mbar_wait(smem_u32(&bar_mma[sa]), ((it - 2) >> 1) & 1u);   // MMAs of chunk it-2 have read this stage
+                float* a_hi = a_ring + sa * 2 * A_ELEMS;
+                float* a_lo = a_hi + A_ELEMS;
+                const int k0 = c * TC_KC;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = half + 2 * jj;
+                    if (p.ln) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float d = (k0 + j * 4 + e < K && cur.p_ok) ? v0[jj][e] - shift : 0.f;
+                            s1 += d;
+                            s2 = fmaf(d, d, s2);
+                        }
+                    }
+                    // x = hi + lo with hi = x truncated to tf32 (1 LOP3; the MMA ignores the low 13 mantissa bits anyway) and
+                    // lo = x - hi exact in fp32
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v0[jj][0]) & 0xffffe000u);
+                    h.y = __uint_as_float(__float_as_uint(v0[jj][1]) & 0xffffe000u);
+                    h.z = __uint_as_float(__float_as_uint(v0[jj][2]) & 0xffffe000u);
+                    h.w = __uint_as_float(__float_as_uint(v0[jj][3]) & 0xffffe000u);
+                    l.x = v0[jj][0] - h.x; l.y = v0[jj][1] - h.y; l.z = v0[jj][2] - h.z; l.w = v0[jj][3] - h.w;
+                    *reinterpret_cast<float4*>(a_hi + j * (TC_M * 4) + px * 4) = h;
+                    *reinterpret_cast<float4*>(a_lo + j * (TC_M * 4) + px * 4) = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_full_a[sa]));
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v0[jj][e] = v1[jj][e];
+                        v1[jj][e] = v2[jj][e];
+                    }
+            }
+            // the next tile's first two chunks fly while this tile's epilogue runs
+            const int next = item + gridDim.x;
+            const Item done = cur;
+            if (next < total_items) {
+                cur = decode(next);
+                load_a(cur, 0, v0);
+                if (n_kchunks > 1) load_a(cur, 1, v1);
+            }
+
+            // ---- per-output epilogue constants of this (frame, output tile) + LayerNorm partial sums -> shared memory
+            if (tid < NT) {
+                const int o = done.o_base + tid;
+                float4 e = make_float4(0.f, 0.f, 0.f, 1.f);
+                if (o < p.O) {
+                    e.x = p.scale ? p.scale[o] : 1.f;
+                    e.y = p.ln ? e.x * wsum[o] : 0.f;
+                    e.z = (p.bias ? p.bias[o] : 0.f) + (p.pbias ? e.x * p.pbias[(long long)done.b * p.O + o] : 0.f);
+                    e.w = p.gamma ? p.gamma[o] : 1.f;
+                }
+                s_ep[tid] = e;
+            }
+            if (p.ln) {
+                s_ln[half][px][0] = s1;
+                s_ln[half][px][1] = s2;
+            }
+            prod_bar();
+            // y = act(rs * (scale*acc) - ms * (scale*wsum) + c)  with rs = rstd, ms = mean*rstd   (rs = 1, ms = 0 without LayerNorm)
+            float rs = 1.f, ms = 0.f;
+            if (p.ln) {
+                const float t1 = (s_ln[0][px][0] + s_ln[1][px][0]) / (float)K;
+                const float t2 = (s_ln[0][px][1] + s_ln[1][px][1]) / (float)K;
+                rs = 1.0f / sqrtf(fmaxf(t2 - t1 * t1, 0.f) + p.ln_eps);
+                ms = (shift + t1) * rs;
+            }
+            mbar_wait(smem_u32(&bar_acc_full), (uint32_t)tile_n & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+            // ---- epilogue: thread = pixel (TMEM lane 32*(warp%4) + lane); this half's NT/2 columns, 16 at a time
+            constexpr int NH = NT / 2;
+            const int pp = done.pp;
+            float* optr = p.out + (long long)done.b * p.out_bs + (long long)(done.o_base + half * NH) * P + pp;
+            const float* rptr = p.res ? p.res + (long long)done.b * p.res_bs + (long long)(done.o_base + half * NH) * P + pp : nullptr;
+            const int o_lim = p.O - done.o_base;   // valid outputs in this tile
+#pragma unroll 1
+            for (int n0 = half * NH; n0 < (half + 1) * NH && n0 < o_lim; n0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(t_lane + (uint32_t)n0, r);
+                if (p.reduce_max) {
+                    // out (B, O) = max over pixels: warp-shuffle max over the warp's 32 pixels, one atomic per (warp, output)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 e = s_ep[n0 + j];
+                        float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
+                        y = done.p_ok ? apply_act(y, ACT) : -INFINITY;
+#pragma unroll
+                        for (int sft = 16; sft > 0; sft >>= 1) y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, sft));
+                        if (lane == 0 && n0 + j < o_lim) atomic_max_float(p.out + (long long)done.b * p.out_bs + done.o_base + n0 + j, y);
+                    }
+                } else if (done.p_ok) {
+                    if (n0 + 16 <= o_lim) {
+                        // full block: no per-output predicate; residual values first, as 16 independent loads (interleaved with
+                        // the stores they would each stall for a memory round trip: a load cannot move above a possibly aliasing store)
+                        float rr[16];
+                        if (rptr) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) rr[j] = rptr[(long long)j * P];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float4 e = s_ep[n0 + j];
+                            float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
+                            y = apply_act(y, ACT);
+                            if (rptr) y = fmaf(e.w, y, rr[j]);
+                            optr[(long long)j * P] = y;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < 16 && n0 + j < o_lim; ++j) {
+                            const float4 e = s_ep[n0 + j];
+                            uint32_t rv = r[0];   // r[] must stay in registers: unrolled select instead of dynamic indexing
+#pragma unroll
+                            for (int q = 1; q < 16; ++q) rv = (j == q) ? r[q] : rv;
+                            float y = fmaf(rs * e.x, __uint_as_float(rv), fmaf(-ms, e.y, e.z));
+                            y = apply_act(y, ACT);
+                            if (rptr) y = fmaf(e.w, y, rptr[(long long)j * P]);
+                            optr[(long long)j * P] = y;
+                        }
+                    }
+                }
+                optr += (long long)16 * P;
+                if (rptr) rptr += (long long)16 * P;
+            }
+            // hand the accumulator back to the MMA thread; s_ep / s_ln are rewritten by the next tile
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty));
+            prod_bar();
+            item = next;
+        }
+    }
+
+    // ---- teardown
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+template <int NT, int ACT>
+static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
+    const int K = p.c0 + p.c1;
+    const int n_kchunks = cdiv(K, TC_KC);
+    constexpr size_t smem = (size_t)WS_SA * 2 * TC_KC * TC_M * 4 + (size_t)WS_SB * 2 * NT * TC_KC * 4;
+    static int ctas_per_wave = 0;
+    if (!ctas_per_wave) {
+        cudaFuncSetAttribute(pw_conv_tc_ws_kernel<NT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT>, WS_PROD + 32, smem, NT < 32 ? 32 : NT);
+        ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
+    }
+    const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);
+    const long long total = (long long)n_pt * n_ot * p.B;
+    ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
+    const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
+    pw_conv_tc_ws_kernel<NT, ACT><<<grid, WS_PROD + 32, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
+    return check_launch("ach_pw_conv_tc");
+}
+
+template <int NT>
+static int launch_ws_nt(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
+    switch (p.act) {
+        case ACT_NONE: return launch_ws<NT, ACT_NONE>(p, w_hi, w_lo, wsum, st);
+        case ACT_RELU: return launch_ws<NT, ACT_RELU>(p, w_hi, w_lo, wsum, st);
+        case ACT_SILU: return launch_ws<NT, ACT_SILU>(p, w_hi, w_lo, wsum, st);
+        case ACT_GELU: return launch_ws<NT, ACT_GELU>(p, w_hi, w_lo, wsum, st);
+        default: break;
+    }
+    set_error("ach_pw_conv_tc: activation %d not instantiated", p.act);
+    return ACH_ERR_INVALID;
+}
+
+// called by ach_pw_conv_tc (pw_conv_tc.cu) after argument validation
+int pw_conv_tc_ws_launch(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
+    const int NT = p.O <= 32 ? 32 : (p.O <= 64 ? 64 : 128);
+    switch (NT) {
+        case 32: return launch_ws_nt<32>(p, w_hi, w_lo, wsum, st);
+        case 64: return launch_ws_nt<64>(p, w_hi, w_lo, wsum, st);
+        default: return launch_ws_nt<128>(p, w_hi, w_lo, wsum, st);
+    }
+}
+
+}  // namespace ach
