@@ -652,11 +652,12 @@ class Engine:
         for i, (cin, cout, down) in enumerate(spec):
             bp = f"{prefix}.rc_blocks.{i}"
             d = bp + ".radar_conv.deformable_conv"
-            # measured (profiles/r1_tc_vs_simt.md): the synchronous tensor-core RCBlock kernel only ties the SIMT one, so it is opt-in
-            use_tc = self.model.use_tensor_cores == "all" and bool(self.lib.ach_rc_deform_tc_supported(cin))
-            # channel-last pooled map [P][ceil4(C)] for the SIMT kernel's 16-byte gathers; the tensor-core kernel reads planes
+            # tensor-core RCBlock (rcblock_tc.cu v2: channel-last gathers, resident weight tiles, chunk ring) for the
+            # high-resolution blocks; use_tensor_cores = True / "all" -> on, False -> SIMT (profiles/r1_tc_vs_simt.md)
+            use_tc = bool(self.model.use_tensor_cores) and self.model.rc_tensor_cores and bool(self.lib.ach_rc_deform_tc_supported(cin))
+            # channel-last pooled map [P][ceil4(C)]: the 3x3 window and every bilinear corner are 16-byte loads
             pooled = self.buf(f"rc{i}.pool", _ceil4(cin), cur.H, cur.W)
-            self._add(f"rc{i}.pool", self.lib.ach_avgpool3 if use_tc else self.lib.ach_avgpool3_cl, cur.ptr, cur.bs, pooled.ptr,
+            self._add(f"rc{i}.pool", self.lib.ach_avgpool3_cl, cur.ptr, cur.bs, pooled.ptr,
                       pooled.bs, self.B, cin, cur.H, cur.W, nbytes=4 * self.B * cur.H * cur.W * (cin + _ceil4(cin)))
 
             def w_om(d=d, cin=cin):
@@ -674,12 +675,15 @@ class Engine:
             s.bias = self._vec(f"rc{i}.b", (lambda bp=bp: self._bn_fold(bp + ".norm", 1e-5, self._p(bp + ".weight_conv1.bias"))[1])).data_ptr()
             y = self.buf(f"rc{i}.y", cin, cur.H, cur.W)
             s.out, s.out_bs, s.B, s.C, s.H, s.W = y.ptr, y.bs, self.B, cin, cur.H, cur.W
-            s.pooled_cl = 0 if use_tc else 1
+            s.pooled_cl = 1
             self._keep.append(s)
             nb_rc = 4 * self.B * cin * cur.H * cur.W * 3
             if use_tc:
                 # both contractions of the block as implicit GEMMs on tcgen05; weights packed on the device at (re)pack time
-                w_om_t = self._weights[f"rc{i}.w_om"][0]
+                def w_om_tap(d=d, cin=cin):     # rows k = tap*C + ch (tap-major, like w_reg_tap), 27 outputs padded to 28
+                    wo = torch.cat([self._p(d + ".offset_conv.weight"), self._p(d + ".modulator_conv.weight")], 0)  # (27, C, 3, 3)
+                    return torch.nn.functional.pad(wo.reshape(27, cin, 9).permute(2, 1, 0).reshape(9 * cin, 27), (0, 1))
+                w_om_t = self._w(f"rc{i}.w_om_tap", w_om_tap)
                 w_reg_t = self._w(f"rc{i}.w_reg_tap", (lambda d=d, cin=cin: torch.nn.functional.pad(
                     self._p(d + ".regular_conv.weight").reshape(cin, cin, 9).permute(2, 1, 0).reshape(9 * cin, cin), (0, _ceil4(cin) - cin))))
                 tiles = []

@@ -188,12 +188,13 @@ typedef struct AchRcDeform {
 } AchRcDeform;
 ACH_API int ach_rc_deform(const AchRcDeform* p, void* stream);
 
-/* Tensor-core version of ach_rc_deform for C in {3, 8, 12} (the high-resolution RCNet blocks): both dense
- * contractions run as implicit GEMMs on tcgen05 (3xTF32).  Weights pre-packed with ach_pack_pw_tc:
- *   wom_hi/lo  <- K-major [C*9][28] (k = ch*9 + tap; 18 offset + 9 modulator outputs), O = 27
- *   wreg_hi/lo <- K-major [9*C][ceil4(C)] with TAP-MAJOR k = tap*C + ch, O = C
- * The AchRcDeform fields w_om / w_reg are ignored; x, pooled (pooled_cl must be 0), b_om, w1, scale, bias, out as in
- * ach_rc_deform. */
+/* Tensor-core version of ach_rc_deform for C in {3, 8, 12, 16} (the high-resolution RCNet blocks): both dense
+ * contractions run as implicit GEMMs on tcgen05 (3xTF32).  Weights pre-packed with ach_pack_pw_tc, both with
+ * TAP-MAJOR rows k = tap*C + ch:
+ *   wom_hi/lo  <- K-major [9*C][28] (18 offset + 9 modulator outputs), O = 27
+ *   wreg_hi/lo <- K-major [9*C][ceil4(C)], O = C
+ * The AchRcDeform fields w_om / w_reg are ignored; x, pooled (channel-last, pooled_cl must be 1), b_om, w1, scale,
+ * bias, out as in ach_rc_deform.  Replaces RadarEncoder.py:65-72 + dcn.py:49-63 like ach_rc_deform. */
 ACH_API int ach_rc_deform_tc_supported(int C);
 ACH_API int ach_rc_deform_tc(const AchRcDeform* p, const float* wom_hi, const float* wom_lo, const float* wreg_hi,
                              const float* wreg_lo, void* stream);

@@ -284,8 +284,9 @@ class _Shim:
 
 def ach_rc_deform_tc(s, wom_hi, wom_lo, wreg_hi, wreg_lo):
     Cc = s.C
+    wom_tap = _tc_unpack(wom_hi, wom_lo, 9 * Cc, 27)                         # rows k = tap*C + ch
     wom = torch.zeros(Cc * 9, 28)
-    wom[:, :27] = _tc_unpack(wom_hi, wom_lo, Cc * 9, 27)
+    wom[:, :27] = wom_tap.reshape(9, Cc, 27).permute(1, 0, 2).reshape(Cc * 9, 27)           # rows ch*9 + tap
     wreg_tap = _tc_unpack(wreg_hi, wreg_lo, 9 * Cc, Cc)                      # rows k = tap*C + ch
     wreg = wreg_tap.reshape(9, Cc, Cc).permute(1, 0, 2).reshape(Cc * 9, Cc).contiguous()   # rows ch*9 + tap
     ach_rc_deform(_Shim(s, w_om=wom.data_ptr(), w_reg=wreg.data_ptr()))

@@ -616,32 +616,39 @@ def test_pn2_interp3(N1, S, C2):
     run_both("ach_pn2_interp3", make, ["out"])
 
 
-@pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (8, 13, 21)])
-def test_rc_deform_tc(Cc, H, W):
+@pytest.mark.parametrize("stages", [1, 2])
+@pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (8, 13, 21), (16, 24, 20), (8, 160, 160)])
+def test_rc_deform_tc(Cc, H, W, stages, monkeypatch):
     B = 2
     lib = _lib.load()
     n_om, n_reg = lib.ach_pack_pw_tc_elems(Cc * 9, 27), lib.ach_pack_pw_tc_elems(9 * Cc, Cc)
     ldr = (Cc + 3) // 4 * 4
+    CP = ldr
 
     def make(A):
-        A.new("x", R(B, Cc, H, W)), A.new("pooled", R(B, Cc, H, W))
-        w_om = torch.zeros(Cc * 9, 28)
-        w_om[:, :27] = R(Cc * 9, 27) / (Cc * 9) ** 0.5
+        A.new("x", R(B, Cc, H, W))
+        pc = torch.zeros(B, H * W, CP)
+        pc[:, :, :Cc] = R(B, H * W, Cc)
+        A.new("pooled", pc)                       # channel-last [P][ceil4(C)]
+        w_om = torch.zeros(9 * Cc, 28)            # rows k = tap*C + ch
+        w_om[:, :27] = R(9 * Cc, 27) / (Cc * 9) ** 0.5
         w_om[:, :18] *= 3.0
         w_reg = torch.zeros(9 * Cc, ldr)
         w_reg[:, :Cc] = R(9 * Cc, Cc) / (Cc * 9) ** 0.5
-        A.new("w_om", w_om), A.new("w_reg_tap", w_reg), A.new("b_om", torch.rand(27) * 2 - 1), A.new("w1", R(Cc, Cc) / Cc ** 0.5)
+        A.new("w_om_tap", w_om), A.new("w_reg_tap", w_reg), A.new("b_om", torch.rand(27) * 2 - 1), A.new("w1", R(Cc, Cc) / Cc ** 0.5)
         A.new("scale", torch.rand(Cc) + 0.5), A.new("bias", R(Cc) * 0.1), A.new("out", torch.zeros(B, Cc, H, W))
         for n_, sz in (("omh", n_om), ("oml", n_om), ("rgh", n_reg), ("rgl", n_reg)):
             A.new(n_, torch.zeros(sz))
         s = AchRcDeform()
         s.x, s.pooled, s.b_om, s.w1 = (A.ptr(n) for n in ("x", "pooled", "b_om", "w1"))
         s.scale, s.bias, s.out = A.ptr("scale"), A.ptr("bias"), A.ptr("out")
-        s.x_bs = s.pooled_bs = s.out_bs = Cc * H * W
+        s.x_bs = s.out_bs = Cc * H * W
+        s.pooled_cl, s.pooled_bs = 1, CP * H * W
         s.B, s.C, s.H, s.W = B, Cc, H, W
-        return [("ach_pack_pw_tc", (A.ptr("w_om"), Cc * 9, 27, 28, A.ptr("omh"), A.ptr("oml"))),
+        return [("ach_pack_pw_tc", (A.ptr("w_om_tap"), Cc * 9, 27, 28, A.ptr("omh"), A.ptr("oml"))),
                 ("ach_pack_pw_tc", (A.ptr("w_reg_tap"), 9 * Cc, Cc, ldr, A.ptr("rgh"), A.ptr("rgl"))),
                 ("ach_rc_deform_tc", (s, A.ptr("omh"), A.ptr("oml"), A.ptr("rgh"), A.ptr("rgl")))]
+    monkeypatch.setenv("ACH_RC_TC_STAGES", str(stages))   # read at every launch (getenv in the C ABI)
     run_seq(make, ["out"], rtol=1e-4)
 
 
