@@ -16,6 +16,13 @@
 // MMAs of a chunk and commits them to the stage's mbarrier, which is only waited for when the stage is rewritten (or
 // when the accumulator is read), so gathers of chunk c+1 overlap the MMAs of chunk c.  All weight tiles (hi + lo of
 // both GEMMs) are copied to shared memory once per persistent CTA.
+//
+// v3: the 128 pixels of a tile are a 16 x 8 block of the image and the pooled map around it (halo RCT_R) is staged in
+// shared memory.  ncu on v2 (profiles/r2_ncu_rc_summary.txt): 5 M gather requests touching ~29 sectors each, l1tex
+// 61-75 % busy, long-scoreboard 5.4-6.7 stalls per issue - every bilinear corner was a warp-wide gather costing one
+// L1 wavefront per 128-byte line touched.  From shared memory a corner is one LDS.128 (a few bank-conflict replays).
+// Taps whose 2x2 corner block leaves the staged window (offsets larger than the halo) fall back to the global gather
+// per lane, so the result does not depend on the window size.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -24,11 +31,14 @@
 namespace ach {
 
 constexpr int RCT_N = 32;   // MMA N for both GEMMs (27 offset/modulator outputs; C <= 16 conv outputs)
+constexpr int RCT_TW = 16, RCT_TH = 8;   // pixel tile (RCT_TW * RCT_TH == TC_M); a warp covers 2 rows of 16 pixels
+constexpr int RCT_R = 3;                 // halo of the staged window: 1 (3x3 tap) + |offset| < 2 + the +1 bilinear corner
+constexpr int RCT_WW = RCT_TW + 2 * RCT_R, RCT_WH = RCT_TH + 2 * RCT_R;
 
 template <int C, int STAGES>
 __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, const float* __restrict__ wom_hi,
                                                            const float* __restrict__ wom_lo, const float* __restrict__ wreg_hi,
-                                                           const float* __restrict__ wreg_lo, int n_pt, int total_items) {
+                                                           const float* __restrict__ wreg_lo, int n_tx, int n_ty, int total_items) {
     constexpr int K1 = C * 9;
     constexpr int NCH = (K1 + TC_KC - 1) / TC_KC;   // K chunks of 16 (same count for both GEMMs)
     constexpr int CP = (C + 3) & ~3;
@@ -37,6 +47,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* a_ring = reinterpret_cast<float*>(smem_raw);          // [STAGES][hi | lo][A_ELEMS]
     float* b_all = a_ring + STAGES * 2 * A_ELEMS;                // [2 GEMMs][NCH][hi | lo][B_ELEMS]
+    float4* win = reinterpret_cast<float4*>(b_all + 2 * NCH * 2 * B_ELEMS);   // [Q][RCT_WH][RCT_WW] pooled window (zero outside the image)
     __shared__ __align__(16) float s_w1[C * CP];    // [c][o]
     __shared__ float s_bom[32];
     __shared__ float s_scale[CP], s_bias[CP];
@@ -126,25 +137,56 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
 
+    // asynchronous (cp.async, zero-filled outside the image) copy of an item's pooled window into shared memory
+    auto fill_window = [&](int item) {
+        const int tx_i = item % n_tx, ty_i = (item / n_tx) % n_ty, b = item / (n_tx * n_ty);
+        const int wy0 = ty_i * RCT_TH - RCT_R, wx0 = tx_i * RCT_TW - RCT_R;
+        const float4* __restrict__ pooled = reinterpret_cast<const float4*>(p.pooled + (long long)b * p.pooled_bs);
+        for (int i = tid; i < RCT_WH * RCT_WW; i += 128) {
+            const int wy = i / RCT_WW, wx = i - wy * RCT_WW;
+            const int yy = wy0 + wy, xx = wx0 + wx;
+            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const float4* src = pooled + (in ? (yy * W + xx) * Q : 0);
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(win + q * (RCT_WH * RCT_WW) + i)), "l"(src + q),
+                             "r"(in ? 16u : 0u)
+                             : "memory");
+        }
+    };
+    if ((int)blockIdx.x < total_items) fill_window(blockIdx.x);
+
 #pragma unroll 1
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int pt = item % n_pt, b = item / n_pt;
-        const int pix = pt * TC_M + tid;
-        const bool ok = pix < P;
-        const int y = ok ? pix / W : 0, x = ok ? pix - (pix / W) * W : 0;
+        const int tx_i = item % n_tx, ty_i = (item / n_tx) % n_ty, b = item / (n_tx * n_ty);
+        const int ly_ = tid / RCT_TW, lx_ = tid % RCT_TW;     // position inside the tile
+        const int y = ty_i * RCT_TH + ly_, x = tx_i * RCT_TW + lx_;
+        const bool ok = y < H && x < W;
+        const int pix = y * W + x;
+        const int wy0 = ty_i * RCT_TH - RCT_R, wx0 = tx_i * RCT_TW - RCT_R;   // image coordinates of the window origin
         const float4* __restrict__ pooled = reinterpret_cast<const float4*>(p.pooled + (long long)b * p.pooled_bs);
+
+        // residual input: requested now, consumed in the epilogue (ncu on the first v3: 24 % of all stall samples sat on
+        // these loads when they were issued there)
+        float xres[C];
+        {
+            const float* __restrict__ xr = p.x + (long long)b * p.x_bs + pix;
+#pragma unroll
+            for (int o = 0; o < C; ++o) xres[o] = ok ? __ldg(xr + (long long)o * P) : 0.f;
+        }
+        // the window of this item was requested one item ago (or before the loop)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
 
         // ---- GEMM 1: offsets / modulators = 3x3 conv of the pooled map (implicit im2col, k = tap*C + ch, zero padding)
         {
             float vbuf[TC_KC];
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-                const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-                const bool in = ok && yy >= 0 && yy < H && xx >= 0 && xx < W;
-                const float4* src = pooled + (in ? (yy * W + xx) * Q : 0);
+                const float4* src = win + (ly_ + RCT_R + t / 3 - 1) * RCT_WW + (lx_ + RCT_R + t % 3 - 1);
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const float4 v4 = in ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 v4 = src[q * (RCT_WH * RCT_WW)];
                     const float v[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -182,27 +224,43 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
             for (int t = 0; t < 9; ++t) {
                 const float py = (float)(y - 1 + t / 3) + om[2 * t];
                 const float px = (float)(x - 1 + t % 3) + om[2 * t + 1];
-                const float m = 2.0f * sigmoidf_(om[18 + t]);
+                // mask = 2*sigmoid(z) = 2 / (1 + 2^(-z*log2 e)) on MUFU.EX2 + MUFU.RCP (relative error <= 2^-21; the
+                // denominator is >= 1, and z -> -inf gives 2/inf = 0 like the exact form)
+                const float m = 2.0f * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * om[18 + t]));
                 const float fy = floorf(py), fx = floorf(px);
                 const int y0 = (int)fy, x0 = (int)fx;
                 const float ly = py - fy, lx = px - fx;
                 const float hy = 1.f - ly, hx = 1.f - lx;
-                const bool in = ok && (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
-                const bool y0ok = in && y0 >= 0, y1ok = in && (y0 + 1 <= H - 1);
-                const bool x0ok = x0 >= 0, x1ok = (x0 + 1 <= W - 1);
-                const float w00 = (y0ok && x0ok) ? hy * hx : 0.f;
-                const float w01 = (y0ok && x1ok) ? hy * lx : 0.f;
-                const float w10 = (y1ok && x0ok) ? ly * hx : 0.f;
-                const float w11 = (y1ok && x1ok) ? ly * lx : 0.f;
-                const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
-                const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
-                const float4* g00 = pooled + (yc0 * W + xc0) * Q;
-                const float4* g01 = pooled + (yc0 * W + xc1) * Q;
-                const float4* g10 = pooled + (yc1 * W + xc0) * Q;
-                const float4* g11 = pooled + (yc1 * W + xc1) * Q;
+                // fast path: the 2x2 corner block lies inside the staged window.  The window is zero outside the image, so
+                // torchvision's per-corner validity tests are implied (an invalid corner contributes weight * 0) and the
+                // four corners are immediate offsets from one shared-memory address.
+                const int ry0 = y0 - wy0, rx0 = x0 - wx0;
+                const bool inwin = (unsigned)ry0 < (unsigned)(RCT_WH - 1) && (unsigned)rx0 < (unsigned)(RCT_WW - 1);
+                float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+                const float4* wbase = win + ry0 * RCT_WW + rx0;
+                int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
+                if (!inwin) {
+                    // offset beyond the halo: per-corner validity and clamped global gathers (dcn semantics spelled out)
+                    const bool in = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
+                    const bool y0ok = in && y0 >= 0, y1ok = in && (y0 + 1 <= H - 1);
+                    const bool x0ok = x0 >= 0, x1ok = (x0 + 1 <= W - 1);
+                    w00 = (y0ok && x0ok) ? w00 : 0.f;
+                    w01 = (y0ok && x1ok) ? w01 : 0.f;
+                    w10 = (y1ok && x0ok) ? w10 : 0.f;
+                    w11 = (y1ok && x1ok) ? w11 : 0.f;
+                    const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+                    const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+                    i00 = (yc0 * W + xc0) * Q, i01 = (yc0 * W + xc1) * Q, i10 = (yc1 * W + xc0) * Q, i11 = (yc1 * W + xc1) * Q;
+                }
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const float4 a4 = __ldg(g00 + q), b4 = __ldg(g01 + q), c4 = __ldg(g10 + q), d4 = __ldg(g11 + q);
+                    float4 a4, b4, c4, d4;
+                    if (inwin) {
+                        const float4* wq = wbase + q * (RCT_WH * RCT_WW);
+                        a4 = wq[0], b4 = wq[1], c4 = wq[RCT_WW], d4 = wq[RCT_WW + 1];
+                    } else {
+                        a4 = __ldg(pooled + i00 + q), b4 = __ldg(pooled + i01 + q), c4 = __ldg(pooled + i10 + q), d4 = __ldg(pooled + i11 + q);
+                    }
                     const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
                     const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
@@ -223,6 +281,8 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
                 }
             }
         }
+        // every gather of this item precedes the barrier of the last push_chunk: the window can take the next item's data
+        if (item + (int)gridDim.x < total_items) fill_window(item + gridDim.x);
         wait_all();
         float acc[16];
         {
@@ -243,10 +303,9 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
 #pragma unroll
                 for (int i = 0; i < CP / 4; ++i) fma4_bcast(z + 4 * i, acc[c], w4[i]);
             }
-            const float* __restrict__ xr = p.x + (long long)b * p.x_bs + pix;
             float* __restrict__ orow = p.out + (long long)b * p.out_bs + pix;
 #pragma unroll
-            for (int o = 0; o < C; ++o) orow[(long long)o * P] = xr[(long long)o * P] + fmaxf(fmaf(s_scale[o], z[o], s_bias[o]), 0.f);
+            for (int o = 0; o < C; ++o) orow[(long long)o * P] = xres[o] + fmaxf(fmaf(s_scale[o], z[o], s_bias[o]), 0.f);
         }
         // the next item's first MMA overwrites the accumulators: order this item's TMEM reads before it
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -261,7 +320,8 @@ template <int C, int STAGES>
 static int launch_rc_tc_s(const AchRcDeform& p, const float* wom_hi, const float* wom_lo, const float* wreg_hi, const float* wreg_lo,
                           cudaStream_t st) {
     constexpr int NCH = (C * 9 + TC_KC - 1) / TC_KC;
-    constexpr size_t smem = (size_t)(STAGES * 2 * TC_KC * TC_M + 2 * NCH * 2 * RCT_N * TC_KC) * sizeof(float);
+    constexpr int Q = (C + 3) / 4;
+    constexpr size_t smem = (size_t)(STAGES * 2 * TC_KC * TC_M + 2 * NCH * 2 * RCT_N * TC_KC + Q * RCT_WH * RCT_WW * 4) * sizeof(float);
     static int ctas_per_wave = 0;
     if (!ctas_per_wave) {
         cudaFuncSetAttribute(rc_deform_tc_kernel<C, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -270,10 +330,10 @@ static int launch_rc_tc_s(const AchRcDeform& p, const float* wom_hi, const float
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         ctas_per_wave = sms * tc_ctas_per_sm(rc_deform_tc_kernel<C, STAGES>, 128, smem, 64);
     }
-    const int n_pt = cdiv((long long)p.H * p.W, TC_M);
-    const long long total = (long long)n_pt * p.B;
+    const int n_tx = cdiv(p.W, RCT_TW), n_ty = cdiv(p.H, RCT_TH);
+    const long long total = (long long)n_tx * n_ty * p.B;
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);
-    rc_deform_tc_kernel<C, STAGES><<<grid, 128, smem, st>>>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, n_pt, (int)total);
+    rc_deform_tc_kernel<C, STAGES><<<grid, 128, smem, st>>>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, n_tx, n_ty, (int)total);
     return check_launch("ach_rc_deform_tc");
 }
 

@@ -616,9 +616,9 @@ def test_pn2_interp3(N1, S, C2):
     run_both("ach_pn2_interp3", make, ["out"])
 
 
-@pytest.mark.parametrize("stages", [1, 2])
+@pytest.mark.parametrize("stages,off_scale", [(1, 3.0), (2, 3.0), (1, 0.5)])   # offsets beyond / within the staged window halo
 @pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (8, 13, 21), (16, 24, 20), (8, 160, 160)])
-def test_rc_deform_tc(Cc, H, W, stages, monkeypatch):
+def test_rc_deform_tc(Cc, H, W, stages, off_scale, monkeypatch):
     B = 2
     lib = _lib.load()
     n_om, n_reg = lib.ach_pack_pw_tc_elems(Cc * 9, 27), lib.ach_pack_pw_tc_elems(9 * Cc, Cc)
@@ -632,7 +632,7 @@ def test_rc_deform_tc(Cc, H, W, stages, monkeypatch):
         A.new("pooled", pc)                       # channel-last [P][ceil4(C)]
         w_om = torch.zeros(9 * Cc, 28)            # rows k = tap*C + ch
         w_om[:, :27] = R(9 * Cc, 27) / (Cc * 9) ** 0.5
-        w_om[:, :18] *= 3.0
+        w_om[:, :18] *= off_scale
         w_reg = torch.zeros(9 * Cc, ldr)
         w_reg[:, :Cc] = R(9 * Cc, Cc) / (Cc * 9) ** 0.5
         A.new("w_om_tap", w_om), A.new("w_reg_tap", w_reg), A.new("b_om", torch.rand(27) * 2 - 1), A.new("w1", R(Cc, Cc) / Cc ** 0.5)
