@@ -31,6 +31,27 @@
 namespace ach {
 
 constexpr int RCT_N = 32;   // MMA N for both GEMMs (27 offset/modulator outputs; C <= 16 conv outputs)
+constexpr int RCT_ACOL = 2 * RCT_N;      // TMEM columns [0, 64): the two accumulators; from 64: A-operand stages (hi 16 | lo 16)
+constexpr int RCT_TMEM_COLS = 128;
+
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (128 lanes x 8 tf32 columns) is read from tensor memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 constexpr int RCT_TW = 16, RCT_TH = 8;   // pixel tile (RCT_TW * RCT_TH == TC_M); a warp covers 2 rows of 16 pixels
 constexpr int RCT_R = 3;                 // halo of the staged window: 1 (3x3 tap) + |offset| < 2 + the +1 bilinear corner
 constexpr int RCT_WW = RCT_TW + 2 * RCT_R, RCT_WH = RCT_TH + 2 * RCT_R;
@@ -43,10 +64,10 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     constexpr int NCH = (K1 + TC_KC - 1) / TC_KC;   // K chunks of 16 (same count for both GEMMs)
     constexpr int CP = (C + 3) & ~3;
     constexpr int Q = CP / 4;
-    constexpr int A_ELEMS = TC_KC * TC_M, B_ELEMS = RCT_N * TC_KC;
+    constexpr int B_ELEMS = RCT_N * TC_KC;
+    static_assert(RCT_ACOL + STAGES * 32 <= RCT_TMEM_COLS, "A stages do not fit the TMEM allocation");
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float* a_ring = reinterpret_cast<float*>(smem_raw);          // [STAGES][hi | lo][A_ELEMS]
-    float* b_all = a_ring + STAGES * 2 * A_ELEMS;                // [2 GEMMs][NCH][hi | lo][B_ELEMS]
+    float* b_all = reinterpret_cast<float*>(smem_raw);           // [2 GEMMs][NCH][hi | lo][B_ELEMS]
     float4* win = reinterpret_cast<float4*>(b_all + 2 * NCH * 2 * B_ELEMS);   // [Q][RCT_WH][RCT_WW] pooled window (zero outside the image)
     __shared__ __align__(16) float s_w1[C * CP];    // [c][o]
     __shared__ float s_bom[32];
@@ -56,7 +77,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
 
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(64) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(RCT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -87,7 +108,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
     const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
-    const uint32_t a_ring_s = smem_u32(a_ring), b_all_s = smem_u32(b_all);
+    const uint32_t b_all_s = smem_u32(b_all);
     constexpr uint32_t idesc = tf32_idesc(RCT_N);
     uint32_t n = 0;   // chunks written so far by this CTA (ring position / mbarrier phase bookkeeping)
 
@@ -96,35 +117,37 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     // hands the 16 k in vbuf (this thread's pixel) to the tensor core as chunk `chunk` of GEMM `g`
     auto push_chunk = [&](const float (&vbuf)[TC_KC], int g, int chunk) {
         const uint32_t s = n % STAGES;
-        if (n >= (uint32_t)STAGES) mbar_wait(smem_u32(&mbar[s]), (n / STAGES - 1u) & 1u);   // MMAs that read this stage are done
-        float* a_hi = a_ring + s * 2 * A_ELEMS;
-        float* a_lo = a_hi + A_ELEMS;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(vbuf[j * 4 + 0]) & 0xffffe000u);
-            h.y = __uint_as_float(__float_as_uint(vbuf[j * 4 + 1]) & 0xffffe000u);
-            h.z = __uint_as_float(__float_as_uint(vbuf[j * 4 + 2]) & 0xffffe000u);
-            h.w = __uint_as_float(__float_as_uint(vbuf[j * 4 + 3]) & 0xffffe000u);
-            l.x = vbuf[j * 4 + 0] - h.x; l.y = vbuf[j * 4 + 1] - h.y; l.z = vbuf[j * 4 + 2] - h.z; l.w = vbuf[j * 4 + 3] - h.w;
-            *reinterpret_cast<float4*>(a_hi + j * (TC_M * 4) + tid * 4) = h;
-            *reinterpret_cast<float4*>(a_lo + j * (TC_M * 4) + tid * 4) = l;
+        if (n >= (uint32_t)STAGES) {   // the MMAs that read this A stage are done
+            mbar_wait(smem_u32(&mbar[s]), (n / STAGES - 1u) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // x = hi + lo, hi = x truncated to tf32 (the MMA ignores the low 13 mantissa bits anyway), lo = x - hi exact.
+        // The A operand goes to TENSOR memory: this thread's lane, 16 hi columns then 16 lo columns - no shared-memory
+        // store, no proxy fence, and the MMA does not re-read A through the shared-memory pipe (ncu on the shared-memory
+        // A ring: l1tex 83 % busy, of which ~35 % were the tensor core's own operand reads at N = 32).
+        uint32_t hi[TC_KC], lo[TC_KC];
+#pragma unroll
+        for (int j = 0; j < TC_KC; ++j) {
+            hi[j] = __float_as_uint(vbuf[j]) & 0xffffe000u;
+            lo[j] = __float_as_uint(vbuf[j] - __uint_as_float(hi[j]));
+        }
+        const uint32_t a_col = (uint32_t)RCT_ACOL + s * 32u;
+        tmem_st16(t_lane + a_col, hi);
+        tmem_st16(t_lane + a_col + 16u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi_s = a_ring_s + s * 2u * A_ELEMS * 4u, a_lo_s = a_hi_s + A_ELEMS * 4u;
             const uint32_t b_hi_s = b_all_s + (uint32_t)((g * NCH + chunk) * 2) * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
             const uint32_t col = tmem_d + (uint32_t)(g * RCT_N);
 #pragma unroll
             for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                const uint64_t ah = kmajor_desc(a_hi_s, TC_M, ks), al = kmajor_desc(a_lo_s, TC_M, ks);
+                const uint32_t ah = tmem_d + a_col + (uint32_t)ks * 8u, al = ah + 16u;
                 const uint64_t bh = kmajor_desc(b_hi_s, RCT_N, ks), bl = kmajor_desc(b_lo_s, RCT_N, ks);
-                mma_tf32(col, ah, bh, idesc, (chunk == 0 && ks == 0) ? 0u : 1u);
-                mma_tf32(col, al, bh, idesc, 1u);
-                mma_tf32(col, ah, bl, idesc, 1u);
+                mma_tf32_ts(col, ah, bh, idesc, (chunk == 0 && ks == 0) ? 0u : 1u);
+                mma_tf32_ts(col, al, bh, idesc, 1u);
+                mma_tf32_ts(col, ah, bl, idesc, 1u);
             }
             tc_commit(smem_u32(&mbar[s]));
         }
@@ -313,7 +336,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(64) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(RCT_TMEM_COLS) : "memory");
 }
 
 template <int C, int STAGES>
@@ -321,14 +344,14 @@ static int launch_rc_tc_s(const AchRcDeform& p, const float* wom_hi, const float
                           cudaStream_t st) {
     constexpr int NCH = (C * 9 + TC_KC - 1) / TC_KC;
     constexpr int Q = (C + 3) / 4;
-    constexpr size_t smem = (size_t)(STAGES * 2 * TC_KC * TC_M + 2 * NCH * 2 * RCT_N * TC_KC + Q * RCT_WH * RCT_WW * 4) * sizeof(float);
+    constexpr size_t smem = (size_t)(2 * NCH * 2 * RCT_N * TC_KC + Q * RCT_WH * RCT_WW * 4) * sizeof(float);
     static int ctas_per_wave = 0;
     if (!ctas_per_wave) {
         cudaFuncSetAttribute(rc_deform_tc_kernel<C, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        ctas_per_wave = sms * tc_ctas_per_sm(rc_deform_tc_kernel<C, STAGES>, 128, smem, 64);
+        ctas_per_wave = sms * tc_ctas_per_sm(rc_deform_tc_kernel<C, STAGES>, 128, smem, RCT_TMEM_COLS);
     }
     const int n_tx = cdiv(p.W, RCT_TW), n_ty = cdiv(p.H, RCT_TH);
     const long long total = (long long)n_tx * n_ty * p.B;
@@ -342,7 +365,7 @@ static int launch_rc_tc(const AchRcDeform& p, const float* wom_hi, const float* 
                         cudaStream_t st) {
     // ACH_RC_TC_STAGES=1|2: A/B switch for tools/op_times.py (1 = less shared memory, more CTAs per SM: occupancy beats the ring)
     const char* env = getenv("ACH_RC_TC_STAGES");
-    const int stages = env ? atoi(env) : 1;   // measured (B=64): 1 stage 0.498 / 0.404 / 0.100 ms (rc0 / rc1 / rc2), 2 stages 0.623 / 0.435 / 0.111
+    const int stages = env ? atoi(env) : 2;   // measured (B=64): 1 stage 0.498 / 0.404 / 0.100 ms (rc0 / rc1 / rc2), 2 stages 0.623 / 0.435 / 0.111
     return stages == 1 ? launch_rc_tc_s<C, 1>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st)
                        : launch_rc_tc_s<C, 2>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
 }
