@@ -7,7 +7,11 @@
 // SMs) 27 % of all stall samples sit on the first use of the loaded registers and on the barrier - 3.3 us per chunk for
 // 24 KB of operands.  Here the three jobs run decoupled, synchronised only through mbarriers:
 //   * warps 0-7 (256 threads, "producers"): activation chunk c+2 is requested from HBM while chunk c is split into
-//     tf32 hi/lo terms and written K-major into a 2-stage shared-memory ring; per-warp mbarrier arrive, no CTA barrier.
+//     tf32 hi/lo terms and written into a ring of A-operand stages in TENSOR MEMORY (tcgen05.st: thread = pixel = TMEM
+//     lane, 8 hi + 8 lo columns per thread and chunk; the MMA takes A from TMEM).  The first version kept the ring in
+//     shared memory: two STS.128 per 4 k plus a proxy fence, and the tensor core re-read every A tile three times
+//     through the shared-memory pipe (ah.bh, al.bh, ah.bl) - on the RCBlock kernel the same change cut 25-35 %.
+//     Per-warp mbarrier arrive, no CTA barrier.
 //     After the last chunk they prefetch the first two chunks of the CTA's NEXT tile, then run the epilogue of the
 //     current one (TMEM -> registers -> LayerNorm / scale / bias / activation / residual -> coalesced stores).
 //   * warp 8, one elected thread ("MMA thread"): streams the pre-packed hi/lo weight tiles with 1-D bulk TMA copies
@@ -26,6 +30,11 @@ constexpr int WS_SA = 2;        // activation ring stages
 constexpr int WS_SB = 4;        // weight ring stages
 constexpr int WS_PF = 2;        // weight chunks in flight ahead of the MMA
 constexpr int WS_PROD = 256;    // producer / epilogue threads (8 warps); warp 8 is the MMA warp
+
+__host__ __device__ constexpr int ws_tmem_cols(int nt) {   // accumulator + A stages, rounded up to a power of two >= 32
+    const int need = nt + WS_SA * 32;
+    return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
@@ -48,10 +57,8 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
     pw_conv_tc_ws_kernel(const AchPwConv p, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
                          const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    constexpr int A_ELEMS = TC_KC * TC_M;   // per hi / lo matrix
     constexpr int B_ELEMS = NT * TC_KC;
-    float* a_ring = reinterpret_cast<float*>(smem_raw);                  // [SA][a_hi | a_lo]
-    float* b_ring = a_ring + WS_SA * 2 * A_ELEMS;                        // [SB][b_hi | b_lo]
+    float* b_ring = reinterpret_cast<float*>(smem_raw);                  // [SB][b_hi | b_lo]
     __shared__ __align__(8) uint64_t bar_full_a[WS_SA], bar_full_b[WS_SB], bar_mma[WS_SA], bar_acc_full, bar_acc_empty;
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_ln[2][TC_M][2];
@@ -59,7 +66,9 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.c0 + p.c1, P = p.P;
-    constexpr int TMEM_COLS = NT < 32 ? 32 : NT;
+    // TMEM columns: [0, NT) accumulator, then WS_SA A-operand stages of 32 columns (hi k 0..15 | lo k 0..15)
+    constexpr int A_COL0 = NT;
+    constexpr int TMEM_COLS = ws_tmem_cols(NT);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
@@ -79,13 +88,13 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
-    const uint32_t a_ring_s = smem_u32(a_ring), b_ring_s = smem_u32(b_ring);
+    const uint32_t b_ring_s = smem_u32(b_ring);
 
     if (warp == WS_PROD / 32) {
         // ================================================================== MMA + weight-TMA thread
         if (lane == 0) {
             constexpr uint32_t idesc = tf32_idesc(NT);
-            constexpr uint32_t B_LBO = (NT / 8) * 128, A_LBO = (TC_M / 8) * 128;
+            constexpr uint32_t B_LBO = (NT / 8) * 128;
             int pit = 0, p_item = blockIdx.x, p_c = 0;   // weight prefetch cursor: chunk counter, (item, chunk)
             auto issue_b = [&]() {
                 if (p_item >= total_items) return;
@@ -120,17 +129,16 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
                     mbar_wait(smem_u32(&bar_full_b[sb]), (uint32_t)(it / WS_SB) & 1u);
                     mbar_wait(smem_u32(&bar_full_a[sa]), (uint32_t)(it >> 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi_s = a_ring_s + (uint32_t)sa * 2u * A_ELEMS * 4u, a_lo_s = a_hi_s + A_ELEMS * 4u;
+                    const uint32_t a_hi_t = tmem_d + (uint32_t)(A_COL0 + sa * 32), a_lo_t = a_hi_t + 16u;
                     const uint32_t b_hi_s = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
 #pragma unroll
                     for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                        const uint64_t ah = make_desc(a_hi_s + ks * 2 * A_LBO, A_LBO, 128u, 0);
-                        const uint64_t al = make_desc(a_lo_s + ks * 2 * A_LBO, A_LBO, 128u, 0);
+                        const uint32_t ah = a_hi_t + (uint32_t)ks * 8u, al = a_lo_t + (uint32_t)ks * 8u;
                         const uint64_t bh = make_desc(b_hi_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
                         const uint64_t bl = make_desc(b_lo_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
-                        mma_tf32(tmem_d, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                        mma_tf32(tmem_d, al, bh, idesc, 1u);
-                        mma_tf32(tmem_d, ah, bl, idesc, 1u);
+                        mma_tf32_ts(tmem_d, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts(tmem_d, al, bh, idesc, 1u);
+                        mma_tf32_ts(tmem_d, ah, bl, idesc, 1u);
                     }
                     tc_commit(smem_u32(&bar_mma[sa]));
                     if (c == n_kchunks - 1) tc_commit(smem_u32(&bar_acc_full));
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
             t.x1 = p.x1 ? p.x1 + (long long)t.b * p.x1_bs : nullptr;
             return t;
         };
-        // activation loads of chunk c (global -> registers only): this thread's 2 k-cores x 4 k
+        // activation loads of chunk c (global -> registers only): this thread's 8 consecutive k (half h: k 8h .. 8h+7 = MMA K-step h)
         auto load_a = [&](const Item& t, int c, float (&v)[2][4]) {
             const int k0 = c * TC_KC;
             if (k0 + TC_KC <= p.c0 || (k0 >= p.c0 && k0 + TC_KC <= K)) {
@@ -169,13 +177,13 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) v[jj][e] = t.p_ok ? __ldg(src + (long long)((half + 2 * jj) * 4 + e) * P) : 0.f;
+                    for (int e = 0; e < 4; ++e) v[jj][e] = t.p_ok ? __ldg(src + (long long)((2 * half + jj) * 4 + e) * P) : 0.f;
             } else {
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int kk = k0 + (half + 2 * jj) * 4 + e;
+                        const int kk = k0 + (2 * half + jj) * 4 + e;
                         float x = 0.f;
                         if (kk < K && t.p_ok) x = (kk < p.c0) ? __ldg(t.x0 + (long long)kk * P + t.pp) : __ldg(t.x1 + (long long)(kk - p.c0) * P + t.pp);
                         v[jj][e] = x;
@@ -199,13 +207,15 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
             for (int c = 0; c < n_kchunks; ++c, ++it) {
                 if (c + 2 < n_kchunks) load_a(cur, c + 2, v2);
                 const uint32_t sa = it & 1u;
-                if (it >= 2) mbar_wait(smem_u32(&bar_mma[sa]), ((it - 2) >> 1) & 1u);   // MMAs of chunk it-2 have read this stage
-                float* a_hi = a_ring + sa * 2 * A_ELEMS;
-                float* a_lo = a_hi + A_ELEMS;
+                if (it >= 2) {   // MMAs of chunk it-2 have read this stage
+                    mbar_wait(smem_u32(&bar_mma[sa]), ((it - 2) >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 const int k0 = c * TC_KC;
+                uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const int j = half + 2 * jj;
+                    const int j = 2 * half + jj;
                     if (p.ln) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -216,16 +226,17 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
                     }
                     // x = hi + lo with hi = x truncated to tf32 (1 LOP3; the MMA ignores the low 13 mantissa bits anyway) and
                     // lo = x - hi exact in fp32
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v0[jj][0]) & 0xffffe000u);
-                    h.y = __uint_as_float(__float_as_uint(v0[jj][1]) & 0xffffe000u);
-                    h.z = __uint_as_float(__float_as_uint(v0[jj][2]) & 0xffffe000u);
-                    h.w = __uint_as_float(__float_as_uint(v0[jj][3]) & 0xffffe000u);
-                    l.x = v0[jj][0] - h.x; l.y = v0[jj][1] - h.y; l.z = v0[jj][2] - h.z; l.w = v0[jj][3] - h.w;
-                    *reinterpret_cast<float4*>(a_hi + j * (TC_M * 4) + px * 4) = h;
-                    *reinterpret_cast<float4*>(a_lo + j * (TC_M * 4) + px * 4) = l;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        hi[jj * 4 + e] = __float_as_uint(v0[jj][e]) & 0xffffe000u;
+                        lo[jj * 4 + e] = __float_as_uint(v0[jj][e] - __uint_as_float(hi[jj * 4 + e]));
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+                const uint32_t a_t = t_lane + (uint32_t)(A_COL0 + sa * 32 + half * 8);
+                tmem_st8(a_t, hi);
+                tmem_st8(a_t + 16u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM writes -> ordered before the MMA thread's reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_full_a[sa]));
 #pragma unroll
@@ -349,14 +360,14 @@ template <int NT, int ACT>
 static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
     const int K = p.c0 + p.c1;
     const int n_kchunks = cdiv(K, TC_KC);
-    constexpr size_t smem = (size_t)WS_SA * 2 * TC_KC * TC_M * 4 + (size_t)WS_SB * 2 * NT * TC_KC * 4;
+    constexpr size_t smem = (size_t)WS_SB * 2 * NT * TC_KC * 4;
     static int ctas_per_wave = 0;
     if (!ctas_per_wave) {
         cudaFuncSetAttribute(pw_conv_tc_ws_kernel<NT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT>, WS_PROD + 32, smem, NT < 32 ? 32 : NT);
+        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT>, WS_PROD + 32, smem, ws_tmem_cols(NT));
         ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);

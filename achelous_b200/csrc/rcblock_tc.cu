@@ -34,24 +34,6 @@ constexpr int RCT_N = 32;   // MMA N for both GEMMs (27 offset/modulator outputs
 constexpr int RCT_ACOL = 2 * RCT_N;      // TMEM columns [0, 64): the two accumulators; from 64: A-operand stages (hi 16 | lo 16)
 constexpr int RCT_TMEM_COLS = 128;
 
-// D[tmem] (+)= A[tmem] . B[smem]: the A operand (128 lanes x 8 tf32 columns) is read from tensor memory
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
-        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
 constexpr int RCT_TW = 16, RCT_TH = 8;   // pixel tile (RCT_TW * RCT_TH == TC_M); a warp covers 2 rows of 16 pixels
 constexpr int RCT_R = 3;                 // halo of the staged window: 1 (3x3 tap) + |offset| < 2 + the +1 bilinear corner
 constexpr int RCT_WW = RCT_TW + 2 * RCT_R, RCT_WH = RCT_TH + 2 * RCT_R;
