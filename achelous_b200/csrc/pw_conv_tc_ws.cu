@@ -295,16 +295,30 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
                 uint32_t r[16];
                 tmem_ld16(t_lane + (uint32_t)n0, r);
                 if (p.reduce_max) {
-                    // out (B, O) = max over pixels: warp-shuffle max over the warp's 32 pixels, one atomic per (warp, output)
+                    // out (B, O) = max over pixels.  16 outputs x 32 lanes -> butterfly reduce-scatter: every exchange halves
+                    // the outputs a lane still carries (xor 16: 8, xor 8: 4, xor 4: 2, xor 2: 1), a last xor-1 exchange
+                    // completes the 32-lane max, and the even lanes each own one output: 16 shuffles and ONE atomic
+                    // instruction per 16 outputs (the straightforward per-output warp max took 80 shuffles and 16 atomics).
+                    float y[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float4 e = s_ep[n0 + j];
-                        float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
-                        y = done.p_ok ? apply_act(y, ACT) : -INFINITY;
-#pragma unroll
-                        for (int sft = 16; sft > 0; sft >>= 1) y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, sft));
-                        if (lane == 0 && n0 + j < o_lim) atomic_max_float(p.out + (long long)done.b * p.out_bs + done.o_base + n0 + j, y);
+                        const float t = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
+                        y[j] = done.p_ok ? apply_act(t, ACT) : -INFINITY;
                     }
+#pragma unroll
+                    for (int w = 8; w >= 1; w >>= 1) {   // lanes with bit (2w) set keep the upper w outputs
+                        const bool up = (lane & (2 * w)) != 0;
+#pragma unroll
+                        for (int i = 0; i < w; ++i) {
+                            const float send = up ? y[i] : y[i + w];
+                            const float keep = up ? y[i + w] : y[i];
+                            y[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2 * w));
+                        }
+                    }
+                    y[0] = fmaxf(y[0], __shfl_xor_sync(0xffffffffu, y[0], 1));
+                    const int jo = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    if ((lane & 1) == 0 && n0 + jo < o_lim) atomic_max_float(p.out + (long long)done.b * p.out_bs + done.o_base + n0 + jo, y[0]);
                 } else if (done.p_ok) {
                     if (n0 + 16 <= o_lim) {
                         // full block: no per-output predicate; residual values first, as 16 independent loads (interleaved with
