@@ -6,8 +6,14 @@
 // (profiles/r1_ncu_final_summary.txt, source page): on the long-K layers (K = 352, 22 chunks, only 200 work items on 148
 // SMs) 27 % of all stall samples sit on the first use of the loaded registers and on the barrier - 3.3 us per chunk for
 // 24 KB of operands.  Here the three jobs run decoupled, synchronised only through mbarriers:
-//   * warps 0-7 (256 threads, "producers"): activation chunk c+2 is requested from HBM while chunk c is split into
-//     tf32 hi/lo terms and written into a ring of A-operand stages in TENSOR MEMORY (tcgen05.st: thread = pixel = TMEM
+//   * warp 9 ("activation loader"): streams the fp32 activation chunks (16 channels x 128 pixels = 16 bulk copies of
+//     512 contiguous bytes, cp.async.bulk + mbarrier complete_tx) into a WS_SG-deep shared-memory ring, running ahead
+//     of the consumers across chunk AND tile boundaries.  The first versions loaded activations into registers two
+//     chunks ahead: ncu showed long-scoreboard stalls of 3.8 per issue on the K = 128 layers and 2 TB/s of DRAM - the
+//     register prefetch was too shallow for HBM latency; the ring holds 5-8 chunks (40-64 KB) in flight per CTA.
+//   * warps 0-7 (256 threads, "producers"): read their pixel's 8 k of a landed chunk from the ring (conflict-free
+//     LDS), split them into
+//     tf32 hi/lo terms and write them into a ring of A-operand stages in TENSOR MEMORY (tcgen05.st: thread = pixel = TMEM
 //     lane, 8 hi + 8 lo columns per thread and chunk; the MMA takes A from TMEM).  The first version kept the ring in
 //     shared memory: two STS.128 per 4 k plus a proxy fence, and the tensor core re-read every A tile three times
 //     through the shared-memory pipe (ah.bh, al.bh, ah.bl) - on the RCBlock kernel the same change cut 25-35 %.
@@ -29,7 +35,9 @@ namespace ach {
 constexpr int WS_SA = 2;        // activation ring stages
 constexpr int WS_SB = 4;        // weight ring stages
 constexpr int WS_PF = 2;        // weight chunks in flight ahead of the MMA
-constexpr int WS_PROD = 256;    // producer / epilogue threads (8 warps); warp 8 is the MMA warp
+constexpr int WS_PROD = 256;    // producer / epilogue threads (8 warps); warp 8 is the MMA warp, warp 9 the activation loader
+constexpr int WS_THREADS = WS_PROD + 64;
+__host__ __device__ constexpr int ws_sg(int nt) { return nt == 128 ? 5 : 8; }   // activation ring depth (8 KB per stage)
 
 __host__ __device__ constexpr int ws_tmem_cols(int nt) {   // accumulator + A stages, rounded up to a power of two >= 32
     const int need = nt + WS_SA * 32;
@@ -53,13 +61,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WS_PROD) : "memory"); }
 
 template <int NT, int ACT>
-__global__ void __launch_bounds__(WS_PROD + 32, 2)
+__global__ void __launch_bounds__(WS_THREADS, 2)
     pw_conv_tc_ws_kernel(const AchPwConv p, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
                          const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int B_ELEMS = NT * TC_KC;
+    constexpr int SG = ws_sg(NT);
+    constexpr int G_ELEMS = TC_KC * TC_M;                                // fp32 activation chunk: [16 channels][128 pixels]
     float* b_ring = reinterpret_cast<float*>(smem_raw);                  // [SB][b_hi | b_lo]
+    float* g_ring = b_ring + WS_SB * 2 * B_ELEMS;                        // [SG][16][128]
     __shared__ __align__(8) uint64_t bar_full_a[WS_SA], bar_full_b[WS_SB], bar_mma[WS_SA], bar_acc_full, bar_acc_empty;
+    __shared__ __align__(8) uint64_t bar_g_full[SG], bar_g_empty[SG];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_ln[2][TC_M][2];
     __shared__ __align__(16) float4 s_ep[NT];   // per output of the current tile: {scale, scale*wsum, bias + scale*pbias, gamma}
@@ -80,6 +92,10 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
             mbar_init(smem_u32(&bar_mma[i]), 1);
         }
         for (int i = 0; i < WS_SB; ++i) mbar_init(smem_u32(&bar_full_b[i]), 1);
+        for (int i = 0; i < SG; ++i) {
+            mbar_init(smem_u32(&bar_g_full[i]), 1);
+            mbar_init(smem_u32(&bar_g_empty[i]), WS_PROD / 32);
+        }
         mbar_init(smem_u32(&bar_acc_full), 1);
         mbar_init(smem_u32(&bar_acc_empty), WS_PROD / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -146,6 +162,33 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
             }
         }
         __syncwarp();
+    } else if (warp == WS_PROD / 32 + 1) {
+        // ================================================================== activation loader (lanes 0-15: one channel row each)
+        const uint32_t g_ring_s = smem_u32(g_ring);
+        uint32_t git = 0;
+#pragma unroll 1
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const int pt = (item / n_ot) % n_pt, b = item / (n_ot * n_pt);
+            const int pp0 = pt * TC_M;
+            const uint32_t bytes = (uint32_t)min(TC_M, P - pp0) * 4u;     // multiple of 16: P % 4 == 0
+            const float* x0 = p.x0 + (long long)b * p.x0_bs + pp0;
+            const float* x1 = p.x1 ? p.x1 + (long long)b * p.x1_bs + pp0 : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < n_kchunks; ++c, ++git) {
+                const uint32_t g = git % SG;
+                if (git >= (uint32_t)SG) mbar_wait(smem_u32(&bar_g_empty[g]), (git / SG - 1u) & 1u);   // every producer warp has read it
+                const int k0 = c * TC_KC;
+                const int nk = min(TC_KC, K - k0);
+                const uint32_t full = smem_u32(&bar_g_full[g]);
+                if (lane == 0) mbar_expect_tx(full, (uint32_t)nk * bytes);
+                __syncwarp();
+                if (lane < nk) {
+                    const int k = k0 + lane;
+                    const float* src = (k < p.c0) ? x0 + (long long)k * P : x1 + (long long)(k - p.c0) * P;
+                    bulk_g2s(g_ring_s + (g * G_ELEMS + (uint32_t)lane * TC_M) * 4u, src, bytes, full);
+                }
+            }
+        }
     } else {
         // ================================================================== producers + epilogue (256 threads)
         const int px = tid & (TC_M - 1), half = tid >> 7;   // half is warp-uniform
@@ -169,49 +212,37 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
             t.x1 = p.x1 ? p.x1 + (long long)t.b * p.x1_bs : nullptr;
             return t;
         };
-        // activation loads of chunk c (global -> registers only): this thread's 8 consecutive k (half h: k 8h .. 8h+7 = MMA K-step h)
-        auto load_a = [&](const Item& t, int c, float (&v)[2][4]) {
-            const int k0 = c * TC_KC;
-            if (k0 + TC_KC <= p.c0 || (k0 >= p.c0 && k0 + TC_KC <= K)) {
-                const float* __restrict__ src = (k0 < p.c0) ? t.x0 + (long long)k0 * P + t.pp : t.x1 + (long long)(k0 - p.c0) * P + t.pp;
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[jj][e] = t.p_ok ? __ldg(src + (long long)((2 * half + jj) * 4 + e) * P) : 0.f;
-            } else {
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int kk = k0 + (2 * half + jj) * 4 + e;
-                        float x = 0.f;
-                        if (kk < K && t.p_ok) x = (kk < p.c0) ? __ldg(t.x0 + (long long)kk * P + t.pp) : __ldg(t.x1 + (long long)(kk - p.c0) * P + t.pp);
-                        v[jj][e] = x;
-                    }
-            }
-        };
-
         uint32_t it = 0;
         int tile_n = 0;
         int item = blockIdx.x;
         Item cur = decode(item);
-        float v0[2][4], v1[2][4], v2[2][4];
-        load_a(cur, 0, v0);
-        if (n_kchunks > 1) load_a(cur, 1, v1);
 #pragma unroll 1
         for (; item < total_items; ++tile_n) {
             // LayerNorm running sums, shifted by the pixel's first channel to avoid cancellation
-            const float shift = (p.ln && cur.p_ok) ? __ldg(cur.x0 + cur.pp) : 0.f;
-            float s1 = 0.f, s2 = 0.f;
+            float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
             for (int c = 0; c < n_kchunks; ++c, ++it) {
-                if (c + 2 < n_kchunks) load_a(cur, c + 2, v2);
+                // this thread's 8 consecutive k of the chunk (half h: k 8h .. 8h+7 = MMA K-step h) from the landed ring stage
+                const uint32_t g = it % SG;
+                mbar_wait(smem_u32(&bar_g_full[g]), (it / SG) & 1u);
+                const float* gs = g_ring + g * G_ELEMS + px;
+                const int k0 = c * TC_KC;
+                if (p.ln && c == 0) shift = cur.p_ok ? gs[0] : 0.f;
+                float v0[2][4];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int kl = (2 * half + jj) * 4 + e;
+                        v0[jj][e] = (cur.p_ok && k0 + kl < K) ? gs[kl * TC_M] : 0.f;   // rows past K / pixels past P were not copied
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bar_g_empty[g]));
                 const uint32_t sa = it & 1u;
                 if (it >= 2) {   // MMAs of chunk it-2 have read this stage
                     mbar_wait(smem_u32(&bar_mma[sa]), ((it - 2) >> 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                const int k0 = c * TC_KC;
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
@@ -239,22 +270,10 @@ __global__ void __launch_bounds__(WS_PROD + 32, 2)
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM writes -> ordered before the MMA thread's reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_full_a[sa]));
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        v0[jj][e] = v1[jj][e];
-                        v1[jj][e] = v2[jj][e];
-                    }
             }
-            // the next tile's first two chunks fly while this tile's epilogue runs
             const int next = item + gridDim.x;
             const Item done = cur;
-            if (next < total_items) {
-                cur = decode(next);
-                load_a(cur, 0, v0);
-                if (n_kchunks > 1) load_a(cur, 1, v1);
-            }
+            if (next < total_items) cur = decode(next);
 
             // ---- per-output epilogue constants of this (frame, output tile) + LayerNorm partial sums -> shared memory
             if (tid < NT) {
@@ -374,21 +393,21 @@ template <int NT, int ACT>
 static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
     const int K = p.c0 + p.c1;
     const int n_kchunks = cdiv(K, TC_KC);
-    constexpr size_t smem = (size_t)WS_SB * 2 * NT * TC_KC * 4;
+    constexpr size_t smem = (size_t)WS_SB * 2 * NT * TC_KC * 4 + (size_t)ws_sg(NT) * TC_KC * TC_M * 4;
     static int ctas_per_wave = 0;
     if (!ctas_per_wave) {
         cudaFuncSetAttribute(pw_conv_tc_ws_kernel<NT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT>, WS_PROD + 32, smem, ws_tmem_cols(NT));
+        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT>, WS_THREADS, smem, ws_tmem_cols(NT));
         ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);
     const long long total = (long long)n_pt * n_ot * p.B;
     ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
-    pw_conv_tc_ws_kernel<NT, ACT><<<grid, WS_PROD + 32, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
+    pw_conv_tc_ws_kernel<NT, ACT><<<grid, WS_THREADS, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
     return check_launch("ach_pw_conv_tc");
 }
 
