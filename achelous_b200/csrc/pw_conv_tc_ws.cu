@@ -32,7 +32,7 @@
 
 namespace ach {
 
-constexpr int WS_SA = 2;        // activation ring stages
+constexpr int WS_SA = 4;        // A-operand stages in tensor memory (32 columns each)
 constexpr int WS_SB = 4;        // weight ring stages
 constexpr int WS_PF = 2;        // weight chunks in flight ahead of the MMA
 constexpr int WS_PROD = 256;    // producer / epilogue threads (8 warps); warp 8 is the MMA warp, warp 9 the activation loader
@@ -60,7 +60,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WS_PROD) : "memory"); }
 
-template <int NT, int ACT>
+template <int NT, int ACT, bool RES>
 __global__ void __launch_bounds__(WS_THREADS, 2)
     pw_conv_tc_ws_kernel(const AchPwConv p, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
                          const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                 if (p_item >= total_items) return;
                 const int sb = pit % WS_SB;
                 const int prev = pit - WS_SB;            // the chunk whose MMAs last read this stage
-                if (prev >= 0) mbar_wait(smem_u32(&bar_mma[prev & 1]), (uint32_t)(prev >> 1) & 1u);
+                if (prev >= 0) mbar_wait(smem_u32(&bar_mma[prev % WS_SA]), (uint32_t)(prev / WS_SA) & 1u);
                 const long long blk = ((long long)(p_item % n_ot) * n_kchunks + p_c) * B_ELEMS;
                 const uint32_t full = smem_u32(&bar_full_b[sb]);
                 const uint32_t dst = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u;
@@ -141,9 +141,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
 #pragma unroll 1
                 for (int c = 0; c < n_kchunks; ++c, ++it) {
                     issue_b();   // chunk it + WS_PF
-                    const int sa = it & 1, sb = it % WS_SB;
+                    const int sa = it % WS_SA, sb = it % WS_SB;
                     mbar_wait(smem_u32(&bar_full_b[sb]), (uint32_t)(it / WS_SB) & 1u);
-                    mbar_wait(smem_u32(&bar_full_a[sa]), (uint32_t)(it >> 1) & 1u);
+                    mbar_wait(smem_u32(&bar_full_a[sa]), (uint32_t)(it / WS_SA) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi_t = tmem_d + (uint32_t)(A_COL0 + sa * 32), a_lo_t = a_hi_t + 16u;
                     const uint32_t b_hi_s = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                     }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_g_empty[g]));
-                const uint32_t sa = it & 1u;
-                if (it >= 2) {   // MMAs of chunk it-2 have read this stage
-                    mbar_wait(smem_u32(&bar_mma[sa]), ((it - 2) >> 1) & 1u);
+                const uint32_t sa = it % WS_SA;
+                if (it >= (uint32_t)WS_SA) {   // MMAs of chunk it-WS_SA have read this stage
+                    mbar_wait(smem_u32(&bar_mma[sa]), (it / WS_SA - 1u) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 uint32_t hi[8], lo[8];
@@ -300,15 +300,24 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                 rs = 1.0f / sqrtf(fmaxf(t2 - t1 * t1, 0.f) + p.ln_eps);
                 ms = (shift + t1) * rs;
             }
-            mbar_wait(smem_u32(&bar_acc_full), (uint32_t)tile_n & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
             // ---- epilogue: thread = pixel (TMEM lane 32*(warp%4) + lane); this half's NT/2 columns, 16 at a time
             constexpr int NH = NT / 2;
             const int pp = done.pp;
             float* optr = p.out + (long long)done.b * p.out_bs + (long long)(done.o_base + half * NH) * P + pp;
-            const float* rptr = p.res ? p.res + (long long)done.b * p.res_bs + (long long)(done.o_base + half * NH) * P + pp : nullptr;
+            const float* rptr = RES ? p.res + (long long)done.b * p.res_bs + (long long)(done.o_base + half * NH) * P + pp : nullptr;
             const int o_lim = p.O - done.o_base;   // valid outputs in this tile
+            // residual values are requested one 16-output block ahead - the first block before waiting for the accumulator
+            // (ncu: 5.2 long-scoreboard stalls per issue on the K = 128 -> 32 layers when they were loaded at their use)
+            float rr[16];
+            auto load_res = [&](const float* rp, int n0) {
+                if (RES && done.p_ok && n0 + 16 <= o_lim) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) rr[j] = __ldg(rp + (long long)j * P);
+                }
+            };
+            if (RES) load_res(rptr, half * NH);
+            mbar_wait(smem_u32(&bar_acc_full), (uint32_t)tile_n & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
             for (int n0 = half * NH; n0 < (half + 1) * NH && n0 < o_lim; n0 += 16) {
                 uint32_t r[16];
@@ -340,21 +349,19 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                     if ((lane & 1) == 0 && n0 + jo < o_lim) atomic_max_float(p.out + (long long)done.b * p.out_bs + done.o_base + n0 + jo, y[0]);
                 } else if (done.p_ok) {
                     if (n0 + 16 <= o_lim) {
-                        // full block: no per-output predicate; residual values first, as 16 independent loads (interleaved with
-                        // the stores they would each stall for a memory round trip: a load cannot move above a possibly aliasing store)
-                        float rr[16];
-                        if (rptr) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) rr[j] = rptr[(long long)j * P];
-                        }
+                        // full block: no per-output predicate
+                        float y[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float4 e = s_ep[n0 + j];
-                            float y = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
-                            y = apply_act(y, ACT);
-                            if (rptr) y = fmaf(e.w, y, rr[j]);
-                            optr[(long long)j * P] = y;
+                            y[j] = fmaf(rs * e.x, __uint_as_float(r[j]), fmaf(-ms, e.y, e.z));
+                            y[j] = apply_act(y[j], ACT);
+                            if (RES) y[j] = fmaf(e.w, y[j], rr[j]);
                         }
+                        // next block's residuals before this block's stores (a load cannot move above a possibly aliasing store)
+                        if (RES && n0 + 16 < (half + 1) * NH) load_res(rptr + (long long)16 * P, n0 + 16);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) optr[(long long)j * P] = y[j];
                     } else {
 #pragma unroll 1
                         for (int j = 0; j < 16 && n0 + j < o_lim; ++j) {
@@ -364,13 +371,13 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                             for (int q = 1; q < 16; ++q) rv = (j == q) ? r[q] : rv;
                             float y = fmaf(rs * e.x, __uint_as_float(rv), fmaf(-ms, e.y, e.z));
                             y = apply_act(y, ACT);
-                            if (rptr) y = fmaf(e.w, y, rptr[(long long)j * P]);
+                            if (RES) y = fmaf(e.w, y, rptr[(long long)j * P]);
                             optr[(long long)j * P] = y;
                         }
                     }
                 }
                 optr += (long long)16 * P;
-                if (rptr) rptr += (long long)16 * P;
+                if (RES) rptr += (long long)16 * P;
             }
             // hand the accumulator back to the MMA thread; s_ep / s_ln are rewritten by the next tile
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -389,35 +396,36 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
     }
 }
 
-template <int NT, int ACT>
+template <int NT, int ACT, bool RES>
 static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
     const int K = p.c0 + p.c1;
     const int n_kchunks = cdiv(K, TC_KC);
     constexpr size_t smem = (size_t)WS_SB * 2 * NT * TC_KC * 4 + (size_t)ws_sg(NT) * TC_KC * TC_M * 4;
     static int ctas_per_wave = 0;
     if (!ctas_per_wave) {
-        cudaFuncSetAttribute(pw_conv_tc_ws_kernel<NT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(pw_conv_tc_ws_kernel<NT, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT>, WS_THREADS, smem, ws_tmem_cols(NT));
+        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT, RES>, WS_THREADS, smem, ws_tmem_cols(NT));
         ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);
     const long long total = (long long)n_pt * n_ot * p.B;
     ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
-    pw_conv_tc_ws_kernel<NT, ACT><<<grid, WS_THREADS, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
+    pw_conv_tc_ws_kernel<NT, ACT, RES><<<grid, WS_THREADS, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
     return check_launch("ach_pw_conv_tc");
 }
 
 template <int NT>
 static int launch_ws_nt(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
+    const bool res = p.res != nullptr;
     switch (p.act) {
-        case ACT_NONE: return launch_ws<NT, ACT_NONE>(p, w_hi, w_lo, wsum, st);
-        case ACT_RELU: return launch_ws<NT, ACT_RELU>(p, w_hi, w_lo, wsum, st);
-        case ACT_SILU: return launch_ws<NT, ACT_SILU>(p, w_hi, w_lo, wsum, st);
-        case ACT_GELU: return launch_ws<NT, ACT_GELU>(p, w_hi, w_lo, wsum, st);
+        case ACT_NONE: return res ? launch_ws<NT, ACT_NONE, true>(p, w_hi, w_lo, wsum, st) : launch_ws<NT, ACT_NONE, false>(p, w_hi, w_lo, wsum, st);
+        case ACT_RELU: return res ? launch_ws<NT, ACT_RELU, true>(p, w_hi, w_lo, wsum, st) : launch_ws<NT, ACT_RELU, false>(p, w_hi, w_lo, wsum, st);
+        case ACT_SILU: return res ? launch_ws<NT, ACT_SILU, true>(p, w_hi, w_lo, wsum, st) : launch_ws<NT, ACT_SILU, false>(p, w_hi, w_lo, wsum, st);
+        case ACT_GELU: return res ? launch_ws<NT, ACT_GELU, true>(p, w_hi, w_lo, wsum, st) : launch_ws<NT, ACT_GELU, false>(p, w_hi, w_lo, wsum, st);
         default: break;
     }
     set_error("ach_pw_conv_tc: activation %d not instantiated", p.act);
