@@ -329,15 +329,19 @@ def measure_dominant(eng, K, torch):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
     traffic = None
-    try:   # dram__bytes_read+write of this launch from the committed `ncu --set full` capture (profiles/r1_traffic.json)
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f).get(eng.op_names[top], {}).get("dram_bytes")
-    except Exception:
-        pass
+    # dram__bytes_read+write of this launch from the newest committed `ncu --set full` capture that holds it
+    for name in ("r1s2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                traffic = json.load(f).get(eng.op_names[top], {}).get("dram_bytes")
+        except Exception:
+            traffic = None
+        if traffic is not None:
+            break
     return {"bound": "hbm", "kernel": f"{eng.op_names[top]} ({fn.__name__})", "share_of_step": t[top] / total,
             "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes": nbytes, "launch_ms": ms, "traffic": traffic,
-            "note": "the top launch by time; every kernel on this path is HBM-bound by arithmetic intensity but the round-1 kernels are "
-                    "instruction-issue bound (profiles/r1_ncu_final_summary.txt)"}
+            "note": "the top launch by time; every kernel on this path is HBM-bound by arithmetic intensity, the kernels themselves are "
+                    "issue / shared-memory-pipe bound (profiles/r1s2_ncu_summary.txt)"}
 
 
 if __name__ == "__main__":
