@@ -99,6 +99,10 @@ _SIGNATURES = {
     "ach_pn2_interp3": ([VP, LL, VP, LL, VP, LL, I, I, I, I, VP, LL, VP], I),
     "ach_seg_softmax": ([VP, LL, VP, LL, I, I, I, VP], I),
     "ach_seg_resize_argmax": ([VP, LL, I, I, I, I, I, I, I, I, VP, I, I, VP], I),
+    "ach_pre_resize_h": ([VP, LL, I, I, I, I, I, VP, VP, I, VP, LL, VP], I),
+    "ach_pre_resize_v_norm": ([VP, LL, I, I, I, VP, VP, I, I, VP, LL, I, I, I, I, VP], I),
+    "ach_pre_radar": ([VP, LL, I, I, LL, VP, LL, VP], I),
+    "ach_pre_points": ([VP, I, I, VP, I, I, VP, VP], I),
     "ach_decode_outputs": ([C.POINTER(VP), C.POINTER(LL), C.POINTER(I), C.POINTER(I), I, VP, I, I, F, F, VP], I),
     "ach_nms_workspace_bytes": ([I, I], LL),
     "ach_nms": ([VP, I, I, I, F, F, VP, VP, VP, VP, LL, VP], I),

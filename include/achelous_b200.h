@@ -341,6 +341,23 @@ ACH_API int ach_seg_softmax(const float* x, long long x_bs, float* out, long lon
 ACH_API int ach_seg_resize_argmax(const float* prob, long long prob_bs, int B, int K, int H, int W, int y_off, int x_off, int nh,
                                   int nw, unsigned char* out, int OH, int OW, void* stream);
 
+/* Input pre-processing on device (achelous.py:200-246, utils/utils.py:20-54).
+ * Image: Pillow's two-pass 8-bit BICUBIC resize (Resample.c; coefficient tables `bounds` [out][2] = (first source
+ * index, tap count) and `kk` [out][ksize] 22-bit fixed point, built on the host exactly as precompute_coeffs +
+ * normalize_coeffs_8bpc do) - ach_pre_resize_h: src (B, ih, iw, 3) uint8, rows [r0, r0+rows) -> tmp (B, rows, nw, 3);
+ * ach_pre_resize_v_norm: vertical pass over tmp (its `bounds` are relative to r0; identity != 0: no vertical pass) fused
+ * with the letterbox paste at (x_off, y_off) on a 128-grey canvas, HWC->CHW and preprocess_input -> out (B, 3, H, W) fp32.
+ * ach_pre_radar: per-sample (x - min) / (max - min) + 1e-13 (utils.py:51-54), src fp32 (is_f64 = 0) or fp64 -> fp32.
+ * ach_pre_points: feat (n_rows, C) fp64 row-major, idx (B, N) -> out (B, C, N) fp32 = feat[idx] / column L2 norm over the
+ * N sampled rows (sklearn normalize(axis=0); zero norm -> 1), achelous.py:224-246. */
+ACH_API int ach_pre_resize_h(const unsigned char* src, long long src_bs, int B, int iw, int r0, int rows, int nw, const int* bounds,
+                             const int* kk, int ksize, unsigned char* tmp, long long tmp_bs, void* stream);
+ACH_API int ach_pre_resize_v_norm(const unsigned char* tmp, long long tmp_bs, int B, int nw, int nh, const int* bounds, const int* kk,
+                                  int ksize, int identity, float* out, long long out_bs, int H, int W, int x_off, int y_off,
+                                  void* stream);
+ACH_API int ach_pre_radar(const void* src, long long src_bs, int is_f64, int B, long long n, float* out, long long out_bs, void* stream);
+ACH_API int ach_pre_points(const double* feat, int n_rows, int C, const int* idx, int B, int N, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
