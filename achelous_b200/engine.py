@@ -641,6 +641,71 @@ class Engine:
         dec("se", prefix, sa_se, w, out_se)
         return (f5, m5), (f4, m4), (f3, m3)
 
+    # ---- CSP-Dual-FPN neck (neck/cspdualfpn.py)
+    def conv3_bn_act(self, name, prefix, x, out, act):
+        """BaseConv with a 3x3 kernel: conv (no bias) + BN(1e-3) + act (normal_conv.py:36-49)"""
+        w = self._pack_conv(name + ".w", prefix + ".conv.weight")
+        sc = self._vec(name + ".s", lambda: self._bn_fold(prefix + ".bn", 1e-3)[0])
+        bi = self._vec(name + ".b", lambda: self._bn_fold(prefix + ".bn", 1e-3)[1])
+        self.conv(name, x, out, w, 3, 1, 1, scale=sc, bias=bi, act=act)
+
+    def bottleneck(self, name, prefix, x, out, x1=None):
+        """Bottleneck (cspdualfpn.py:42-56): 1x1+BN+SiLU -> 3x3+BN+ReLU, + x when in == out"""
+        hidden = self._p(prefix + ".conv1.conv.weight").shape[0]
+        h = self.buf(name + ".h", hidden, x.H, x.W)
+        self.pw_bn_act(name + ".conv1", prefix + ".conv1.conv", prefix + ".conv1.bn", 1e-3, x, h, ACT_SILU, x1=x1)
+        if x1 is None and x.C == out.C:
+            t = self.buf(name + ".t", out.C, x.H, x.W)
+            self.conv3_bn_act(name + ".conv2", prefix + ".conv2", h, t, ACT_RELU)
+            self._add(name + ".add", self.lib.ach_add, t.ptr, t.bs, x.ptr, x.bs, out.ptr, out.bs, self.B, out.C, x.H * x.W,
+                      nbytes=4 * self.B * out.C * x.H * x.W * 3)
+        else:
+            self.conv3_bn_act(name + ".conv2", prefix + ".conv2", h, out, ACT_RELU)
+
+    def csp_layer(self, name, prefix, xa, xb, outc):
+        """CSPLayer over cat(xa, xb) (cspdualfpn.py:59-78); both concatenations are channel slices / two-source reads"""
+        hidden = outc // 2
+        x1 = self.buf(name + ".x1", hidden, xa.H, xa.W)
+        cat = self.buf(name + ".cat", 2 * hidden, xa.H, xa.W)
+        self.pw_bn_act(name + ".conv1", prefix + ".conv1.conv", prefix + ".conv1.bn", 1e-3, xa, x1, ACT_SILU, x1=xb)
+        self.pw_bn_act(name + ".conv2", prefix + ".conv2.conv", prefix + ".conv2.bn", 1e-3, xa, self.sl(cat, hidden, 2 * hidden), ACT_SILU, x1=xb)
+        self.bottleneck(name + ".m0", prefix + ".m.0", x1, self.sl(cat, 0, hidden))
+        out = self.buf(name + ".out", outc, xa.H, xa.W)
+        self.pw_bn_act(name + ".conv3", prefix + ".conv3.conv", prefix + ".conv3.bn", 1e-3, cat, out, ACT_SILU)
+        return out
+
+    def seg_decoder_csp(self, name, prefix, x, widths, out):
+        chans = [widths[1], widths[0], widths[0]]
+        cur = x
+        for stage, c in zip(("3_to_2", "2_to_1", "1_to_0"), chans):
+            up = self.buf(f"{name}.{stage}.up", c, cur.H * 2, cur.W * 2)
+            self.upsample_block(f"{name}.{stage}", f"{prefix}.{name}_seg_{stage}", cur, up)
+            g = self.buf(f"{name}.{stage}.bneck", c, up.H, up.W)
+            self.bottleneck(f"{name}.{stage}.bneck", f"{prefix}.{name}_seg_ghost_{stage}", up, g)
+            self.taps[f"neck.{name}_{stage}"] = g
+            cur = g
+        self.bottleneck(f"{name}.head", f"{prefix}.{name}_seg_head", cur, out)
+
+    def cdf_neck(self, feats, prefix, phi, out_se, out_lane):
+        w = Hd.WIDTHS[phi]
+        m2, m3, m4, m5 = feats
+        f5 = self.spp(m5, prefix + ".spp")
+        up4 = self.buf("fpn.up4", w[2], m4.H, m4.W)
+        self.upsample_block("fpn.up54", prefix + ".upsample_5_to_4", f5, up4)
+        f4 = self.csp_layer("fpn.c54", prefix + ".ghost_5_to_4", up4, m4, w[2])
+        up3 = self.buf("fpn.up3", w[1], m3.H, m3.W)
+        self.upsample_block("fpn.up43", prefix + ".upsample_4_to_3", f4, up3)
+        f3 = self.csp_layer("fpn.c43", prefix + ".ghost_4_to_3", up3, m3, w[1])
+        sa_lane = self.shuffle_attention("fpn.sa_lane", prefix + ".stage_3_lane_seg", f3)
+        sa_se = self.shuffle_attention("fpn.sa_se", prefix + ".stage_3_semantic_seg", f3)
+        self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
+        self.cur_lane = 3                  # the two decoders are independent of each other
+        self.wait(3, 0)
+        self.seg_decoder_csp("lane", prefix, sa_lane, w, out_lane)
+        self.cur_lane = 0
+        self.seg_decoder_csp("se", prefix, sa_se, w, out_se)
+        return (f5, m5), (f4, m4), (f3, m3)
+
     # ---- radar encoder
     def rcnet(self, x, prefix, phi):
         w = [c // 4 for c in Hd.WIDTHS[phi]]
@@ -934,7 +999,7 @@ class Engine:
             feats = self.edgenext(self.x_in, ire + ".fpn.backbone", m.phi)
         else:
             feats = self.mobilevit(self.x_in, ire + ".fpn.backbone", m.phi)
-        maps = self.gdf_neck(feats, ire + ".fpn", m.phi, out_se, out_lane)
+        maps = (self.gdf_neck if m.neck == "gdf" else self.cdf_neck)(feats, ire + ".fpn", m.phi, out_se, out_lane)
         self.cur_lane = 2                  # radar encoder: independent until the fusion stages
         self.wait(2, 0)
         radar = self.rcnet(self.r_in, ire + ".radar_encoder", m.phi)

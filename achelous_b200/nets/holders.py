@@ -357,6 +357,58 @@ class GhostDualFPN(Holder):
             setattr(self, f"{name}_seg_head", GhostModule(w[0], k))
 
 
+class Bottleneck(Holder):
+    """cspdualfpn.py:42-56 (conv1 SiLU, conv2 3x3 with BaseConv's default ReLU)"""
+
+    def __init__(self, cin, cout, shortcut=True, expansion=0.5):
+        super().__init__()
+        hidden = int(cout * expansion)
+        self.conv1 = BaseConv(cin, hidden, 1)
+        self.conv2 = BaseConv(hidden, cout, 3)
+        self.use_add = shortcut and cin == cout
+
+
+class CSPLayer(Holder):
+    """cspdualfpn.py:59-78 (n = 1)"""
+
+    def __init__(self, cin, cout, expansion=0.5):
+        super().__init__()
+        hidden = int(cout * expansion)
+        self.conv1 = BaseConv(cin, hidden, 1)
+        self.conv2 = BaseConv(cin, hidden, 1)
+        self.conv3 = BaseConv(2 * hidden, cout, 1)
+        self.m = nn.Sequential(Bottleneck(hidden, hidden, True, 1.0))
+
+
+class CSPDualFPN(Holder):
+    """cspdualfpn.py:81-191 (EN / MV backbones only)"""
+
+    def __init__(self, num_class_seg, phi, backbone):
+        super().__init__()
+        w = WIDTHS[phi]
+        if backbone == "en":
+            self.backbone = EdgeNeXt(phi)
+        elif backbone == "mv":
+            self.backbone = MobileViT(phi)
+        else:
+            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en' and 'mv' (SURVEY.md §8b)")
+        self.spp = SPP(w[3], w[3])
+        self.upsample_5_to_4 = Upsample(w[3], w[2])
+        self.ghost_5_to_4 = CSPLayer(w[2] * 2, w[2])
+        self.upsample_4_to_3 = Upsample(w[2], w[1])
+        self.ghost_4_to_3 = CSPLayer(w[1] * 2, w[1])
+        self.stage_3_lane_seg = ShuffleAttention(w[1], 4)
+        self.stage_3_semantic_seg = ShuffleAttention(w[1], 4)
+        for name, k in (("lane", 2), ("se", num_class_seg)):
+            setattr(self, f"{name}_seg_3_to_2", Upsample(w[1], w[1]))
+            setattr(self, f"{name}_seg_ghost_3_to_2", Bottleneck(w[1], w[1]))
+            setattr(self, f"{name}_seg_2_to_1", Upsample(w[1], w[0]))
+            setattr(self, f"{name}_seg_ghost_2_to_1", Bottleneck(w[0], w[0]))
+            setattr(self, f"{name}_seg_1_to_0", Upsample(w[0], w[0]))
+            setattr(self, f"{name}_seg_ghost_1_to_0", Bottleneck(w[0], w[0]))
+            setattr(self, f"{name}_seg_head", Bottleneck(w[0], k))
+
+
 class ECA(Holder):
     """eca.py:5-14"""
 
@@ -372,10 +424,10 @@ class IREncoder(Holder):
 
     def __init__(self, num_class_seg, phi, backbone, neck, radar_channels=3):
         super().__init__()
-        if neck != "gdf":
-            raise NotImplementedError(f"neck={neck!r}: achelous_b200 implements 'gdf' (SURVEY.md §8b)")
+        if neck not in ("gdf", "cdf"):
+            raise NotImplementedError(f"neck={neck!r}: achelous_b200 implements 'gdf' and 'cdf' (SURVEY.md §8b, §8f rank 3)")
         w = WIDTHS[phi]
-        self.fpn = GhostDualFPN(num_class_seg, phi, backbone)
+        self.fpn = (GhostDualFPN if neck == "gdf" else CSPDualFPN)(num_class_seg, phi, backbone)
         self.radar_encoder = RCNet(radar_channels, phi)
         for s, c in zip((3, 4, 5), w[1:]):
             setattr(self, f"channel_attn_stage{s}", nn.ModuleList([ECA(c), ECA(c // 4)]))

@@ -419,9 +419,50 @@ def ghost_dual_fpn(x, p, phi, backbone, num_seg, taps=None):
     return se, lane, (f5 + m5, f4 + m4, f3 + m3)
 
 
-def ir_encoder(x, x_radar, p, phi, backbone, num_seg, taps=None):
-    """IREncoder.forward.  backbone/IREncoder.py:72-91"""
-    se, lane, (map5, map4, map3) = ghost_dual_fpn(x, p.sub("fpn"), phi, backbone, num_seg, taps)
+def bottleneck(x, p, add):
+    """Bottleneck: BaseConv 1x1 (SiLU) -> BaseConv 3x3 (BaseConv's default ReLU), + x when in == out.  cspdualfpn.py:42-56"""
+    y = base_conv(base_conv(x, p.sub("conv1"), 1, "silu"), p.sub("conv2"), 3, "relu")
+    return y + x if add else y
+
+
+def csp_layer(x, p):
+    """CSPLayer (n = 1, expansion 0.5, SiLU).  cspdualfpn.py:59-78"""
+    x1 = base_conv(x, p.sub("conv1"), 1, "silu")
+    x2 = base_conv(x, p.sub("conv2"), 1, "silu")
+    x1 = bottleneck(x1, p.sub("m.0"), True)
+    return base_conv(torch.cat((x1, x2), 1), p.sub("conv3"), 1, "silu")
+
+
+def seg_decoder_csp(x, p, name, num_out, taps=None):
+    """One segmentation decoder of the CSP neck: Upsample -> Bottleneck x3, Bottleneck head.  cspdualfpn.py:213-237"""
+    for stage in ("3_to_2", "2_to_1", "1_to_0"):
+        x = upsample_block(x, p.sub(f"{name}_seg_{stage}"))
+        x = bottleneck(x, p.sub(f"{name}_seg_ghost_{stage}"), True)
+        if taps is not None:
+            taps[f"neck.{name}_{stage}"] = x
+    return bottleneck(x, p.sub(f"{name}_seg_head"), x.shape[1] == num_out)
+
+
+def csp_dual_fpn(x, p, phi, backbone, num_seg, taps=None):
+    """CSPDualFPN.forward.  cspdualfpn.py:193-239"""
+    bb = p.sub("backbone")
+    m2, m3, m4, m5 = edgenext(x, bb, phi, taps) if backbone == "en" else mobilevit(x, bb, phi, taps)
+    f5 = spp(m5, p.sub("spp"))
+    f4 = csp_layer(torch.cat([upsample_block(f5, p.sub("upsample_5_to_4")), m4], 1), p.sub("ghost_5_to_4"))
+    f3 = csp_layer(torch.cat([upsample_block(f4, p.sub("upsample_4_to_3")), m3], 1), p.sub("ghost_4_to_3"))
+    f3_lane = shuffle_attention(f3, p.sub("stage_3_lane_seg"))
+    f3_se = shuffle_attention(f3, p.sub("stage_3_semantic_seg"))
+    if taps is not None:
+        taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": f3_lane, "neck.sa_se": f3_se})
+    lane = seg_decoder_csp(f3_lane, p, "lane", 2, taps)
+    se = seg_decoder_csp(f3_se, p, "se", num_seg, taps)
+    return se, lane, (f5 + m5, f4 + m4, f3 + m3)
+
+
+def ir_encoder(x, x_radar, p, phi, backbone, num_seg, taps=None, neck="gdf"):
+    """IREncoder.forward.  backbone/IREncoder.py:72-91 (neck selection :33-41)"""
+    fpn = {"gdf": ghost_dual_fpn, "cdf": csp_dual_fpn}[neck]
+    se, lane, (map5, map4, map3) = fpn(x, p.sub("fpn"), phi, backbone, num_seg, taps)
     r3, r4, r5 = rcnet(x_radar, p.sub("radar_encoder"), taps)
     outs = []
     for s, m, r in ((3, map3, r3), (4, map4, r4), (5, map5, r5)):
@@ -493,7 +534,7 @@ def pointnet_seg(x, p, taps=None):
 
 
 # ----------------------------------------------------------------------------- facade
-def achelous_forward(sd, x, x_radar, x_pc, phi="S0", backbone="en", num_seg=9, pc_seg="pn", taps=None):
+def achelous_forward(sd, x, x_radar, x_pc, phi="S0", backbone="en", num_seg=9, pc_seg="pn", taps=None, neck="gdf"):
     """Achelous.forward -> (det[3], se_seg, lane_seg, pc_seg).  nets/Achelous.py:49-53"""
     p = SD(sd)
     with torch.no_grad():
@@ -504,6 +545,6 @@ def achelous_forward(sd, x, x_radar, x_pc, phi="S0", backbone="en", num_seg=9, p
             pc = pointnet2_seg(x_pc, p.sub("pc_seg_model"), taps)
         else:
             pc = None
-        fpn_out, se, lane = ir_encoder(x, x_radar, p.sub("image_radar_encoder"), phi, backbone, num_seg, taps)
+        fpn_out, se, lane = ir_encoder(x, x_radar, p.sub("image_radar_encoder"), phi, backbone, num_seg, taps, neck)
         det = decouple_head(fpn_out, p.sub("det_head"))
     return det, se, lane, pc

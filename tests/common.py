@@ -12,7 +12,14 @@ GOLDEN_CONFIGS = {
     "en_gdf_pn_s0": ("S0", "en", 2, 11),
     "en_gdf_pn_s2": ("S2", "en", 0, 12),
     "mv_gdf_pn_s0": ("S0", "mv", 0, 13),
+    "en_cdf_pn_s0": ("S0", "en", 3, 14),   # CSP-Dual-FPN neck
 }
+GOLDEN_NECK = {"en_cdf_pn_s0": "cdf"}      # every other config uses the Ghost-Dual-FPN
+
+
+def neck_of(name):
+    return GOLDEN_NECK.get(name, "gdf")
+
 MODEL_KW = dict(num_det=7, num_seg=9, resolution=320, neck="gdf", pc_seg="pn", pc_channels=5, pc_classes=8,
                 nano_head=True, spp=True)
 WH_BIAS = 1.3

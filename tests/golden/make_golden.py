@@ -30,8 +30,9 @@ CONFIGS = {
     "en_gdf_pn_s0": dict(phi="S0", backbone="en", weight_seed=2, input_seed=11),
     "en_gdf_pn_s2": dict(phi="S2", backbone="en", weight_seed=0, input_seed=12),
     "mv_gdf_pn_s0": dict(phi="S0", backbone="mv", weight_seed=0, input_seed=13),
+    "en_cdf_pn_s0": dict(phi="S0", backbone="en", weight_seed=3, input_seed=14, neck="cdf"),
 }
-MODEL_KW = dict(num_det=7, num_seg=9, resolution=320, neck="gdf", pc_seg="pn", pc_channels=5, pc_classes=8,
+MODEL_KW = dict(num_det=7, num_seg=9, resolution=320, pc_seg="pn", pc_channels=5, pc_classes=8,
                 nano_head=True, spp=True)
 WH_BIAS = 1.3  # widens boxes to ~3.7 cells so that NMS actually suppresses
 TARGET_CANDIDATES = 120  # obj logits are shifted so ~this many anchors/img pass conf >= 0.35
@@ -83,8 +84,11 @@ def summarize(t, n=512):
 def main():
     ns = load_reference()
     torch.set_num_threads(max(1, os.cpu_count() // 2))
+    only = set(sys.argv[1:])       # python tests/golden/make_golden.py [config ...]: regenerate just those
     for name, cfg in CONFIGS.items():
-        model = ns.Achelous(phi=cfg["phi"], backbone=cfg["backbone"], **MODEL_KW).eval()
+        if only and name not in only:
+            continue
+        model = ns.Achelous(phi=cfg["phi"], backbone=cfg["backbone"], neck=cfg.get("neck", "gdf"), **MODEL_KW).eval()
         sd0 = model.state_dict()
         with open(os.path.join(HERE, name + ".keys.json"), "w") as f:
             json.dump({k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd0.items()}, f, indent=0)

@@ -14,10 +14,11 @@ from tests.common import MODEL_KW, argmax_mismatch, rel_err
 TOL = 5e-5
 
 
-@pytest.mark.parametrize("phi,backbone,seed,fuse,tc", [("S0", "en", 2, True, "all"), ("S0", "en", 2, False, False), ("S2", "en", 0, True, True), ("S0", "mv", 0, True, True)])
-def test_plan_matches_oracle(phi, backbone, seed, fuse, tc):
+@pytest.mark.parametrize("phi,backbone,seed,fuse,tc,neck", [("S0", "en", 2, True, "all", "gdf"), ("S0", "en", 2, False, False, "gdf"), ("S2", "en", 0, True, True, "gdf"),
+                                                             ("S0", "mv", 0, True, True, "gdf"), ("S0", "en", 3, True, True, "cdf")])
+def test_plan_matches_oracle(phi, backbone, seed, fuse, tc, neck):
     torch.set_num_threads(4)
-    model = Achelous(phi=phi, backbone=backbone, **MODEL_KW).eval()
+    model = Achelous(phi=phi, backbone=backbone, **dict(MODEL_KW, neck=neck)).eval()
     model.fuse_seg_decoder = fuse
     model.fuse_seg_chain = fuse and phi == "S0" and backbone == "en" and tc == "all" or (phi == "S2")
     model.use_tensor_cores = tc
@@ -31,7 +32,7 @@ def test_plan_matches_oracle(phi, backbone, seed, fuse, tc):
     emulate_engine(eng)
     det, se, lane, pcs = eng.output_views()
     taps = {}
-    o_det, o_se, o_lane, o_pc = OF.achelous_forward(sd, x, xr, pc, phi=phi, backbone=backbone, taps=taps)
+    o_det, o_se, o_lane, o_pc = OF.achelous_forward(sd, x, xr, pc, phi=phi, backbone=backbone, taps=taps, neck=neck)
     for name in eng.taps:
         assert rel_err(eng.tap(name), taps[name]) < TOL, name
     for i in range(3):

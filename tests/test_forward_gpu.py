@@ -17,7 +17,7 @@ from achelous_b200.nets.Achelous import Achelous, Achelous3T
 from achelous_b200.synthetic import make_inputs
 from achelous_b200.weights import fill_state_dict
 from oracle import functional as OF
-from tests.common import (GOLDEN_CONFIGS, MODEL_KW, REL_TOL, argmax_mismatch, load_golden, rel_err, summarize,
+from tests.common import (GOLDEN_CONFIGS, neck_of, MODEL_KW, REL_TOL, argmax_mismatch, load_golden, rel_err, summarize,
                           summary_rel_err)
 
 pytestmark = pytest.mark.gpu
@@ -26,8 +26,8 @@ TIGHT = 2e-4
 SUPPORTED = list(GOLDEN_CONFIGS)
 
 
-def build(phi, bb, wseed, graph=True, fuse="chain", tc=True):
-    model = Achelous(phi=phi, backbone=bb, **MODEL_KW).eval()
+def build(phi, bb, wseed, graph=True, fuse="chain", tc=True, neck="gdf"):
+    model = Achelous(phi=phi, backbone=bb, **dict(MODEL_KW, neck=neck)).eval()
     model.fuse_seg_decoder = bool(fuse)
     model.fuse_seg_chain = fuse == "chain"
     model.use_tensor_cores = tc
@@ -41,7 +41,7 @@ def build(phi, bb, wseed, graph=True, fuse="chain", tc=True):
 @pytest.mark.parametrize("name", SUPPORTED)
 def test_forward_vs_golden_and_oracle(name, fuse, tc):
     phi, bb, wseed, iseed = GOLDEN_CONFIGS[name]
-    model, sd = build(phi, bb, wseed, fuse=fuse, tc=tc)
+    model, sd = build(phi, bb, wseed, fuse=fuse, tc=tc, neck=neck_of(name))
     x, xr, pc = make_inputs(2, seed=iseed)
     det, se, lane, pcs = model(x.cuda(), xr.cuda(), pc.cuda())
     torch.cuda.synchronize()
@@ -62,7 +62,7 @@ def test_forward_vs_golden_and_oracle(name, fuse, tc):
     assert (z_ref != z_mine).mean() < 1e-3
     # (a) per-block taps against the oracle
     taps = {}
-    OF.achelous_forward(sd, x, xr, pc, phi=phi, backbone=bb, taps=taps)
+    OF.achelous_forward(sd, x, xr, pc, phi=phi, backbone=bb, taps=taps, neck=neck_of(name))
     eng = next(iter(model._engines.values()))
     worst = {}
     for tname in eng.taps:

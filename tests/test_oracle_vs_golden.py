@@ -8,7 +8,7 @@ from achelous_b200.synthetic import make_inputs
 from achelous_b200.weights import fill_state_dict
 from oracle import functional as OF
 from oracle import postprocess as OP
-from tests.common import (GOLDEN_CONFIGS, WH_BIAS, argmax_mismatch, load_golden, load_keys, rel_err, summarize,
+from tests.common import (GOLDEN_CONFIGS, neck_of, WH_BIAS, argmax_mismatch, load_golden, load_keys, rel_err, summarize,
                           summary_rel_err)
 
 TOL = 2e-5  # oracle vs reference: same fp32 ATen ops, different op order in a few places
@@ -22,7 +22,7 @@ def run(request):
     x, xr, pc = make_inputs(2, seed=iseed)
     taps = {}
     torch.set_num_threads(4)
-    out = OF.achelous_forward(sd, x, xr, pc, phi=phi, backbone=bb, taps=taps)
+    out = OF.achelous_forward(sd, x, xr, pc, phi=phi, backbone=bb, taps=taps, neck=neck_of(name))
     return name, load_golden(name), out, taps
 
 
