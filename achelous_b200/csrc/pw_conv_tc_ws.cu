@@ -32,15 +32,21 @@
 
 namespace ach {
 
-constexpr int WS_SA = 4;        // A-operand stages in tensor memory (32 columns each)
+// Tile-width dependent shape of a CTA.  Narrow tiles (NT <= 64) run with ONE producer/epilogue thread per pixel
+// (128 threads + MMA warp + loader warp = 192) and two A stages, so that TMEM (<= 128 columns), registers and shared
+// memory admit 3-4 resident CTAs per SM; NT = 128 keeps two threads per pixel (half the columns / k each) and 2 CTAs.
+// Measured: halving the resident CTAs (a deeper ring that no longer fitted twice) cost 58 % on the K=128 -> 32 layers -
+// CTA-level overlap of produce / MMA wait / epilogue phases is what hides the serial chain inside one CTA.
+__host__ __device__ constexpr int ws_halves(int nt) { return nt == 128 ? 2 : 1; }
+__host__ __device__ constexpr int ws_sa(int nt) { return nt == 128 ? 4 : 2; }   // A-operand stages in tensor memory (32 columns each)
 constexpr int WS_SB = 4;        // weight ring stages
 constexpr int WS_PF = 2;        // weight chunks in flight ahead of the MMA
-constexpr int WS_PROD = 256;    // producer / epilogue threads (8 warps); warp 8 is the MMA warp, warp 9 the activation loader
-constexpr int WS_THREADS = WS_PROD + 64;
-__host__ __device__ constexpr int ws_sg(int nt) { return nt == 128 ? 5 : 8; }   // activation ring depth (8 KB per stage)
+__host__ __device__ constexpr int ws_prod(int nt) { return 128 * ws_halves(nt); }   // producer / epilogue threads; then the MMA warp, then the loader warp
+__host__ __device__ constexpr int ws_threads(int nt) { return ws_prod(nt) + 64; }
+__host__ __device__ constexpr int ws_sg(int nt) { return nt == 32 ? 6 : 5; }   // activation ring depth (8 KB per stage), sized so that 3 narrow CTAs fit an SM
 
 __host__ __device__ constexpr int ws_tmem_cols(int nt) {   // accumulator + A stages, rounded up to a power of two >= 32
-    const int need = nt + WS_SA * 32;
+    const int need = nt + ws_sa(nt) * 32;
     return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
 }
 
@@ -58,22 +64,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(mbar)
                  : "memory");
 }
-__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n"(WS_PROD) : "memory"); }
+template <int N_THREADS>
+__device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N_THREADS) : "memory"); }
 
 template <int NT, int ACT, bool RES>
-__global__ void __launch_bounds__(WS_THREADS, 2)
+__global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
     pw_conv_tc_ws_kernel(const AchPwConv p, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
                          const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int B_ELEMS = NT * TC_KC;
     constexpr int SG = ws_sg(NT);
+    constexpr int WS_SA = ws_sa(NT), HALVES = ws_halves(NT), WS_PROD = ws_prod(NT);
+    constexpr int KPT = TC_KC / HALVES;                                   // k per producer thread and chunk (8 or 16)
     constexpr int G_ELEMS = TC_KC * TC_M;                                // fp32 activation chunk: [16 channels][128 pixels]
     float* b_ring = reinterpret_cast<float*>(smem_raw);                  // [SB][b_hi | b_lo]
     float* g_ring = b_ring + WS_SB * 2 * B_ELEMS;                        // [SG][16][128]
     __shared__ __align__(8) uint64_t bar_full_a[WS_SA], bar_full_b[WS_SB], bar_mma[WS_SA], bar_acc_full, bar_acc_empty;
     __shared__ __align__(8) uint64_t bar_g_full[SG], bar_g_empty[SG];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_ln[2][TC_M][2];
+    __shared__ float s_ln[HALVES][TC_M][2];
     __shared__ __align__(16) float4 s_ep[NT];   // per output of the current tile: {scale, scale*wsum, bias + scale*pbias, gamma}
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -228,14 +237,12 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                 const float* gs = g_ring + g * G_ELEMS + px;
                 const int k0 = c * TC_KC;
                 if (p.ln && c == 0) shift = cur.p_ok ? gs[0] : 0.f;
-                float v0[2][4];
+                float v0[KPT];
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int kl = (2 * half + jj) * 4 + e;
-                        v0[jj][e] = (cur.p_ok && k0 + kl < K) ? gs[kl * TC_M] : 0.f;   // rows past K / pixels past P were not copied
-                    }
+                for (int e = 0; e < KPT; ++e) {
+                    const int kl = half * KPT + e;
+                    v0[e] = (cur.p_ok && k0 + kl < K) ? gs[kl * TC_M] : 0.f;   // rows past K / pixels past P were not copied
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bar_g_empty[g]));
                 const uint32_t sa = it % WS_SA;
@@ -243,29 +250,27 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                     mbar_wait(smem_u32(&bar_mma[sa]), (it / WS_SA - 1u) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                uint32_t hi[8], lo[8];
+                uint32_t hi[KPT], lo[KPT];
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int j = 2 * half + jj;
+                for (int e = 0; e < KPT; ++e) {
                     if (p.ln) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float d = (k0 + j * 4 + e < K && cur.p_ok) ? v0[jj][e] - shift : 0.f;
-                            s1 += d;
-                            s2 = fmaf(d, d, s2);
-                        }
+                        const float d = (k0 + half * KPT + e < K && cur.p_ok) ? v0[e] - shift : 0.f;
+                        s1 += d;
+                        s2 = fmaf(d, d, s2);
                     }
                     // x = hi + lo with hi = x truncated to tf32 (1 LOP3; the MMA ignores the low 13 mantissa bits anyway) and
                     // lo = x - hi exact in fp32
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        hi[jj * 4 + e] = __float_as_uint(v0[jj][e]) & 0xffffe000u;
-                        lo[jj * 4 + e] = __float_as_uint(v0[jj][e] - __uint_as_float(hi[jj * 4 + e]));
-                    }
+                    hi[e] = __float_as_uint(v0[e]) & 0xffffe000u;
+                    lo[e] = __float_as_uint(v0[e] - __uint_as_float(hi[e]));
                 }
-                const uint32_t a_t = t_lane + (uint32_t)(A_COL0 + sa * 32 + half * 8);
-                tmem_st8(a_t, hi);
-                tmem_st8(a_t + 16u, lo);
+                const uint32_t a_t = t_lane + (uint32_t)(A_COL0 + sa * 32 + half * KPT);
+                if constexpr (KPT == 8) {
+                    tmem_st8(a_t, hi);
+                    tmem_st8(a_t + 16u, lo);
+                } else {
+                    tmem_st16(a_t, hi);
+                    tmem_st16(a_t + 16u, lo);
+                }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // TMEM writes -> ordered before the MMA thread's reads
                 __syncwarp();
@@ -291,17 +296,17 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
                 s_ln[half][px][0] = s1;
                 s_ln[half][px][1] = s2;
             }
-            prod_bar();
+            prod_bar<WS_PROD>();
             // y = act(rs * (scale*acc) - ms * (scale*wsum) + c)  with rs = rstd, ms = mean*rstd   (rs = 1, ms = 0 without LayerNorm)
             float rs = 1.f, ms = 0.f;
             if (p.ln) {
-                const float t1 = (s_ln[0][px][0] + s_ln[1][px][0]) / (float)K;
-                const float t2 = (s_ln[0][px][1] + s_ln[1][px][1]) / (float)K;
+                const float t1 = (s_ln[0][px][0] + (HALVES == 2 ? s_ln[HALVES - 1][px][0] : 0.f)) / (float)K;
+                const float t2 = (s_ln[0][px][1] + (HALVES == 2 ? s_ln[HALVES - 1][px][1] : 0.f)) / (float)K;
                 rs = 1.0f / sqrtf(fmaxf(t2 - t1 * t1, 0.f) + p.ln_eps);
                 ms = (shift + t1) * rs;
             }
             // ---- epilogue: thread = pixel (TMEM lane 32*(warp%4) + lane); this half's NT/2 columns, 16 at a time
-            constexpr int NH = NT / 2;
+            constexpr int NH = NT / HALVES;
             const int pp = done.pp;
             float* optr = p.out + (long long)done.b * p.out_bs + (long long)(done.o_base + half * NH) * P + pp;
             const float* rptr = RES ? p.res + (long long)done.b * p.res_bs + (long long)(done.o_base + half * NH) * P + pp : nullptr;
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty));
-            prod_bar();
+            prod_bar<WS_PROD>();
             item = next;
         }
     }
@@ -407,14 +412,14 @@ static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, c
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT, RES>, WS_THREADS, smem, ws_tmem_cols(NT));
+        const int per_sm = tc_ctas_per_sm(pw_conv_tc_ws_kernel<NT, ACT, RES>, ws_threads(NT), smem, ws_tmem_cols(NT));
         ctas_per_wave = sms * (per_sm < 1 ? 1 : per_sm);
     }
     const int n_pt = cdiv(p.P, TC_M), n_ot = cdiv(p.O, NT);
     const long long total = (long long)n_pt * n_ot * p.B;
     ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
-    pw_conv_tc_ws_kernel<NT, ACT, RES><<<grid, WS_THREADS, smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
+    pw_conv_tc_ws_kernel<NT, ACT, RES><<<grid, ws_threads(NT), smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
     return check_launch("ach_pw_conv_tc");
 }
 
