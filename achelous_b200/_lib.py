@@ -40,6 +40,11 @@ class AchConvDense(C.Structure):
                 ("stride", I), ("pad", I), ("act", I), ("ln_out", I), ("ln_eps", F)]
 
 
+class AchConv3x3Tc(C.Structure):
+    _fields_ = [("x", VP), ("scale", VP), ("bias", VP), ("res", VP), ("out", VP), ("x_bs", LL), ("res_bs", LL), ("out_bs", LL),
+                ("B", I), ("Cin", I), ("H", I), ("W", I), ("O", I), ("act", I)]
+
+
 class AchRcDeform(C.Structure):
     _fields_ = [("x", VP), ("pooled", VP), ("w_om", VP), ("b_om", VP), ("w_reg", VP), ("w1", VP), ("scale", VP),
                 ("bias", VP), ("out", VP), ("x_bs", LL), ("pooled_bs", LL), ("out_bs", LL),
@@ -99,6 +104,8 @@ _SIGNATURES = {
     "ach_pn2_interp3": ([VP, LL, VP, LL, VP, LL, I, I, I, I, VP, LL, VP], I),
     "ach_seg_softmax": ([VP, LL, VP, LL, I, I, I, VP], I),
     "ach_seg_resize_argmax": ([VP, LL, I, I, I, I, I, I, I, I, VP, I, I, VP], I),
+    "ach_conv3x3_tc_k": ([I], I),
+    "ach_conv3x3_tc": ([C.POINTER(AchConv3x3Tc), VP, VP, VP], I),
     "ach_pre_resize_h": ([VP, LL, I, I, I, I, I, VP, VP, I, VP, LL, VP], I),
     "ach_pre_resize_v_norm": ([VP, LL, I, I, I, VP, VP, I, I, VP, LL, I, I, I, I, VP], I),
     "ach_pre_radar": ([VP, LL, I, I, LL, VP, LL, VP], I),

@@ -16,7 +16,7 @@ from collections import namedtuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost,
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConv3x3Tc, AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost,
                    AchUpGhostHead, AchUpGhostPw2)
 from .nets import holders as Hd
 
@@ -214,6 +214,33 @@ class Engine:
         self._keep.append(s)
         nb = 4 * (self.B * (x.C * x.H * x.W + out.C * out.H * out.W) + w.numel())
         self._add(name, self.lib.ach_conv_dense, C.byref(s), nbytes=nb)
+
+    def conv3_tc(self, name, x, out, wname, scale=None, bias=None, act=ACT_NONE, res=None):
+        """3x3 / stride 1 / pad 1 dense conv as an implicit GEMM on tcgen05 (conv3x3_tc.cu); `res` is added after the activation"""
+        cin, O = x.C, out.C
+        kpad = self.lib.ach_conv3x3_tc_k(cin)
+
+        def wt(wname=wname, cin=cin, O=O, kpad=kpad):   # rows k = (g*9 + tap)*16 + c for channel 16g + c
+            w = self._p(wname)
+            wp = torch.zeros(O, kpad // 9, 9, dtype=w.dtype, device=w.device)
+            wp[:, :cin] = w.reshape(O, cin, 9)
+            m = wp.reshape(O, kpad // 144, 16, 9).permute(1, 3, 2, 0).reshape(kpad, O)
+            return torch.nn.functional.pad(m, (0, _ceil4(O) - O))
+        w_t = self._w(name + ".wt3", wt)
+        n_ = self.lib.ach_pack_pw_tc_elems(kpad, O)
+        hi = torch.zeros(n_, device=self.device, dtype=torch.float32)
+        lo = torch.zeros(n_, device=self.device, dtype=torch.float32)
+        self._keep += [hi, lo]
+        self.pack_ops.append((self.lib.ach_pack_pw_tc, (w_t.data_ptr(), kpad, O, w_t.shape[-1], hi.data_ptr(), lo.data_ptr())))
+        s = AchConv3x3Tc()
+        s.x, s.x_bs, s.out, s.out_bs = x.ptr, x.bs, out.ptr, out.bs
+        s.scale, s.bias = self._ptr(scale), self._ptr(bias)
+        if res is not None:
+            s.res, s.res_bs = res.ptr, res.bs
+        s.B, s.Cin, s.H, s.W, s.O, s.act = self.B, cin, x.H, x.W, O, act
+        self._keep.append(s)
+        nb = 4 * (self.B * x.H * x.W * (cin + O * (2 if res is not None else 1)) + kpad * O)
+        self._add(name, self.lib.ach_conv3x3_tc, C.byref(s), hi.data_ptr(), lo.data_ptr(), nbytes=nb)
 
     def _pack_conv(self, key, wname):
         """(O, Cin, k, k) -> [Cin][k*k][ceil4(O)]"""
@@ -418,7 +445,10 @@ class Engine:
         else:
             sc = self._vec(name + ".s", lambda: self._bn_fold(prefix + ".1", 1e-5)[0])
             bi = self._vec(name + ".b", lambda: self._bn_fold(prefix + ".1", 1e-5)[1])
-            self.conv(name, x, out, self._pack_conv(name + ".w", prefix + ".0.weight"), k, stride, 1, scale=sc, bias=bi, act=ACT_SILU)
+            if k == 3 and stride == 1 and self.model.use_tensor_cores:
+                self.conv3_tc(name, x, out, prefix + ".0.weight", scale=sc, bias=bi, act=ACT_SILU)
+            else:
+                self.conv(name, x, out, self._pack_conv(name + ".w", prefix + ".0.weight"), k, stride, 1, scale=sc, bias=bi, act=ACT_SILU)
 
     def mv2(self, name, prefix, x, out, stride, expansion):
         """MV2Block: pw+BN+SiLU -> dw3x3(stride)+BN+SiLU -> pw+BN (+x)  (mobilevit.py:93-131)"""
@@ -642,12 +672,16 @@ class Engine:
         return (f5, m5), (f4, m4), (f3, m3)
 
     # ---- CSP-Dual-FPN neck (neck/cspdualfpn.py)
-    def conv3_bn_act(self, name, prefix, x, out, act):
-        """BaseConv with a 3x3 kernel: conv (no bias) + BN(1e-3) + act (normal_conv.py:36-49)"""
-        w = self._pack_conv(name + ".w", prefix + ".conv.weight")
+    def conv3_bn_act(self, name, prefix, x, out, act, res=None):
+        """BaseConv with a 3x3 kernel: conv (no bias) + BN(1e-3) + act (normal_conv.py:36-49); returns True when `res` was
+        added by the kernel (tensor-core path), False when the caller still has to add it"""
         sc = self._vec(name + ".s", lambda: self._bn_fold(prefix + ".bn", 1e-3)[0])
         bi = self._vec(name + ".b", lambda: self._bn_fold(prefix + ".bn", 1e-3)[1])
-        self.conv(name, x, out, w, 3, 1, 1, scale=sc, bias=bi, act=act)
+        if self.model.use_tensor_cores and x.C >= 12:   # below ~12 input channels the 16-wide K chunks are mostly padding
+            self.conv3_tc(name, x, out, prefix + ".conv.weight", scale=sc, bias=bi, act=act, res=res)
+            return True
+        self.conv(name, x, out, self._pack_conv(name + ".w", prefix + ".conv.weight"), 3, 1, 1, scale=sc, bias=bi, act=act)
+        return False
 
     def bottleneck(self, name, prefix, x, out, x1=None):
         """Bottleneck (cspdualfpn.py:42-56): 1x1+BN+SiLU -> 3x3+BN+ReLU, + x when in == out"""
@@ -655,6 +689,9 @@ class Engine:
         h = self.buf(name + ".h", hidden, x.H, x.W)
         self.pw_bn_act(name + ".conv1", prefix + ".conv1.conv", prefix + ".conv1.bn", 1e-3, x, h, ACT_SILU, x1=x1)
         if x1 is None and x.C == out.C:
+            if self.model.use_tensor_cores and h.C >= 12:      # the "+ x" shortcut rides in the implicit-GEMM epilogue
+                self.conv3_bn_act(name + ".conv2", prefix + ".conv2", h, out, ACT_RELU, res=x)
+                return
             t = self.buf(name + ".t", out.C, x.H, x.W)
             self.conv3_bn_act(name + ".conv2", prefix + ".conv2", h, t, ACT_RELU)
             self._add(name + ".add", self.lib.ach_add, t.ptr, t.bs, x.ptr, x.bs, out.ptr, out.bs, self.B, out.C, x.H * x.W,

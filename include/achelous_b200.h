@@ -123,6 +123,24 @@ typedef struct AchConvDense {
 } AchConvDense;
 ACH_API int ach_conv_dense(const AchConvDense* p, void* stream);
 
+/* Dense 3x3 convolution, stride 1, pad 1, as an implicit GEMM on tcgen05 (3xTF32, fp32-accurate):
+ *   out[b, o, y, x] = act(scale[o] * sum_{c, i, j} w[o, c, i, j] * x[b, c, y-1+i, x-1+j] + bias[o]) (+ res[b, o, y, x])
+ * Replaces BaseConv(ksize=3) of the CSP Bottlenecks (neck/cspdualfpn.py:42-56 incl. the "+ x" shortcut, normal_conv.py:36-49)
+ * and conv_nxn_bn of the MobileViT blocks (mobilevit.py:14-21).  Weights: ach_pack_pw_tc tiles of a K-major matrix
+ * [ach_conv3x3_tc_k(Cin)][ldw >= O] whose rows are ordered k = (g * 9 + tap) * 16 + c for input channel 16 g + c, tap = 3 i + j
+ * (zero rows past Cin). */
+typedef struct AchConv3x3Tc {
+    const float* x;
+    const float* scale;
+    const float* bias;
+    const float* res;
+    float* out;
+    long long x_bs, res_bs, out_bs;
+    int B, Cin, H, W, O, act;
+} AchConv3x3Tc;
+ACH_API int ach_conv3x3_tc_k(int Cin);
+ACH_API int ach_conv3x3_tc(const AchConv3x3Tc* p, const float* w_hi, const float* w_lo, void* stream);
+
 /* Channels-first LayerNorm over C for every (b, p): layers.py:21-26 (biased variance). */
 ACH_API int ach_layernorm_cf(const float* x, long long x_bs, const float* w, const float* b, float* out, long long out_bs,
                      int B, int C, int P, float eps, void* stream);

@@ -167,6 +167,23 @@ def ach_conv_dense(s):
     fview(s.out, (B, O, s.Ho, s.Wo), (s.out_bs, s.Ho * s.Wo, s.Wo, 1)).copy_(y)
 
 
+def ach_conv3x3_tc(s, w_hi, w_lo):
+    B, Cin, H, W, O = s.B, s.Cin, s.H, s.W, s.O
+    kpad = -(-Cin // 16) * 144
+    m = _tc_unpack(w_hi, w_lo, kpad, O)                                       # rows k = (g*9 + tap)*16 + c
+    w = m.reshape(kpad // 144, 9, 16, O).permute(3, 0, 2, 1).reshape(O, kpad // 9, 3, 3)[:, :Cin]
+    x = fview(s.x, (B, Cin, H, W), (s.x_bs, H * W, W, 1))
+    y = F.conv2d(x, w, None, 1, 1)
+    if s.scale:
+        y = y * _vec(s.scale, O)[None, :, None, None]
+    if s.bias:
+        y = y + _vec(s.bias, O)[None, :, None, None]
+    y = _act(y, s.act)
+    if s.res:
+        y = y + fview(s.res, (B, O, H, W), (s.res_bs, H * W, W, 1))
+    fview(s.out, (B, O, H, W), (s.out_bs, H * W, W, 1)).copy_(y)
+
+
 def ach_layernorm_cf(x, x_bs, w, b, out, out_bs, B, Cc, P, eps):
     xv = fview(x, (B, Cc, P), (x_bs, P, 1))
     u = xv.mean(1, keepdim=True)
@@ -436,7 +453,7 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc)}
 
 
 def _unwrap(a):

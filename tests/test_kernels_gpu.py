@@ -667,3 +667,36 @@ def test_up_ghost_pw2(Ci, h, w):
         s.B, s.Ci, s.C1, s.N2, s.h, s.w = B, Ci, C1, N2, h, w
         return (s,)
     run_both("ach_up_ghost_pw2", make, ["out"])
+
+
+@pytest.mark.parametrize("Cin,O,H,W,act,res", [(16, 32, 40, 48, 1, 1), (24, 48, 24, 24, 1, 1), (4, 9, 33, 21, 1, 0), (1, 2, 16, 16, 1, 0),
+                                               (48, 48, 20, 20, 1, 1), (96, 96, 20, 20, 2, 0), (160, 80, 10, 10, 2, 0), (16, 32, 320, 320, 1, 1),
+                                               (40, 130, 12, 20, 0, 0)])
+def test_conv3x3_tc(Cin, O, H, W, act, res):
+    """implicit-GEMM 3x3 conv on tcgen05 vs F.conv2d (emulator): CSP Bottleneck / MobileViT shapes, ragged tiles, channel
+    counts that are not multiples of 16, several output tiles (O > 128), residual epilogue"""
+    B = 2 if H < 100 else 1
+    lib = _lib.load()
+    kpad = lib.ach_conv3x3_tc_k(Cin)
+    ldw = (O + 3) // 4 * 4
+    n_el = lib.ach_pack_pw_tc_elems(kpad, O)
+
+    def make(A):
+        A.new("x", R(B, Cin, H, W)), A.new("out", torch.zeros(B, O, H, W))
+        w = R(O, Cin, 3, 3) / (Cin * 9) ** 0.5
+        wp = torch.zeros(O, kpad // 9, 9)
+        wp[:, :Cin] = w.reshape(O, Cin, 9)
+        m = torch.zeros(kpad, ldw)
+        m[:, :O] = wp.reshape(O, kpad // 144, 16, 9).permute(1, 3, 2, 0).reshape(kpad, O)
+        A.new("wt", m), A.new("hi", torch.zeros(n_el)), A.new("lo", torch.zeros(n_el))
+        A.new("scale", torch.rand(O) + 0.5), A.new("bias", R(O) * 0.2)
+        if res:
+            A.new("res", R(B, O, H, W))
+        s = _lib.AchConv3x3Tc()
+        s.x, s.x_bs, s.out, s.out_bs = A.ptr("x"), Cin * H * W, A.ptr("out"), O * H * W
+        s.scale, s.bias = A.ptr("scale"), A.ptr("bias")
+        if res:
+            s.res, s.res_bs = A.ptr("res"), O * H * W
+        s.B, s.Cin, s.H, s.W, s.O, s.act = B, Cin, H, W, O, act
+        return [("ach_pack_pw_tc", (A.ptr("wt"), kpad, O, ldw, A.ptr("hi"), A.ptr("lo"))), ("ach_conv3x3_tc", (s, A.ptr("hi"), A.ptr("lo")))]
+    run_seq(make, ["out"])
