@@ -11,6 +11,7 @@ frame live in ONE packed buffer ``[det40 | det20 | det10 | se_seg | lane_seg | p
 """
 import ctypes as C
 import math
+import os
 from collections import namedtuple
 
 import torch
@@ -176,9 +177,10 @@ class Engine:
         nb = 4 * (self.B * K_ * P + (self.B * O if reduce_max else self.B * O * P) + (self.B * O * P if res is not None else 0)
                   + K_ * s.ldw * (self.B if wt_bs else 1))
         tc_mode = self.model.use_tensor_cores
-        # measured on B200 (profiles/r1_tc_vs_simt.md): the persistent tcgen05 kernel beats the SIMT GEMM on every
-        # shared-weight layer with >= 24 outputs; narrower outputs waste most of a 32-column MMA tile
-        tc_ok = (tc_mode == "all" and O >= 16) or (tc_mode is True and O >= 24)
+        # measured on B200: the warp-specialised tcgen05 kernel beats (or ties) the SIMT GEMM on every shared-weight layer with
+        # >= 16 outputs (32 -> 16 at 320^2: 0.51 -> 0.47 ms); below that the two are within noise of each other
+        min_o = int(os.environ.get("ACH_TC_MIN_O", "16"))      # A/B switch for tools/op_times.py
+        tc_ok = (tc_mode == "all" and O >= 16) or (tc_mode is True and O >= min_o)
         if tc_ok and wt_bs == 0 and isinstance(wt, torch.Tensor) and not self.in_pack:
             # tcgen05 path: weights re-packed on the device into hi/lo UMMA tile images whenever they change
             n = self.lib.ach_pack_pw_tc_elems(K_, O)
