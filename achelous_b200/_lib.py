@@ -96,6 +96,8 @@ _SIGNATURES = {
     "ach_up_ghost": ([C.POINTER(AchUpGhost), VP], I),
     "ach_up_ghost_pw2_supported": ([I, I, I], I),
     "ach_up_ghost_pw2": ([C.POINTER(AchUpGhostPw2), VP], I),
+    "ach_up_ghost_pw2_tc_supported": ([I, I, I], I),
+    "ach_up_ghost_pw2_tc": ([C.POINTER(AchUpGhostPw2), VP, VP, VP, VP, VP], I),
     "ach_up_ghost_head_supported": ([I, I, I], I),
     "ach_up_ghost_head": ([C.POINTER(AchUpGhostHead), VP], I),
     "ach_pn2_fps": ([VP, LL, I, I, I, VP, VP, LL, VP], I),

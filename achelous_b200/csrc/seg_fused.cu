@@ -16,6 +16,7 @@
 // per-channel weights of ach_up_ghost_head travel as kernel parameters (constant bank) so the inner FMAs
 // take them as immediate constant operands - no load instructions for weights at all.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace ach {
 
@@ -432,6 +433,220 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_kernel(const AchUpGhostPw
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core version of ach_up_ghost_pw2: the two 1x1 convolutions (2*CI -> 32 -> 16, 1 536 of the ~1 750 FMAs per
+// output pixel) run on tcgen05 as 3xTF32 GEMMs; the upsampling and the depthwise 3x3 stay on the CUDA cores.
+// Same 16 x 32 output tile and shared-memory staging.  The CTA's 512 pixels are 4 M-tiles of 128: each half of the CTA
+// (warps 0-3 / 4-7) owns one M-tile per round (round r = the thread's pixel 2*rp + r) with its own TMEM columns,
+// mbarrier and named barrier.  Per round and half:
+//   thread = pixel = TMEM lane: [x1 | x2] (2*CI values) split hi/lo -> tcgen05.st (A operand in tensor memory)
+//   GEMM 1 (N = 32) -> D;  D + c1, ReLU, split -> tcgen05.st over the dead A columns;  GEMM 2 (N = 32, 16 used) -> D
+//   D -> 16 coalesced channel-plane stores.
+// Weights: ach_pack_pw_tc tiles of w1t (K = 2*CI, O = 32) and w2t (K = 32, O = 16), resident in shared memory.
+template <int CI>
+__global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhostPw2 p, const float* __restrict__ w1_hi,
+                                                                 const float* __restrict__ w1_lo, const float* __restrict__ w2_hi,
+                                                                 const float* __restrict__ w2_lo) {
+    constexpr int K1 = 2 * CI, NCH1 = K1 / TC_KC, NCH2 = UP_C1 / TC_KC;
+    constexpr int AK = K1 > UP_C1 ? K1 : UP_C1;              // columns of one A half (hi or lo)
+    constexpr int HALF_COLS = 2 * AK + 32;                   // [A hi | A lo | D]
+    constexpr int TMEM_COLS = 2 * HALF_COLS <= 256 ? 256 : 512;
+    constexpr int BT = 32 * TC_KC;                           // floats per packed weight tile (NT = 32)
+    static_assert(K1 % TC_KC == 0, "2*CI must be a multiple of 16");
+    extern __shared__ __align__(128) uint8_t smem_tc_raw[];
+    float* b1t = reinterpret_cast<float*>(smem_tc_raw);  // [NCH1][hi | lo][BT]
+    float* b2t = b1t + NCH1 * 2 * BT;                    // [NCH2][hi | lo][BT]
+    float* x1s = b2t + NCH2 * 2 * BT;                    // [CI][18][35]
+    float* vs = x1s + CI * UP_XH * UP_XP;                // [CI][12][20+1]
+    float* dws = vs + CI * UP_VH * (UP_VW + 1);          // [CI][12]: 9 taps, s2, b2, b1
+    float* c1s = dws + CI * 12;                          // [32]
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int h = p.h, w = p.w, H = 2 * h, W = 2 * w;
+    const int tiles_x = (W + UP_TW - 1) / UP_TW;
+    const int ty0 = (blockIdx.x / tiles_x) * UP_TH, tx0 = (blockIdx.x % tiles_x) * UP_TW;
+    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, half = tid >> 7;
+    const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
+    const int vy0 = (int)(sy * (float)max(ty0 - 1, 0)), vx0 = (int)(sx * (float)max(tx0 - 1, 0));
+    const long long plane_lo = (long long)h * w, plane_hi = (long long)H * W;
+    const float* vb = p.v + (long long)b * p.v_bs;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < NCH1 * BT / 4; i += 256) {
+        const int c = i / (BT / 4), r = i - c * (BT / 4);
+        reinterpret_cast<float4*>(b1t)[(c * 2 + 0) * (BT / 4) + r] = __ldg(reinterpret_cast<const float4*>(w1_hi) + i);
+        reinterpret_cast<float4*>(b1t)[(c * 2 + 1) * (BT / 4) + r] = __ldg(reinterpret_cast<const float4*>(w1_lo) + i);
+    }
+    for (int i = tid; i < NCH2 * BT / 4; i += 256) {
+        const int c = i / (BT / 4), r = i - c * (BT / 4);
+        reinterpret_cast<float4*>(b2t)[(c * 2 + 0) * (BT / 4) + r] = __ldg(reinterpret_cast<const float4*>(w2_hi) + i);
+        reinterpret_cast<float4*>(b2t)[(c * 2 + 1) * (BT / 4) + r] = __ldg(reinterpret_cast<const float4*>(w2_lo) + i);
+    }
+    for (int i = tid; i < CI * 12; i += 256) {
+        const int c = i / 12, k = i - c * 12;
+        dws[i] = k < 9 ? p.w2[c * 9 + k] : (k == 9 ? p.s2[c] : (k == 10 ? p.b2[c] : p.b1[c]));
+    }
+    if (tid < UP_C1) c1s[tid] = p.c1[tid];
+    for (int i = tid; i < CI * UP_VH * UP_VW; i += 256) {
+        const int c = i / (UP_VH * UP_VW);
+        const int r = i - c * (UP_VH * UP_VW);
+        const int yy = r / UP_VW, xx = r - yy * UP_VW;
+        const int gy = min(vy0 + yy, h - 1), gx = min(vx0 + xx, w - 1);
+        vs[(c * UP_VH + yy) * (UP_VW + 1) + xx] = __ldg(vb + (long long)c * plane_lo + gy * w + gx);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // weight tiles are read by the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- x1 on the halo tile (0 outside the image: dw zero padding)
+    for (int i = tid; i < UP_XH * UP_XW; i += 256) {
+        const int yy = i / UP_XW, xx = i - yy * UP_XW;
+        const int gy = ty0 - 1 + yy, gx = tx0 - 1 + xx;
+        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
+        float ly = 0.f, lx = 0.f;
+        if (in) {
+            bilin_src(gy, sy, h, y0, y1, ly);
+            bilin_src(gx, sx, w, x0, x1, lx);
+            y0 -= vy0; y1 -= vy0; x0 -= vx0; x1 -= vx0;
+        }
+        const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll 4
+        for (int c = 0; c < CI; ++c) {
+            const float* vc = vs + c * UP_VH * (UP_VW + 1);
+            float val = hy * (hx * vc[y0 * (UP_VW + 1) + x0] + lx * vc[y0 * (UP_VW + 1) + x1]) +
+                        ly * (hx * vc[y1 * (UP_VW + 1) + x0] + lx * vc[y1 * (UP_VW + 1) + x1]);
+            x1s[(c * UP_XH + yy) * UP_XP + xx] = in ? fmaxf(val + dws[c * 12 + 11], 0.f) : 0.f;
+        }
+    }
+    __syncthreads();
+
+    const int col = tid & 31, rp = tid >> 5;
+    const uint32_t tm = tmem_base_s + (uint32_t)(half * HALF_COLS);          // this half's columns
+    const uint32_t t_lane = tm + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t mb = smem_u32(&mbar[half]);
+    const uint32_t b1_s = smem_u32(b1t), b2_s = smem_u32(b2t);
+    constexpr uint32_t idesc = tf32_idesc(32);
+    float* ob = p.out + (long long)b * p.out_bs;
+    const int gx = tx0 + col;
+    uint32_t commits = 0;
+
+    auto put16 = [&](const float (&a)[16], int col0) {      // 16 A values of this pixel -> hi / lo columns col0 .. col0+15
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            hi[j] = __float_as_uint(a[j]) & 0xffffe000u;
+            lo[j] = __float_as_uint(a[j] - __uint_as_float(hi[j]));
+        }
+        tmem_st16(t_lane + (uint32_t)col0, hi);
+        tmem_st16(t_lane + (uint32_t)(AK + col0), lo);
+    };
+    auto gemm = [&](uint32_t b_s, int n_chunks) {            // elected thread of the half: D = A . B over n_chunks K chunks
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        if ((tid & 127) == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c = 0; c < n_chunks; ++c) {
+                const uint32_t bh_s = b_s + (uint32_t)(c * 2) * BT * 4u, bl_s = bh_s + BT * 4u;
+#pragma unroll
+                for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                    const uint32_t ah = tm + (uint32_t)(c * TC_KC + ks * 8), al = ah + (uint32_t)AK;
+                    const uint64_t bh = kmajor_desc(bh_s, 32, ks), bl = kmajor_desc(bl_s, 32, ks);
+                    mma_tf32_ts(tm + 2u * AK, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    mma_tf32_ts(tm + 2u * AK, al, bh, idesc, 1u);
+                    mma_tf32_ts(tm + 2u * AK, ah, bl, idesc, 1u);
+                }
+            }
+            tc_commit(mb);
+        }
+        mbar_wait(mb, commits & 1u);
+        ++commits;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+        // ---- A1 = [x1 | x2] of pixel (2*rp + r, col), 16 k at a time
+        const float* xrow = x1s + (2 * rp + r) * UP_XP + col;          // x1 halo row of the output row above this pixel
+#pragma unroll
+        for (int piece = 0; piece < NCH1; ++piece) {
+            float a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int k = piece * 16 + j;                           // compile-time
+                if (k < CI) {
+                    a[j] = xrow[(k * UP_XH + 1) * UP_XP + 1];           // x1: the window centre
+                } else {
+                    const int c = k - CI;
+                    const float* xc = xrow + c * UP_XH * UP_XP;
+                    const float* dk = dws + c * 12;
+                    float d = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) d = fmaf(xc[ky * UP_XP + kx], dk[ky * 3 + kx], d);
+                    a[j] = fmaxf(fmaf(dk[9], d, dk[10]), 0.f);
+                }
+            }
+            put16(a, piece * 16);
+        }
+        gemm(b1_s, NCH1);
+        // ---- t = relu(D + c1) -> A2 (over the dead A1 columns)
+#pragma unroll
+        for (int piece = 0; piece < NCH2; ++piece) {
+            uint32_t d[16];
+            tmem_ld16(t_lane + (uint32_t)(2 * AK + piece * 16), d);
+            float a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = fmaxf(__uint_as_float(d[j]) + c1s[piece * 16 + j], 0.f);
+            put16(a, piece * 16);
+        }
+        gemm(b2_s, NCH2);
+        // ---- v' = D[:, 0:16]
+        {
+            uint32_t d[16];
+            tmem_ld16(t_lane + (uint32_t)(2 * AK), d);
+            const int gy = ty0 + 2 * rp + r;
+            if (gy < H && gx < W) {
+#pragma unroll
+                for (int o = 0; o < UP_N2; ++o) ob[(long long)o * plane_hi + (long long)gy * W + gx] = __uint_as_float(d[o]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // D / A reads before the next round's writes
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(TMEM_COLS) : "memory");
+}
+
+template <int CI>
+static int launch_up_ghost_pw2_tc(const AchUpGhostPw2& p, const float* w1_hi, const float* w1_lo, const float* w2_hi, const float* w2_lo,
+                                  cudaStream_t st) {
+    constexpr int NCH1 = 2 * CI / TC_KC, NCH2 = UP_C1 / TC_KC;
+    const size_t smem = (size_t)((NCH1 + NCH2) * 2 * 32 * TC_KC + CI * UP_XH * UP_XP + CI * UP_VH * (UP_VW + 1) + CI * 12 + UP_C1) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(up_ghost_pw2_tc_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int H = 2 * p.h, W = 2 * p.w;
+    dim3 grid(cdiv(W, UP_TW) * cdiv(H, UP_TH), p.B);
+    up_ghost_pw2_tc_kernel<CI><<<grid, 256, smem, st>>>(p, w1_hi, w1_lo, w2_hi, w2_lo);
+    return check_launch("ach_up_ghost_pw2_tc");
+}
+
 template <int CI>
 static int launch_up_ghost_pw2(const AchUpGhostPw2& p, cudaStream_t st) {
     const size_t smem = (size_t)(CI * UP_XH * UP_XP + CI * UP_VH * (UP_VW + 1) + 2 * CI * UP_C1 + UP_C1 * UP_N2 + CI * 12 + UP_C1) * sizeof(float);
@@ -463,5 +678,25 @@ extern "C" int ach_up_ghost_pw2(const AchUpGhostPw2* pp, void* stream) {
         case 16: return launch_up_ghost_pw2<16>(p, st);
         case 24: return launch_up_ghost_pw2<24>(p, st);
         default: return launch_up_ghost_pw2<32>(p, st);
+    }
+}
+
+extern "C" int ach_up_ghost_pw2_tc_supported(int ci, int c1, int n2) {
+    return (ci == 16 || ci == 24 || ci == 32) && c1 == ach::UP_C1 && n2 == ach::UP_N2;
+}
+
+extern "C" int ach_up_ghost_pw2_tc(const AchUpGhostPw2* pp, const float* w1_hi, const float* w1_lo, const float* w2_hi, const float* w2_lo,
+                                   void* stream) {
+    using namespace ach;
+    const AchUpGhostPw2& p = *pp;
+    ACH_REQUIRE(p.v && p.out && p.b1 && p.w2 && p.s2 && p.b2 && p.c1 && w1_hi && w1_lo && w2_hi && w2_lo, "ach_up_ghost_pw2_tc: null arg");
+    ACH_REQUIRE(p.B > 0 && p.B <= 65535 && p.h > 1 && p.w > 1, "ach_up_ghost_pw2_tc: bad dims");
+    ACH_REQUIRE(ach_up_ghost_pw2_tc_supported(p.Ci, p.C1, p.N2), "ach_up_ghost_pw2_tc: (Ci=%d, C1=%d, N2=%d) not instantiated", p.Ci, p.C1, p.N2);
+    ACH_REQUIRE(aligned16(w1_hi) && aligned16(w1_lo) && aligned16(w2_hi) && aligned16(w2_lo), "ach_up_ghost_pw2_tc: weight tiles must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (p.Ci) {
+        case 16: return launch_up_ghost_pw2_tc<16>(p, w1_hi, w1_lo, w2_hi, w2_lo, st);
+        case 24: return launch_up_ghost_pw2_tc<24>(p, w1_hi, w1_lo, w2_hi, w2_lo, st);
+        default: return launch_up_ghost_pw2_tc<32>(p, w1_hi, w1_lo, w2_hi, w2_lo, st);
     }
 }

@@ -614,8 +614,21 @@ class Engine:
                                                                        * self._p(g_n + ".primary_conv.0.weight").flatten(1)).t())).data_ptr()
                     u.B, u.Ci, u.C1, u.N2, u.h, u.w = self.B, init, c_next, init_next, v.H, v.W
                     self._keep.append(u)
-                    self._add(n + ".up_ghost_pw2", self.lib.ach_up_ghost_pw2, C.byref(u),
-                              nbytes=4 * self.B * v.H * v.W * (init + 4 * init_next))
+                    nb_u = 4 * self.B * v.H * v.W * (init + 4 * init_next)
+                    if self.model.use_tensor_cores and self.model.seg_tensor_cores and self.lib.ach_up_ghost_pw2_tc_supported(init, c_next, init_next):
+                        # the two 1x1 convs of the chain on tcgen05: weight tiles packed on the device at (re)pack time
+                        tiles = []
+                        for key, K_, O_ in ((n + ".chain.w1t", 2 * init, c_next), (n + ".chain.w2t", c_next, init_next)):
+                            wt_ = self._weights[key][0]
+                            n_ = self.lib.ach_pack_pw_tc_elems(K_, O_)
+                            hi = torch.zeros(n_, device=self.device, dtype=torch.float32)
+                            lo = torch.zeros(n_, device=self.device, dtype=torch.float32)
+                            self._keep += [hi, lo]
+                            self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt_.data_ptr(), K_, O_, wt_.shape[-1], hi.data_ptr(), lo.data_ptr())))
+                            tiles += [hi.data_ptr(), lo.data_ptr()]
+                        self._add(n + ".up_ghost_pw2", self.lib.ach_up_ghost_pw2_tc, C.byref(u), *tiles, nbytes=nb_u)
+                    else:
+                        self._add(n + ".up_ghost_pw2", self.lib.ach_up_ghost_pw2, C.byref(u), nbytes=nb_u)
                     chained_v = vn
                     cur = vn   # only its spatial size is used below
                     continue

@@ -313,6 +313,11 @@ typedef struct AchUpGhostPw2 {
 } AchUpGhostPw2;
 ACH_API int ach_up_ghost_pw2_supported(int ci, int c1, int n2);
 ACH_API int ach_up_ghost_pw2(const AchUpGhostPw2* p, void* stream);
+/* Same stage with the two 1x1 convolutions on tcgen05 (3xTF32): w1_hi/lo = ach_pack_pw_tc tiles of w1t (K = 2*Ci, O = 32,
+ * ldw = 32), w2_hi/lo = tiles of w2t (K = 32, O = 16, ldw = 16); the struct's w1t / w2t fields are ignored. */
+ACH_API int ach_up_ghost_pw2_tc_supported(int ci, int c1, int n2);
+ACH_API int ach_up_ghost_pw2_tc(const AchUpGhostPw2* p, const float* w1_hi, const float* w1_lo, const float* w2_hi, const float* w2_lo,
+                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PointNet++ (pc_seg='pn2') building blocks.  The reference advertises PN2 (README.md:63) but contains no code

@@ -390,6 +390,12 @@ def ach_up_ghost_pw2(s):
     fview(s.out, (B, N2, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(o)
 
 
+def ach_up_ghost_pw2_tc(s, w1_hi, w1_lo, w2_hi, w2_lo):
+    w1 = _tc_unpack(w1_hi, w1_lo, 2 * s.Ci, s.C1).contiguous()
+    w2 = _tc_unpack(w2_hi, w2_lo, s.C1, s.N2).contiguous()
+    ach_up_ghost_pw2(_Shim(s, w1t=w1.data_ptr(), w2t=w2.data_ptr()))
+
+
 def ach_up_ghost_head(s):
     B, Cc, init, K, h, w = s.B, s.C, s.init, s.K, s.h, s.w
     v = fview(s.v, (B, Cc, h, w), (s.v_bs, h * w, w, 1))
@@ -453,7 +459,7 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc)}
 
 
 def _unwrap(a):

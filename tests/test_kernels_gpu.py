@@ -700,3 +700,27 @@ def test_conv3x3_tc(Cin, O, H, W, act, res):
         s.B, s.Cin, s.H, s.W, s.O, s.act = B, Cin, H, W, O, act
         return [("ach_pack_pw_tc", (A.ptr("wt"), kpad, O, ldw, A.ptr("hi"), A.ptr("lo"))), ("ach_conv3x3_tc", (s, A.ptr("hi"), A.ptr("lo")))]
     run_seq(make, ["out"])
+
+
+@pytest.mark.parametrize("Ci,h,w", [(16, 80, 80), (24, 40, 40), (32, 40, 40), (16, 23, 37)])
+def test_up_ghost_pw2_tc(Ci, h, w):
+    """chained decoder stage with both 1x1 convs on tcgen05 (A operand in tensor memory) vs the emulator"""
+    B, C1, N2 = 2, 32, 16
+    lib = _lib.load()
+    n1, n2 = lib.ach_pack_pw_tc_elems(2 * Ci, C1), lib.ach_pack_pw_tc_elems(C1, N2)
+
+    def make(A):
+        A.new("v", R(B, Ci + 1, h, w)), A.new("out", torch.zeros(B, N2, 2 * h, 2 * w))
+        A.new("b1", R(Ci) * 0.3), A.new("w2", R(Ci, 9) / 3), A.new("s2", torch.rand(Ci) + 0.5), A.new("b2", R(Ci) * 0.3)
+        A.new("w1t", R(2 * Ci, C1) / (2 * Ci) ** 0.5), A.new("c1", R(C1) * 0.2), A.new("w2t", R(C1, N2) / C1 ** 0.5)
+        for nm, sz in (("h1", n1), ("l1", n1), ("h2", n2), ("l2", n2)):
+            A.new(nm, torch.zeros(sz))
+        s = AchUpGhostPw2()
+        s.v, s.v_bs, s.out, s.out_bs = A.ptr("v", h * w), (Ci + 1) * h * w, A.ptr("out"), N2 * 4 * h * w
+        for n in ("b1", "w2", "s2", "b2", "c1"):
+            setattr(s, n, A.ptr(n))
+        s.B, s.Ci, s.C1, s.N2, s.h, s.w = B, Ci, C1, N2, h, w
+        return [("ach_pack_pw_tc", (A.ptr("w1t"), 2 * Ci, C1, C1, A.ptr("h1"), A.ptr("l1"))),
+                ("ach_pack_pw_tc", (A.ptr("w2t"), C1, N2, N2, A.ptr("h2"), A.ptr("l2"))),
+                ("ach_up_ghost_pw2_tc", (s, A.ptr("h1"), A.ptr("l1"), A.ptr("h2"), A.ptr("l2")))]
+    run_seq(make, ["out"])
