@@ -6,9 +6,12 @@
 // (profiles/r1_ncu_final_summary.txt, source page): on the long-K layers (K = 352, 22 chunks, only 200 work items on 148
 // SMs) 27 % of all stall samples sit on the first use of the loaded registers and on the barrier - 3.3 us per chunk for
 // 24 KB of operands.  Here the three jobs run decoupled, synchronised only through mbarriers:
-//   * warp 9 ("activation loader"): streams the fp32 activation chunks (16 channels x 128 pixels = 16 bulk copies of
-//     512 contiguous bytes, cp.async.bulk + mbarrier complete_tx) into a WS_SG-deep shared-memory ring, running ahead
-//     of the consumers across chunk AND tile boundaries.  The first versions loaded activations into registers two
+//   * warp 9 ("activation loader"): streams the fp32 activation chunks (16 channels x 128 pixels) into a WS_SG-deep
+//     shared-memory ring, running ahead of the consumers across chunk AND tile boundaries.  One 3-D tensor-map TMA
+//     (cp.async.bulk.tensor, box 128 px x 16 ch x 1 frame, zero-filled past P / past the channel count) per chunk;
+//     the first version issued 16 row copies of 512 bytes per chunk and the K = 128 layers then sat at ~2.3 TB/s with
+//     23 % of the stall samples waiting for a chunk to land - a per-copy cost, not a byte cost.  Chunks that straddle
+//     the two sources of a concat-free layer still use the row copies.  The first versions loaded activations into registers two
 //     chunks ahead: ncu showed long-scoreboard stalls of 3.8 per issue on the K = 128 layers and 2 TB/s of DRAM - the
 //     register prefetch was too shallow for HBM latency; the ring holds 5-8 chunks (40-64 KB) in flight per CTA.
 //   * warps 0-7 (256 threads, "producers"): read their pixel's 8 k of a landed chunk from the ring (conflict-free
@@ -26,6 +29,8 @@
 //     stage's "MMA done" barrier, which is what lets producers and TMA reuse a stage.
 // The accumulator (NT TMEM columns) is handed back and forth with two more barriers (acc_full / acc_empty).
 #include <cstdlib>
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -70,7 +75,8 @@ __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n
 template <int NT, int ACT, bool RES>
 __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
     pw_conv_tc_ws_kernel(const AchPwConv p, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
-                         const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items) {
+                         const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items,
+                         const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, int use_tmap) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int B_ELEMS = NT * TC_KC;
     constexpr int SG = ws_sg(NT);
@@ -189,6 +195,21 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
                 const int k0 = c * TC_KC;
                 const int nk = min(TC_KC, K - k0);
                 const uint32_t full = smem_u32(&bar_g_full[g]);
+                const bool straddle = k0 < p.c0 && k0 + TC_KC > p.c0 && p.c1 > 0;
+                if (use_tmap && !straddle) {
+                    if (lane == 0) {
+                        const bool first = k0 < p.c0;
+                        const CUtensorMap* tm = first ? &tm0 : &tm1;
+                        const int ch = first ? k0 : k0 - p.c0;
+                        mbar_expect_tx(full, (uint32_t)G_ELEMS * 4u);          // the box is always complete: out-of-range parts are zero-filled
+                        asm volatile(
+                            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                                g_ring_s + g * G_ELEMS * 4u),
+                            "l"(tm), "r"(pp0), "r"(ch), "r"(b), "r"(full)
+                            : "memory");
+                    }
+                    continue;
+                }
                 if (lane == 0) mbar_expect_tx(full, (uint32_t)nk * bytes);
                 __syncwarp();
                 if (lane < nk) {
@@ -401,6 +422,37 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
     }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no direct libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// (P, C, B) fp32 view with strides (1, P, bs) elements; box = 128 pixels x 16 channels x 1 frame
+static bool make_act_tmap(CUtensorMap* tm, const float* base, int P, int Cc, int B, long long bs) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || !base || Cc <= 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)Cc, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)P * 4ull, (cuuint64_t)(B > 1 ? bs : (long long)P * Cc) * 4ull};
+    const cuuint32_t box[3] = {(cuuint32_t)TC_M, (cuuint32_t)TC_KC, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (strides[1] % 16 != 0 || strides[1] >= (1ull << 40)) return false;
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NT, int ACT, bool RES>
 static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
     const int K = p.c0 + p.c1;
@@ -419,7 +471,14 @@ static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, c
     const long long total = (long long)n_pt * n_ot * p.B;
     ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
-    pw_conv_tc_ws_kernel<NT, ACT, RES><<<grid, ws_threads(NT), smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total);
+    // tensor maps of the activation views (ACH_TC_TMAP=0: row copies everywhere, the A/B switch for tools/op_times.py)
+    alignas(64) CUtensorMap tm0, tm1;
+    memset(&tm0, 0, sizeof(tm0));
+    memset(&tm1, 0, sizeof(tm1));
+    static const bool tmap_on = !(getenv("ACH_TC_TMAP") && atoi(getenv("ACH_TC_TMAP")) == 0);
+    int use_tmap = tmap_on && make_act_tmap(&tm0, p.x0, p.P, p.c0, p.B, p.x0_bs) ? 1 : 0;
+    if (use_tmap && p.c1 > 0) use_tmap = make_act_tmap(&tm1, p.x1, p.P, p.c1, p.B, p.x1_bs) ? 1 : 0;
+    pw_conv_tc_ws_kernel<NT, ACT, RES><<<grid, ws_threads(NT), smem, st>>>(p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, (int)total, tm0, tm1, use_tmap);
     return check_launch("ach_pw_conv_tc");
 }
 
