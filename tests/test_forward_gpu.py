@@ -167,3 +167,23 @@ def test_stream_forward_matches_forward():
             assert torch.equal(a, b_)
         n += 1
     assert n == 5
+
+
+@pytest.mark.parametrize("sizes", [[2], [2, 2], [2, 2, 3, 3, 2, 1, 1, 1]])
+def test_stream_forward_lookahead_and_batch_size_changes(sizes):
+    """Inputs are staged one batch ahead; a change of batch size drains the pipeline and rebinds the slot's buffers.
+    Every yielded result must equal forward() on the same batch, in order, for any length / size pattern."""
+    model, _ = build("S0", "en", 2)
+    batches = [make_inputs(b, seed=200 + i) for i, b in enumerate(sizes)]
+    ref = []
+    for b in batches:
+        r = model(*[t.cuda() for t in b])
+        ref.append([d.cpu().clone() for d in r[0]] + [r[1].cpu().clone(), r[2].cpu().clone(), r[3].cpu().clone()])
+    pinned = [tuple(t.pin_memory() for t in b) for b in batches]
+    n = 0
+    for out, r in zip(model.stream_forward(iter(pinned)), ref):
+        got = list(out[0]) + [out[1], out[2], out[3]]
+        for a, b_ in zip(got, r):
+            assert a.shape == b_.shape and torch.equal(a, b_), n
+        n += 1
+    assert n == len(sizes)
