@@ -519,10 +519,12 @@ def test_pw_conv_tc(case):
     run_seq(make, ["hi", "lo", "out"])
 
 
-@pytest.mark.parametrize("H,W", [(40, 40), (20, 20), (10, 10), (6, 14)])
-def test_mvit_attention(H, W):
+@pytest.mark.parametrize("tc", [1, 0], ids=["tcgen05", "cuda-cores"])
+@pytest.mark.parametrize("H,W", [(40, 40), (20, 20), (10, 10), (6, 14), (52, 52), (2, 2)])
+def test_mvit_attention(H, W, tc, monkeypatch):
     B, heads, d = 2, 4, 8
     P = H * W
+    monkeypatch.setenv("ACH_MVIT_TC", str(tc))   # read at every launch
 
     def make(A):
         A.new("qkv", R(B, 3 * heads * d + 5, P) * 1.5), A.new("out", torch.zeros(B, heads * d, P))
