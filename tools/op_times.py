@@ -21,11 +21,12 @@ def main():
     ap.add_argument("--phi", default="S0")
     ap.add_argument("--backbone", default="en")
     ap.add_argument("--neck", default="gdf")
+    ap.add_argument("--pc-seg", default="pn")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--tc", default="default", help="default | all | off")
     ap.add_argument("--out", default="gpurun_out/op_times.json")
     a = ap.parse_args()
-    kw = dict(num_det=7, num_seg=9, phi=a.phi, resolution=320, backbone=a.backbone, neck=a.neck, pc_seg="pn", pc_channels=5,
+    kw = dict(num_det=7, num_seg=9, phi=a.phi, resolution=320, backbone=a.backbone, neck=a.neck, pc_seg=a.pc_seg, pc_channels=5,
               pc_classes=8, nano_head=True, spp=True)
     model = Achelous(**kw).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=0))
