@@ -26,11 +26,16 @@ __global__ void __launch_bounds__(256) xca_fold_kernel(const float* __restrict__
     float* ks = qs + d * (XCA_CHUNK + 1);         // [d][XCA_CHUNK + 1]
     float* nrm = ks + d * (XCA_CHUNK + 1);        // [2d]
     float* attn = nrm + 2 * d;                    // [d][d]
+    float* pw = attn + d * d;                     // [d][ldw]: this head's rows of the projection weight
 
     const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* q = qkv + (long long)b * qkv_bs + (long long)(h * d) * N;
     const float* k = q + (long long)C * N;
+
+    // this head's projection rows -> shared memory (all loads in flight at once; step 4 used to read them from L2 inside a
+    // d-long dependent FMA loop: ~1 300 L2 round trips per thread and half of the kernel's 92 us at C = 176)
+    for (int i = tid; i < d * ldw; i += 256) pw[i] = __ldg(proj_wt + (long long)(h * d) * ldw + i);
 
     // 1. row norms (F.normalize: x / max(||x||, 1e-12))
     for (int r = warp; r < 2 * d; r += 8) {
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(256) xca_fold_kernel(const float* __restrict__
         const int j = idx / ldw, o = idx - j * ldw;
         float s = 0.f;
         if (o < C)
-            for (int i = 0; i < d; ++i) s = fmaf(proj_wt[(long long)(h * d + i) * ldw + o], attn[i * d + j], s);
+            for (int i = 0; i < d; ++i) s = fmaf(pw[i * ldw + o], attn[i * d + j], s);
         wo[(long long)(h * d + j) * ldw + o] = s;
     }
 }
@@ -118,10 +123,11 @@ extern "C" int ach_xca_fold(const float* qkv, long long qkv_bs, const float* tem
     const int d = C / heads;
     ACH_REQUIRE(d <= XCA_MAX_D, "ach_xca_fold: head dim %d > %d", d, XCA_MAX_D);
     ACH_REQUIRE(ldw >= C, "ach_xca_fold: ldw < C");
-    const size_t smem = (size_t)(2 * d * (XCA_CHUNK + 1) + 2 * d + d * d) * sizeof(float);
+    const size_t smem = (size_t)(2 * d * (XCA_CHUNK + 1) + 2 * d + d * d + d * ldw) * sizeof(float);
+    ACH_REQUIRE(smem <= 160 * 1024, "ach_xca_fold: d=%d, ldw=%d do not fit shared memory", d, ldw);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(xca_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(xca_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set = true;
     }
     xca_fold_kernel<<<dim3(heads, B), 256, smem, (cudaStream_t)stream>>>(qkv, qkv_bs, temperature, proj_wt, ldw, wt_eff, wt_eff_bs,
