@@ -1,0 +1,142 @@
+// EdgeViT building blocks (backbone/vision/edgevit_modules/edgevit.py) that the existing
+// kernels do not cover:
+//   ach_subsample   GlobalSparseAttn's sampler nn.AvgPool2d(1, sr) (:66,76): kernel 1, stride sr = every sr-th pixel
+//   ach_mhsa        token self-attention softmax(q k^T * scale) v per (frame, head) (:81-87), qkv channel-major
+//                   (B, 3*heads*d, N) as the fused LN+qkv GEMM produces it; one CTA = 128 queries of one head, K/V of the
+//                   head in shared memory, online softmax in the log2 domain (one MUFU.EX2 per key), thread = query
+//   ach_dw_convT    LocalProp = depthwise ConvTranspose2d with kernel = stride = sr (:68,91): every output pixel has
+//                   exactly one source pixel: out[c, y, x] = in[c, y/sr, x/sr] * w[c, y%sr, x%sr] + bias[c]
+#include "common.cuh"
+
+namespace ach {
+
+__global__ void __launch_bounds__(256) subsample_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                        long long out_bs, int H, int W, int ho, int wo, int sr) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= ho * wo) return;
+    const int y = i / wo, xx = i - y * wo;
+    const int c = blockIdx.y;
+    out[(long long)blockIdx.z * out_bs + (long long)c * ho * wo + i] =
+        __ldg(x + (long long)blockIdx.z * x_bs + ((long long)c * H + y * sr) * W + xx * sr);
+}
+
+__global__ void __launch_bounds__(256) dw_convT_kernel(const float* __restrict__ x, long long x_bs, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out, long long out_bs,
+                                                       int h, int ww, int sr) {
+    const int H = h * sr, W = ww * sr;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= H * W) return;
+    const int y = i / W, xx = i - y * W;
+    const int c = blockIdx.y;
+    const float v = __ldg(x + (long long)blockIdx.z * x_bs + ((long long)c * h + y / sr) * ww + xx / sr);
+    const float wt = __ldg(w + (c * sr + y % sr) * sr + xx % sr);
+    out[(long long)blockIdx.z * out_bs + (long long)c * H * W + i] = fmaf(v, wt, bias ? __ldg(bias + c) : 0.f);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) mhsa_kernel(const float* __restrict__ qkv, long long qkv_bs, float* __restrict__ out,
+                                                   long long out_bs, int heads, int d, int N, float scale2) {
+    extern __shared__ float smem[];
+    float* ks = smem;            // [N][D] (zero padded past d)
+    float* vs = smem + N * D;    // [N][D]
+    const int head = blockIdx.x, qt = blockIdx.y, b = blockIdx.z;
+    const int inner = heads * d;
+    const float* qb = qkv + (long long)b * qkv_bs + (long long)(head * d) * N;
+    const float* kb = qb + (long long)inner * N;
+    const float* vb = kb + (long long)inner * N;
+    for (int i = threadIdx.x; i < N * D; i += 128) {
+        const int dd = i / N, n = i - dd * N;           // consecutive threads -> consecutive tokens of one channel
+        ks[n * D + dd] = dd < d ? __ldg(kb + (long long)dd * N + n) : 0.f;
+        vs[n * D + dd] = dd < d ? __ldg(vb + (long long)dd * N + n) : 0.f;
+    }
+    __syncthreads();
+    const int n = qt * 128 + threadIdx.x;
+    if (n >= N) return;
+    float q[D], acc[D];
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd) {
+        q[dd] = dd < d ? __ldg(qb + (long long)dd * N + n) * scale2 : 0.f;     // log2 units: exp(x) = 2^(x * log2 e)
+        acc[dd] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < N; ++j) {
+        const float4* kj = reinterpret_cast<const float4*>(ks + j * D);
+        float s = 0.f;
+#pragma unroll
+        for (int dd = 0; dd < D / 4; ++dd) {
+            const float4 kk = kj[dd];
+            s = fmaf(q[4 * dd], kk.x, s);
+            s = fmaf(q[4 * dd + 1], kk.y, s);
+            s = fmaf(q[4 * dd + 2], kk.z, s);
+            s = fmaf(q[4 * dd + 3], kk.w, s);
+        }
+        if (s > m) {                      // rescale only when the running max moves
+            const float c = ex2_approx(m - s);
+            l *= c;
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) acc[dd] *= c;
+            m = s;
+        }
+        const float e = ex2_approx(s - m);
+        l += e;
+        const float4* vj = reinterpret_cast<const float4*>(vs + j * D);
+#pragma unroll
+        for (int dd = 0; dd < D / 4; ++dd) {
+            const float4 vv = vj[dd];
+            acc[4 * dd] = fmaf(e, vv.x, acc[4 * dd]);
+            acc[4 * dd + 1] = fmaf(e, vv.y, acc[4 * dd + 1]);
+            acc[4 * dd + 2] = fmaf(e, vv.z, acc[4 * dd + 2]);
+            acc[4 * dd + 3] = fmaf(e, vv.w, acc[4 * dd + 3]);
+        }
+    }
+    const float inv = 1.0f / l;
+    float* ob = out + (long long)b * out_bs + (long long)(head * d) * N + n;
+#pragma unroll
+    for (int dd = 0; dd < D; ++dd)
+        if (dd < d) ob[(long long)dd * N] = acc[dd] * inv;
+}
+
+template <int D>
+static int launch_mhsa(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int d, int N, float scale,
+                       cudaStream_t st) {
+    const size_t smem = (size_t)2 * N * D * sizeof(float);
+    ACH_REQUIRE(smem <= 200 * 1024, "ach_mhsa: %d tokens x %d dims do not fit shared memory", N, D);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(mhsa_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    mhsa_kernel<D><<<dim3(heads, cdiv(N, 128), B), 128, smem, st>>>(qkv, qkv_bs, out, out_bs, heads, d, N, scale * 1.4426950408889634f);
+    return check_launch("ach_mhsa");
+}
+
+}  // namespace ach
+
+extern "C" int ach_subsample(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W, int sr, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(x && out && B > 0 && B <= 65535 && C > 0 && C <= 65535 && H > 0 && W > 0 && sr >= 1, "ach_subsample: bad args");
+    const int ho = (H - 1) / sr + 1, wo = (W - 1) / sr + 1;
+    subsample_kernel<<<dim3(cdiv((long long)ho * wo, 256), C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, H, W, ho, wo, sr);
+    return check_launch("ach_subsample");
+}
+
+extern "C" int ach_dw_convT(const float* x, long long x_bs, const float* w, const float* bias, float* out, long long out_bs, int B, int C,
+                            int h, int w_in, int sr, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(x && w && out && B > 0 && B <= 65535 && C > 0 && C <= 65535 && h > 0 && w_in > 0 && sr >= 1, "ach_dw_convT: bad args");
+    dw_convT_kernel<<<dim3(cdiv((long long)h * sr * w_in * sr, 256), C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, w, bias, out, out_bs, h,
+                                                                                                          w_in, sr);
+    return check_launch("ach_dw_convT");
+}
+
+extern "C" int ach_mhsa(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head, int N, float scale,
+                        void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(qkv && out && B > 0 && B <= 65535 && heads > 0 && dim_head > 0 && N > 0, "ach_mhsa: bad args");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dim_head <= 24) return launch_mhsa<24>(qkv, qkv_bs, out, out_bs, B, heads, dim_head, N, scale, st);
+    if (dim_head <= 32) return launch_mhsa<32>(qkv, qkv_bs, out, out_bs, B, heads, dim_head, N, scale, st);
+    if (dim_head <= 48) return launch_mhsa<48>(qkv, qkv_bs, out, out_bs, B, heads, dim_head, N, scale, st);
+    set_error("ach_mhsa: dim_head=%d not instantiated (<= 48)", dim_head);
+    return ACH_ERR_INVALID;
+}

@@ -439,6 +439,123 @@ class Engine:
             feats.append(cur)
         return feats
 
+    # ---- EdgeViT (edgevit_modules/edgevit.py)
+    def _ev_pos_embed(self, name, prefix, x):
+        """x + dwconv3x3(x): the identity is folded into the centre tap"""
+        def w(prefix=prefix):
+            wt = self._p(prefix + ".weight").flatten(1).clone()
+            wt[:, 4] += 1.0
+            return wt
+        out = self.buf(name, x.C, x.H, x.W)
+        self.dw(name, x, out, self._w(name + ".w", w), 3, bias=self._vec(name + ".b", lambda: self._p(prefix + ".bias")))
+        return out
+
+    def _ev_lin(self, name, lin, x, out, act=ACT_NONE, res=None, ln=None, ln_eps=1e-6, bn=None):
+        """Linear / 1x1 conv (+bias) over channels, optionally behind a LayerNorm (affine folded, statistics in the GEMM) or
+        an eval BatchNorm (folded into weight and bias: W' = W diag(s), b' = b + W t)"""
+        def w2d():
+            return self._p(lin + ".weight").flatten(1)
+        if ln is not None:
+            wt = self._w(name + ".wt", lambda: self._kmajor(w2d() * self._p(ln + ".weight")[None, :]))
+            bi = self._vec(name + ".b", lambda: self._p(lin + ".bias") + w2d() @ self._p(ln + ".bias"))
+            self.pw(name, x, out, wt, out.C, bias=bi, ln=True, ln_eps=ln_eps, act=act, res=res)
+        elif bn is not None:
+            wt = self._w(name + ".wt", lambda: self._kmajor(w2d() * self._bn_fold(bn, 1e-5)[0][None, :]))
+            bi = self._vec(name + ".b", lambda: self._p(lin + ".bias") + w2d() @ self._bn_fold(bn, 1e-5)[1])
+            self.pw(name, x, out, wt, out.C, bias=bi, act=act, res=res)
+        else:
+            wt = self._w(name + ".wt", lambda: self._kmajor(w2d()))
+            self.pw(name, x, out, wt, out.C, bias=self._vec(name + ".b", lambda: self._p(lin + ".bias")), act=act, res=res)
+
+    def ev_local_agg(self, name, prefix, x):
+        """LocalAgg (edgevit.py:101-119)"""
+        C_, H, W = x.C, x.H, x.W
+        xa = self._ev_pos_embed(name + ".pos", prefix + ".pos_embed", x)
+        c1 = self.buf(name + ".c1", C_, H, W)
+        self._ev_lin(name + ".conv1", prefix + ".conv1", xa, c1, bn=prefix + ".norm1")
+        a5 = self.buf(name + ".a5", C_, H, W)
+        self.dw(name + ".attn", c1, a5, self._w(name + ".attn.w", lambda: self._p(prefix + ".attn.weight").flatten(1)), 5,
+                bias=self._vec(name + ".attn.b", lambda: self._p(prefix + ".attn.bias")))
+        xb = self.buf(name + ".xb", C_, H, W)
+        self._ev_lin(name + ".conv2", prefix + ".conv2", a5, xb, res=xa)
+        h = self.buf(name + ".h", 4 * C_, H, W)
+        self._ev_lin(name + ".fc1", prefix + ".mlp.fc1", xb, h, act=ACT_GELU, bn=prefix + ".norm2")
+        out = self.buf(name + ".out", C_, H, W)
+        self._ev_lin(name + ".fc2", prefix + ".mlp.fc2", h, out, res=xb)
+        return out
+
+    def ev_self_attn(self, name, prefix, x, heads, sr):
+        """SelfAttn with GlobalSparseAttn (edgevit.py:50-98,122-148): tokens stay channel-major (C, H*W)"""
+        C_, H, W = x.C, x.H, x.W
+        a = prefix + ".attn"
+        xa = self._ev_pos_embed(name + ".pos", prefix + ".pos_embed", x)
+        xs = xa
+        if sr > 1:
+            xs = self.buf(name + ".sub", C_, H // sr, W // sr)
+            self._add(name + ".sub", self.lib.ach_subsample, xa.ptr, xa.bs, xs.ptr, xs.bs, self.B, C_, H, W, sr)
+        n = xs.H * xs.W
+        qkv = self.buf(name + ".qkv", 3 * C_, xs.H, xs.W)
+        self._ev_lin(name + ".qkv", a + ".qkv", xs, qkv, ln=prefix + ".norm1", ln_eps=1e-6)   # LN per token commutes with the sampling
+        ao = self.buf(name + ".ao", C_, xs.H, xs.W)
+        d = C_ // heads
+        self._add(name + ".mhsa", self.lib.ach_mhsa, qkv.ptr, qkv.bs, ao.ptr, ao.bs, self.B, heads, d, n, float(d) ** -0.5)
+        t = self.buf(name + ".t", C_, H, W)
+        if sr > 1:
+            up = self.buf(name + ".up", C_, H, W)
+            wT = self._w(name + ".lp.w", lambda: self._p(a + ".LocalProp.weight").flatten(1))
+            bT = self._vec(name + ".lp.b", lambda: self._p(a + ".LocalProp.bias"))
+            self._add(name + ".localprop", self.lib.ach_dw_convT, ao.ptr, ao.bs, wT.data_ptr(), bT.data_ptr(), up.ptr, up.bs, self.B, C_,
+                      xs.H, xs.W, sr)
+            self._ev_lin(name + ".proj", a + ".proj", up, t, res=xa, ln=a + ".norm", ln_eps=1e-5)
+        else:
+            self._ev_lin(name + ".proj", a + ".proj", ao, t, res=xa)
+        h = self.buf(name + ".h", 4 * C_, H, W)
+        self._ev_lin(name + ".fc1", prefix + ".mlp.fc1", t, h, act=ACT_GELU, ln=prefix + ".norm2", ln_eps=1e-6)
+        out = self.buf(name + ".out", C_, H, W)
+        self._ev_lin(name + ".fc2", prefix + ".mlp.fc2", h, out, res=t)
+        return out
+
+    def edgevit(self, x, prefix, phi):
+        cfg = Hd.EDGEVIT_CFG[phi]
+        dims, depth = cfg["dims"], cfg["depth"]
+        heads = [d // cfg["head_dim"] for d in dims]
+        feats, cur, H = [], x, self.res
+        for i in range(4):
+            patch = 4 if i == 0 else 2
+            H //= patch
+            pe = f"{prefix}.patch_embed{i + 1}"
+            emb = self.buf(f"bb.pe{i}", dims[i], H, H)
+            w = self._pack_conv(f"bb.pe{i}.w", pe + ".proj.weight")
+            b = self._vec(f"bb.pe{i}.b", (lambda pe=pe: self._p(pe + ".proj.bias")))
+            lw = self._vec(f"bb.pe{i}.lnw", (lambda pe=pe: self._p(pe + ".norm.weight")))
+            lb = self._vec(f"bb.pe{i}.lnb", (lambda pe=pe: self._p(pe + ".norm.bias")))
+            if dims[i] <= 32:      # conv_dense applies the channel LayerNorm in its epilogue
+                self.conv(f"bb.pe{i}", cur, emb, w, patch, patch, 0, bias=b, ln_w=lw, ln_b=lb, ln_eps=1e-5)
+            else:
+                tmp = self.buf(f"bb.pe{i}.conv", dims[i], H, H)
+                self.conv(f"bb.pe{i}.conv", cur, tmp, w, patch, patch, 0, bias=b)
+                self._add(f"bb.pe{i}.ln", self.lib.ach_layernorm_cf, tmp.ptr, tmp.bs, lw.data_ptr(), lb.data_ptr(), emb.ptr, emb.bs,
+                          self.B, dims[i], H * H, 1e-5)
+            cur = emb
+            if i < 3:
+                feats.append(cur)
+            for j in range(depth[i]):
+                bp = f"{prefix}.blocks{i + 1}.{j}"
+                if Hd.EDGEVIT_SR[i] > 1:
+                    cur = self.ev_local_agg(f"bb.s{i}.{j}.la", bp + ".LocalAgg", cur)
+                cur = self.ev_self_attn(f"bb.s{i}.{j}.sa", bp + ".SelfAttn", cur, heads[i], Hd.EDGEVIT_SR[i])
+                self.taps[f"backbone.stage{i}.{j}"] = cur
+        # final BatchNorm2d: a per-channel affine, run as a GEMM with the identity matrix
+        f5 = self.buf("bb.f5", dims[3], H, H)
+        eye = self._w("bb.norm.eye", lambda: self._kmajor(torch.eye(dims[3])))
+        sc = self._vec("bb.norm.s", lambda: self._bn_fold(prefix + ".norm", 1e-5)[0])
+        bi = self._vec("bb.norm.b", lambda: self._bn_fold(prefix + ".norm", 1e-5)[1])
+        self.pw("bb.norm", cur, f5, eye, dims[3], scale=sc, bias=bi)
+        feats.append(f5)
+        for n_, f in zip("2345", feats):
+            self.taps[f"backbone.feat{n_}"] = f
+        return feats
+
     # ---- MobileViT (mobilevit_modules/mobilevit.py)
     def conv_bn_silu(self, name, prefix, x, out, k, stride=1):
         """conv_nxn_bn / conv_1x1_bn: conv (no bias) + BN(1e-5) + SiLU  (mobilevit.py:7-21)"""
@@ -1049,6 +1166,8 @@ class Engine:
         ire = "image_radar_encoder"
         if m.backbone == "en":
             feats = self.edgenext(self.x_in, ire + ".fpn.backbone", m.phi)
+        elif m.backbone == "ev":
+            feats = self.edgevit(self.x_in, ire + ".fpn.backbone", m.phi)
         else:
             feats = self.mobilevit(self.x_in, ire + ".fpn.backbone", m.phi)
         maps = (self.gdf_neck if m.neck == "gdf" else self.cdf_neck)(feats, ire + ".fpn", m.phi, out_se, out_lane)

@@ -286,6 +286,97 @@ class MobileViT(Holder):
 
 
 # ------------------------------------------------------------------ neck (ghostdualfpn.py, spp.py, attention_modules)
+# ------------------------------------------------------------------ EdgeViT (edgevit_modules/edgevit.py)
+EDGEVIT_CFG = {
+    "S0": dict(depth=[1, 1, 3, 2], dims=[32, 48, 96, 176], head_dim=20),
+    "S1": dict(depth=[1, 1, 3, 1], dims=[32, 48, 120, 224], head_dim=32),
+    "S2": dict(depth=[1, 2, 5, 3], dims=[32, 64, 144, 288], head_dim=32),
+}
+EDGEVIT_SR = [4, 2, 2, 1]
+
+
+class EVMlp(Holder):
+    """edgevit.py:13-29 (Linear) / :32-47 (CMlp, 1x1 convs)"""
+
+    def __init__(self, dim, hidden, conv):
+        super().__init__()
+        self.fc1 = nn.Conv2d(dim, hidden, 1) if conv else nn.Linear(dim, hidden)
+        self.fc2 = nn.Conv2d(hidden, dim, 1) if conv else nn.Linear(hidden, dim)
+
+
+class EVGlobalSparseAttn(Holder):
+    """edgevit.py:50-73"""
+
+    def __init__(self, dim, num_heads, sr_ratio):
+        super().__init__()
+        self.num_heads, self.sr = num_heads, sr_ratio
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+        if sr_ratio > 1:
+            self.LocalProp = nn.ConvTranspose2d(dim, dim, sr_ratio, stride=sr_ratio, groups=dim)
+            self.norm = nn.LayerNorm(dim)
+
+
+class EVLocalAgg(Holder):
+    """edgevit.py:101-113"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.pos_embed = nn.Conv2d(dim, dim, 3, padding=1, groups=dim)
+        self.norm1 = nn.BatchNorm2d(dim)
+        self.conv1 = nn.Conv2d(dim, dim, 1)
+        self.conv2 = nn.Conv2d(dim, dim, 1)
+        self.attn = nn.Conv2d(dim, dim, 5, padding=2, groups=dim)
+        self.norm2 = nn.BatchNorm2d(dim)
+        self.mlp = EVMlp(dim, int(dim * 4.0), conv=True)
+
+
+class EVSelfAttn(Holder):
+    """edgevit.py:122-138 (norm_layer = LayerNorm eps 1e-6)"""
+
+    def __init__(self, dim, num_heads, sr_ratio):
+        super().__init__()
+        self.pos_embed = nn.Conv2d(dim, dim, 3, padding=1, groups=dim)
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = EVGlobalSparseAttn(dim, num_heads, sr_ratio)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = EVMlp(dim, int(dim * 4.0), conv=False)
+
+
+class EVLGLBlock(Holder):
+    """edgevit.py:151-168"""
+
+    def __init__(self, dim, num_heads, sr_ratio):
+        super().__init__()
+        self.LocalAgg = EVLocalAgg(dim) if sr_ratio > 1 else nn.Identity()
+        self.SelfAttn = EVSelfAttn(dim, num_heads, sr_ratio)
+
+
+class EVPatchEmbed(Holder):
+    """edgevit.py:171-184"""
+
+    def __init__(self, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(embed_dim)
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+class EdgeViT(Holder):
+    """edgevit.py:196-263"""
+
+    def __init__(self, phi):
+        super().__init__()
+        cfg = EDGEVIT_CFG[phi]
+        dims, depth = cfg["dims"], cfg["depth"]
+        heads = [d // cfg["head_dim"] for d in dims]
+        cin = [3] + dims[:3]
+        for i in range(4):
+            setattr(self, f"patch_embed{i + 1}", EVPatchEmbed(4 if i == 0 else 2, cin[i], dims[i]))
+        for i in range(4):
+            setattr(self, f"blocks{i + 1}", nn.ModuleList([EVLGLBlock(dims[i], heads[i], EDGEVIT_SR[i]) for _ in range(depth[i])]))
+        self.norm = nn.BatchNorm2d(dims[-1])
+
+
 class SPPConv(Holder):
     """spp.py:27-31"""
 
@@ -338,8 +429,10 @@ class GhostDualFPN(Holder):
             self.backbone = EdgeNeXt(phi)
         elif backbone == "mv":
             self.backbone = MobileViT(phi)
+        elif backbone == "ev":
+            self.backbone = EdgeViT(phi)
         else:
-            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en' and 'mv' (SURVEY.md §8b)")
+            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en', 'mv' and 'ev' (SURVEY.md §8b, §8f)")
         self.spp = SPP(w[3], w[3])
         self.upsample_5_to_4 = Upsample(w[3], w[2])
         self.ghost_5_to_4 = GhostBottleneck(w[2] * 2, w[2] * 2, w[2])
@@ -390,8 +483,10 @@ class CSPDualFPN(Holder):
             self.backbone = EdgeNeXt(phi)
         elif backbone == "mv":
             self.backbone = MobileViT(phi)
+        elif backbone == "ev":
+            self.backbone = EdgeViT(phi)
         else:
-            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en' and 'mv' (SURVEY.md §8b)")
+            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en', 'mv' and 'ev' (SURVEY.md §8b, §8f)")
         self.spp = SPP(w[3], w[3])
         self.upsample_5_to_4 = Upsample(w[3], w[2])
         self.ghost_5_to_4 = CSPLayer(w[2] * 2, w[2])

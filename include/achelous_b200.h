@@ -230,6 +230,18 @@ ACH_API int ach_xca_fold(const float* qkv, long long qkv_bs, const float* temper
 ACH_API int ach_mvit_attention(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head,
                                int H, int W, void* stream);
 
+/* EdgeViT blocks (backbone/vision/edgevit_modules/edgevit.py, backbone='ev'):
+ * ach_subsample: out (B, C, ceil(H/sr), ceil(W/sr)) = x[:, :, ::sr, ::sr]  (the sampler nn.AvgPool2d(1, sr), :66,76).
+ * ach_mhsa: qkv (B, 3*heads*d, N) channel-major [q | k | v], each (heads d) ordered -> out (B, heads*d, N) =
+ *   softmax(q k^T * scale) v per (frame, head)  (:81-87).  dim_head <= 48.
+ * ach_dw_convT: LocalProp, depthwise ConvTranspose2d with kernel = stride = sr (:68,91): x (B, C, h, w), w (C, sr*sr),
+ *   bias (C) or NULL -> out (B, C, h*sr, w*sr). */
+ACH_API int ach_subsample(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W, int sr, void* stream);
+ACH_API int ach_mhsa(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head, int N, float scale,
+                     void* stream);
+ACH_API int ach_dw_convT(const float* x, long long x_bs, const float* w, const float* bias, float* out, long long out_bs, int B, int C,
+                         int h, int w_in, int sr, void* stream);
+
 /* Fully connected on (B, K) rows: out[b, o] = act(scale[o] * (w[o, :] . x[b, :]) + bias[o]).
  * pointnet_utils.py:16-18,38-40 (fc + BN1d + ReLU), and the global-feature half of
  * pointnet_sem_seg.py:18 (Conv1d over a point-wise constant). */

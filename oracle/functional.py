@@ -380,6 +380,89 @@ def mobilevit(x, p, phi, taps=None):
     return [f2, f3, f4, f5]
 
 
+# ----------------------------------------------------------------------------- EdgeViT
+EDGEVIT_CFG = {  # edgevit_modules/edgevit.py:320-349
+    "S0": dict(depth=[1, 1, 3, 2], dims=[32, 48, 96, 176], head_dim=20),
+    "S1": dict(depth=[1, 1, 3, 1], dims=[32, 48, 120, 224], head_dim=32),
+    "S2": dict(depth=[1, 2, 5, 3], dims=[32, 64, 144, 288], head_dim=32),
+}
+EDGEVIT_SR = [4, 2, 2, 1]
+
+
+def ev_patch_embed(x, p, patch):
+    """PatchEmbed: conv k = s = patch, then nn.LayerNorm (eps 1e-5) over the channels of every token.  edgevit.py:171-193"""
+    return layer_norm_cf(conv(x, p.sub("proj"), patch), p.sub("norm"), 1e-5)
+
+
+def ev_local_agg(x, p):
+    """LocalAgg.  edgevit.py:101-119"""
+    C = x.shape[1]
+    x = x + conv(x, p.sub("pos_embed"), 1, 1, groups=C)
+    y = conv(bn(x, p.sub("norm1"), 1e-5), p.sub("conv1"))
+    y = conv(conv(y, p.sub("attn"), 1, 2, groups=C), p.sub("conv2"))
+    x = x + y
+    y = conv(F.gelu(conv(bn(x, p.sub("norm2"), 1e-5), p.sub("mlp.fc1"))), p.sub("mlp.fc2"))
+    return x + y
+
+
+def ev_global_sparse_attn(t, p, H, W, heads, sr):
+    """GlobalSparseAttn on tokens t (B, N, C).  edgevit.py:50-98"""
+    B, N, C = t.shape
+    h, w = H, W
+    if sr > 1:
+        t = t.transpose(1, 2).reshape(B, C, H, W)[:, :, ::sr, ::sr]        # AvgPool2d(1, sr): kernel 1, stride sr
+        h, w = t.shape[2], t.shape[3]
+        t = t.flatten(2).transpose(1, 2)
+    d = C // heads
+    qkv = F.linear(t, p("qkv.weight"), p("qkv.bias")).reshape(B, -1, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = ((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(B, -1, C)
+    if sr > 1:
+        o = o.permute(0, 2, 1).reshape(B, C, h, w)
+        o = F.conv_transpose2d(o, p("LocalProp.weight"), p("LocalProp.bias"), stride=sr, groups=C)
+        o = o.reshape(B, C, -1).permute(0, 2, 1)
+        o = F.layer_norm(o, (C,), p("norm.weight"), p("norm.bias"), 1e-5)
+    return F.linear(o, p("proj.weight"), p("proj.bias"))
+
+
+def ev_self_attn(x, p, heads, sr):
+    """SelfAttn.  edgevit.py:122-148 (norm_layer = LayerNorm eps 1e-6, :334)"""
+    B, C, H, W = x.shape
+    x = x + conv(x, p.sub("pos_embed"), 1, 1, groups=C)
+    t = x.flatten(2).transpose(1, 2)
+    t = t + ev_global_sparse_attn(F.layer_norm(t, (C,), p("norm1.weight"), p("norm1.bias"), 1e-6), p.sub("attn"), H, W, heads, sr)
+    m = F.linear(F.gelu(F.linear(F.layer_norm(t, (C,), p("norm2.weight"), p("norm2.bias"), 1e-6), p("mlp.fc1.weight"), p("mlp.fc1.bias"))),
+                 p("mlp.fc2.weight"), p("mlp.fc2.bias"))
+    t = t + m
+    return t.transpose(1, 2).reshape(B, C, H, W)
+
+
+def edgevit(x, p, phi, taps=None):
+    """EdgeVit.forward_features -> 4 maps (feat2..4 are the patch embeddings, taken BEFORE their stage's blocks).
+    edgevit.py:288-311"""
+    cfg = EDGEVIT_CFG[phi]
+    feats = []
+    for i in range(4):
+        dim = cfg["dims"][i]
+        heads, sr = dim // cfg["head_dim"], EDGEVIT_SR[i]
+        x = ev_patch_embed(x, p.sub(f"patch_embed{i + 1}"), 4 if i == 0 else 2)
+        if i < 3:
+            feats.append(x)
+        for j in range(cfg["depth"][i]):
+            bp = p.sub(f"blocks{i + 1}.{j}")
+            if sr > 1:
+                x = ev_local_agg(x, bp.sub("LocalAgg"))
+            x = ev_self_attn(x, bp.sub("SelfAttn"), heads, sr)
+            if taps is not None:
+                taps[f"backbone.stage{i}.{j}"] = x
+    feats.append(bn(x, p.sub("norm"), 1e-5))
+    if taps is not None:
+        for n, f in zip("2345", feats):
+            taps[f"backbone.feat{n}"] = f
+    return feats
+
+
 # ----------------------------------------------------------------------------- neck / fusion / heads
 def spp(x, p):
     """SPP(5,9,13).  neck/spp.py:41-52"""
@@ -404,7 +487,7 @@ def ghost_dual_fpn(x, p, phi, backbone, num_seg, taps=None):
     """GhostDualFPN.forward.  ghostdualfpn.py:156-200"""
     w = WIDTHS[phi]
     bb = p.sub("backbone")
-    m2, m3, m4, m5 = edgenext(x, bb, phi, taps) if backbone == "en" else mobilevit(x, bb, phi, taps)
+    m2, m3, m4, m5 = {"en": edgenext, "mv": mobilevit, "ev": edgevit}[backbone](x, bb, phi, taps)
     f5 = spp(m5, p.sub("spp"))
     f4 = ghost_bottleneck(torch.cat([upsample_block(f5, p.sub("upsample_5_to_4")), m4], 1),
                           p.sub("ghost_5_to_4"), w[2] * 2, w[2])
@@ -446,7 +529,7 @@ def seg_decoder_csp(x, p, name, num_out, taps=None):
 def csp_dual_fpn(x, p, phi, backbone, num_seg, taps=None):
     """CSPDualFPN.forward.  cspdualfpn.py:193-239"""
     bb = p.sub("backbone")
-    m2, m3, m4, m5 = edgenext(x, bb, phi, taps) if backbone == "en" else mobilevit(x, bb, phi, taps)
+    m2, m3, m4, m5 = {"en": edgenext, "mv": mobilevit, "ev": edgevit}[backbone](x, bb, phi, taps)
     f5 = spp(m5, p.sub("spp"))
     f4 = csp_layer(torch.cat([upsample_block(f5, p.sub("upsample_5_to_4")), m4], 1), p.sub("ghost_5_to_4"))
     f3 = csp_layer(torch.cat([upsample_block(f4, p.sub("upsample_4_to_3")), m3], 1), p.sub("ghost_4_to_3"))

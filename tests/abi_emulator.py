@@ -184,6 +184,29 @@ def ach_conv3x3_tc(s, w_hi, w_lo):
     fview(s.out, (B, O, H, W), (s.out_bs, H * W, W, 1)).copy_(y)
 
 
+def ach_subsample(x, x_bs, out, out_bs, B, Cc, H, W, sr):
+    xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))[:, :, ::sr, ::sr]
+    ho, wo = xv.shape[2], xv.shape[3]
+    fview(out, (B, Cc, ho, wo), (out_bs, ho * wo, wo, 1)).copy_(xv)
+
+
+def ach_mhsa(qkv, qkv_bs, out, out_bs, B, heads, d, N, scale):
+    inner = heads * d
+    q = fview(qkv, (B, heads, d, N), (qkv_bs, d * N, N, 1))
+    k = fview(qkv + inner * N * 4, (B, heads, d, N), (qkv_bs, d * N, N, 1))
+    v = fview(qkv + 2 * inner * N * 4, (B, heads, d, N), (qkv_bs, d * N, N, 1))
+    attn = ((q.transpose(-2, -1) @ k) * scale).softmax(-1)            # (B, h, Nq, Nk)
+    o = v @ attn.transpose(-2, -1)                                    # (B, h, d, Nq)
+    fview(out, (B, heads, d, N), (out_bs, d * N, N, 1)).copy_(o)
+
+
+def ach_dw_convT(x, x_bs, w, bias, out, out_bs, B, Cc, h, w_in, sr):
+    xv = fview(x, (B, Cc, h, w_in), (x_bs, h * w_in, w_in, 1))
+    wt = _vec(w, Cc * sr * sr).reshape(Cc, 1, sr, sr)
+    y = F.conv_transpose2d(xv, wt, _vec(bias, Cc) if bias else None, stride=sr, groups=Cc)
+    fview(out, (B, Cc, h * sr, w_in * sr), (out_bs, h * sr * w_in * sr, w_in * sr, 1)).copy_(y)
+
+
 def ach_layernorm_cf(x, x_bs, w, b, out, out_bs, B, Cc, P, eps):
     xv = fview(x, (B, Cc, P), (x_bs, P, 1))
     u = xv.mean(1, keepdim=True)
@@ -459,7 +482,7 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT)}
 
 
 def _unwrap(a):

@@ -31,6 +31,7 @@ CONFIGS = {
     "en_gdf_pn_s2": dict(phi="S2", backbone="en", weight_seed=0, input_seed=12),
     "mv_gdf_pn_s0": dict(phi="S0", backbone="mv", weight_seed=0, input_seed=13),
     "en_cdf_pn_s0": dict(phi="S0", backbone="en", weight_seed=3, input_seed=14, neck="cdf"),
+    "ev_gdf_pn_s0": dict(phi="S0", backbone="ev", weight_seed=4, input_seed=15),
 }
 MODEL_KW = dict(num_det=7, num_seg=9, resolution=320, pc_seg="pn", pc_channels=5, pc_classes=8,
                 nano_head=True, spp=True)
@@ -59,6 +60,11 @@ def tap_map(phi, backbone):
             m[f"{fpn}backbone.downsample_layers.{i}"] = f"backbone.down{i}"
             for j in range(depths[i]):
                 m[f"{fpn}backbone.stages.{i}.{j}"] = f"backbone.stage{i}.{j}"
+    if backbone == "ev":
+        depth = {"S0": [1, 1, 3, 2], "S1": [1, 1, 3, 1], "S2": [1, 2, 5, 3]}[phi]
+        for i in range(4):
+            for j in range(depth[i]):
+                m[f"{fpn}backbone.blocks{i + 1}.{j}"] = f"backbone.stage{i}.{j}"
     m[f"{fpn}spp"] = "neck.spp"
     m[f"{fpn}ghost_5_to_4"] = "neck.fpn4"
     m[f"{fpn}ghost_4_to_3"] = "neck.fpn3"

@@ -726,3 +726,29 @@ def test_up_ghost_pw2_tc(Ci, h, w):
                 ("ach_pack_pw_tc", (A.ptr("w2t"), C1, N2, N2, A.ptr("h2"), A.ptr("l2"))),
                 ("ach_up_ghost_pw2_tc", (s, A.ptr("h1"), A.ptr("l1"), A.ptr("h2"), A.ptr("l2")))]
     run_seq(make, ["out"])
+
+
+@pytest.mark.parametrize("Cc,H,W,sr", [(32, 80, 80, 4), (48, 40, 40, 2), (5, 13, 21, 2), (7, 10, 10, 1)])
+def test_subsample_and_dw_convT(Cc, H, W, sr):
+    """EdgeViT sampler (AvgPool2d(1, sr)) and LocalProp (depthwise ConvTranspose2d, kernel = stride = sr)"""
+    B = 2
+    ho, wo = (H - 1) // sr + 1, (W - 1) // sr + 1
+
+    def make(A):
+        A.new("x", R(B, Cc, H, W)), A.new("sub", torch.zeros(B, Cc, ho, wo)), A.new("w", R(Cc, sr * sr)), A.new("b", R(Cc))
+        A.new("up", torch.zeros(B, Cc, ho * sr, wo * sr))
+        return [("ach_subsample", (A.ptr("x"), Cc * H * W, A.ptr("sub"), Cc * ho * wo, B, Cc, H, W, sr)),
+                ("ach_dw_convT", (A.ptr("sub"), Cc * ho * wo, A.ptr("w"), A.ptr("b"), A.ptr("up"), Cc * ho * sr * wo * sr, B, Cc, ho, wo, sr))]
+    run_seq(make, ["sub", "up"])
+
+
+@pytest.mark.parametrize("heads,d,N", [(1, 32, 400), (2, 24, 400), (4, 24, 100), (8, 22, 100), (3, 40, 100), (2, 20, 37)])
+def test_mhsa(heads, d, N):
+    """EdgeViT GlobalSparseAttn core: softmax(q k^T * scale) v per (frame, head), any head dim <= 48, ragged token counts"""
+    B = 2
+    Cc = heads * d
+
+    def make(A):
+        A.new("qkv", R(B, 3 * Cc + 3, N) * 1.5), A.new("out", torch.zeros(B, Cc, N))
+        return (A.ptr("qkv", 3 * N), (3 * Cc + 3) * N, A.ptr("out"), Cc * N, B, heads, d, N, float(d) ** -0.5)
+    run_both("ach_mhsa", make, ["out"])
