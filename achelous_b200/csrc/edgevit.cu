@@ -33,6 +33,20 @@ __global__ void __launch_bounds__(256) dw_convT_kernel(const float* __restrict__
     out[(long long)blockIdx.z * out_bs + (long long)c * H * W + i] = fmaf(v, wt, bias ? __ldg(bias + c) : 0.f);
 }
 
+// patch x patch space-to-depth: the im2col of a conv with kernel = stride = patch (PatchEmbed.proj, edgevit.py:184), which then
+// runs as a pointwise GEMM over K = C * patch^2 on tcgen05.  Thread = one input row segment of `patch` pixels.
+__global__ void __launch_bounds__(256) s2d_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out, long long out_bs,
+                                                  int H, int W, int patch) {
+    const int ho = H / patch, wo = W / patch;
+    const int i = blockIdx.x * 256 + threadIdx.x;          // (ky, oy, ox): consecutive threads -> consecutive ox
+    if (i >= patch * ho * wo) return;
+    const int ox = i % wo, oy = (i / wo) % ho, ky = i / (wo * ho);
+    const int c = blockIdx.y;
+    const float* __restrict__ src = x + (long long)blockIdx.z * x_bs + ((long long)c * H + oy * patch + ky) * W + ox * patch;
+    float* __restrict__ dst = out + (long long)blockIdx.z * out_bs + ((long long)(c * patch + ky) * patch) * ho * wo + oy * wo + ox;
+    for (int kx = 0; kx < patch; ++kx) dst[(long long)kx * ho * wo] = __ldg(src + kx);
+}
+
 template <int D>
 __global__ void __launch_bounds__(128) mhsa_kernel(const float* __restrict__ qkv, long long qkv_bs, float* __restrict__ out,
                                                    long long out_bs, int heads, int d, int N, float scale2) {
@@ -118,6 +132,13 @@ extern "C" int ach_subsample(const float* x, long long x_bs, float* out, long lo
     const int ho = (H - 1) / sr + 1, wo = (W - 1) / sr + 1;
     subsample_kernel<<<dim3(cdiv((long long)ho * wo, 256), C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, H, W, ho, wo, sr);
     return check_launch("ach_subsample");
+}
+
+extern "C" int ach_s2d(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W, int patch, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(x && out && B > 0 && B <= 65535 && C > 0 && C <= 65535 && patch >= 1 && H % patch == 0 && W % patch == 0, "ach_s2d: bad args");
+    s2d_kernel<<<dim3(cdiv((long long)H * W / patch, 256), C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, H, W, patch);
+    return check_launch("ach_s2d");
 }
 
 extern "C" int ach_dw_convT(const float* x, long long x_bs, const float* w, const float* bias, float* out, long long out_bs, int B, int C,

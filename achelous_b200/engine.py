@@ -525,15 +525,19 @@ class Engine:
             H //= patch
             pe = f"{prefix}.patch_embed{i + 1}"
             emb = self.buf(f"bb.pe{i}", dims[i], H, H)
-            w = self._pack_conv(f"bb.pe{i}.w", pe + ".proj.weight")
-            b = self._vec(f"bb.pe{i}.b", (lambda pe=pe: self._p(pe + ".proj.bias")))
             lw = self._vec(f"bb.pe{i}.lnw", (lambda pe=pe: self._p(pe + ".norm.weight")))
             lb = self._vec(f"bb.pe{i}.lnb", (lambda pe=pe: self._p(pe + ".norm.bias")))
             if dims[i] <= 32:      # conv_dense applies the channel LayerNorm in its epilogue
+                w = self._pack_conv(f"bb.pe{i}.w", pe + ".proj.weight")
+                b = self._vec(f"bb.pe{i}.b", (lambda pe=pe: self._p(pe + ".proj.bias")))
                 self.conv(f"bb.pe{i}", cur, emb, w, patch, patch, 0, bias=b, ln_w=lw, ln_b=lb, ln_eps=1e-5)
             else:
+                # kernel = stride conv == space-to-depth + pointwise GEMM over K = C p^2 (tcgen05); the direct conv took 0.2-0.3 ms
                 tmp = self.buf(f"bb.pe{i}.conv", dims[i], H, H)
-                self.conv(f"bb.pe{i}.conv", cur, tmp, w, patch, patch, 0, bias=b)
+                s2d = self.buf(f"bb.pe{i}.s2d", cur.C * patch * patch, H, H)
+                self._add(f"bb.pe{i}.s2d", self.lib.ach_s2d, cur.ptr, cur.bs, s2d.ptr, s2d.bs, self.B, cur.C, cur.H, cur.W, patch,
+                          nbytes=8 * self.B * cur.C * cur.H * cur.W)
+                self.pw_bias(f"bb.pe{i}.conv", pe + ".proj", s2d, tmp)
                 self._add(f"bb.pe{i}.ln", self.lib.ach_layernorm_cf, tmp.ptr, tmp.bs, lw.data_ptr(), lb.data_ptr(), emb.ptr, emb.bs,
                           self.B, dims[i], H * H, 1e-5)
             cur = emb

@@ -236,6 +236,9 @@ ACH_API int ach_mvit_attention(const float* qkv, long long qkv_bs, float* out, l
  *   softmax(q k^T * scale) v per (frame, head)  (:81-87).  dim_head <= 48.
  * ach_dw_convT: LocalProp, depthwise ConvTranspose2d with kernel = stride = sr (:68,91): x (B, C, h, w), w (C, sr*sr),
  *   bias (C) or NULL -> out (B, C, h*sr, w*sr). */
+ /* ach_s2d: out (B, C*p*p, H/p, W/p) with out[b, (c*p + ky)*p + kx, oy, ox] = x[b, c, oy*p + ky, ox*p + kx] - the im2col of
+ * PatchEmbed.proj (kernel = stride = p, edgevit.py:184), in the order of conv.weight.flatten(1). */
+ACH_API int ach_s2d(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W, int patch, void* stream);
 ACH_API int ach_subsample(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W, int sr, void* stream);
 ACH_API int ach_mhsa(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head, int N, float scale,
                      void* stream);

@@ -184,6 +184,12 @@ def ach_conv3x3_tc(s, w_hi, w_lo):
     fview(s.out, (B, O, H, W), (s.out_bs, H * W, W, 1)).copy_(y)
 
 
+def ach_s2d(x, x_bs, out, out_bs, B, Cc, H, W, p):
+    xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))
+    y = xv.reshape(B, Cc, H // p, p, W // p, p).permute(0, 1, 3, 5, 2, 4).reshape(B, Cc * p * p, H // p, W // p)
+    fview(out, (B, Cc * p * p, H // p, W // p), (out_bs, (H // p) * (W // p), W // p, 1)).copy_(y)
+
+
 def ach_subsample(x, x_bs, out, out_bs, B, Cc, H, W, sr):
     xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))[:, :, ::sr, ::sr]
     ho, wo = xv.shape[2], xv.shape[3]
@@ -482,7 +488,7 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT, ach_s2d)}
 
 
 def _unwrap(a):

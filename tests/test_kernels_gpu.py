@@ -752,3 +752,13 @@ def test_mhsa(heads, d, N):
         A.new("qkv", R(B, 3 * Cc + 3, N) * 1.5), A.new("out", torch.zeros(B, Cc, N))
         return (A.ptr("qkv", 3 * N), (3 * Cc + 3) * N, A.ptr("out"), Cc * N, B, heads, d, N, float(d) ** -0.5)
     run_both("ach_mhsa", make, ["out"])
+
+
+@pytest.mark.parametrize("Cc,H,W,p", [(32, 80, 80, 2), (3, 64, 48, 4), (5, 6, 10, 2)])
+def test_s2d(Cc, H, W, p):
+    B = 2
+
+    def make(A):
+        A.new("x", R(B, Cc, H, W)), A.new("out", torch.zeros(B, Cc * p * p, H // p, W // p))
+        return (A.ptr("x"), Cc * H * W, A.ptr("out"), Cc * H * W, B, Cc, H, W, p)
+    run_both("ach_s2d", make, ["out"])
