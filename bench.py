@@ -49,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -315,7 +315,8 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "how": "Achelous.stream_forward (public pipelined API): every batch is copied host->device from pinned memory, "
-                               "run, and its 6 outputs copied device->host; copies overlap the neighbouring batches' kernels; wall clock",
+                               "run, and its 6 outputs copied device->host; copies overlap the neighbouring batches' kernels (inputs staged one batch "
+                               "ahead); wall clock",
                         "serial_forward_value": e2e_serial,
                         "serial_how": "Achelous.forward(pinned host tensors) then .copy_ of the 6 outputs to pinned host, one batch at a time"},
                 "gpu_launches": K * len(eng.ops),
