@@ -8,6 +8,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def pytest_sessionstart(session):
+    """Build the in-tree sm_100a library when it is missing or stale (nvcc cross-compiles without a GPU), so that a fresh
+    checkout can run the suite without calling __graft_entry__.build() first.  A failed build is reported by the tests that
+    load the library, not here."""
+    try:
+        from achelous_b200.build import build_library
+        build_library(force=False)
+    except Exception as e:  # pragma: no cover
+        print(f"[conftest] could not build libachelous_b200.so: {e}")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "needs_reference: needs /root/reference (skipped where it is absent)")
