@@ -106,6 +106,8 @@ _SIGNATURES = {
     "ach_pn2_interp3": ([VP, LL, VP, LL, VP, LL, I, I, I, I, VP, LL, VP], I),
     "ach_seg_softmax": ([VP, LL, VP, LL, I, I, I, VP], I),
     "ach_seg_resize_argmax": ([VP, LL, I, I, I, I, I, I, I, I, VP, I, I, VP], I),
+    "ach_ef_attention": ([VP, LL, VP, LL, VP, LL, VP, VP, VP, VP, LL, VP, LL, I, I, I, I, I, I, F, I, VP], I),
+    "ach_upsample2x_hp": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
     "ach_s2d": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
     "ach_subsample": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
     "ach_mhsa": ([VP, LL, VP, LL, I, I, I, I, F, VP], I),

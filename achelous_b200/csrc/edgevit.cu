@@ -161,3 +161,175 @@ extern "C" int ach_mhsa(const float* qkv, long long qkv_bs, float* out, long lon
     set_error("ach_mhsa: dim_head=%d not instantiated (<= 48)", dim_head);
     return ACH_ERR_INVALID;
 }
+
+// ------------------------------------------------------------------------------------------------
+// EfficientFormerV2 ("ImageEncoder", backbone='ef') attention: Attention4D (ImageEncoder.py:131-160) and
+// Attention4DDownsample (:267-289).  All heads of a query tile are processed together because the talking-head 1x1
+// convolutions mix the heads of every (query, key) score before and after the softmax:
+//   S[h][q][k]  = scale * sum_c q[h*kd + c][q] k[h*kd + c][k] + ab[h][q][k]
+//   S           = th1 S + b1           (optional)        P = softmax_k(S)        P = th2 P + b2   (optional)
+//   out[h*d + j][q] = sum_k P[h][q][k] v[h*d + j][k]  (+ add[h*d + j][q], then GELU if `gelu`)
+// One CTA per (frame, tile of TQ queries); the (heads x TQ x Nk) score block lives in shared memory.
+namespace ach {
+
+constexpr int EFA_TQ = 4;      // queries per CTA
+constexpr int EFA_MAXH = 8;
+
+__global__ void __launch_bounds__(256) ef_attention_kernel(const float* __restrict__ q, long long q_bs, const float* __restrict__ k,
+                                                           long long k_bs, const float* __restrict__ v, long long v_bs,
+                                                           const float* __restrict__ ab, const float* __restrict__ th1,
+                                                           const float* __restrict__ th2, const float* __restrict__ add, long long add_bs,
+                                                           float* __restrict__ out, long long out_bs, int heads, int kd, int d, int Nq,
+                                                           int Nk, float scale, int gelu) {
+    extern __shared__ float smem[];
+    float* S = smem;                              // [heads][TQ][Nk]
+    float* qs = S + heads * EFA_TQ * Nk;          // [heads*kd][TQ]
+    float* ths = qs + heads * kd * EFA_TQ;        // th1 (h*h + h) | th2 (h*h + h)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * EFA_TQ, b = blockIdx.y;
+    const float* qb = q + (long long)b * q_bs;
+    const float* kb = k + (long long)b * k_bs;
+    const float* vb = v + (long long)b * v_bs;
+    for (int i = tid; i < heads * kd * EFA_TQ; i += 256) {
+        const int c = i / EFA_TQ, t = i - c * EFA_TQ;
+        qs[i] = (q0 + t < Nq) ? __ldg(qb + (long long)c * Nq + q0 + t) * scale : 0.f;
+    }
+    const int nth = heads * heads + heads;
+    for (int i = tid; i < 2 * nth; i += 256) ths[i] = (i < nth) ? (th1 ? th1[i] : 0.f) : (th2 ? th2[i - nth] : 0.f);
+    __syncthreads();
+    // ---- scores: thread per (head, key), TQ accumulators
+    for (int i = tid; i < heads * Nk; i += 256) {
+        const int h = i / Nk, kk = i - h * Nk;
+        float acc[EFA_TQ];
+#pragma unroll
+        for (int t = 0; t < EFA_TQ; ++t) acc[t] = 0.f;
+        for (int c = 0; c < kd; ++c) {
+            const float kv = __ldg(kb + (long long)(h * kd + c) * Nk + kk);
+            const float* qc = qs + (h * kd + c) * EFA_TQ;
+#pragma unroll
+            for (int t = 0; t < EFA_TQ; ++t) acc[t] = fmaf(qc[t], kv, acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < EFA_TQ; ++t) {
+            const int qq = min(q0 + t, Nq - 1);
+            S[(h * EFA_TQ + t) * Nk + kk] = acc[t] + __ldg(ab + ((long long)h * Nq + qq) * Nk + kk);
+        }
+    }
+    __syncthreads();
+    // ---- talking head 1 (mixes the heads of every (query, key) score)
+    if (th1) {
+        for (int i = tid; i < EFA_TQ * Nk; i += 256) {
+            float s[EFA_MAXH], o[EFA_MAXH];
+            for (int h = 0; h < heads; ++h) s[h] = S[h * EFA_TQ * Nk + i];
+            for (int ho = 0; ho < heads; ++ho) {
+                float a = ths[heads * heads + ho];
+                for (int h = 0; h < heads; ++h) a = fmaf(ths[ho * heads + h], s[h], a);
+                o[ho] = a;
+            }
+            for (int h = 0; h < heads; ++h) S[h * EFA_TQ * Nk + i] = o[h];
+        }
+        __syncthreads();
+    }
+    // ---- softmax over the keys: one warp per (head, query) row
+    for (int r = warp; r < heads * EFA_TQ; r += 8) {
+        float* row = S + r * Nk;
+        float m = -INFINITY;
+        for (int j = lane; j < Nk; j += 32) m = fmaxf(m, row[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < Nk; j += 32) {
+            const float e = expf(row[j] - m);
+            row[j] = e;
+            s += e;
+        }
+        s = warp_sum(s);
+        const float inv = 1.0f / s;
+        for (int j = lane; j < Nk; j += 32) row[j] *= inv;
+    }
+    __syncthreads();
+    if (th2) {
+        const float* t2 = ths + nth;
+        for (int i = tid; i < EFA_TQ * Nk; i += 256) {
+            float s[EFA_MAXH], o[EFA_MAXH];
+            for (int h = 0; h < heads; ++h) s[h] = S[h * EFA_TQ * Nk + i];
+            for (int ho = 0; ho < heads; ++ho) {
+                float a = t2[heads * heads + ho];
+                for (int h = 0; h < heads; ++h) a = fmaf(t2[ho * heads + h], s[h], a);
+                o[ho] = a;
+            }
+            for (int h = 0; h < heads; ++h) S[h * EFA_TQ * Nk + i] = o[h];
+        }
+        __syncthreads();
+    }
+    // ---- out = P v: one warp per value channel, lanes over the keys
+    for (int r = warp; r < heads * d; r += 8) {
+        const int h = r / d;
+        const float* vr = vb + (long long)r * Nk;
+        float acc[EFA_TQ];
+#pragma unroll
+        for (int t = 0; t < EFA_TQ; ++t) acc[t] = 0.f;
+        for (int j = lane; j < Nk; j += 32) {
+            const float vv = __ldg(vr + j);
+#pragma unroll
+            for (int t = 0; t < EFA_TQ; ++t) acc[t] = fmaf(S[(h * EFA_TQ + t) * Nk + j], vv, acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < EFA_TQ; ++t) acc[t] = warp_sum(acc[t]);
+        if (lane < EFA_TQ && q0 + lane < Nq) {
+            float y = acc[0];
+#pragma unroll
+            for (int t = 1; t < EFA_TQ; ++t) y = (lane == t) ? acc[t] : y;
+            if (add) y += __ldg(add + (long long)b * add_bs + (long long)r * Nq + q0 + lane);
+            if (gelu) y = apply_act(y, ACT_GELU);
+            out[(long long)b * out_bs + (long long)r * Nq + q0 + lane] = y;
+        }
+    }
+}
+
+// bilinear x2, align_corners=False (nn.Upsample(scale_factor=2, mode='bilinear'), ImageEncoder.py:80), optional GELU
+__global__ void __launch_bounds__(256) upsample2x_hp_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
+                                                            long long out_bs, int H, int W, int gelu) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Ho * Wo) return;
+    const int oy = i / Wo, ox = i - oy * Wo;
+    const int c = blockIdx.y;
+    // ATen area_pixel_compute_source_index (align_corners=False): src = max((dst + 0.5) * 0.5 - 0.5, 0)
+    const float fy = fmaxf(((float)oy + 0.5f) * 0.5f - 0.5f, 0.f), fx = fmaxf(((float)ox + 0.5f) * 0.5f - 0.5f, 0.f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* xp = x + (long long)blockIdx.z * x_bs + (long long)c * H * W;
+    float v = hy * (hx * __ldg(xp + y0 * W + x0) + lx * __ldg(xp + y0 * W + x1)) + ly * (hx * __ldg(xp + y1 * W + x0) + lx * __ldg(xp + y1 * W + x1));
+    if (gelu) v = apply_act(v, ACT_GELU);
+    out[(long long)blockIdx.z * out_bs + (long long)c * Ho * Wo + i] = v;
+}
+
+}  // namespace ach
+
+extern "C" int ach_ef_attention(const float* q, long long q_bs, const float* k, long long k_bs, const float* v, long long v_bs,
+                                const float* ab, const float* th1, const float* th2, const float* add, long long add_bs, float* out,
+                                long long out_bs, int B, int heads, int key_dim, int d, int Nq, int Nk, float scale, int gelu, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(q && k && v && ab && out, "ach_ef_attention: null arg");
+    ACH_REQUIRE(B > 0 && B <= 65535 && heads > 0 && heads <= EFA_MAXH && key_dim > 0 && d > 0 && Nq > 0 && Nk > 0, "ach_ef_attention: bad dims");
+    const size_t smem = (size_t)(heads * EFA_TQ * Nk + heads * key_dim * EFA_TQ + 2 * (heads * heads + heads)) * sizeof(float);
+    ACH_REQUIRE(smem <= 160 * 1024, "ach_ef_attention: %d keys do not fit shared memory", Nk);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ef_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    ef_attention_kernel<<<dim3(cdiv(Nq, EFA_TQ), B), 256, smem, (cudaStream_t)stream>>>(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out,
+                                                                                      out_bs, heads, key_dim, d, Nq, Nk, scale, gelu);
+    return check_launch("ach_ef_attention");
+}
+
+extern "C" int ach_upsample2x_hp(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W, int gelu,
+                                 void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(x && out && B > 0 && B <= 65535 && C > 0 && C <= 65535 && H > 0 && W > 0, "ach_upsample2x_hp: bad args");
+    upsample2x_hp_kernel<<<dim3(cdiv((long long)4 * H * W, 256), C, B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, H, W, gelu);
+    return check_launch("ach_upsample2x_hp");
+}

@@ -560,6 +560,140 @@ class Engine:
             self.taps[f"backbone.feat{n_}"] = f
         return feats
 
+    # ---- EfficientFormerV2 "ImageEncoder" (backbone/vision/ImageEncoder.py)
+    def _ef_cbn(self, name, prefixes, x, out, act=ACT_NONE, res=None, gamma=None, conv_bn=None):
+        """1x1 Conv2d (bias) + BatchNorm2d as one GEMM; several (conv, bn) pairs are concatenated along the outputs"""
+        pairs = conv_bn if conv_bn is not None else [(p_ + ".0", p_ + ".1") for p_ in prefixes]
+        wt = self._w(name + ".wt", lambda: self._kmajor(torch.cat([self._p(c + ".weight").flatten(1) for c, _ in pairs], 0)))
+        sc = self._vec(name + ".s", lambda: torch.cat([self._bn_fold(b_, 1e-5, self._p(c + ".bias"))[0] for c, b_ in pairs]))
+        bi = self._vec(name + ".b", lambda: torch.cat([self._bn_fold(b_, 1e-5, self._p(c + ".bias"))[1] for c, b_ in pairs]))
+        self.pw(name, x, out, wt, out.C, scale=sc, bias=bi, act=act, res=res, gamma=gamma)
+
+    def _ef_dwbn(self, name, conv, bnp, x, out, stride=1, act=ACT_NONE, center_identity=False):
+        """depthwise 3x3 (bias) [+ BatchNorm]; center_identity adds the input pixel under the centre tap (LGQuery's pool branch)"""
+        def w(conv=conv):
+            wt = self._p(conv + ".weight").flatten(1).clone()
+            if center_identity:
+                wt[:, 4] += 1.0
+            return wt
+        if bnp is None:
+            self.dw(name, x, out, self._w(name + ".w", w), 3, stride=stride, bias=self._vec(name + ".b", lambda: self._p(conv + ".bias")), act=act)
+        else:
+            sc = self._vec(name + ".s", lambda: self._bn_fold(bnp, 1e-5, self._p(conv + ".bias"))[0])
+            bi = self._vec(name + ".b", lambda: self._bn_fold(bnp, 1e-5, self._p(conv + ".bias"))[1])
+            self.dw(name, x, out, self._w(name + ".w", w), 3, stride=stride, scale=sc, bias=bi, act=act)
+
+    def _ef_conv3s2(self, name, conv, bnp, x, out, act=ACT_NONE):
+        sc = self._vec(name + ".s", lambda: self._bn_fold(bnp, 1e-5, self._p(conv + ".bias"))[0])
+        bi = self._vec(name + ".b", lambda: self._bn_fold(bnp, 1e-5, self._p(conv + ".bias"))[1])
+        self.conv(name, x, out, self._pack_conv(name + ".w", conv + ".weight"), 3, 2, 1, scale=sc, bias=bi, act=act)
+
+    def ef_mlp(self, name, prefix, x, ls_key):
+        """x + layer_scale_2 * Mlp(x)  (ImageEncoder.py:374-389,444-449)"""
+        hidden = self._params[prefix + ".fc1.weight"].shape[0]
+        h1 = self.buf(name + ".h1", hidden, x.H, x.W)
+        self._ef_cbn(name + ".fc1", None, x, h1, act=ACT_GELU, conv_bn=[(prefix + ".fc1", prefix + ".norm1")])
+        h2 = self.buf(name + ".h2", hidden, x.H, x.W)
+        self._ef_dwbn(name + ".mid", prefix + ".mid", prefix + ".mid_norm", h1, h2, act=ACT_GELU)
+        out = self.buf(name + ".out", x.C, x.H, x.W)
+        ls = self._vec(name + ".ls", lambda: self._p(ls_key).flatten())
+        self._ef_cbn(name + ".fc2", None, h2, out, res=x, gamma=ls, conv_bn=[(prefix + ".fc2", prefix + ".norm2")])
+        return out
+
+    def _ef_ab(self, name, prefix):
+        return self._w(name + ".ab", lambda: self._p(prefix + ".attention_biases")[:, self._params[prefix + ".attention_bias_idxs"]])
+
+    def ef_attention4d(self, name, prefix, x, ls_key, stride):
+        """x + layer_scale_1 * Attention4D(x)  (ImageEncoder.py:63-160,415-418)"""
+        heads, kd, d = 8, 32, 128
+        C_, H, W = x.C, x.H, x.W
+        xs = x
+        if stride is not None:
+            xs = self.buf(name + ".sc", C_, H // stride, W // stride)
+            self._ef_dwbn(name + ".stride_conv", prefix + ".stride_conv.0", prefix + ".stride_conv.1", x, xs, stride=stride)
+        n = xs.H * xs.W
+        qkv = self.buf(name + ".qkv", heads * (2 * kd + d), xs.H, xs.W)
+        self._ef_cbn(name + ".qkv", [prefix + ".q", prefix + ".k", prefix + ".v"], xs, qkv)
+        q, k, v = self.sl(qkv, 0, heads * kd), self.sl(qkv, heads * kd, 2 * heads * kd), self.sl(qkv, 2 * heads * kd, heads * (2 * kd + d))
+        vl = self.buf(name + ".vlocal", heads * d, xs.H, xs.W)
+        self._ef_dwbn(name + ".v_local", prefix + ".v_local.0", prefix + ".v_local.1", v, vl)
+        ab = self._ef_ab(name, prefix)
+        th = [self._w(f"{name}.th{i}", (lambda i=i: torch.cat([self._p(f"{prefix}.talking_head{i}.weight").flatten(),
+                                                              self._p(f"{prefix}.talking_head{i}.bias")]))) for i in (1, 2)]
+        o = self.buf(name + ".o", heads * d, xs.H, xs.W)
+        self._add(name + ".attn", self.lib.ach_ef_attention, q.ptr, q.bs, k.ptr, k.bs, v.ptr, v.bs, ab.data_ptr(), th[0].data_ptr(),
+                  th[1].data_ptr(), vl.ptr, vl.bs, o.ptr, o.bs, self.B, heads, kd, d, n, n, float(kd) ** -0.5, 0 if stride is not None else 1)
+        src = o
+        if stride is not None:
+            src = self.buf(name + ".up", heads * d, H, W)
+            self._add(name + ".up", self.lib.ach_upsample2x_hp, o.ptr, o.bs, src.ptr, src.bs, self.B, heads * d, xs.H, xs.W, 1)
+        out = self.buf(name + ".out", C_, H, W)
+        ls = self._vec(name + ".ls", lambda: self._p(ls_key).flatten())
+        self._ef_cbn(name + ".proj", None, src, out, res=x, gamma=ls, conv_bn=[(prefix + ".proj.1", prefix + ".proj.2")])
+        return out
+
+    def ef_embedding_asub(self, name, prefix, x, cout):
+        """Embedding(asub=True): Attention4DDownsample(x) + BN(conv3x3 s2(x))  (ImageEncoder.py:193-289,329-336)"""
+        heads, kd, d = 8, 16, 64
+        a = prefix + ".attn"
+        C_, H, W = x.C, x.H, x.W
+        h2, w2 = H // 2, W // 2
+        qd = self.buf(name + ".qd", C_, h2, w2)
+        self._ef_dwbn(name + ".q.local", a + ".q.local.0", None, x, qd, stride=2, center_identity=True)   # local(x) + AvgPool2d(1, 2)(x)
+        q = self.buf(name + ".q", heads * kd, h2, w2)
+        self._ef_cbn(name + ".q.proj", [a + ".q.proj"], qd, q)
+        kv = self.buf(name + ".kv", heads * (kd + d), H, W)
+        self._ef_cbn(name + ".kv", [a + ".k", a + ".v"], x, kv)
+        k, v = self.sl(kv, 0, heads * kd), self.sl(kv, heads * kd, heads * (kd + d))
+        vl = self.buf(name + ".vlocal", heads * d, h2, w2)
+        self._ef_dwbn(name + ".v_local", a + ".v_local.0", a + ".v_local.1", v, vl, stride=2)
+        ab = self._ef_ab(name, a)
+        o = self.buf(name + ".o", heads * d, h2, w2)
+        self._add(name + ".attn", self.lib.ach_ef_attention, q.ptr, q.bs, k.ptr, k.bs, v.ptr, v.bs, ab.data_ptr(), None, None, vl.ptr, vl.bs,
+                  o.ptr, o.bs, self.B, heads, kd, d, h2 * w2, H * W, float(kd) ** -0.5, 1)
+        cb = self.buf(name + ".conv", cout, h2, w2)
+        self._ef_conv3s2(name + ".conv", prefix + ".conv", prefix + ".bn", x, cb)
+        out = self.buf(name + ".out", cout, h2, w2)
+        self._ef_cbn(name + ".proj", None, o, out, res=cb, conv_bn=[(a + ".proj.1", a + ".proj.2")])
+        return out
+
+    def efficientformer(self, x, prefix, phi):
+        dims, depth, vit = Hd.WIDTHS[phi], Hd.EF_DEPTH[phi], Hd.EF_VIT_NUM[phi]
+        H = self.res // 2
+        s1 = self.buf("bb.stem1", dims[0] // 2, H, H)
+        self._ef_conv3s2("bb.stem1", prefix + ".patch_embed.0", prefix + ".patch_embed.1", x, s1, act=ACT_GELU)
+        H //= 2
+        cur = self.buf("bb.stem2", dims[0], H, H)
+        self._ef_conv3s2("bb.stem2", prefix + ".patch_embed.3", prefix + ".patch_embed.4", s1, cur, act=ACT_GELU)
+        feats, idx = [], 0
+        for i in range(4):
+            for j in range(depth[i]):
+                bp = f"{prefix}.network.{idx}.{j}"
+                if i >= 2 and j > depth[i] - 1 - vit:
+                    cur = self.ef_attention4d(f"bb.s{i}.{j}.tm", bp + ".token_mixer", cur, bp + ".layer_scale_1", 2 if i == 2 else None)
+                cur = self.ef_mlp(f"bb.s{i}.{j}.mlp", bp + ".mlp", cur, bp + ".layer_scale_2")
+                self.taps[f"backbone.stage{i}.{j}"] = cur
+            # forked output: BatchNorm2d as a per-channel affine (identity GEMM)
+            f = self.buf(f"bb.f{i}", dims[i], cur.H, cur.W)
+            eye = self._w(f"bb.norm{idx}.eye", (lambda c=dims[i]: self._kmajor(torch.eye(c))))
+            sc = self._vec(f"bb.norm{idx}.s", (lambda idx=idx: self._bn_fold(f"{prefix}.norm{idx}", 1e-5)[0]))
+            bi = self._vec(f"bb.norm{idx}.b", (lambda idx=idx: self._bn_fold(f"{prefix}.norm{idx}", 1e-5)[1]))
+            self.pw(f"bb.norm{idx}", cur, f, eye, dims[i], scale=sc, bias=bi)
+            feats.append(f)
+            idx += 1
+            if i < 3:
+                ep = f"{prefix}.network.{idx}"
+                if i >= 2:
+                    cur = self.ef_embedding_asub(f"bb.emb{i}", ep, cur, dims[i + 1])
+                else:
+                    nxt = self.buf(f"bb.emb{i}", dims[i + 1], cur.H // 2, cur.W // 2)
+                    self._ef_conv3s2(f"bb.emb{i}", ep + ".proj", ep + ".norm", cur, nxt)
+                    cur = nxt
+                idx += 1
+        for n_, f in zip("2345", feats):
+            self.taps[f"backbone.feat{n_}"] = f
+        return feats
+
     # ---- MobileViT (mobilevit_modules/mobilevit.py)
     def conv_bn_silu(self, name, prefix, x, out, k, stride=1):
         """conv_nxn_bn / conv_1x1_bn: conv (no bias) + BN(1e-5) + SiLU  (mobilevit.py:7-21)"""
@@ -1172,6 +1306,8 @@ class Engine:
             feats = self.edgenext(self.x_in, ire + ".fpn.backbone", m.phi)
         elif m.backbone == "ev":
             feats = self.edgevit(self.x_in, ire + ".fpn.backbone", m.phi)
+        elif m.backbone == "ef":
+            feats = self.efficientformer(self.x_in, ire + ".fpn.backbone", m.phi)
         else:
             feats = self.mobilevit(self.x_in, ire + ".fpn.backbone", m.phi)
         maps = (self.gdf_neck if m.neck == "gdf" else self.cdf_neck)(feats, ire + ".fpn", m.phi, out_se, out_lane)

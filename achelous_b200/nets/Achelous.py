@@ -239,7 +239,7 @@ class Achelous(_AchelousBase):
         else:
             raise NotImplementedError(f"pc_seg={pc_seg!r}: implemented: 'pn', 'pn2'")
         self.image_radar_encoder = Hd.IREncoder(num_class_seg=num_seg, phi=phi, backbone=backbone, neck=neck,
-                                                radar_channels=radar_channels)
+                                                radar_channels=radar_channels, resolution=resolution)
         self.det_head = Hd.DecoupleHead(num_classes=num_det, phi=phi, nano_head=nano_head)
 
     def forward(self, x, x_radar, x_point_clouds):
@@ -257,7 +257,7 @@ class Achelous3T(_AchelousBase):
         self._init_common(num_det, num_seg, phi, image_channels, radar_channels, resolution, backbone, neck, pc_seg,
                           pc_channels, pc_classes, nano_head, spp)
         self.image_radar_encoder = Hd.IREncoder(num_class_seg=num_seg, phi=phi, backbone=backbone, neck=neck,
-                                                radar_channels=radar_channels)
+                                                radar_channels=radar_channels, resolution=resolution)
         self.det_head = Hd.DecoupleHead(num_classes=num_det, phi=phi, nano_head=nano_head)
 
     def forward(self, x, x_radar):

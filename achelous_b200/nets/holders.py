@@ -377,6 +377,147 @@ class EdgeViT(Holder):
         self.norm = nn.BatchNorm2d(dims[-1])
 
 
+# ------------------------------------------------------------------ EfficientFormerV2 "ImageEncoder" (backbone/vision/ImageEncoder.py)
+EF_DEPTH = {"S0": [2, 2, 6, 4], "S1": [3, 3, 9, 6], "S2": [4, 4, 12, 8]}
+EF_VIT_NUM = {"S0": 2, "S1": 2, "S2": 4}
+EF_RATIOS = {
+    "S0": [[4, 4], [4, 4], [4, 3, 3, 3, 4, 4], [4, 3, 3, 4]],
+    "S1": [[4, 4, 4], [4, 4, 4], [4, 4, 3, 3, 3, 3, 4, 4, 4], [4, 4, 3, 3, 4, 4]],
+    "S2": [[4, 4, 4, 4], [4, 4, 4, 4], [4, 4, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4], [4, 4, 3, 3, 3, 3, 4, 4]],
+}
+
+
+def _ef_bias_table(res_q, res_k):
+    """(number of distinct offsets, index table (res_q^2, res_k^2)): ImageEncoder.py:104-120 / :245-264"""
+    import itertools
+    step = math.ceil(res_k / res_q)
+    offsets, idxs = {}, []
+    for p1 in itertools.product(range(res_q), range(res_q)):
+        for p2 in itertools.product(range(res_k), range(res_k)):
+            off = (abs(p1[0] * step - p2[0]), abs(p1[1] * step - p2[1]))
+            if off not in offsets:
+                offsets[off] = len(offsets)
+            idxs.append(offsets[off])
+    return len(offsets), torch.LongTensor(idxs).view(res_q * res_q, res_k * res_k)
+
+
+def _cbn_seq(cin, cout, k=1, stride=1, groups=1):
+    return nn.Sequential(nn.Conv2d(cin, cout, k, stride, k // 2, groups=groups), nn.BatchNorm2d(cout))
+
+
+class EFMlp(Holder):
+    """ImageEncoder.py:342-366 (mid_conv=True)"""
+
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Conv2d(dim, hidden, 1)
+        self.fc2 = nn.Conv2d(hidden, dim, 1)
+        self.mid = nn.Conv2d(hidden, hidden, 3, 1, 1, groups=hidden)
+        self.mid_norm = nn.BatchNorm2d(hidden)
+        self.norm1 = nn.BatchNorm2d(hidden)
+        self.norm2 = nn.BatchNorm2d(dim)
+
+
+class EFAttention4D(Holder):
+    """ImageEncoder.py:63-121"""
+
+    def __init__(self, dim, resolution, stride, key_dim=32, num_heads=8, attn_ratio=4):
+        super().__init__()
+        self.num_heads, self.key_dim, self.stride = num_heads, key_dim, stride
+        if stride is not None:
+            resolution = math.ceil(resolution / stride)
+            self.stride_conv = _cbn_seq(dim, dim, 3, stride, groups=dim)
+        self.resolution = resolution
+        self.d = attn_ratio * key_dim
+        dh = self.d * num_heads
+        self.q = _cbn_seq(dim, num_heads * key_dim)
+        self.k = _cbn_seq(dim, num_heads * key_dim)
+        self.v = _cbn_seq(dim, dh)
+        self.v_local = _cbn_seq(dh, dh, 3, 1, groups=dh)
+        self.talking_head1 = nn.Conv2d(num_heads, num_heads, 1)
+        self.talking_head2 = nn.Conv2d(num_heads, num_heads, 1)
+        self.proj = nn.Sequential(nn.GELU(), nn.Conv2d(dh, dim, 1), nn.BatchNorm2d(dim))
+        n_off, idx = _ef_bias_table(resolution, resolution)
+        self.attention_biases = nn.Parameter(torch.zeros(num_heads, n_off))
+        self.register_buffer("attention_bias_idxs", idx)
+
+
+class EFLGQuery(Holder):
+    """ImageEncoder.py:174-183"""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.local = nn.Sequential(nn.Conv2d(in_dim, in_dim, 3, 2, 1, groups=in_dim))
+        self.proj = _cbn_seq(in_dim, out_dim)
+
+
+class EFAttention4DDownsample(Holder):
+    """ImageEncoder.py:193-264"""
+
+    def __init__(self, dim, out_dim, resolution, key_dim=16, num_heads=8, attn_ratio=4):
+        super().__init__()
+        self.num_heads, self.key_dim, self.resolution = num_heads, key_dim, resolution
+        self.d = attn_ratio * key_dim
+        dh = self.d * num_heads
+        self.resolution2 = math.ceil(resolution / 2)
+        self.q = EFLGQuery(dim, num_heads * key_dim)
+        self.k = _cbn_seq(dim, num_heads * key_dim)
+        self.v = _cbn_seq(dim, dh)
+        self.v_local = _cbn_seq(dh, dh, 3, 2, groups=dh)
+        self.proj = nn.Sequential(nn.GELU(), nn.Conv2d(dh, out_dim, 1), nn.BatchNorm2d(out_dim))
+        n_off, idx = _ef_bias_table(self.resolution2, resolution)
+        self.attention_biases = nn.Parameter(torch.zeros(num_heads, n_off))
+        self.register_buffer("attention_bias_idxs", idx)
+
+
+class EFEmbedding(Holder):
+    """ImageEncoder.py:292-339 (light=False)"""
+
+    def __init__(self, cin, cout, asub, resolution):
+        super().__init__()
+        self.asub = asub
+        if asub:
+            self.attn = EFAttention4DDownsample(cin, cout, resolution)
+            self.conv = nn.Conv2d(cin, cout, 3, 2, 1)
+            self.bn = nn.BatchNorm2d(cout)
+        else:
+            self.proj = nn.Conv2d(cin, cout, 3, 2, 1)
+            self.norm = nn.BatchNorm2d(cout)
+
+
+class EFBlock(Holder):
+    """FFN (ImageEncoder.py:426-449) or AttnFFN (:392-423)"""
+
+    def __init__(self, dim, ratio, attn, resolution=None, stride=None):
+        super().__init__()
+        if attn:
+            self.layer_scale_1 = nn.Parameter(1e-5 * torch.ones(dim, 1, 1))
+        self.layer_scale_2 = nn.Parameter(1e-5 * torch.ones(dim, 1, 1))
+        if attn:
+            self.token_mixer = EFAttention4D(dim, resolution, stride)
+        self.mlp = EFMlp(dim, int(dim * ratio))
+
+
+class EfficientFormer(Holder):
+    """ImageEncoder.py:488-568 (fork_feat=True)"""
+
+    def __init__(self, phi, resolution):
+        super().__init__()
+        dims, depth, ratios, vit = WIDTHS[phi], EF_DEPTH[phi], EF_RATIOS[phi], EF_VIT_NUM[phi]
+        self.patch_embed = nn.Sequential(nn.Conv2d(3, dims[0] // 2, 3, 2, 1), nn.BatchNorm2d(dims[0] // 2), nn.GELU(),
+                                         nn.Conv2d(dims[0] // 2, dims[0], 3, 2, 1), nn.BatchNorm2d(dims[0]), nn.GELU())
+        net = []
+        for i in range(4):
+            res = math.ceil(resolution / (2 ** (i + 2)))
+            net.append(nn.Sequential(*[EFBlock(dims[i], ratios[i][j], i >= 2 and j > depth[i] - 1 - vit, res, 2 if i == 2 else None)
+                                       for j in range(depth[i])]))
+            if i < 3:
+                net.append(EFEmbedding(dims[i], dims[i + 1], i >= 2, res))
+        self.network = nn.ModuleList(net)
+        for i_emb, i_layer in enumerate((0, 2, 4, 6)):
+            self.add_module(f"norm{i_layer}", nn.BatchNorm2d(dims[i_emb]))
+
+
 class SPPConv(Holder):
     """spp.py:27-31"""
 
@@ -422,7 +563,7 @@ class ShuffleAttention(Holder):
 class GhostDualFPN(Holder):
     """ghostdualfpn.py:42-151 (EN / MV backbones only)"""
 
-    def __init__(self, num_class_seg, phi, backbone):
+    def __init__(self, num_class_seg, phi, backbone, resolution=320):
         super().__init__()
         w = WIDTHS[phi]
         if backbone == "en":
@@ -431,8 +572,10 @@ class GhostDualFPN(Holder):
             self.backbone = MobileViT(phi)
         elif backbone == "ev":
             self.backbone = EdgeViT(phi)
+        elif backbone == "ef":
+            self.backbone = EfficientFormer(phi, resolution)
         else:
-            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en', 'mv' and 'ev' (SURVEY.md §8b, §8f)")
+            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en', 'mv', 'ev' and 'ef' (SURVEY.md §8b, §8f)")
         self.spp = SPP(w[3], w[3])
         self.upsample_5_to_4 = Upsample(w[3], w[2])
         self.ghost_5_to_4 = GhostBottleneck(w[2] * 2, w[2] * 2, w[2])
@@ -476,7 +619,7 @@ class CSPLayer(Holder):
 class CSPDualFPN(Holder):
     """cspdualfpn.py:81-191 (EN / MV backbones only)"""
 
-    def __init__(self, num_class_seg, phi, backbone):
+    def __init__(self, num_class_seg, phi, backbone, resolution=320):
         super().__init__()
         w = WIDTHS[phi]
         if backbone == "en":
@@ -485,8 +628,10 @@ class CSPDualFPN(Holder):
             self.backbone = MobileViT(phi)
         elif backbone == "ev":
             self.backbone = EdgeViT(phi)
+        elif backbone == "ef":
+            self.backbone = EfficientFormer(phi, resolution)
         else:
-            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en', 'mv' and 'ev' (SURVEY.md §8b, §8f)")
+            raise NotImplementedError(f"backbone={backbone!r}: achelous_b200 implements 'en', 'mv', 'ev' and 'ef' (SURVEY.md §8b, §8f)")
         self.spp = SPP(w[3], w[3])
         self.upsample_5_to_4 = Upsample(w[3], w[2])
         self.ghost_5_to_4 = CSPLayer(w[2] * 2, w[2])
@@ -517,12 +662,12 @@ class ECA(Holder):
 class IREncoder(Holder):
     """IREncoder.py:26-70"""
 
-    def __init__(self, num_class_seg, phi, backbone, neck, radar_channels=3):
+    def __init__(self, num_class_seg, phi, backbone, neck, radar_channels=3, resolution=320):
         super().__init__()
         if neck not in ("gdf", "cdf"):
             raise NotImplementedError(f"neck={neck!r}: achelous_b200 implements 'gdf' and 'cdf' (SURVEY.md §8b, §8f rank 3)")
         w = WIDTHS[phi]
-        self.fpn = (GhostDualFPN if neck == "gdf" else CSPDualFPN)(num_class_seg, phi, backbone)
+        self.fpn = (GhostDualFPN if neck == "gdf" else CSPDualFPN)(num_class_seg, phi, backbone, resolution)
         self.radar_encoder = RCNet(radar_channels, phi)
         for s, c in zip((3, 4, 5), w[1:]):
             setattr(self, f"channel_attn_stage{s}", nn.ModuleList([ECA(c), ECA(c // 4)]))

@@ -46,7 +46,22 @@ def fill_state_dict(spec, seed: int = 0):
         shape, g = shapes[k], _gen(seed, k)
         leaf = k.rsplit(".", 1)[-1]
         prefix = k[: len(k) - len(leaf)]
-        if leaf == "num_batches_tracked":
+        if leaf == "attention_bias_idxs":
+            # EfficientFormerV2 relative-position index table (ImageEncoder.py:104-120,245-264): a function of the two grid sizes
+            import itertools
+            import math
+            n_q, n_k = shape
+            r_q, r_k = math.isqrt(n_q), math.isqrt(n_k)
+            step = math.ceil(r_k / r_q)
+            offsets, idxs = {}, []
+            for p1 in itertools.product(range(r_q), range(r_q)):
+                for p2 in itertools.product(range(r_k), range(r_k)):
+                    off = (abs(p1[0] * step - p2[0]), abs(p1[1] * step - p2[1]))
+                    if off not in offsets:
+                        offsets[off] = len(offsets)
+                    idxs.append(offsets[off])
+            t = torch.tensor(idxs, dtype=torch.int64).view(n_q, n_k)
+        elif leaf == "num_batches_tracked":
             t = torch.zeros(shape, dtype=dtypes[k])
         elif leaf == "running_mean":
             t = _normal(shape, g, 0.0, 0.1)
@@ -60,12 +75,16 @@ def fill_state_dict(spec, seed: int = 0):
             t = _normal(shape, g, 0.0, 0.1)
         elif leaf in ("gamma", "gamma_xca"):
             t = _uniform(shape, g, 0.5, 1.5)
+        elif leaf in ("layer_scale_1", "layer_scale_2"):
+            t = _uniform(shape, g, 0.1, 0.3)   # EfficientFormerV2: 14 residual blocks with BatchNorm-ed (unit-scale) branches
         elif leaf == "temperature":
             t = _uniform(shape, g, 0.5, 2.0)
         elif leaf in ("cweight", "sweight"):
             t = _normal(shape, g, 0.0, 1.0)
         elif leaf in ("cbias", "sbias"):
             t = _normal(shape, g, 1.0, 0.5)
+        elif leaf == "bias" and "talking_head" in k:
+            t = _normal(shape, g, 0.0, 0.002)  # added to every one of N_k attention entries of a row: keep the row sums O(1)
         elif leaf == "bias" and "offset_conv" in k:
             t = _uniform(shape, g, -1.0, 1.0)  # leave the integer sampling grid
         elif leaf == "bias":

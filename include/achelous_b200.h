@@ -245,6 +245,18 @@ ACH_API int ach_mhsa(const float* qkv, long long qkv_bs, float* out, long long o
 ACH_API int ach_dw_convT(const float* x, long long x_bs, const float* w, const float* bias, float* out, long long out_bs, int B, int C,
                          int h, int w_in, int sr, void* stream);
 
+/* EfficientFormerV2 "ImageEncoder" blocks (backbone/vision/ImageEncoder.py, backbone='ef'):
+ * ach_ef_attention: Attention4D / Attention4DDownsample core (:131-160, :267-289).  q (B, heads*key_dim, Nq), k (B, heads*key_dim,
+ *   Nk), v (B, heads*d, Nk) channel-major views; ab (heads, Nq, Nk) = attention_biases[:, attention_bias_idxs]; th1 / th2 =
+ *   talking-head 1x1 convs as [heads*heads weights (out, in) | heads biases], or NULL; add (B, heads*d, Nq) (v_local) or NULL;
+ *   out (B, heads*d, Nq) = [gelu](softmax-attention(q, k, v) + add).  heads <= 8.
+ * ach_upsample2x_hp: bilinear x2 with align_corners=False (nn.Upsample(scale_factor=2, mode='bilinear'), :80), optional GELU. */
+ACH_API int ach_ef_attention(const float* q, long long q_bs, const float* k, long long k_bs, const float* v, long long v_bs,
+                             const float* ab, const float* th1, const float* th2, const float* add, long long add_bs, float* out,
+                             long long out_bs, int B, int heads, int key_dim, int d, int Nq, int Nk, float scale, int gelu, void* stream);
+ACH_API int ach_upsample2x_hp(const float* x, long long x_bs, float* out, long long out_bs, int B, int C, int H, int W, int gelu,
+                              void* stream);
+
 /* Fully connected on (B, K) rows: out[b, o] = act(scale[o] * (w[o, :] . x[b, :]) + bias[o]).
  * pointnet_utils.py:16-18,38-40 (fc + BN1d + ReLU), and the global-feature half of
  * pointnet_sem_seg.py:18 (Conv1d over a point-wise constant). */

@@ -463,6 +463,99 @@ def edgevit(x, p, phi, taps=None):
     return feats
 
 
+# ----------------------------------------------------------------------------- EfficientFormerV2 "ImageEncoder" (backbone='ef')
+EF_DEPTH = {"S0": [2, 2, 6, 4], "S1": [3, 3, 9, 6], "S2": [4, 4, 12, 8]}          # ImageEncoder.py:23-28
+EF_VIT_NUM = {"S0": 2, "S1": 2, "S2": 4}                                           # :627-670
+EF_RATIOS = {                                                                      # :30-60
+    "S0": [[4, 4], [4, 4], [4, 3, 3, 3, 4, 4], [4, 3, 3, 4]],
+    "S1": [[4, 4, 4], [4, 4, 4], [4, 4, 3, 3, 3, 3, 4, 4, 4], [4, 4, 3, 3, 4, 4]],
+    "S2": [[4, 4, 4, 4], [4, 4, 4, 4], [4, 4, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4], [4, 4, 3, 3, 3, 3, 4, 4]],
+}
+
+
+def _cbn(x, p, stride=1, padding=0, groups=1):
+    """nn.Sequential(Conv2d, BatchNorm2d) with keys 0 / 1"""
+    return bn(conv(x, p.sub("0"), stride, padding, groups), p.sub("1"), 1e-5)
+
+
+def ef_mlp(x, p):
+    """Mlp with mid depthwise conv.  ImageEncoder.py:342-389"""
+    x = F.gelu(bn(conv(x, p.sub("fc1")), p.sub("norm1"), 1e-5))
+    x = F.gelu(bn(conv(x, p.sub("mid"), 1, 1, groups=x.shape[1]), p.sub("mid_norm"), 1e-5))
+    return bn(conv(x, p.sub("fc2")), p.sub("norm2"), 1e-5)
+
+
+def ef_attention4d(x, p, resolution, stride, heads=8, key_dim=32, attn_ratio=4):
+    """Attention4D with talking heads and relative-position biases.  ImageEncoder.py:63-160"""
+    B, C, H, W = x.shape
+    d = attn_ratio * key_dim
+    if stride is not None:
+        resolution = math.ceil(resolution / stride)
+        x = _cbn(x, p.sub("stride_conv"), stride, 1, groups=C)
+    N = resolution * resolution
+    q = _cbn(x, p.sub("q")).flatten(2).reshape(B, heads, -1, N).permute(0, 1, 3, 2)
+    k = _cbn(x, p.sub("k")).flatten(2).reshape(B, heads, -1, N)
+    v = _cbn(x, p.sub("v"))
+    v_local = _cbn(v, p.sub("v_local"), 1, 1, groups=v.shape[1])
+    v = v.flatten(2).reshape(B, heads, -1, N).permute(0, 1, 3, 2)
+    attn = (q @ k) * key_dim ** -0.5 + p("attention_biases")[:, p("attention_bias_idxs")]
+    attn = conv(attn, p.sub("talking_head1")).softmax(dim=-1)
+    attn = conv(attn, p.sub("talking_head2"))
+    out = (attn @ v).transpose(2, 3).reshape(B, heads * d, resolution, resolution) + v_local
+    if stride is not None:
+        out = F.interpolate(out, scale_factor=stride, mode="bilinear")
+    return bn(conv(F.gelu(out), p.sub("proj.1")), p.sub("proj.2"), 1e-5)
+
+
+def ef_attention4d_down(x, p, resolution, heads=8, key_dim=16, attn_ratio=4):
+    """Attention4DDownsample with the LGQuery.  ImageEncoder.py:174-289"""
+    B, C, H, W = x.shape
+    d = attn_ratio * key_dim
+    res2 = math.ceil(resolution / 2)
+    N, N2 = resolution * resolution, res2 * res2
+    qp = p.sub("q")
+    q = conv(x, qp.sub("local.0"), 2, 1, groups=C) + x[:, :, ::2, ::2]          # local dw conv + AvgPool2d(1, 2, 0)
+    q = _cbn(q, qp.sub("proj")).flatten(2).reshape(B, heads, -1, N2).permute(0, 1, 3, 2)
+    k = _cbn(x, p.sub("k")).flatten(2).reshape(B, heads, -1, N)
+    v = _cbn(x, p.sub("v"))
+    v_local = _cbn(v, p.sub("v_local"), 2, 1, groups=v.shape[1])
+    v = v.flatten(2).reshape(B, heads, -1, N).permute(0, 1, 3, 2)
+    attn = ((q @ k) * key_dim ** -0.5 + p("attention_biases")[:, p("attention_bias_idxs")]).softmax(dim=-1)
+    out = (attn @ v).transpose(2, 3).reshape(B, heads * d, res2, res2) + v_local
+    return bn(conv(F.gelu(out), p.sub("proj.1")), p.sub("proj.2"), 1e-5)
+
+
+def efficientformer(x, p, phi, resolution=320, taps=None):
+    """ImageEncoder.forward (fork_feat) -> 4 normed maps.  ImageEncoder.py:488-612"""
+    depth, ratios, vit_num = EF_DEPTH[phi], EF_RATIOS[phi], EF_VIT_NUM[phi]
+    pe = p.sub("patch_embed")
+    x = F.gelu(bn(conv(x, pe.sub("0"), 2, 1), pe.sub("1"), 1e-5))
+    x = F.gelu(bn(conv(x, pe.sub("3"), 2, 1), pe.sub("4"), 1e-5))
+    feats, idx = [], 0
+    for i in range(4):
+        res = math.ceil(resolution / (2 ** (i + 2)))
+        for j in range(depth[i]):
+            bp = p.sub(f"network.{idx}.{j}")
+            if i >= 2 and j > depth[i] - 1 - vit_num:
+                x = x + bp("layer_scale_1") * ef_attention4d(x, bp.sub("token_mixer"), res, 2 if i == 2 else None)
+            x = x + bp("layer_scale_2") * ef_mlp(x, bp.sub("mlp"))
+            if taps is not None:
+                taps[f"backbone.stage{i}.{j}"] = x
+        feats.append(bn(x, p.sub(f"norm{idx}"), 1e-5))
+        idx += 1
+        if i < 3:
+            ep = p.sub(f"network.{idx}")
+            if i >= 2:   # asub: attention downsample + strided conv
+                x = ef_attention4d_down(x, ep.sub("attn"), res) + bn(conv(x, ep.sub("conv"), 2, 1), ep.sub("bn"), 1e-5)
+            else:
+                x = bn(conv(x, ep.sub("proj"), 2, 1), ep.sub("norm"), 1e-5)
+            idx += 1
+    if taps is not None:
+        for n, f in zip("2345", feats):
+            taps[f"backbone.feat{n}"] = f
+    return feats
+
+
 # ----------------------------------------------------------------------------- neck / fusion / heads
 def spp(x, p):
     """SPP(5,9,13).  neck/spp.py:41-52"""
@@ -487,7 +580,7 @@ def ghost_dual_fpn(x, p, phi, backbone, num_seg, taps=None):
     """GhostDualFPN.forward.  ghostdualfpn.py:156-200"""
     w = WIDTHS[phi]
     bb = p.sub("backbone")
-    m2, m3, m4, m5 = {"en": edgenext, "mv": mobilevit, "ev": edgevit}[backbone](x, bb, phi, taps)
+    m2, m3, m4, m5 = {"en": edgenext, "mv": mobilevit, "ev": edgevit, "ef": lambda x_, b_, p_, t_: efficientformer(x_, b_, p_, x_.shape[-1], t_)}[backbone](x, bb, phi, taps)
     f5 = spp(m5, p.sub("spp"))
     f4 = ghost_bottleneck(torch.cat([upsample_block(f5, p.sub("upsample_5_to_4")), m4], 1),
                           p.sub("ghost_5_to_4"), w[2] * 2, w[2])
@@ -529,7 +622,7 @@ def seg_decoder_csp(x, p, name, num_out, taps=None):
 def csp_dual_fpn(x, p, phi, backbone, num_seg, taps=None):
     """CSPDualFPN.forward.  cspdualfpn.py:193-239"""
     bb = p.sub("backbone")
-    m2, m3, m4, m5 = {"en": edgenext, "mv": mobilevit, "ev": edgevit}[backbone](x, bb, phi, taps)
+    m2, m3, m4, m5 = {"en": edgenext, "mv": mobilevit, "ev": edgevit, "ef": lambda x_, b_, p_, t_: efficientformer(x_, b_, p_, x_.shape[-1], t_)}[backbone](x, bb, phi, taps)
     f5 = spp(m5, p.sub("spp"))
     f4 = csp_layer(torch.cat([upsample_block(f5, p.sub("upsample_5_to_4")), m4], 1), p.sub("ghost_5_to_4"))
     f3 = csp_layer(torch.cat([upsample_block(f4, p.sub("upsample_4_to_3")), m3], 1), p.sub("ghost_4_to_3"))

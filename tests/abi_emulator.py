@@ -184,6 +184,33 @@ def ach_conv3x3_tc(s, w_hi, w_lo):
     fview(s.out, (B, O, H, W), (s.out_bs, H * W, W, 1)).copy_(y)
 
 
+def ach_ef_attention(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out, out_bs, B, heads, kd, d, Nq, Nk, scale, gelu):
+    qv = fview(q, (B, heads, kd, Nq), (q_bs, kd * Nq, Nq, 1))
+    kv = fview(k, (B, heads, kd, Nk), (k_bs, kd * Nk, Nk, 1))
+    vv = fview(v, (B, heads, d, Nk), (v_bs, d * Nk, Nk, 1))
+    attn = (qv.transpose(-2, -1) @ kv) * scale + fview(ab, (heads, Nq, Nk), (Nq * Nk, Nk, 1))[None]
+    if th1:
+        t = _vec(th1, heads * heads + heads)
+        attn = F.conv2d(attn, t[:heads * heads].reshape(heads, heads, 1, 1), t[heads * heads:])
+    attn = attn.softmax(-1)
+    if th2:
+        t = _vec(th2, heads * heads + heads)
+        attn = F.conv2d(attn, t[:heads * heads].reshape(heads, heads, 1, 1), t[heads * heads:])
+    o = vv @ attn.transpose(-2, -1)                       # (B, h, d, Nq)
+    if add:
+        o = o + fview(add, (B, heads, d, Nq), (add_bs, d * Nq, Nq, 1))
+    if gelu:
+        o = F.gelu(o)
+    fview(out, (B, heads, d, Nq), (out_bs, d * Nq, Nq, 1)).copy_(o)
+
+
+def ach_upsample2x_hp(x, x_bs, out, out_bs, B, Cc, H, W, gelu):
+    y = F.interpolate(fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1)), scale_factor=2, mode="bilinear")
+    if gelu:
+        y = F.gelu(y)
+    fview(out, (B, Cc, 2 * H, 2 * W), (out_bs, 4 * H * W, 2 * W, 1)).copy_(y)
+
+
 def ach_s2d(x, x_bs, out, out_bs, B, Cc, H, W, p):
     xv = fview(x, (B, Cc, H, W), (x_bs, H * W, W, 1))
     y = xv.reshape(B, Cc, H // p, p, W // p, p).permute(0, 1, 3, 5, 2, 4).reshape(B, Cc * p * p, H // p, W // p)
@@ -488,7 +515,7 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT, ach_s2d)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT, ach_s2d, ach_ef_attention, ach_upsample2x_hp)}
 
 
 def _unwrap(a):

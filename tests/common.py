@@ -14,6 +14,7 @@ GOLDEN_CONFIGS = {
     "mv_gdf_pn_s0": ("S0", "mv", 0, 13),
     "en_cdf_pn_s0": ("S0", "en", 3, 14),   # CSP-Dual-FPN neck
     "ev_gdf_pn_s0": ("S0", "ev", 4, 15),   # EdgeViT backbone
+    "ef_gdf_pn_s0": ("S0", "ef", 5, 16),   # EfficientFormerV2 backbone
 }
 GOLDEN_NECK = {"en_cdf_pn_s0": "cdf"}      # every other config uses the Ghost-Dual-FPN
 

@@ -32,6 +32,7 @@ CONFIGS = {
     "mv_gdf_pn_s0": dict(phi="S0", backbone="mv", weight_seed=0, input_seed=13),
     "en_cdf_pn_s0": dict(phi="S0", backbone="en", weight_seed=3, input_seed=14, neck="cdf"),
     "ev_gdf_pn_s0": dict(phi="S0", backbone="ev", weight_seed=4, input_seed=15),
+    "ef_gdf_pn_s0": dict(phi="S0", backbone="ef", weight_seed=5, input_seed=16),
 }
 MODEL_KW = dict(num_det=7, num_seg=9, resolution=320, pc_seg="pn", pc_channels=5, pc_classes=8,
                 nano_head=True, spp=True)
@@ -60,6 +61,11 @@ def tap_map(phi, backbone):
             m[f"{fpn}backbone.downsample_layers.{i}"] = f"backbone.down{i}"
             for j in range(depths[i]):
                 m[f"{fpn}backbone.stages.{i}.{j}"] = f"backbone.stage{i}.{j}"
+    if backbone == "ef":
+        depth = {"S0": [2, 2, 6, 4], "S1": [3, 3, 9, 6], "S2": [4, 4, 12, 8]}[phi]
+        for i in range(4):
+            for j in range(depth[i]):
+                m[f"{fpn}backbone.network.{2 * i}.{j}"] = f"backbone.stage{i}.{j}"
     if backbone == "ev":
         depth = {"S0": [1, 1, 3, 2], "S1": [1, 1, 3, 1], "S2": [1, 2, 5, 3]}[phi]
         for i in range(4):
@@ -99,6 +105,8 @@ def main():
         with open(os.path.join(HERE, name + ".keys.json"), "w") as f:
             json.dump({k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in sd0.items()}, f, indent=0)
         model.load_state_dict(fill_state_dict(sd0, seed=cfg["weight_seed"]), strict=True)
+        model.eval()   # achelous.py:171-176 loads the weights and THEN calls .eval(): EfficientFormerV2's Attention4D caches
+        #                attention_biases[:, idxs] in .train(False) (ImageEncoder.py:122-128) and would otherwise keep the zeros
         x, xr, pc = make_inputs(2, seed=cfg["input_seed"])
         store = {}
         hooks = []

@@ -762,3 +762,30 @@ def test_s2d(Cc, H, W, p):
         A.new("x", R(B, Cc, H, W)), A.new("out", torch.zeros(B, Cc * p * p, H // p, W // p))
         return (A.ptr("x"), Cc * H * W, A.ptr("out"), Cc * H * W, B, Cc, H, W, p)
     run_both("ach_s2d", make, ["out"])
+
+
+@pytest.mark.parametrize("heads,kd,d,Nq,Nk,th,add,gelu", [(8, 32, 128, 100, 100, 1, 1, 1), (8, 32, 128, 100, 100, 1, 1, 0), (8, 16, 64, 100, 400, 0, 1, 1),
+                                                          (4, 8, 12, 37, 50, 1, 0, 0), (8, 16, 64, 25, 100, 0, 0, 1)])
+def test_ef_attention(heads, kd, d, Nq, Nk, th, add, gelu):
+    """EfficientFormerV2 Attention4D / Attention4DDownsample core: biases, talking heads, softmax, P.V, + v_local, GELU"""
+    B = 2
+
+    def make(A):
+        A.new("q", R(B, heads * kd, Nq)), A.new("k", R(B, heads * kd, Nk)), A.new("v", R(B, heads * d, Nk))
+        A.new("ab", R(heads, Nq, Nk) * 0.5), A.new("out", torch.zeros(B, heads * d, Nq))
+        A.new("th1", torch.cat([R(heads * heads) / heads ** 0.5, R(heads) * 0.1])), A.new("th2", torch.cat([R(heads * heads) / heads ** 0.5, R(heads) * 0.1]))
+        A.new("add", R(B, heads * d, Nq))
+        return (A.ptr("q"), heads * kd * Nq, A.ptr("k"), heads * kd * Nk, A.ptr("v"), heads * d * Nk, A.ptr("ab"),
+                A.ptr("th1") if th else None, A.ptr("th2") if th else None, A.ptr("add") if add else None, heads * d * Nq,
+                A.ptr("out"), heads * d * Nq, B, heads, kd, d, Nq, Nk, float(kd) ** -0.5, gelu)
+    run_both("ach_ef_attention", make, ["out"])
+
+
+@pytest.mark.parametrize("Cc,H,W,gelu", [(16, 10, 10, 1), (5, 7, 9, 0)])
+def test_upsample2x_hp(Cc, H, W, gelu):
+    B = 2
+
+    def make(A):
+        A.new("x", R(B, Cc, H, W)), A.new("out", torch.zeros(B, Cc, 2 * H, 2 * W))
+        return (A.ptr("x"), Cc * H * W, A.ptr("out"), 4 * Cc * H * W, B, Cc, H, W, gelu)
+    run_both("ach_upsample2x_hp", make, ["out"])
