@@ -286,6 +286,140 @@ __global__ void __launch_bounds__(256) ef_attention_kernel(const float* __restri
     }
 }
 
+template <int TQ>
+__global__ void __launch_bounds__(256) ef_attention_v2_kernel(const float* __restrict__ q, long long q_bs, const float* __restrict__ k,
+                                                           long long k_bs, const float* __restrict__ v, long long v_bs,
+                                                           const float* __restrict__ ab, const float* __restrict__ th1,
+                                                           const float* __restrict__ th2, const float* __restrict__ add, long long add_bs,
+                                                           float* __restrict__ out, long long out_bs, int heads, int kd, int d, int Nq,
+                                                           int Nk, float scale, int gelu) {
+    extern __shared__ float smem[];
+    float* S = smem;                              // [heads][TQ][Nk]
+    float* qs = S + heads * TQ * Nk;          // [heads*kd][TQ]
+    float* ths = qs + heads * kd * TQ;        // th1 (h*h + h) | th2 (h*h + h)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * TQ, b = blockIdx.y;
+    const float* qb = q + (long long)b * q_bs;
+    const float* kb = k + (long long)b * k_bs;
+    const float* vb = v + (long long)b * v_bs;
+    for (int i = tid; i < heads * kd * TQ; i += 256) {
+        const int c = i / TQ, t = i - c * TQ;
+        qs[i] = (q0 + t < Nq) ? __ldg(qb + (long long)c * Nq + q0 + t) * scale : 0.f;
+    }
+    const int nth = heads * heads + heads;
+    for (int i = tid; i < 2 * nth; i += 256) ths[i] = (i < nth) ? (th1 ? th1[i] : 0.f) : (th2 ? th2[i - nth] : 0.f);
+    __syncthreads();
+    // ---- scores: thread per (head, key), TQ accumulators
+    for (int i = tid; i < heads * Nk; i += 256) {
+        const int h = i / Nk, kk = i - h * Nk;
+        float acc[TQ];
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) acc[t] = 0.f;
+        for (int c = 0; c < kd; ++c) {
+            const float kv = __ldg(kb + (long long)(h * kd + c) * Nk + kk);
+            const float* qc = qs + (h * kd + c) * TQ;
+#pragma unroll
+            for (int t = 0; t < TQ; ++t) acc[t] = fmaf(qc[t], kv, acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < TQ; ++t) {
+            const int qq = min(q0 + t, Nq - 1);
+            S[(h * TQ + t) * Nk + kk] = acc[t] + __ldg(ab + ((long long)h * Nq + qq) * Nk + kk);
+        }
+    }
+    __syncthreads();
+    // ---- talking head 1 (mixes the heads of every (query, key) score)
+    if (th1) {
+        for (int i = tid; i < TQ * Nk; i += 256) {
+            float s[EFA_MAXH], o[EFA_MAXH];
+            for (int h = 0; h < heads; ++h) s[h] = S[h * TQ * Nk + i];
+            for (int ho = 0; ho < heads; ++ho) {
+                float a = ths[heads * heads + ho];
+                for (int h = 0; h < heads; ++h) a = fmaf(ths[ho * heads + h], s[h], a);
+                o[ho] = a;
+            }
+            for (int h = 0; h < heads; ++h) S[h * TQ * Nk + i] = o[h];
+        }
+        __syncthreads();
+    }
+    // ---- softmax over the keys: one warp per (head, query) row
+    for (int r = warp; r < heads * TQ; r += 8) {
+        float* row = S + r * Nk;
+        float m = -INFINITY;
+        for (int j = lane; j < Nk; j += 32) m = fmaxf(m, row[j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < Nk; j += 32) {
+            const float e = expf(row[j] - m);
+            row[j] = e;
+            s += e;
+        }
+        s = warp_sum(s);
+        const float inv = 1.0f / s;
+        for (int j = lane; j < Nk; j += 32) row[j] *= inv;
+    }
+    __syncthreads();
+    if (th2) {
+        const float* t2 = ths + nth;
+        for (int i = tid; i < TQ * Nk; i += 256) {
+            float s[EFA_MAXH], o[EFA_MAXH];
+            for (int h = 0; h < heads; ++h) s[h] = S[h * TQ * Nk + i];
+            for (int ho = 0; ho < heads; ++ho) {
+                float a = t2[heads * heads + ho];
+                for (int h = 0; h < heads; ++h) a = fmaf(t2[ho * heads + h], s[h], a);
+                o[ho] = a;
+            }
+            for (int h = 0; h < heads; ++h) S[h * TQ * Nk + i] = o[h];
+        }
+        __syncthreads();
+    }
+    // ---- out = P v, one head at a time: V_h^T staged in shared memory ([key][d], 16-byte aligned rows), every thread
+    // a 4 (value channels) x 4 (queries) register tile - per key one LDS.128 of V and four broadcast loads of P feed 16 FMAs
+    // (v1 reduced every output over a warp: 20 shuffles per 4 outputs and V re-read from L2 by every 4-query CTA)
+    float* vs = ths + 2 * nth;
+    vs += (4 - ((vs - smem) & 3)) & 3;            // 16-byte alignment
+    const int vp = d + 4;                         // row pitch (floats)
+    const int jt = tid % (d / 4), tt = tid / (d / 4);
+    const bool active = tt < TQ / 4;
+    for (int h = 0; h < heads; ++h) {
+        __syncthreads();
+        for (int i = tid; i < d * Nk; i += 256) {
+            const int r = i / Nk, kk = i - r * Nk;
+            vs[kk * vp + r] = __ldg(vb + (long long)(h * d + r) * Nk + kk);
+        }
+        __syncthreads();
+        if (!active) continue;
+        float acc[4][4];
+#pragma unroll
+        for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) acc[a_][t] = 0.f;
+        const float* sp = S + (h * TQ + 4 * tt) * Nk;
+        for (int kk = 0; kk < Nk; ++kk) {
+            const float4 vv = *reinterpret_cast<const float4*>(vs + kk * vp + 4 * jt);
+            const float p0 = sp[kk], p1 = sp[Nk + kk], p2 = sp[2 * Nk + kk], p3 = sp[3 * Nk + kk];
+            acc[0][0] = fmaf(vv.x, p0, acc[0][0]); acc[0][1] = fmaf(vv.x, p1, acc[0][1]); acc[0][2] = fmaf(vv.x, p2, acc[0][2]); acc[0][3] = fmaf(vv.x, p3, acc[0][3]);
+            acc[1][0] = fmaf(vv.y, p0, acc[1][0]); acc[1][1] = fmaf(vv.y, p1, acc[1][1]); acc[1][2] = fmaf(vv.y, p2, acc[1][2]); acc[1][3] = fmaf(vv.y, p3, acc[1][3]);
+            acc[2][0] = fmaf(vv.z, p0, acc[2][0]); acc[2][1] = fmaf(vv.z, p1, acc[2][1]); acc[2][2] = fmaf(vv.z, p2, acc[2][2]); acc[2][3] = fmaf(vv.z, p3, acc[2][3]);
+            acc[3][0] = fmaf(vv.w, p0, acc[3][0]); acc[3][1] = fmaf(vv.w, p1, acc[3][1]); acc[3][2] = fmaf(vv.w, p2, acc[3][2]); acc[3][3] = fmaf(vv.w, p3, acc[3][3]);
+        }
+#pragma unroll
+        for (int a_ = 0; a_ < 4; ++a_) {
+            const int r = h * d + 4 * jt + a_;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int qq = q0 + 4 * tt + t;
+                if (qq < Nq) {
+                    float y = acc[a_][t];
+                    if (add) y += __ldg(add + (long long)b * add_bs + (long long)r * Nq + qq);
+                    if (gelu) y = apply_act(y, ACT_GELU);
+                    out[(long long)b * out_bs + (long long)r * Nq + qq] = y;
+                }
+            }
+        }
+    }
+}
+
 // bilinear x2, align_corners=False (nn.Upsample(scale_factor=2, mode='bilinear'), ImageEncoder.py:80), optional GELU
 __global__ void __launch_bounds__(256) upsample2x_hp_kernel(const float* __restrict__ x, long long x_bs, float* __restrict__ out,
                                                             long long out_bs, int H, int W, int gelu) {
@@ -314,6 +448,26 @@ extern "C" int ach_ef_attention(const float* q, long long q_bs, const float* k, 
     using namespace ach;
     ACH_REQUIRE(q && k && v && ab && out, "ach_ef_attention: null arg");
     ACH_REQUIRE(B > 0 && B <= 65535 && heads > 0 && heads <= EFA_MAXH && key_dim > 0 && d > 0 && Nq > 0 && Nk > 0, "ach_ef_attention: bad dims");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // v2 (register-tiled P.V with V_h^T in shared memory) when the tiles fit; v1 (4 queries per CTA, warp reductions) otherwise
+    for (int tq : {16}) {   // measured: the 8-query variant (Nk = 400, d = 64) keeps only 32 threads busy in P.V and loses to v1 (1.36 vs 0.54 ms)
+        if ((tq == 16 && Nk > 128) || d % 4 != 0 || 256 / (d / 4) < tq / 4) continue;
+        const size_t smem2 = (size_t)(heads * tq * Nk + heads * key_dim * tq + 2 * (heads * heads + heads) + 4 + Nk * (d + 4)) * sizeof(float);
+        if (smem2 > 220 * 1024) continue;
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaFuncSetAttribute(ef_attention_v2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            cudaFuncSetAttribute(ef_attention_v2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            attr2 = true;
+        }
+        if (tq == 16)
+            ef_attention_v2_kernel<16><<<dim3(cdiv(Nq, 16), B), 256, smem2, st>>>(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out, out_bs,
+                                                                                 heads, key_dim, d, Nq, Nk, scale, gelu);
+        else
+            ef_attention_v2_kernel<8><<<dim3(cdiv(Nq, 8), B), 256, smem2, st>>>(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out, out_bs,
+                                                                               heads, key_dim, d, Nq, Nk, scale, gelu);
+        return check_launch("ach_ef_attention");
+    }
     const size_t smem = (size_t)(heads * EFA_TQ * Nk + heads * key_dim * EFA_TQ + 2 * (heads * heads + heads)) * sizeof(float);
     ACH_REQUIRE(smem <= 160 * 1024, "ach_ef_attention: %d keys do not fit shared memory", Nk);
     static bool attr_set = false;
@@ -321,8 +475,8 @@ extern "C" int ach_ef_attention(const float* q, long long q_bs, const float* k, 
         cudaFuncSetAttribute(ef_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set = true;
     }
-    ef_attention_kernel<<<dim3(cdiv(Nq, EFA_TQ), B), 256, smem, (cudaStream_t)stream>>>(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out,
-                                                                                      out_bs, heads, key_dim, d, Nq, Nk, scale, gelu);
+    ef_attention_kernel<<<dim3(cdiv(Nq, EFA_TQ), B), 256, smem, st>>>(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out,
+                                                                      out_bs, heads, key_dim, d, Nq, Nk, scale, gelu);
     return check_launch("ach_ef_attention");
 }
 
