@@ -114,7 +114,9 @@ def test_errors_are_loud():
     with pytest.raises(NotImplementedError):
         model.train()(x, xr, pc)
     with pytest.raises(NotImplementedError):
-        Achelous(phi="S0", backbone="ef", **MODEL_KW)
+        Achelous(phi="S0", backbone="rv", **MODEL_KW)      # RepViT / PoolFormer are outside SURVEY.md §8 ('en', 'mv', 'ev', 'ef' are built)
+    with pytest.raises(NotImplementedError):
+        Achelous(phi="S0", backbone="en", **dict(MODEL_KW, neck="rdf"))
 
 
 def test_weight_update_invalidates_packs():
