@@ -15,7 +15,7 @@ TOL = 5e-5
 
 
 @pytest.mark.parametrize("phi,backbone,seed,fuse,tc,neck", [("S0", "en", 2, True, "all", "gdf"), ("S0", "en", 2, False, False, "gdf"), ("S2", "en", 0, True, True, "gdf"),
-                                                             ("S0", "mv", 0, True, True, "gdf"), ("S0", "en", 3, True, True, "cdf"), ("S0", "ev", 4, True, True, "gdf"), ("S0", "ef", 5, True, True, "gdf")])
+                                                             ("S0", "mv", 0, True, True, "gdf"), ("S0", "en", 3, True, True, "cdf"), ("S0", "ev", 4, True, True, "gdf"), ("S0", "ef", 5, True, True, "gdf"), ("S1", "ev", 7, True, True, "gdf"), ("S2", "ef", 7, True, True, "cdf")])
 def test_plan_matches_oracle(phi, backbone, seed, fuse, tc, neck):
     torch.set_num_threads(4)
     model = Achelous(phi=phi, backbone=backbone, **dict(MODEL_KW, neck=neck)).eval()
