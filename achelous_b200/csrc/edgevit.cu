@@ -6,6 +6,8 @@
 //                   head in shared memory, online softmax in the log2 domain (one MUFU.EX2 per key), thread = query
 //   ach_dw_convT    LocalProp = depthwise ConvTranspose2d with kernel = stride = sr (:68,91): every output pixel has
 //                   exactly one source pixel: out[c, y, x] = in[c, y/sr, x/sr] * w[c, y%sr, x%sr] + bias[c]
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ach {
@@ -295,8 +297,9 @@ __global__ void __launch_bounds__(256) ef_attention_v2_kernel(const float* __res
                                                            int Nk, float scale, int gelu) {
     extern __shared__ float smem[];
     float* S = smem;                              // [heads][TQ][Nk]
-    float* qs = S + heads * TQ * Nk;          // [heads*kd][TQ]
-    float* ths = qs + heads * kd * TQ;        // th1 (h*h + h) | th2 (h*h + h)
+    float* ths = S + heads * TQ * Nk;         // th1 (h*h + h) | th2 (h*h + h)
+    float* qs = ths + 2 * (heads * heads + heads);
+    qs += (4 - ((qs - smem) & 3)) & 3;        // [heads*kd][TQ]; the same (16-byte aligned) region later holds V_h^T: q is dead after the scores
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * TQ, b = blockIdx.y;
     const float* qb = q + (long long)b * q_bs;
@@ -376,8 +379,7 @@ __global__ void __launch_bounds__(256) ef_attention_v2_kernel(const float* __res
     // ---- out = P v, one head at a time: V_h^T staged in shared memory ([key][d], 16-byte aligned rows), every thread
     // a 4 (value channels) x 4 (queries) register tile - per key one LDS.128 of V and four broadcast loads of P feed 16 FMAs
     // (v1 reduced every output over a warp: 20 shuffles per 4 outputs and V re-read from L2 by every 4-query CTA)
-    float* vs = ths + 2 * nth;
-    vs += (4 - ((vs - smem) & 3)) & 3;            // 16-byte alignment
+    float* vs = qs;                               // q tile is dead (several barriers ago): 105 KB per CTA -> two CTAs per SM
     const int vp = d + 4;                         // row pitch (floats)
     const int jt = tid % (d / 4), tt = tid / (d / 4);
     const bool active = tt < TQ / 4;
@@ -452,7 +454,8 @@ extern "C" int ach_ef_attention(const float* q, long long q_bs, const float* k, 
     // v2 (register-tiled P.V with V_h^T in shared memory) when the tiles fit; v1 (4 queries per CTA, warp reductions) otherwise
     for (int tq : {16}) {   // measured: the 8-query variant (Nk = 400, d = 64) keeps only 32 threads busy in P.V and loses to v1 (1.36 vs 0.54 ms)
         if ((tq == 16 && Nk > 128) || d % 4 != 0 || 256 / (d / 4) < tq / 4) continue;
-        const size_t smem2 = (size_t)(heads * tq * Nk + heads * key_dim * tq + 2 * (heads * heads + heads) + 4 + Nk * (d + 4)) * sizeof(float);
+        const size_t uni = (size_t)std::max(heads * key_dim * tq, Nk * (d + 4));
+        const size_t smem2 = ((size_t)heads * tq * Nk + 2 * (heads * heads + heads) + 4 + uni) * sizeof(float);
         if (smem2 > 220 * 1024) continue;
         static bool attr2 = false;
         if (!attr2) {
