@@ -88,6 +88,7 @@ _SIGNATURES = {
     "ach_rc_deform_tc": ([C.POINTER(AchRcDeform), VP, VP, VP, VP, VP], I),
     "ach_xca_fold": ([VP, LL, VP, VP, I, VP, LL, I, I, I, I, VP], I),
     "ach_mvit_attention": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
+    "ach_mvit_attention_tc": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
     "ach_fc": ([VP, LL, VP, VP, VP, VP, LL, I, I, I, I, VP], I),
     "ach_logsoftmax_t": ([VP, LL, VP, LL, I, I, I, VP], I),
     "ach_copy_add": ([VP, LL, VP, VP, LL, I, I, I, VP], I),
@@ -100,12 +101,16 @@ _SIGNATURES = {
     "ach_up_ghost_pw2_tc": ([C.POINTER(AchUpGhostPw2), VP, VP, VP, VP, VP], I),
     "ach_up_ghost_head_supported": ([I, I, I], I),
     "ach_up_ghost_head": ([C.POINTER(AchUpGhostHead), VP], I),
+    "ach_up_ghost_head_argmax": ([C.POINTER(AchUpGhostHead), VP, LL, C.c_uint, VP], I),
     "ach_pn2_fps": ([VP, LL, I, I, I, VP, VP, LL, VP], I),
     "ach_pn2_group": ([VP, LL, VP, LL, I, VP, LL, I, I, I, I, F, VP, LL, VP, VP], I),
     "ach_pn2_group_max": ([VP, LL, VP, LL, I, I, I, I, VP], I),
     "ach_pn2_interp3": ([VP, LL, VP, LL, VP, LL, I, I, I, I, VP, LL, VP], I),
     "ach_seg_softmax": ([VP, LL, VP, LL, I, I, I, VP], I),
     "ach_seg_resize_argmax": ([VP, LL, I, I, I, I, I, I, I, I, VP, I, I, VP], I),
+    "ach_seg_softmax_resize_argmax": ([VP, LL, I, I, I, I, I, I, I, I, VP, LL, I, I, C.c_uint, VP], I),
+    "ach_seg_argmax_u8": ([VP, LL, I, I, I, C.c_uint, VP, LL, VP], I),
+    "ach_logsoftmax_argmax_t": ([VP, LL, VP, LL, I, I, I, VP], I),
     "ach_ef_attention": ([VP, LL, VP, LL, VP, LL, VP, VP, VP, VP, LL, VP, LL, I, I, I, I, I, I, F, I, VP], I),
     "ach_upsample2x_hp": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
     "ach_s2d": ([VP, LL, VP, LL, I, I, I, I, I, VP], I),
@@ -121,6 +126,7 @@ _SIGNATURES = {
     "ach_decode_outputs": ([C.POINTER(VP), C.POINTER(LL), C.POINTER(I), C.POINTER(I), I, VP, I, I, F, F, VP], I),
     "ach_nms_workspace_bytes": ([I, I], LL),
     "ach_nms": ([VP, I, I, I, F, F, VP, VP, VP, VP, LL, VP], I),
+    "ach_nms_rows": ([VP, I, I, I, F, F, VP, LL, I, VP, LL, VP, LL, VP], I),
 }
 
 EXPORTED_SYMBOLS = ["ach_last_error"] + list(_SIGNATURES)

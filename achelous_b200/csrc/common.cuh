@@ -1,6 +1,7 @@
 // Shared device/host helpers for the achelous_b200 sm_100a kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -111,5 +112,21 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float val) {
 }
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncSetAttribute (opt-in dynamic shared memory) and occupancy figures are PER DEVICE; nn.DataParallel drives several GPUs
+// from one process (one host thread per GPU), so "done once" flags are kept per device ordinal.
+constexpr int ACH_MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev & (ACH_MAX_DEVICES - 1);
+}
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool first() {
+        const unsigned long long bit = 1ull << current_device();
+        return !(done.fetch_or(bit) & bit);
+    }
+};
 
 }  // namespace ach

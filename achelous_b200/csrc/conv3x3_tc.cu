@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(C3_THREADS, NT == 128 ? 2 : 3)
 template <int NT, int ACT, bool RES>
 static int launch_c3(const AchConv3x3Tc& p, const float* w_hi, const float* w_lo, cudaStream_t st) {
     constexpr size_t smem = (size_t)C3_SB * 2 * NT * TC_KC * 4 + (size_t)C3_SW * C3_WIN * 4;
-    static int ctas_per_wave = 0;
+    static int ctas_per_wave_dev[ACH_MAX_DEVICES] = {};
+    int& ctas_per_wave = ctas_per_wave_dev[current_device()];
     if (!ctas_per_wave) {
         cudaFuncSetAttribute(conv3x3_tc_kernel<NT, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;

@@ -119,10 +119,9 @@ static int launch_conv_dense(const AchConvDense& p, cudaStream_t st) {
     CC = min(CC, p.Cin);
     const size_t smem = per_c * CC;
     ACH_REQUIRE(smem <= 200 * 1024, "ach_conv_dense: tile does not fit shared memory (k=%d s=%d)", k, S);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(conv_dense_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
     }
     const int tiles_x = cdiv(p.Wo, 16), tiles_y = cdiv(p.Ho, 16);
     dim3 grid(tiles_x * tiles_y, cdiv(p.O, OT), p.B);

@@ -271,10 +271,9 @@ static int launch_dw(const AchDwConv& p, cudaStream_t st) {
     while (CPB > 1 && (size_t)CPB * (IH * IWp + KS * KS) * 4 > 96 * 1024) --CPB;
     const size_t smem = (size_t)CPB * (IH * IWp + KS * KS) * sizeof(float);
     const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, TH);
-    static bool attr_set = false;  // benign race: idempotent
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(dw_conv_kernel<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
     }
     dim3 grid(tiles_x * tiles_y, cdiv(p.C, CPB), p.B);
     dw_conv_kernel<KS, S><<<grid, 256, smem, st>>>(p, TH, TW, CPB, tiles_x);
@@ -294,8 +293,7 @@ extern "C" int ach_dw_conv(const AchDwConv* pp, void* stream) {
                 "ach_dw_conv: output size (%d,%d) inconsistent with input (%d,%d) k=%d s=%d", p.Ho, p.Wo, p.H, p.W, p.k, p.stride);
     ACH_REQUIRE(p.B <= 65535 && p.C <= 65535, "ach_dw_conv: grid too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static const bool tiled_only = getenv("ACH_DW_TILED") != nullptr;   // A/B switch for tools/op_times.py
-    if (p.stride == 1 && !tiled_only) {
+    if (p.stride == 1) {
         switch (p.k) {
             case 3: return launch_rows_k<3>(p, st);
             case 5: return launch_rows_k<5>(p, st);

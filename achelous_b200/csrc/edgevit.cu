@@ -117,10 +117,9 @@ static int launch_mhsa(const float* qkv, long long qkv_bs, float* out, long long
                        cudaStream_t st) {
     const size_t smem = (size_t)2 * N * D * sizeof(float);
     ACH_REQUIRE(smem <= 200 * 1024, "ach_mhsa: %d tokens x %d dims do not fit shared memory", N, D);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(mhsa_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
     }
     mhsa_kernel<D><<<dim3(heads, cdiv(N, 128), B), 128, smem, st>>>(qkv, qkv_bs, out, out_bs, heads, d, N, scale * 1.4426950408889634f);
     return check_launch("ach_mhsa");
@@ -457,11 +456,10 @@ extern "C" int ach_ef_attention(const float* q, long long q_bs, const float* k, 
         const size_t uni = (size_t)std::max(heads * key_dim * tq, Nk * (d + 4));
         const size_t smem2 = ((size_t)heads * tq * Nk + 2 * (heads * heads + heads) + 4 + uni) * sizeof(float);
         if (smem2 > 220 * 1024) continue;
-        static bool attr2 = false;
-        if (!attr2) {
+        static PerDeviceOnce attr2_once;
+        if (attr2_once.first()) {
             cudaFuncSetAttribute(ef_attention_v2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
             cudaFuncSetAttribute(ef_attention_v2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-            attr2 = true;
         }
         if (tq == 16)
             ef_attention_v2_kernel<16><<<dim3(cdiv(Nq, 16), B), 256, smem2, st>>>(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out, out_bs,
@@ -473,10 +471,9 @@ extern "C" int ach_ef_attention(const float* q, long long q_bs, const float* k, 
     }
     const size_t smem = (size_t)(heads * EFA_TQ * Nk + heads * key_dim * EFA_TQ + 2 * (heads * heads + heads)) * sizeof(float);
     ACH_REQUIRE(smem <= 160 * 1024, "ach_ef_attention: %d keys do not fit shared memory", Nk);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(ef_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
     }
     ef_attention_kernel<<<dim3(cdiv(Nq, EFA_TQ), B), 256, smem, st>>>(q, q_bs, k, k_bs, v, v_bs, ab, th1, th2, add, add_bs, out,
                                                                       out_bs, heads, key_dim, d, Nq, Nk, scale, gelu);

@@ -86,25 +86,31 @@ extern "C" int ach_mvit_attention(const float* qkv, long long qkv_bs, float* out
     ACH_REQUIRE(qkv && out && B > 0 && B <= 65535 && heads > 0, "ach_mvit_attention: bad args");
     ACH_REQUIRE(dim_head == 8, "ach_mvit_attention: dim_head=%d not instantiated (MobileViT uses 8)", dim_head);
     ACH_REQUIRE(H % 2 == 0 && W % 2 == 0, "ach_mvit_attention: H, W must be even (2x2 patches)");
-    const float scale_tc = 1.0f / sqrtf((float)dim_head);
-    // ACH_MVIT_TC=1 selects the tensor-core kernel (mvit_attn_tc.cu).  Measured on B200 at 40x40 (400 tokens per group, B = 64):
-    // tcgen05 0.375 ms vs 0.221 ms for this file's CUDA-core kernel - with d = 8 each 16-key step of P.V is a full
+    // The tensor-core variant is a separate entry point (ach_mvit_attention_tc below).  Measured on B200 at 40x40 (400 tokens per
+    // group, B = 64): tcgen05 0.375 ms vs 0.221 ms for this file's CUDA-core kernel - with d = 8 each 16-key step of P.V is a full
     // TMEM round trip (ld -> 2^x -> split -> st -> barrier -> MMA) for 256 MACs per query, and TMEM (256 columns per CTA)
-    // caps the SM at two such chains; the CUDA-core kernel stays the default.
-    const char* env = getenv("ACH_MVIT_TC");
-    if (env && atoi(env) == 1) {
-        const int rc = mvit_attention_tc_launch(qkv, qkv_bs, out, out_bs, B, heads, H, W, scale_tc, (cudaStream_t)stream);
-        if (rc >= 0) return rc;
-    }
+    // caps the SM at two such chains; the plan therefore calls this CUDA-core kernel.
     const int N = (H / 2) * (W / 2);
     const size_t smem = (size_t)2 * N * dim_head * sizeof(float);
     ACH_REQUIRE(smem <= 200 * 1024, "ach_mvit_attention: %d tokens per group do not fit shared memory", N);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(mvit_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
     }
     const float scale = 1.0f / sqrtf((float)dim_head);
     mvit_attn_kernel<8><<<dim3(4 * heads, B), 256, smem, (cudaStream_t)stream>>>(qkv, qkv_bs, out, out_bs, heads, H, W, scale);
     return check_launch("ach_mvit_attention");
+}
+
+// tcgen05 variant of the same contract (mvit_attn_tc.cu): parity-tested, not on the default plan (see above).  Shapes whose
+// token count does not fit its shared-memory layout are rejected with ACH_ERR_INVALID - there is no silent fallback.
+extern "C" int ach_mvit_attention_tc(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head,
+                                     int H, int W, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(qkv && out && B > 0 && B <= 65535 && heads > 0, "ach_mvit_attention_tc: bad args");
+    ACH_REQUIRE(dim_head == 8, "ach_mvit_attention_tc: dim_head=%d not instantiated (MobileViT uses 8)", dim_head);
+    ACH_REQUIRE(H % 2 == 0 && W % 2 == 0, "ach_mvit_attention_tc: H, W must be even (2x2 patches)");
+    const int rc = mvit_attention_tc_launch(qkv, qkv_bs, out, out_bs, B, heads, H, W, 1.0f / sqrtf((float)dim_head), (cudaStream_t)stream);
+    ACH_REQUIRE(rc >= 0, "ach_mvit_attention_tc: %d x %d tokens do not fit the tensor-core kernel's shared-memory layout", H, W);
+    return rc;
 }

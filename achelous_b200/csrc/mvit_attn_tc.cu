@@ -245,10 +245,9 @@ int mvit_attention_tc_launch(const float* qkv, long long qkv_bs, float* out, lon
     const int Npad = (N + 15) & ~15;
     const size_t smem = (size_t)(2 * Npad * MA_D + 2 * Npad * 16) * sizeof(float);
     if (smem > 100 * 1024 || B > 65535) return -1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(mvit_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        attr_set = true;
     }
     mvit_attn_tc_kernel<<<dim3(4 * heads, cdiv(N, 128), B), 128, smem, st>>>(qkv, qkv_bs, out, out_bs, heads, H, W, scale, N, Npad);
     return check_launch("ach_mvit_attention");

@@ -160,10 +160,9 @@ extern "C" int ach_pn2_fps(const float* xyz, long long xyz_bs, int B, int N, int
     using namespace ach;
     ACH_REQUIRE(xyz && idx_out && new_xyz && B > 0 && B <= 65535 && N > 0 && npoint > 0 && npoint <= N, "ach_pn2_fps: bad args");
     ACH_REQUIRE((size_t)N * 16 <= 96 * 1024, "ach_pn2_fps: N=%d too large for the shared-memory path", N);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(pn2_fps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr_set = true;
     }
     pn2_fps_kernel<<<B, 256, (size_t)N * 16, (cudaStream_t)stream>>>(xyz, xyz_bs, N, npoint, idx_out, new_xyz, new_bs);
     return check_launch("ach_pn2_fps");

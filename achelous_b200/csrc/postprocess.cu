@@ -66,8 +66,9 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int* warp_tot, int* ru
 }
 
 __global__ void __launch_bounds__(NMS_T) nms_kernel(const float* __restrict__ decoded, int A, int K, float conf_thres,
-                                                    float nms_thres, float* __restrict__ kept, int* __restrict__ kept_idx,
-                                                    int* __restrict__ counts, char* __restrict__ workspace, long long ws_per_img) {
+                                                    float nms_thres, float* __restrict__ kept, long long kept_bs, int max_keep,
+                                                    int* __restrict__ kept_idx, int* __restrict__ counts, long long counts_bs,
+                                                    char* __restrict__ workspace, long long ws_per_img) {
     extern __shared__ unsigned char removed[];  // [A]
     __shared__ int warp_tot[NMS_T / 32];
     __shared__ int running;
@@ -140,7 +141,9 @@ __global__ void __launch_bounds__(NMS_T) nms_kernel(const float* __restrict__ de
     }
     __syncthreads();
     if (n == 0) {
-        if (tid == 0) counts[b] = 0;
+        if (tid == 0) counts[(long long)b * counts_bs] = 0;
+        if (max_keep < A)   // compact rows: deterministic zeros behind the kept rows
+            for (int i = tid; i < max_keep * 7; i += NMS_T) kept[(long long)b * kept_bs + i] = 0.f;
         return;
     }
     const float shift = __fadd_rn(s_maxc, 1.0f);
@@ -192,12 +195,12 @@ __global__ void __launch_bounds__(NMS_T) nms_kernel(const float* __restrict__ de
         const int r = r0 + tid;
         const bool flag = (r < n) && !removed[r];
         const int pos = block_scan_flag(flag, warp_tot, &running);
-        if (flag) {
+        if (flag && pos < max_keep) {
             const int s = order[r];
             const int a = c_anchor[s];
             const float* row = pred + (long long)a * CH;
             const float hw = __fmul_rn(row[2], 0.5f), hh = __fmul_rn(row[3], 0.5f);
-            float* o = kept + ((long long)b * A + pos) * 7;
+            float* o = kept + (long long)b * kept_bs + (long long)pos * 7;
             o[0] = __fsub_rn(row[0], hw);
             o[1] = __fsub_rn(row[1], hh);
             o[2] = __fadd_rn(row[0], hw);
@@ -205,11 +208,13 @@ __global__ void __launch_bounds__(NMS_T) nms_kernel(const float* __restrict__ de
             o[4] = row[4];
             o[5] = row[5 + c_cls[s]];
             o[6] = (float)c_cls[s];
-            kept_idx[(long long)b * A + pos] = a;
+            if (kept_idx) kept_idx[(long long)b * A + pos] = a;
         }
     }
     __syncthreads();
-    if (tid == 0) counts[b] = running;
+    if (tid == 0) counts[(long long)b * counts_bs] = running;   // the TRUE number of survivors (may exceed max_keep)
+    if (max_keep < A)
+        for (int i = min(running, max_keep) * 7 + tid; i < max_keep * 7; i += NMS_T) kept[(long long)b * kept_bs + i] = 0.f;
 }
 
 static long long nms_ws_per_img(int A) {
@@ -250,9 +255,26 @@ extern "C" int ach_nms(const float* decoded, int B, int A, int K, float conf_thr
     ACH_REQUIRE(A <= NMS_MAX_A, "ach_nms: A=%d anchors per image exceeds the supported %d", A, NMS_MAX_A);
     ACH_REQUIRE(workspace_bytes >= ach_nms_workspace_bytes(B, A), "ach_nms: workspace too small");
     ACH_REQUIRE(aligned16(workspace), "ach_nms: workspace must be 16-byte aligned");
-    nms_kernel<<<B, NMS_T, (size_t)((A + 15) & ~15), (cudaStream_t)stream>>>(decoded, A, K, conf_thres, nms_thres, kept, kept_idx,
-                                                                           counts, static_cast<char*>(workspace), nms_ws_per_img(A));
+    nms_kernel<<<B, NMS_T, (size_t)((A + 15) & ~15), (cudaStream_t)stream>>>(decoded, A, K, conf_thres, nms_thres, kept, 7LL * A, A, kept_idx,
+                                                                           counts, 1, static_cast<char*>(workspace), nms_ws_per_img(A));
     return check_launch("ach_nms");
+}
+
+// Same NMS writing at most max_keep rows per image (score-descending, so the cap keeps the best ones) at a caller-chosen
+// row-block stride, with the true survivor count next to them: the detection part of the compact output record.
+extern "C" int ach_nms_rows(const float* decoded, int B, int A, int K, float conf_thres, float nms_thres, float* kept, long long kept_bs,
+                            int max_keep, int* counts, long long counts_bs, void* workspace, long long workspace_bytes, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(decoded && kept && counts && workspace, "ach_nms_rows: null arg");
+    ACH_REQUIRE(B > 0 && A > 0 && K >= 1 && max_keep > 0 && max_keep <= A, "ach_nms_rows: bad dims");
+    ACH_REQUIRE(kept_bs >= 7LL * max_keep && counts_bs >= 1, "ach_nms_rows: strides smaller than one image's record");
+    ACH_REQUIRE(A <= NMS_MAX_A, "ach_nms_rows: A=%d anchors per image exceeds the supported %d", A, NMS_MAX_A);
+    ACH_REQUIRE(workspace_bytes >= ach_nms_workspace_bytes(B, A), "ach_nms_rows: workspace too small");
+    ACH_REQUIRE(aligned16(workspace), "ach_nms_rows: workspace must be 16-byte aligned");
+    nms_kernel<<<B, NMS_T, (size_t)((A + 15) & ~15), (cudaStream_t)stream>>>(decoded, A, K, conf_thres, nms_thres, kept, kept_bs, max_keep,
+                                                                           nullptr, counts, counts_bs, static_cast<char*>(workspace),
+                                                                           nms_ws_per_img(A));
+    return check_launch("ach_nms_rows");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -314,7 +336,144 @@ __global__ void __launch_bounds__(256) seg_resize_argmax_kernel(const float* __r
     out[((long long)b * OH + oy) * OW + ox] = (unsigned char)arg;
 }
 
+// argmax over the class planes at network resolution, 4 pixels per thread (one 16-byte load per class, one 4-byte store);
+// first maximum like torch.argmax; classes whose keep_mask bit is clear map to 0 (achelous.py:297)
+__global__ void __launch_bounds__(256) seg_argmax_u8_kernel(const float* __restrict__ x, long long x_bs, int K, int P, unsigned keep_mask,
+                                                            unsigned char* __restrict__ out, long long out_bs) {
+    const int p4 = blockIdx.x * 256 + threadIdx.x;
+    if (p4 * 4 >= P) return;
+    const float4* xp = reinterpret_cast<const float4*>(x + (long long)blockIdx.y * x_bs) + p4;
+    float4 best = xp[0];
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int k = 1; k < K; ++k) {
+        const float4 v = xp[(long long)k * (P / 4)];
+        if (v.x > best.x) { best.x = v.x; a0 = k; }
+        if (v.y > best.y) { best.y = v.y; a1 = k; }
+        if (v.z > best.z) { best.z = v.z; a2 = k; }
+        if (v.w > best.w) { best.w = v.w; a3 = k; }
+    }
+    a0 = ((keep_mask >> a0) & 1u) ? a0 : 0;
+    a1 = ((keep_mask >> a1) & 1u) ? a1 : 0;
+    a2 = ((keep_mask >> a2) & 1u) ? a2 : 0;
+    a3 = ((keep_mask >> a3) & 1u) ? a3 : 0;
+    reinterpret_cast<unsigned*>(out + (long long)blockIdx.y * out_bs)[p4] = (unsigned)a0 | ((unsigned)a1 << 8) | ((unsigned)a2 << 16) | ((unsigned)a3 << 24);
+}
+
+// softmax + crop + cv2 INTER_LINEAR resize + argmax in ONE pass over the logits: the probabilities of the four source pixels are
+// rebuilt in registers with exactly seg_softmax_kernel's arithmetic (max, sum of expf in class order, expf / sum), so the class
+// map equals the two-kernel sequence bit for bit while the (K, H, W) fp32 probability map never exists in HBM.
+template <int KMAX>
+__global__ void __launch_bounds__(256) seg_softmax_resize_argmax_kernel(const float* __restrict__ logits, long long bs, int K, int H, int W,
+                                                                        int y_off, int x_off, int nh, int nw, unsigned char* __restrict__ out,
+                                                                        long long out_bs, int OH, int OW, unsigned keep_mask) {
+    const int ox = blockIdx.x * 256 + threadIdx.x;
+    const int oy = blockIdx.y, b = blockIdx.z;
+    if (ox >= OW) return;
+    int sx0, sx1, sy0, sy1;
+    float ax0, ax1, ay0, ay1;
+    cv_linear_coord(ox, (double)nw / (double)OW, nw, sx0, sx1, ax0, ax1);
+    cv_linear_coord(oy, (double)nh / (double)OH, nh, sy0, sy1, ay0, ay1);
+    const long long P = (long long)H * W;
+    const float* pb = logits + (long long)b * bs;
+    const long long off[4] = {(long long)(y_off + sy0) * W + x_off + sx0, (long long)(y_off + sy0) * W + x_off + sx1,
+                              (long long)(y_off + sy1) * W + x_off + sx0, (long long)(y_off + sy1) * W + x_off + sx1};
+    float pr[4][KMAX];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) {
+                pr[c][k] = __ldg(pb + (long long)k * P + off[c]);
+                m = fmaxf(m, pr[c][k]);
+            }
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) s += expf(pr[c][k] - m);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) pr[c][k] = expf(pr[c][k] - m) / s;
+    }
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+            const float h0 = __fadd_rn(__fmul_rn(pr[0][k], ax0), __fmul_rn(pr[1][k], ax1));
+            const float h1 = __fadd_rn(__fmul_rn(pr[2][k], ax0), __fmul_rn(pr[3][k], ax1));
+            const float v = __fadd_rn(__fmul_rn(h0, ay0), __fmul_rn(h1, ay1));
+            if (v > best) { best = v; arg = k; }
+        }
+    out[(long long)b * out_bs + (long long)oy * OW + ox] = (unsigned char)(((keep_mask >> arg) & 1u) ? arg : 0);
+}
+
+// per point: log_softmax over the classes exactly as logsoftmax_t_kernel (misc.cu) computes it, then the first maximum of those
+// values - the class torch.argmax returns on the raw path's output (achelous.py:262) - as one byte
+__global__ void __launch_bounds__(256) logsoftmax_argmax_t_kernel(const float* __restrict__ x, long long x_bs, unsigned char* __restrict__ out,
+                                                                  long long out_bs, int K, int N) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= N) return;
+    const float* xp = x + (long long)blockIdx.y * x_bs + n;
+    float v[32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < K) {
+            v[k] = xp[(long long)k * N];
+            m = fmaxf(m, v[k]);
+        }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < K) s += expf(v[k] - m);
+    const float lse = logf(s);
+    float best = -INFINITY;
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k < K) {
+            const float lp = (v[k] - m) - lse;
+            if (lp > best) { best = lp; arg = k; }
+        }
+    out[(long long)blockIdx.y * out_bs + n] = (unsigned char)arg;
+}
+
 }  // namespace ach
+
+extern "C" int ach_seg_argmax_u8(const float* x, long long x_bs, int B, int K, int P, unsigned keep_mask, unsigned char* out,
+                                 long long out_bs, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(x && out && B > 0 && B <= 65535 && K > 0 && K <= 32 && P > 0, "ach_seg_argmax_u8: bad args");
+    ACH_REQUIRE(P % 4 == 0 && x_bs % 4 == 0 && out_bs % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(out) & 3u) == 0,
+                "ach_seg_argmax_u8: P and the batch strides must be multiples of 4, x 16-byte and out 4-byte aligned");
+    seg_argmax_u8_kernel<<<dim3(cdiv(P / 4, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, K, P, keep_mask, out, out_bs);
+    return check_launch("ach_seg_argmax_u8");
+}
+
+extern "C" int ach_seg_softmax_resize_argmax(const float* logits, long long bs, int B, int K, int H, int W, int y_off, int x_off, int nh,
+                                             int nw, unsigned char* out, long long out_bs, int OH, int OW, unsigned keep_mask, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(logits && out && B > 0 && B <= 65535 && K > 0 && K <= 16, "ach_seg_softmax_resize_argmax: bad args (K=%d must be <= 16)", K);
+    ACH_REQUIRE(nh > 0 && nw > 0 && y_off >= 0 && x_off >= 0 && y_off + nh <= H && x_off + nw <= W,
+                "ach_seg_softmax_resize_argmax: crop window outside the map");
+    ACH_REQUIRE(OH > 0 && OH <= 65535 && OW > 0 && out_bs >= (long long)OH * OW, "ach_seg_softmax_resize_argmax: bad output size");
+    const dim3 grid(cdiv(OW, 256), OH, B);
+    if (K <= 2)
+        seg_softmax_resize_argmax_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, bs, K, H, W, y_off, x_off, nh, nw, out, out_bs, OH, OW, keep_mask);
+    else if (K <= 9)
+        seg_softmax_resize_argmax_kernel<9><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, bs, K, H, W, y_off, x_off, nh, nw, out, out_bs, OH, OW, keep_mask);
+    else
+        seg_softmax_resize_argmax_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(logits, bs, K, H, W, y_off, x_off, nh, nw, out, out_bs, OH, OW, keep_mask);
+    return check_launch("ach_seg_softmax_resize_argmax");
+}
+
+extern "C" int ach_logsoftmax_argmax_t(const float* x, long long x_bs, unsigned char* out, long long out_bs, int B, int K, int N, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(x && out && B > 0 && K > 0 && K <= 32 && N > 0 && B <= 65535, "ach_logsoftmax_argmax_t: bad args (K=%d must be <= 32)", K);
+    logsoftmax_argmax_t_kernel<<<dim3(cdiv(N, 256), B), 256, 0, (cudaStream_t)stream>>>(x, x_bs, out, out_bs, K, N);
+    return check_launch("ach_logsoftmax_argmax_t");
+}
 
 extern "C" int ach_seg_softmax(const float* x, long long x_bs, float* out, long long out_bs, int B, int K, int P, void* stream) {
     using namespace ach;

@@ -461,7 +461,8 @@ static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, c
     const int K = p.c0 + p.c1;
     const int n_kchunks = cdiv(K, TC_KC);
     constexpr size_t smem = (size_t)WS_SB * 2 * NT * TC_KC * 4 + (size_t)ws_sg(NT) * TC_KC * TC_M * 4;
-    static int ctas_per_wave = 0;
+    static int ctas_per_wave_dev[ACH_MAX_DEVICES] = {};
+    int& ctas_per_wave = ctas_per_wave_dev[current_device()];
     if (!ctas_per_wave) {
         cudaFuncSetAttribute(pw_conv_tc_ws_kernel<NT, ACT, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
@@ -474,26 +475,21 @@ static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, c
     const long long total = (long long)n_pt * n_ot * p.B;
     ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
-    // tensor maps of the activation views (ACH_TC_TMAP=0: row copies everywhere, the A/B switch for tools/op_times.py)
+    // tensor maps of the activation views (views a tensor map cannot describe fall back to per-row bulk copies inside the kernel)
     alignas(64) CUtensorMap tm0, tm1;
     memset(&tm0, 0, sizeof(tm0));
     memset(&tm1, 0, sizeof(tm1));
-    static const bool tmap_on = !(getenv("ACH_TC_TMAP") && atoi(getenv("ACH_TC_TMAP")) == 0);
-    int use_tmap = tmap_on && make_act_tmap(&tm0, p.x0, p.P, p.c0, p.B, p.x0_bs) ? 1 : 0;
+    int use_tmap = make_act_tmap(&tm0, p.x0, p.P, p.c0, p.B, p.x0_bs) ? 1 : 0;
     if (use_tmap && p.c1 > 0) use_tmap = make_act_tmap(&tm1, p.x1, p.P, p.c1, p.B, p.x1_bs) ? 1 : 0;
-    // ACH_PDL=1 launches with the programmatic-dependent-launch attribute (prologue overlaps the previous kernel's tail).
-    // Measured inside the CUDA graph: 5.664 vs 5.674 ms per step - the graph already hides launch latency - so it is off.
-    static const bool pdl = getenv("ACH_PDL") && atoi(getenv("ACH_PDL")) == 1;
+    // programmatic dependent launch was measured inside the CUDA graph at 5.664 vs 5.674 ms per step - the graph already hides
+    // launch latency - so the attribute is not set
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(ws_threads(NT));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
     const int total_i = (int)total;
     cudaLaunchKernelEx(&cfg, pw_conv_tc_ws_kernel<NT, ACT, RES>, p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, total_i, tm0, tm1, use_tmap);
     return check_launch("ach_pw_conv_tc");

@@ -226,11 +226,10 @@ template <int C>
 static int launch_rc(const AchRcDeform& p, cudaStream_t st) {
     constexpr int CP = (C + 3) & ~3;
     const size_t smem = (size_t)(C * 9 * 28 + C * 9 * CP + C * CP + 28) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(rc_deform_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(rc_deform_cl_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
     }
     const dim3 grid(cdiv((long long)p.H * p.W, 128), p.B);
     if (p.pooled_cl) rc_deform_cl_kernel<C><<<grid, 128, smem, st>>>(p);

@@ -327,7 +327,8 @@ static int launch_rc_tc_s(const AchRcDeform& p, const float* wom_hi, const float
     constexpr int NCH = (C * 9 + TC_KC - 1) / TC_KC;
     constexpr int Q = (C + 3) / 4;
     constexpr size_t smem = (size_t)(2 * NCH * 2 * RCT_N * TC_KC + Q * RCT_WH * RCT_WW * 4) * sizeof(float);
-    static int ctas_per_wave = 0;
+    static int ctas_per_wave_dev[ACH_MAX_DEVICES] = {};
+    int& ctas_per_wave = ctas_per_wave_dev[current_device()];
     if (!ctas_per_wave) {
         cudaFuncSetAttribute(rc_deform_tc_kernel<C, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
@@ -345,11 +346,8 @@ static int launch_rc_tc_s(const AchRcDeform& p, const float* wom_hi, const float
 template <int C>
 static int launch_rc_tc(const AchRcDeform& p, const float* wom_hi, const float* wom_lo, const float* wreg_hi, const float* wreg_lo,
                         cudaStream_t st) {
-    // ACH_RC_TC_STAGES=1|2: A/B switch for tools/op_times.py (1 = less shared memory, more CTAs per SM: occupancy beats the ring)
-    const char* env = getenv("ACH_RC_TC_STAGES");
-    const int stages = env ? atoi(env) : 2;   // measured (B=64): 1 stage 0.498 / 0.404 / 0.100 ms (rc0 / rc1 / rc2), 2 stages 0.623 / 0.435 / 0.111
-    return stages == 1 ? launch_rc_tc_s<C, 1>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st)
-                       : launch_rc_tc_s<C, 2>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
+    // two A stages in tensor memory (a 1-stage build was the better one only while A still lived in shared memory: DESIGN.md §7)
+    return launch_rc_tc_s<C, 2>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
 }
 
 }  // namespace ach

@@ -125,10 +125,15 @@ struct UpGhostHeadParams {
     float b4[KOUT - INIT];
 };
 
-template <int INIT, int KOUT>
+// ARGMAX: instead of the K logit planes the kernel writes the per-pixel class index (first maximum, like torch.argmax
+// over the very same fp32 logits) as one byte - 4*K bytes per pixel less to write, copy out and all-gather
+// (achelous.py:283-297 only ever uses the argmax of these maps).  Classes whose bit in keep_mask is clear are mapped to 0
+// (the reference's `output_seg[(output_seg != 0) & (output_seg != 8)] = 0`).
+template <int INIT, int KOUT, bool ARGMAX>
 __global__ void __launch_bounds__(256, 2) up_ghost_head_kernel(const float* __restrict__ v, long long v_bs, float* __restrict__ out,
                                                                long long out_bs, int h, int w,
-                                                               const __grid_constant__ UpGhostHeadParams<INIT, KOUT> P) {
+                                                               const __grid_constant__ UpGhostHeadParams<INIT, KOUT> P,
+                                                               unsigned char* __restrict__ mask, long long mask_bs, unsigned keep_mask) {
     extern __shared__ __align__(16) float smem[];
     float* x1s = smem;                                  // [16][34][35]
     float* vs = smem + UH_C * UH_X1 * UH_X1P;           // [16][20][21]
@@ -223,14 +228,24 @@ __global__ void __launch_bounds__(256, 2) up_ghost_head_kernel(const float* __re
     __syncthreads();
 
     // ---- outputs: channels [0, INIT) = p, [INIT, KOUT) = relu(s4 * dw3x3(p) + b4)
-    float* ob = out + (long long)b * out_bs;
+    float* ob = ARGMAX ? nullptr : out + (long long)b * out_bs;
+    unsigned char* mb = ARGMAX ? mask + (long long)b * mask_bs : nullptr;
     for (int i = threadIdx.x; i < UH_T * UH_T; i += 256) {
         const int yy = i / UH_T, xx = i - yy * UH_T;
         const int gy = ty0 + yy, gx = tx0 + xx;
         if (gy >= H || gx >= W) continue;
         const long long o = (long long)gy * W + gx;
+        float best = -INFINITY;
+        int arg = 0;
 #pragma unroll
-        for (int k = 0; k < INIT; ++k) ob[k * plane_hi + o] = ps[(k * UH_P + yy + 1) * PP + xx + 1];
+        for (int k = 0; k < INIT; ++k) {
+            const float val = ps[(k * UH_P + yy + 1) * PP + xx + 1];
+            if (ARGMAX) {
+                if (val > best) { best = val; arg = k; }
+            } else {
+                ob[k * plane_hi + o] = val;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < KOUT - INIT; ++k) {
             float d = 0.f;
@@ -238,13 +253,20 @@ __global__ void __launch_bounds__(256, 2) up_ghost_head_kernel(const float* __re
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) d = fmaf(ps[(k * UH_P + yy + ky) * PP + xx + kx], P.w4[k * 9 + ky * 3 + kx], d);
-            ob[(INIT + k) * plane_hi + o] = fmaxf(fmaf(P.s4[k], d, P.b4[k]), 0.f);
+            const float val = fmaxf(fmaf(P.s4[k], d, P.b4[k]), 0.f);
+            if (ARGMAX) {
+                if (val > best) { best = val; arg = INIT + k; }
+            } else {
+                ob[(INIT + k) * plane_hi + o] = val;
+            }
         }
+        if (ARGMAX) mb[o] = (unsigned char)(((keep_mask >> arg) & 1u) ? arg : 0);
     }
 }
 
-template <int INIT, int KOUT>
-static int launch_head(const AchUpGhostHead& a, cudaStream_t st) {
+template <int INIT, int KOUT, bool ARGMAX>
+static int launch_head(const AchUpGhostHead& a, cudaStream_t st, unsigned char* mask = nullptr, long long mask_bs = 0,
+                       unsigned keep_mask = 0xffffffffu) {
     UpGhostHeadParams<INIT, KOUT> P;
     memcpy(P.b1, a.b1, sizeof(P.b1));
     memcpy(P.w2, a.w2, sizeof(P.w2));
@@ -256,14 +278,13 @@ static int launch_head(const AchUpGhostHead& a, cudaStream_t st) {
     memcpy(P.s4, a.s4, sizeof(P.s4));
     memcpy(P.b4, a.b4, sizeof(P.b4));
     constexpr size_t smem = (size_t)(UH_C * UH_X1 * UH_X1P + UH_C * UH_V * (UH_V + 1)) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(up_ghost_head_kernel<INIT, KOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
+        cudaFuncSetAttribute(up_ghost_head_kernel<INIT, KOUT, ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     const int H = 2 * a.h, W = 2 * a.w;
     dim3 grid(cdiv(W, UH_T) * cdiv(H, UH_T), a.B);
-    up_ghost_head_kernel<INIT, KOUT><<<grid, 256, smem, st>>>(a.v, a.v_bs, a.out, a.out_bs, a.h, a.w, P);
+    up_ghost_head_kernel<INIT, KOUT, ARGMAX><<<grid, 256, smem, st>>>(a.v, a.v_bs, a.out, a.out_bs, a.h, a.w, P, mask, mask_bs, keep_mask);
     return check_launch("ach_up_ghost_head");
 }
 
@@ -292,8 +313,21 @@ extern "C" int ach_up_ghost_head(const AchUpGhostHead* pp, void* stream) {
     ACH_REQUIRE(a.B > 0 && a.B <= 65535 && a.h > 1 && a.w > 1, "ach_up_ghost_head: bad dims");
     ACH_REQUIRE(ach_up_ghost_head_supported(a.C, a.init, a.K), "ach_up_ghost_head: (C=%d, init=%d, K=%d) not instantiated", a.C, a.init, a.K);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (a.init == 1) return launch_head<1, 2>(a, st);
-    return launch_head<5, 9>(a, st);
+    if (a.init == 1) return launch_head<1, 2, false>(a, st);
+    return launch_head<5, 9, false>(a, st);
+}
+
+extern "C" int ach_up_ghost_head_argmax(const AchUpGhostHead* pp, unsigned char* mask, long long mask_bs, unsigned keep_mask,
+                                        void* stream) {
+    using namespace ach;
+    const AchUpGhostHead& a = *pp;
+    ACH_REQUIRE(a.v && mask && a.b1 && a.w2 && a.s2 && a.b2 && a.w3 && a.b3 && a.w4 && a.s4 && a.b4, "ach_up_ghost_head_argmax: null arg");
+    ACH_REQUIRE(a.B > 0 && a.B <= 65535 && a.h > 1 && a.w > 1, "ach_up_ghost_head_argmax: bad dims");
+    ACH_REQUIRE(mask_bs >= 4LL * a.h * a.w, "ach_up_ghost_head_argmax: mask batch stride smaller than one map");
+    ACH_REQUIRE(ach_up_ghost_head_supported(a.C, a.init, a.K), "ach_up_ghost_head_argmax: (C=%d, init=%d, K=%d) not instantiated", a.C, a.init, a.K);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (a.init == 1) return launch_head<1, 2, true>(a, st, mask, mask_bs, keep_mask);
+    return launch_head<5, 9, true>(a, st, mask, mask_bs, keep_mask);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -636,10 +670,9 @@ static int launch_up_ghost_pw2_tc(const AchUpGhostPw2& p, const float* w1_hi, co
                                   cudaStream_t st) {
     constexpr int NCH1 = 2 * CI / TC_KC, NCH2 = UP_C1 / TC_KC;
     const size_t smem = (size_t)((NCH1 + NCH2) * 2 * 32 * TC_KC + CI * UP_XH * UP_XP + CI * UP_VH * (UP_VW + 1) + CI * 12 + UP_C1) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(up_ghost_pw2_tc_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
     }
     const int H = 2 * p.h, W = 2 * p.w;
     dim3 grid(cdiv(W, UP_TW) * cdiv(H, UP_TH), p.B);
@@ -650,10 +683,9 @@ static int launch_up_ghost_pw2_tc(const AchUpGhostPw2& p, const float* w1_hi, co
 template <int CI>
 static int launch_up_ghost_pw2(const AchUpGhostPw2& p, cudaStream_t st) {
     const size_t smem = (size_t)(CI * UP_XH * UP_XP + CI * UP_VH * (UP_VW + 1) + 2 * CI * UP_C1 + UP_C1 * UP_N2 + CI * 12 + UP_C1) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(up_ghost_pw2_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
     }
     const int H = 2 * p.h, W = 2 * p.w;
     dim3 grid(cdiv(W, UP_TW) * cdiv(H, UP_TH), p.B);

@@ -125,10 +125,9 @@ extern "C" int ach_xca_fold(const float* qkv, long long qkv_bs, const float* tem
     ACH_REQUIRE(ldw >= C, "ach_xca_fold: ldw < C");
     const size_t smem = (size_t)(2 * d * (XCA_CHUNK + 1) + 2 * d + d * d + d * ldw) * sizeof(float);
     ACH_REQUIRE(smem <= 160 * 1024, "ach_xca_fold: d=%d, ldw=%d do not fit shared memory", d, ldw);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first()) {
         cudaFuncSetAttribute(xca_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
     }
     xca_fold_kernel<<<dim3(heads, B), 256, smem, (cudaStream_t)stream>>>(qkv, qkv_bs, temperature, proj_wt, ldw, wt_eff, wt_eff_bs,
                                                                         C, heads, N);

@@ -23,15 +23,65 @@ from .nets import holders as Hd
 
 View = namedtuple("View", "ptr bs C H W")
 
+# what the compact output record holds per frame (forward(..., outputs="compact"), stream_forward(compact=True)):
+#   det_rows (B, max_det, 7) fp32 [x1, y1, x2, y2, obj, cls_conf, cls] in network-input-normalised corner form = the rows
+#            utils_bbox.non_max_suppression keeps (score-descending) BEFORE its host-side letterbox un-warp; rows >= det_count are 0
+#   det_count (B,) int32  survivors of the NMS (if > max_det the record was truncated to the max_det best)
+#   se_mask / lane_mask (B, H, W) uint8  argmax class maps (network resolution, or the original image size when image_shape is set)
+#   pc_cls (B, N) uint8  argmax class per radar point
+CompactOutputs = namedtuple("CompactOutputs", "det_rows det_count se_mask lane_mask pc_cls")
+COMPACT_DEFAULTS = dict(conf_thres=0.35, nms_thres=0.35,   # achelous.py:52,56
+                        max_det=256, keep_classes=None, image_shape=None, letterbox_image=True)
+
+
+def compact_spec(spec=None, **kw):
+    """Normalised, hashable compact-output specification"""
+    d = dict(COMPACT_DEFAULTS)
+    d.update(spec or {})
+    d.update(kw)
+    unknown = set(d) - set(COMPACT_DEFAULTS)
+    if unknown:
+        raise TypeError(f"unknown compact-output options: {sorted(unknown)}")
+    if d["keep_classes"] is not None:
+        d["keep_classes"] = tuple(sorted(int(c) for c in d["keep_classes"]))
+    if d["image_shape"] is not None:
+        d["image_shape"] = (int(d["image_shape"][0]), int(d["image_shape"][1]))
+    d["conf_thres"], d["nms_thres"], d["max_det"] = float(d["conf_thres"]), float(d["nms_thres"]), int(d["max_det"])
+    d["letterbox_image"] = bool(d["letterbox_image"])
+    return tuple(sorted(d.items()))
+
+
+def _align16(n):
+    return (n + 15) // 16 * 16
+
+
+class _LazyOut:
+    """Full-resolution logit map that is only allocated when a kernel really has to write it (compact mode: the fused head
+    writes class indices straight away and the fp32 planes never exist)."""
+
+    def __init__(self, eng, name, C_, H, W):
+        self.eng, self.name, self.C, self.H, self.W, self._v = eng, name, C_, H, W, None
+
+    def view(self):
+        if self._v is None:
+            self._v = self.eng.buf(self.name, self.C, self.H, self.W)
+        return self._v
+
+    @property
+    def allocated(self):
+        return self._v is not None
+
 
 def _ceil4(n):
     return (n + 3) // 4 * 4
 
 
 class Engine:
-    def __init__(self, model, batch, device, use_graph=True, dry_run=False):
+    def __init__(self, model, batch, device, use_graph=True, dry_run=False, n_points=None, compact=None):
         """dry_run=True builds the plan and packs the weights without a GPU (host-logic tests only):
-        nothing can be launched from such an engine."""
+        nothing can be launched from such an engine.  `model` is the module that OWNS the parameters (under
+        nn.DataParallel: the wrapped module, not a replica); `device` may differ from the parameters' device -
+        the folded weights are produced on the host and copied to `device`."""
         self.lib = _lib.load()
         self.model = model
         self.B = int(batch)
@@ -41,7 +91,8 @@ class Engine:
             raise _lib.AchelousKernelError("achelous_b200 runs on CUDA devices only (no CPU fallback)")
         self.use_graph = use_graph
         self.res = model.resolution
-        self.n_points = model.n_points
+        self.n_points = int(model.n_points if n_points is None else n_points)
+        self.compact = dict(compact_spec(compact) if isinstance(compact, dict) else compact) if compact else None
         self.ops = []          # (cfunc, args) - stream appended at call time
         self.op_names = []
         self.op_bytes = []
@@ -65,11 +116,41 @@ class Engine:
                 self._build()
 
     # ------------------------------------------------------------------ parameter access / packing
+    def _resolve_params(self):
+        """Looks every parameter / buffer up BY NAME on the owning module (load_state_dict(assign=True) and
+        `module.weight = nn.Parameter(...)` replace the objects) and remembers the module's weight epoch."""
+        m = self.model
+        self._params = {k: v for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+        self._epoch = getattr(m, "_weights_epoch", 0)
+        self._cpu64 = {}
+
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self._params.values())
 
     def _p(self, name):
-        return self._params[name].detach().to(torch.float64)
+        """Parameter as float64 ON THE HOST: BN / LayerNorm folding and layout packing are host arithmetic (one
+        device->host copy per parameter and (re)pack), so no ATen kernel runs on the GPU for them."""
+        t = self._cpu64.get(name)
+        if t is None:
+            t = self._params[name].detach().to(device="cpu", dtype=torch.float64)
+            self._cpu64[name] = t
+        return t
+
+    def _pi(self, name):
+        """Integer buffer (index tables) on the host"""
+        return self._params[name].detach().cpu()
+
+    def _zeros(self, n):
+        """Zero-filled fp32 device slot carved out of a few large arenas (one fill launch per arena, not per weight tile)"""
+        n = (int(n) + 63) // 64 * 64
+        a = getattr(self, "_arena", None)
+        if a is None or a[1] + n > a[0].numel():
+            a = [torch.zeros(max(n, 1 << 22), device=self.device, dtype=torch.float32), 0]
+            self._arena = a
+            self._keep.append(a[0])
+        t = a[0][a[1]:a[1] + n]
+        a[1] += n
+        return t
 
     def _dev(self, t):
         t = t.to(device=self.device, dtype=torch.float32).contiguous()
@@ -95,6 +176,7 @@ class Engine:
         return C.addressof(arr)
 
     def repack(self):
+        self._cpu64 = {}
         for key, (t, fn) in self._weights.items():
             t.copy_(fn().to(device=self.device, dtype=torch.float32))
         for key, (arr, fn) in self._host.items():
@@ -102,6 +184,7 @@ class Engine:
             C.memmove(arr, val.data_ptr(), val.numel() * 4)
         if self._host:
             self.graph = None  # kernel-parameter weights are baked into a captured graph: re-capture
+        self._cpu64 = {}
         self._sig = self._signature()
 
     def _bn_fold(self, prefix, eps, conv_bias=None):
@@ -179,16 +262,15 @@ class Engine:
         tc_mode = self.model.use_tensor_cores
         # measured on B200: the warp-specialised tcgen05 kernel beats (or ties) the SIMT GEMM on every shared-weight layer with
         # >= 16 outputs (32 -> 16 at 320^2: 0.51 -> 0.47 ms); below that the two are within noise of each other
-        min_o = int(os.environ.get("ACH_TC_MIN_O", "16"))      # A/B switch for tools/op_times.py
-        tc_ok = (tc_mode == "all" and O >= 16) or (tc_mode is True and O >= min_o)
+        tc_ok = tc_mode in (True, "all") and O >= 16
         if tc_ok and wt_bs == 0 and isinstance(wt, torch.Tensor) and not self.in_pack:
             # tcgen05 path: weights re-packed on the device into hi/lo UMMA tile images whenever they change
             n = self.lib.ach_pack_pw_tc_elems(K_, O)
-            hi = torch.zeros(n, device=self.device, dtype=torch.float32)
-            lo = torch.zeros(n, device=self.device, dtype=torch.float32)
+            hi = self._zeros(n)
+            lo = self._zeros(n)
             self._keep += [hi, lo]
             self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt.data_ptr(), K_, O, s.ldw, hi.data_ptr(), lo.data_ptr())))
-            wsum = self._w(name + ".wsum", lambda wt=wt, O=O: wt[:, :O].double().sum(0)) if ln else None
+            wsum = self._w(name + ".wsum", lambda wt=wt, O=O: wt.detach().cpu()[:, :O].double().sum(0)) if ln else None
             self._add(name, self.lib.ach_pw_conv_tc, C.byref(s), hi.data_ptr(), lo.data_ptr(), self._ptr(wsum), nbytes=nb)
             return
         self._add(name, self.lib.ach_pw_conv, C.byref(s), nbytes=nb)
@@ -230,8 +312,8 @@ class Engine:
             return torch.nn.functional.pad(m, (0, _ceil4(O) - O))
         w_t = self._w(name + ".wt3", wt)
         n_ = self.lib.ach_pack_pw_tc_elems(kpad, O)
-        hi = torch.zeros(n_, device=self.device, dtype=torch.float32)
-        lo = torch.zeros(n_, device=self.device, dtype=torch.float32)
+        hi = self._zeros(n_)
+        lo = self._zeros(n_)
         self._keep += [hi, lo]
         self.pack_ops.append((self.lib.ach_pack_pw_tc, (w_t.data_ptr(), kpad, O, w_t.shape[-1], hi.data_ptr(), lo.data_ptr())))
         s = AchConv3x3Tc()
@@ -601,7 +683,7 @@ class Engine:
         return out
 
     def _ef_ab(self, name, prefix):
-        return self._w(name + ".ab", lambda: self._p(prefix + ".attention_biases")[:, self._params[prefix + ".attention_bias_idxs"]])
+        return self._w(name + ".ab", lambda: self._p(prefix + ".attention_biases")[:, self._pi(prefix + ".attention_bias_idxs")])
 
     def ef_attention4d(self, name, prefix, x, ls_key, stride):
         """x + layer_scale_1 * Attention4D(x)  (ImageEncoder.py:63-160,415-418)"""
@@ -813,7 +895,8 @@ class Engine:
                   x.H * x.W, 4, 1e-5)
         return out
 
-    def seg_decoder(self, name, prefix, x, widths, out):
+    def seg_decoder(self, name, prefix, x, widths, out, mask=None):
+        out = out.view() if isinstance(out, _LazyOut) else out
         chans = [widths[1], widths[0], widths[0]]
         cur = x
         for stage, c in zip(("3_to_2", "2_to_1", "1_to_0"), chans):
@@ -825,9 +908,11 @@ class Engine:
             cur = g
         self.ghost(f"{name}.head", f"{prefix}.{name}_seg_head", cur, out, True)
 
-    def seg_decoder_fused(self, name, prefix, x, widths, out):
+    def seg_decoder_fused(self, name, prefix, x, widths, out, mask=None):
         """Same decoder with the Ghost primary conv hoisted below the upsampling (it commutes with the
-        bilinear interpolation) and the full-resolution work in the fused ach_up_ghost[_head] kernels."""
+        bilinear interpolation) and the full-resolution work in the fused ach_up_ghost[_head] kernels.
+        mask = (uint8 pointer, batch stride in bytes, keep_mask): compact mode - the fused head writes class indices
+        instead of logit planes (`out` is then a _LazyOut that stays unallocated)."""
         chans = [widths[1], widths[0], widths[0]]
         stages = ("3_to_2", "2_to_1", "1_to_0")
         cur = x
@@ -876,8 +961,8 @@ class Engine:
                         for key, K_, O_ in ((n + ".chain.w1t", 2 * init, c_next), (n + ".chain.w2t", c_next, init_next)):
                             wt_ = self._weights[key][0]
                             n_ = self.lib.ach_pack_pw_tc_elems(K_, O_)
-                            hi = torch.zeros(n_, device=self.device, dtype=torch.float32)
-                            lo = torch.zeros(n_, device=self.device, dtype=torch.float32)
+                            hi = self._zeros(n_)
+                            lo = self._zeros(n_)
                             self._keep += [hi, lo]
                             self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt_.data_ptr(), K_, O_, wt_.shape[-1], hi.data_ptr(), lo.data_ptr())))
                             tiles += [hi.data_ptr(), lo.data_ptr()]
@@ -893,7 +978,10 @@ class Engine:
             if si == 2 and self.lib.ach_up_ghost_head_supported(init, hinit, K) and cn == init:
                 h_p = f"{prefix}.{name}_seg_head"
                 a = AchUpGhostHead()
-                a.v, a.v_bs, a.out, a.out_bs = v.ptr, v.bs, out.ptr, out.bs
+                if mask is None:
+                    out = out.view() if isinstance(out, _LazyOut) else out
+                    a.out, a.out_bs = out.ptr, out.bs
+                a.v, a.v_bs = v.ptr, v.bs
                 a.b1, a.w2, a.s2, a.b2 = self._h(n + ".b1", b1f), self._h(n + ".w2", w2f), self._h(n + ".s2", s2f), self._h(n + ".b2", b2f)
                 a.w3 = self._h(n + ".w3", lambda: (self._bn_fold(h_p + ".primary_conv.1", 1e-5)[0][:, None]
                                                    * self._p(h_p + ".primary_conv.0.weight").flatten(1)).t())
@@ -903,8 +991,12 @@ class Engine:
                 a.b4 = self._h(n + ".b4", lambda: self._bn_fold(h_p + ".cheap_operation.1", 1e-5)[1][:K - hinit])
                 a.B, a.C, a.init, a.K, a.h, a.w = self.B, init, hinit, K, cur.H, cur.W
                 self._keep.append(a)
-                self._add(n + ".up_ghost_head", self.lib.ach_up_ghost_head, C.byref(a),
-                          nbytes=4 * self.B * (init * cur.H * cur.W + K * 4 * cur.H * cur.W))
+                if mask is not None:
+                    self._add(n + ".up_ghost_head", self.lib.ach_up_ghost_head_argmax, C.byref(a), mask[0], mask[1], mask[2],
+                              nbytes=self.B * cur.H * cur.W * (4 * init + 4))
+                else:
+                    self._add(n + ".up_ghost_head", self.lib.ach_up_ghost_head, C.byref(a),
+                              nbytes=4 * self.B * (init * cur.H * cur.W + K * 4 * cur.H * cur.W))
                 return
             g = self.buf(n + ".ghost", c, cur.H * 2, cur.W * 2)
             u = AchUpGhost()
@@ -918,9 +1010,10 @@ class Engine:
             self._add(n + ".up_ghost", self.lib.ach_up_ghost, C.byref(u), nbytes=4 * self.B * cur.H * cur.W * (init + 4 * c))
             self.taps[f"neck.{name}_{stage}"] = g
             cur = g
+        out = out.view() if isinstance(out, _LazyOut) else out
         self.ghost(f"{name}.head", f"{prefix}.{name}_seg_head", cur, out, True)
 
-    def gdf_neck(self, feats, prefix, phi, out_se, out_lane):
+    def gdf_neck(self, feats, prefix, phi, out_se, out_lane, masks=None):
         w = Hd.WIDTHS[phi]
         m2, m3, m4, m5 = feats
         f5 = self.spp(m5, prefix + ".spp")
@@ -934,11 +1027,14 @@ class Engine:
         sa_se = self.shuffle_attention("fpn.sa_se", prefix + ".stage_3_semantic_seg", f3)
         self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
         dec = self.seg_decoder_fused if self.model.fuse_seg_decoder else self.seg_decoder
+        masks = masks or {}
         self.cur_lane = 3                  # the two decoders are independent of each other
         self.wait(3, 0)
-        dec("lane", prefix, sa_lane, w, out_lane)
+        dec("lane", prefix, sa_lane, w, out_lane, mask=masks.get("lane"))
+        self._seg_finish("lane", out_lane)
         self.cur_lane = 0
-        dec("se", prefix, sa_se, w, out_se)
+        dec("se", prefix, sa_se, w, out_se, mask=masks.get("se"))
+        self._seg_finish("se", out_se)
         return (f5, m5), (f4, m4), (f3, m3)
 
     # ---- CSP-Dual-FPN neck (neck/cspdualfpn.py)
@@ -982,6 +1078,7 @@ class Engine:
         return out
 
     def seg_decoder_csp(self, name, prefix, x, widths, out):
+        out = out.view() if isinstance(out, _LazyOut) else out
         chans = [widths[1], widths[0], widths[0]]
         cur = x
         for stage, c in zip(("3_to_2", "2_to_1", "1_to_0"), chans):
@@ -993,7 +1090,7 @@ class Engine:
             cur = g
         self.bottleneck(f"{name}.head", f"{prefix}.{name}_seg_head", cur, out)
 
-    def cdf_neck(self, feats, prefix, phi, out_se, out_lane):
+    def cdf_neck(self, feats, prefix, phi, out_se, out_lane, masks=None):
         w = Hd.WIDTHS[phi]
         m2, m3, m4, m5 = feats
         f5 = self.spp(m5, prefix + ".spp")
@@ -1009,9 +1106,74 @@ class Engine:
         self.cur_lane = 3                  # the two decoders are independent of each other
         self.wait(3, 0)
         self.seg_decoder_csp("lane", prefix, sa_lane, w, out_lane)
+        self._seg_finish("lane", out_lane)
         self.cur_lane = 0
         self.seg_decoder_csp("se", prefix, sa_se, w, out_se)
+        self._seg_finish("se", out_se)
         return (f5, m5), (f4, m4), (f3, m3)
+
+    # ---- compact output record (achelous.py:259-318 on the device, inside the launch plan)
+    def _keep_mask(self, K):
+        kc = self.compact["keep_classes"]
+        if kc is None:
+            return 0xFFFFFFFF
+        m = 0
+        for c in kc:
+            if not 0 <= c < min(K, 32):
+                raise ValueError(f"keep_classes: class {c} outside [0, {K})")
+            m |= 1 << c
+        return m
+
+    def _seg_finish(self, name, out):
+        """compact mode: logits that were materialised (no fused argmax head, or masks at the original image size) -> uint8 map"""
+        if self.compact is None or not isinstance(out, _LazyOut) or not out.allocated:
+            return
+        from .utils.seg_post import letterbox_window
+        v = out.view()
+        ptr, nbytes = self._mask_slots[name]
+        bs = self.packed_out.stride(0)
+        shape = self.compact["image_shape"]
+        keep_mask = self._keep_mask(v.C) if name == "se" else 0xFFFFFFFF   # achelous.py:297 masks the semantic map only
+        if shape is None:
+            self._add(name + ".argmax", self.lib.ach_seg_argmax_u8, v.ptr, v.bs, self.B, v.C, v.H * v.W, keep_mask, ptr, bs,
+                      nbytes=self.B * v.H * v.W * (4 * v.C + 1))
+        else:
+            y_off, x_off, nh, nw = letterbox_window((v.H, v.W), shape, self.compact["letterbox_image"])
+            self._add(name + ".softmax_resize_argmax", self.lib.ach_seg_softmax_resize_argmax, v.ptr, v.bs, self.B, v.C, v.H, v.W,
+                      y_off, x_off, nh, nw, ptr, bs, shape[0], shape[1], keep_mask,
+                      nbytes=self.B * (4 * v.C * nh * nw + shape[0] * shape[1]))
+
+    def _pc_out(self, logits, num_class, N):
+        """log_softmax over the classes into the output record: fp32 (B, N, K) rows, or (compact) the argmax class byte"""
+        if self.compact is None:
+            self._add("pc.logsoftmax", self.lib.ach_logsoftmax_t, logits.ptr, logits.bs, self._pc_slot, self.packed_out.stride(0), self.B,
+                      num_class, N)
+        else:
+            self._add("pc.logsoftmax_argmax", self.lib.ach_logsoftmax_argmax_t, logits.ptr, logits.bs, self._pc_slot,
+                      self.packed_out.stride(0), self.B, num_class, N)
+
+    def _det_finish(self, det_views, K):
+        """compact mode: decode_outputs + non_max_suppression (utils_bbox.py:33-130) as two launches of the plan"""
+        n = len(det_views)
+        A = sum(v.H * v.W for v in det_views)
+        ptrs = (C.c_void_p * n)(*[v.ptr for v in det_views])
+        bss = (C.c_longlong * n)(*[v.bs for v in det_views])
+        hs = (C.c_int * n)(*[v.H for v in det_views])
+        ws = (C.c_int * n)(*[v.W for v in det_views])
+        decoded = torch.empty(self.B, A, 5 + K, device=self.device, dtype=torch.float32)
+        ws_bytes = self.lib.ach_nms_workspace_bytes(self.B, A)
+        work = torch.empty(ws_bytes, device=self.device, dtype=torch.uint8)
+        self._keep += [ptrs, bss, hs, ws, decoded, work]
+        self._bufs["out.decoded"] = decoded
+        R = float(self.res)
+        self._add("det.decode", self.lib.ach_decode_outputs, ptrs, bss, hs, ws, n, decoded.data_ptr(), self.B, K, R, R,
+                  nbytes=4 * self.B * A * (5 + K) * 2)
+        cp = self.compact
+        base, bs = self.packed_out.data_ptr(), self.packed_out.stride(0)
+        md = min(cp["max_det"], A)
+        self._add("det.nms", self.lib.ach_nms_rows, decoded.data_ptr(), self.B, A, K, cp["conf_thres"], cp["nms_thres"],
+                  base + self.rec["det"][0], bs // 4, md, base + self.rec["count"][0], bs // 4, work.data_ptr(), ws_bytes,
+                  nbytes=4 * self.B * (A * (5 + K) + md * 7))
 
     # ---- radar encoder
     def rcnet(self, x, prefix, phi):
@@ -1061,8 +1223,8 @@ class Engine:
                 tiles = []
                 for wt_, K_, O_ in ((w_om_t, cin * 9, 27), (w_reg_t, 9 * cin, cin)):
                     n_ = self.lib.ach_pack_pw_tc_elems(K_, O_)
-                    hi = torch.zeros(n_, device=self.device, dtype=torch.float32)
-                    lo = torch.zeros(n_, device=self.device, dtype=torch.float32)
+                    hi = self._zeros(n_)
+                    lo = self._zeros(n_)
                     self._keep += [hi, lo]
                     self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt_.data_ptr(), K_, O_, wt_.shape[-1], hi.data_ptr(), lo.data_ptr())))
                     tiles += [hi.data_ptr(), lo.data_ptr()]
@@ -1173,7 +1335,7 @@ class Engine:
             return out.flatten()
         return self._fc(name + ".fc3", f, 256, self._w(name + ".fc3.w", w3), kpad * ldw, None, self._vec(name + ".fc3.b", b3))
 
-    def pointnet(self, x, prefix, out_pc, num_class):
+    def pointnet(self, x, prefix, num_class):
         D, N = x.C, x.H * x.W
         f = prefix + ".feat"
         ldw5 = _ceil4(D)
@@ -1204,12 +1366,12 @@ class Engine:
         h3 = self._c1_bn("pn.h3", prefix + ".conv3", prefix + ".bn3", h2, 64, ACT_RELU)
         h4 = self.buf("pn.h4", num_class, N)
         self.pw_bias("pn.h4", prefix + ".conv4", h3, h4)
-        self._add("pn.logsoftmax", self.lib.ach_logsoftmax_t, h4.ptr, h4.bs, out_pc, self.packed_out.stride(0), self.B, num_class, N)
+        self._pc_out(h4, num_class, N)
         self.taps_raw = {"pc.trans": t3, "pc.trans_feat": tf, "pc.global": g}
         self.taps["pc.pointfeat"] = pointfeat
 
     # ---- PointNet++ (builder-defined, oracle/pn2.py)
-    def pointnet2(self, x, prefix, out_pc, num_class):
+    def pointnet2(self, x, prefix, num_class):
         D, N = x.C, x.H * x.W
         ibuf = lambda name, *shape: self._keep.append(torch.zeros(*shape, device=self.device, dtype=torch.int32)) or self._keep[-1]
         xyz = [self.sl(x, 0, 3)]
@@ -1259,13 +1421,13 @@ class Engine:
         self.pw_bn_act("pn2.h1", prefix + ".conv1", prefix + ".bn1", 1e-5, f0, h, ACT_RELU, conv_bias=True)
         h2 = self.buf("pn2.h2", num_class, N)
         self.pw_bias("pn2.h2", prefix + ".conv2", h, h2)
-        self._add("pn2.logsoftmax", self.lib.ach_logsoftmax_t, h2.ptr, h2.bs, out_pc, self.packed_out.stride(0), self.B, num_class, N)
+        self._pc_out(h2, num_class, N)
 
     # ------------------------------------------------------------------ plan
     def _build(self):
         m = self.model
         B, R, N = self.B, self.res, self.n_points
-        self._params = {k: v for k, v in list(m.named_parameters()) + list(m.named_buffers())}
+        self._resolve_params()
         self.taps = {}
         self.pack_ops = []
         K, S, PC = m.num_det, m.num_seg, m.pc_classes
@@ -1277,27 +1439,51 @@ class Engine:
         for s_ in sizes:
             self.out_offsets.append(self.out_offsets[-1] + s_)
         self.frame_elems = self.out_offsets[-1]
-        self.packed_out = torch.empty(B, self.frame_elems, device=self.device, dtype=torch.float32)
         self.x_in = self.buf("in.x", m.image_channels, R, R)
         self.r_in = self.buf("in.radar", m.radar_channels, R, R)
-        base, bs = self.packed_out.data_ptr(), self.packed_out.stride(0)
+        masks = None
+        if self.compact is None:
+            self.packed_out = torch.empty(B, self.frame_elems, device=self.device, dtype=torch.float32)
+            base, bs = self.packed_out.data_ptr(), self.packed_out.stride(0)
 
-        def oview(i, C_, H, W):
-            return View(base + self.out_offsets[i] * 4, bs, C_, H, W)
-        det_views = [oview(0, 5 + K, h3, h3), oview(1, 5 + K, h4, h4), oview(2, 5 + K, h5, h5)]
-        out_se, out_lane = oview(3, S, R, R), oview(4, 2, R, R)
+            def oview(i, C_, H, W):
+                return View(base + self.out_offsets[i] * 4, bs, C_, H, W)
+            det_views = [oview(0, 5 + K, h3, h3), oview(1, 5 + K, h4, h4), oview(2, 5 + K, h5, h5)]
+            out_se, out_lane = oview(3, S, R, R), oview(4, 2, R, R)
+            self._pc_slot = base + self.out_offsets[5] * 4 if m.has_pc else None
+        else:
+            # compact record, bytes per frame: [count i32 | pad | det rows fp32 (max_det, 7) | se mask u8 | lane mask u8 | pc class u8]
+            cp = self.compact
+            md = min(cp["max_det"], h3 * h3 + h4 * h4 + h5 * h5)
+            mh, mw = cp["image_shape"] if cp["image_shape"] is not None else (R, R)
+            self.rec, off = {}, 0
+            for key, nbytes in (("count", 16), ("det", md * 28), ("se", mh * mw), ("lane", mh * mw), ("pc", N if m.has_pc else 0)):
+                self.rec[key] = (off, nbytes)
+                off = _align16(off + nbytes)
+            self.rec["shape"] = (md, mh, mw)
+            self.frame_bytes = off
+            self.packed_out = torch.zeros(B, off, device=self.device, dtype=torch.uint8)
+            base, bs = self.packed_out.data_ptr(), self.packed_out.stride(0)
+            raw_det = torch.empty(B, sum(sizes[:3]), device=self.device, dtype=torch.float32)
+            self._bufs["out.det_raw"] = raw_det
+            det_views = [View(raw_det.data_ptr() + self.out_offsets[i] * 4, raw_det.stride(0), 5 + K, h_, h_) for i, h_ in enumerate((h3, h4, h5))]
+            out_se, out_lane = _LazyOut(self, "out.se_logits", S, R, R), _LazyOut(self, "out.lane_logits", 2, R, R)
+            self._mask_slots = {"se": (base + self.rec["se"][0], mh * mw), "lane": (base + self.rec["lane"][0], mh * mw)}
+            if cp["image_shape"] is None:   # network-resolution masks: the fused head writes the class byte itself
+                masks = {"se": (base + self.rec["se"][0], bs, self._keep_mask(S)), "lane": (base + self.rec["lane"][0], bs, 0xFFFFFFFF)}
+            self._pc_slot = base + self.rec["pc"][0] if m.has_pc else None
 
         if m.has_pc:
             self.pc_in = self.buf("in.pc", m.pc_channels, N, 1)
             if m.pc_seg == "pn":
                 self.cur_lane = 1          # the point-cloud branch is independent of the image/radar graph
                 self.wait(1, 0)
-                self.pointnet(self.pc_in, "pc_seg_model", base + self.out_offsets[5] * 4, PC)
+                self.pointnet(self.pc_in, "pc_seg_model", PC)
                 self.cur_lane = 0
             elif m.pc_seg == "pn2":
                 self.cur_lane = 1
                 self.wait(1, 0)
-                self.pointnet2(self.pc_in, "pc_seg_model", base + self.out_offsets[5] * 4, PC)
+                self.pointnet2(self.pc_in, "pc_seg_model", PC)
                 self.cur_lane = 0
             else:
                 raise NotImplementedError(f"pc_seg={m.pc_seg!r}")
@@ -1310,7 +1496,7 @@ class Engine:
             feats = self.efficientformer(self.x_in, ire + ".fpn.backbone", m.phi)
         else:
             feats = self.mobilevit(self.x_in, ire + ".fpn.backbone", m.phi)
-        maps = (self.gdf_neck if m.neck == "gdf" else self.cdf_neck)(feats, ire + ".fpn", m.phi, out_se, out_lane)
+        maps = (self.gdf_neck if m.neck == "gdf" else self.cdf_neck)(feats, ire + ".fpn", m.phi, out_se, out_lane, masks=masks)
         self.cur_lane = 2                  # radar encoder: independent until the fusion stages
         self.wait(2, 0)
         radar = self.rcnet(self.r_in, ire + ".radar_encoder", m.phi)
@@ -1323,8 +1509,12 @@ class Engine:
                 self.wait(lane, 0)
             self.det_level(k, "det_head", fused[k], det_views[k], K)
         self.cur_lane = 0
+        if self.compact is not None:
+            self.wait(0, 4)
+            self.wait(0, 5)
+            self._det_finish(det_views, K)
         self.sync_end = [(0, l) for l in sorted(set(self.op_lane)) if l]
-        self.repack()
+        self._cpu64 = {}
         self._sig = self._signature()
 
     # ------------------------------------------------------------------ execution
@@ -1365,9 +1555,18 @@ class Engine:
         for fn, args in self.pack_ops:
             _lib.check(fn(*args, stream), "pack op")
 
-    def ensure_packed(self):
+    def refresh_weights(self):
+        """Host part of the stale-weight check: True when the packed weights were re-derived"""
+        if getattr(self.model, "_weights_epoch", 0) != self._epoch:
+            self._resolve_params()      # load_state_dict / invalidate(): parameter objects may have been replaced
+            self._sig = None
         if self._signature() != self._sig:
             self.repack()
+            return True
+        return False
+
+    def ensure_packed(self):
+        if self.refresh_weights():
             self._packs_done = False
         if not getattr(self, "_packs_done", False):
             self.run_packs(torch.cuda.current_stream(self.device).cuda_stream)
@@ -1381,7 +1580,8 @@ class Engine:
                 self._launch_all()  # warm-up: module loading, function attributes
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                # thread_local: nn.DataParallel runs one Python thread per GPU, each may be capturing its own plan
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self._launch_all()
                 self.graph = g
             self.graph.replay()
@@ -1394,16 +1594,28 @@ class Engine:
             t.append(self._bufs["in.pc"].view(self.B, self.model.pc_channels, self.n_points))
         return t
 
-    def output_views(self):
+    def unpack(self, po):
+        """Views of one packed output buffer - this engine's `packed_out` or a host / gathered copy with the same row layout
+        (any number of rows).  Raw mode: (det[3], se_seg, lane_seg, pc_seg) fp32; compact mode: CompactOutputs."""
         m = self.model
         K, S, R = m.num_det, m.num_seg, self.res
+        if self.compact is not None:
+            rec = self.rec
+            md, mh, mw = rec["shape"]
+            sl = lambda key: po[:, rec[key][0]:rec[key][0] + rec[key][1]]
+            count = sl("count")[:, :4].view(torch.int32)[:, 0]
+            rows = sl("det").view(torch.float32).unflatten(1, (md, 7))
+            pc = sl("pc") if m.has_pc else None
+            return CompactOutputs(rows, count, sl("se").unflatten(1, (mh, mw)), sl("lane").unflatten(1, (mh, mw)), pc)
         o = self.out_offsets
-        po = self.packed_out
         det = [po[:, o[i]:o[i + 1]].unflatten(1, (5 + K, R // s, R // s)) for i, s in enumerate((8, 16, 32))]
         se = po[:, o[3]:o[4]].unflatten(1, (S, R, R))
         lane = po[:, o[4]:o[5]].unflatten(1, (2, R, R))
         pc = po[:, o[5]:o[6]].unflatten(1, (self.n_points, m.pc_classes)) if m.has_pc else None
         return det, se, lane, pc
+
+    def output_views(self):
+        return self.unpack(self.packed_out)
 
     def tap(self, name):
         """Intermediate activation by oracle tap name (tests only)."""

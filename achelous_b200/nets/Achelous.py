@@ -9,6 +9,8 @@ or eager fallback: a missing CUDA library or a non-CUDA input raises).
                    pc_seg='pn', pc_channels=5, pc_classes=8, nano_head=True, spp=True).eval().cuda()
     det, se_seg, lane_seg, pc_seg = net(x, x_radar, x_point_clouds)
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -26,8 +28,10 @@ class _AchelousBase(nn.Module):
             raise NotImplementedError(f"phi={phi!r}: achelous_b200 implements S0/S1/S2")
         if not spp:
             raise NotImplementedError("spp=False (SPPF) is outside the accelerated path")
-        if resolution % 32 != 0:
-            raise ValueError("resolution must be a multiple of 32")
+        if resolution % 64 != 0:
+            # the stride-32 map must hold a multiple of 4 positions ((R/32)^2 % 4 == 0: 16-byte vector rows in every kernel);
+            # the reference's constructor default (416 = 13 * 32) is therefore not runnable here - predict.py / train.py use 320
+            raise ValueError(f"resolution={resolution}: achelous_b200 needs a multiple of 64 (e.g. 320, 384, 448)")
         self.num_det, self.num_seg, self.resolution = num_det, num_seg, resolution
         self.phi, self.image_channels, self.radar_channels = phi, image_channels, radar_channels
         self.backbone, self.neck, self.pc_seg = backbone, neck, pc_seg
@@ -41,20 +45,56 @@ class _AchelousBase(nn.Module):
         self.fuse_seg_chain = True     # decoder stages chained through ach_up_ghost_pw2 (no full-width maps in HBM)
         self._engines = {}
         self._host_bufs = {}
+        self._weights_epoch = 0
+        self._origin_ref = weakref.ref(self)
+        self.register_load_state_dict_post_hook(_bump_weights_epoch)
 
-    # ---- engine cache: one plan per (device, batch); weights are re-packed when parameters change
-    def _engine(self, device, batch, n_points, slot=0):
+    # ---- weight ownership
+    def _owner(self):
+        """The module that owns the parameters.  nn.DataParallel replicas (achelous.py:176) are shallow copies whose
+        `_parameters` are empty (torch/nn/parallel/replicate.py): they run on the wrapped module's packed weights, copied
+        once per device, and share its engine cache (the replica's `__dict__` is a shallow copy, so `_engines` is the
+        same dict object)."""
+        if getattr(self, "_is_replica", False):
+            owner = self._origin_ref()
+            if owner is None:
+                raise RuntimeError("nn.DataParallel replica outlived the module it was replicated from")
+            return owner
+        return self
+
+    def invalidate(self):
+        """Call after writing parameters in a way autograd's version counter cannot see (`p.data.copy_()`, `nn.init.*_(p.data)`,
+        the reference's `weights_init`): the packed device weights are re-derived on the next forward.  In-place ops on the
+        parameters themselves, `load_state_dict` (also `assign=True`) and `.to()/.cuda()` are detected automatically."""
+        self._owner()._weights_epoch += 1
+
+    refresh_weights = invalidate
+
+    # ---- engine cache: one plan per (device, batch, output mode); weights are re-packed when parameters change
+    def _engine(self, device, batch, n_points, slot=0, compact=None):
         from ..engine import Engine
-        key = (device.index if device.index is not None else torch.cuda.current_device(), batch, n_points, slot)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), batch, n_points, slot, compact)
         eng = self._engines.get(key)
         if eng is None:
-            self.n_points = n_points
-            eng = Engine(self, batch, torch.device("cuda", key[0]), use_graph=self.use_cuda_graph)
+            owner = self._owner()
+            eng = Engine(owner, batch, torch.device("cuda", key[0]), use_graph=owner.use_cuda_graph, n_points=n_points, compact=compact)
             self._engines[key] = eng
         return eng
 
+    def _compact_key(self, outputs, options):
+        """None for the raw fp32 outputs, else the normalised compact-output specification (engine cache key)"""
+        from ..engine import compact_spec
+        if outputs in (None, "raw"):
+            if options:
+                raise TypeError("compact-output options given with outputs='raw'")
+            return None
+        if outputs != "compact":
+            raise ValueError(f"outputs={outputs!r}: expected 'raw' or 'compact'")
+        return compact_spec(getattr(self._owner(), "compact_options", None), **options)
+
     def _apply(self, fn, *a, **k):
         self._engines = {}  # .to() / .cuda() / .float(): parameter storage moves, plans are rebuilt lazily
+        self._weights_epoch += 1
         return super()._apply(fn, *a, **k)
 
     def __deepcopy__(self, memo):  # ModelEMA deep-copies the model (detection_loss.py:441)
@@ -63,8 +103,37 @@ class _AchelousBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k == "_origin_ref":
+                continue
             new.__dict__[k] = {} if k in ("_engines", "_host_bufs") else copy.deepcopy(v, memo)
+        new.__dict__["_origin_ref"] = weakref.ref(new)
         return new
+
+    def __getstate__(self):  # torch.save(model): plans, pinned buffers and the weak self-reference are per-process state
+        st = self.__dict__.copy()
+        st["_engines"], st["_host_bufs"] = {}, {}
+        st.pop("_origin_ref", None)
+        return st
+
+    def __setstate__(self, st):
+        super().__setstate__(st)
+        self._origin_ref = weakref.ref(self)
+
+    def _device_for(self, x):
+        """Device the forward runs on: the parameters' device; for a DataParallel replica the device its inputs were
+        scattered to."""
+        owner = self._owner()
+        if owner.training:
+            raise NotImplementedError("achelous_b200 is inference-only: call .eval() first (no autograd kernels)")
+        p = next(owner.parameters(), None)
+        pdev = p.device if p is not None else torch.device("cpu")
+        if pdev.type != "cuda":
+            raise RuntimeError("achelous_b200 has no CPU path: move the module to a CUDA device")
+        if owner is not self:
+            return x.device if isinstance(x, torch.Tensor) and x.is_cuda else pdev
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.device != pdev:
+            raise RuntimeError(f"x is on {x.device} but the module's parameters are on {pdev}")
+        return pdev
 
     def _check(self, t, name, shape_tail):
         if not isinstance(t, torch.Tensor):
@@ -74,28 +143,31 @@ class _AchelousBase(nn.Module):
         if tuple(t.shape[1:]) != tuple(shape_tail):
             raise RuntimeError(f"{name}: expected shape (B, {', '.join(map(str, shape_tail))}), got {tuple(t.shape)}")
 
-    def _run(self, x, x_radar, x_pc):
-        if self.training:
-            raise NotImplementedError("achelous_b200 is inference-only: call .eval() first (no autograd kernels)")
-        dev = next(self.parameters()).device
-        if dev.type != "cuda":
-            raise RuntimeError("achelous_b200 has no CPU path: move the module to a CUDA device")
+    def _check_batch(self, x, x_radar, x_pc):
+        """dtype / shape validation of one batch; returns (B, n_points)"""
         R = self.resolution
         self._check(x, "x", (self.image_channels, R, R))
         self._check(x_radar, "x_radar", (self.radar_channels, R, R))
         B = x.shape[0]
         n_points = self.n_points
         if self.has_pc:
-            if x_pc.dim() != 3 or x_pc.shape[1] != self.pc_channels:
-                raise RuntimeError(f"x_point_clouds: expected (B, {self.pc_channels}, N), got {tuple(x_pc.shape)}")
+            if not isinstance(x_pc, torch.Tensor) or x_pc.dim() != 3 or x_pc.shape[1] != self.pc_channels:
+                raise RuntimeError(f"x_point_clouds: expected (B, {self.pc_channels}, N), got "
+                                   f"{tuple(x_pc.shape) if isinstance(x_pc, torch.Tensor) else type(x_pc)}")
             n_points = x_pc.shape[2]
             self._check(x_pc, "x_point_clouds", (self.pc_channels, n_points))
             if n_points % 4:
                 raise RuntimeError("x_point_clouds: N must be a multiple of 4")
         if x_radar.shape[0] != B or (self.has_pc and x_pc.shape[0] != B):
             raise RuntimeError("batch sizes of x / x_radar / x_point_clouds differ")
+        return B, n_points
+
+    def _run(self, x, x_radar, x_pc, outputs="raw", **options):
+        dev = self._device_for(x)
+        B, n_points = self._check_batch(x, x_radar, x_pc)
+        ckey = self._compact_key(outputs, options)
         with torch.cuda.device(dev), torch.no_grad():
-            eng = self._engine(dev, B, n_points)
+            eng = self._engine(dev, B, n_points, compact=ckey)
             ins = eng.input_tensors()
             # inputs may still be on the host (achelous.py:212 never moves x_radar): copy_ handles both
             ins[0].copy_(x, non_blocking=True)
@@ -103,63 +175,60 @@ class _AchelousBase(nn.Module):
             if self.has_pc:
                 ins[2].copy_(x_pc, non_blocking=True)
             eng.forward_static()
-            det, se, lane, pc = eng.output_views()
-            det = [d.contiguous() for d in det]  # fresh tensors owned by the caller
-            se, lane = se.contiguous(), lane.contiguous()
-            pc = pc.contiguous() if pc is not None else None
-        return det, se, lane, pc
-
+            # fresh tensors owned by the caller.  clone(), not contiguous(): with B == 1 the slices of the static output
+            # buffer already count as contiguous and would be handed out aliased (the next forward would overwrite them)
+            fresh = lambda t: None if t is None else t.clone(memory_format=torch.contiguous_format)
+            out = eng.output_views()
+            if ckey is not None:
+                return type(out)(*[fresh(t) for t in out])
+            det, se, lane, pc = out
+            return [fresh(d) for d in det], fresh(se), fresh(lane), fresh(pc)
 
     # ------------------------------------------------------------------ throughput API (host batches in, host results out)
-    def stream_forward(self, batches):
+    def stream_forward(self, batches, outputs="raw", compact=False, **options):
         """Pipelined inference over an iterable of HOST batches ``(x, x_radar[, x_point_clouds])`` (pinned memory
-        recommended).  Yields, per batch and in order, ``(det[3], se_seg, lane_seg, pc_seg)`` as views of a pinned host
-        buffer that stays valid until two further batches have been requested.
+        recommended).  Yields, per batch and in order, what ``forward`` returns for it - ``(det[3], se_seg, lane_seg,
+        pc_seg)``, or a ``CompactOutputs`` record with ``compact=True`` / ``outputs="compact"`` (decode + NMS rows, uint8 class
+        maps: ~0.23 MB instead of 4.6 MB per frame cross PCIe) - as views of a pinned host buffer.
+
+        Lifetime of a yielded batch: it stays intact while the NEXT batch is requested and consumed; requesting the batch after
+        that recycles its buffer (three host buffers rotate).  ``list(model.stream_forward(...))`` therefore needs a ``.clone()``
+        per batch.
 
         Same results as ``forward`` (same kernels, same plan); what changes is the schedule: two plans (double
         buffering) and three streams overlap the host->device copy of batch i+1 and the device->host copy of
         batch i-1 with the kernels of batch i, so a PCIe-bound caller sees max(copy, compute) per batch instead of
         their sum.  The reference has no equivalent (achelous.py:244-266 copies, runs and reads back serially)."""
-        if self.training:
-            raise NotImplementedError("achelous_b200 is inference-only: call .eval() first")
-        dev = next(self.parameters()).device
-        if dev.type != "cuda":
-            raise RuntimeError("achelous_b200 has no CPU path: move the module to a CUDA device")
+        if compact:
+            outputs = "compact"
+        dev = self._device_for(None)
+        ckey = self._compact_key(outputs, options)
+        NH = 3   # host buffers in rotation
         with torch.cuda.device(dev), torch.no_grad():
             main = torch.cuda.current_stream(dev)
             h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-            engines, host, ev = [None, None], [None, None], [dict(), dict()]
-            pending = []   # slots whose results have not been yielded yet, oldest first
+            engines, ev = [None, None], [dict(), dict()]
+            pending = []   # (engine, host buffer, copied event) of batches not handed out yet, oldest first
+            host_free = {}  # host-buffer id -> event of the last D2H into it (a buffer is rewritten two requests after its yield)
 
-            def views(slot):
-                eng, hb = engines[slot], host[slot]
-                o = eng.out_offsets
-                K, S, R = self.num_det, self.num_seg, self.resolution
-                det = [hb[:, o[i]:o[i + 1]].unflatten(1, (5 + K, R // s_, R // s_)) for i, s_ in enumerate((8, 16, 32))]
-                se = hb[:, o[3]:o[4]].unflatten(1, (S, R, R))
-                lane = hb[:, o[4]:o[5]].unflatten(1, (2, R, R))
-                pc = hb[:, o[5]:o[6]].unflatten(1, (eng.n_points, self.pc_classes)) if self.has_pc else None
-                return det, se, lane, pc
+            def host_buffer(eng, i):
+                hk = (dev.index, eng.B, eng.n_points, ckey, i % NH)
+                hb = self._host_bufs.get(hk)
+                if hb is None:      # pinning 300 MB costs ~100 ms: once per (device, batch, mode, rotation slot)
+                    hb = torch.empty(eng.packed_out.shape, dtype=eng.packed_out.dtype).pin_memory()
+                    self._host_bufs[hk] = hb
+                return hb
 
             def stage_in(slot, batch):
-                """Binds the slot's engine / pinned output buffer and enqueues the host->device copies of `batch`.  Called one
-                batch AHEAD of its compute: issued only when the consumer asks for the next result, the copy of batch i+1
-                started 5.3 ms (one D2H) after compute(i-1) ended and compute(i+1) then waited ~2.6 ms for its inputs."""
+                """Binds the slot's engine and enqueues the host->device copies of `batch`.  Called one batch AHEAD of its
+                compute: issued only when the consumer asks for the next result, the copy of batch i+1 started one D2H after
+                compute(i-1) ended and compute(i+1) then waited ~2.6 ms for its inputs."""
                 x, xr = batch[0], batch[1]
                 xp = batch[2] if self.has_pc else None
-                B = x.shape[0]
-                n_points = xp.shape[2] if self.has_pc else self.n_points
-                if engines[slot] is None or engines[slot].B != B:
-                    engines[slot] = self._engine(dev, B, n_points, slot=slot)
+                B, n_points = self._check_batch(x, xr, xp)
+                if engines[slot] is None or engines[slot].B != B or engines[slot].n_points != n_points:
+                    engines[slot] = self._engine(dev, B, n_points, slot=slot, compact=ckey)
                     engines[slot].ensure_packed()
-                    hk = (dev.index, B, n_points, slot)
-                    if hk not in self._host_bufs:       # pinning 300 MB costs ~100 ms: do it once per (device, batch, slot)
-                        self._host_bufs[hk] = torch.empty(B, engines[slot].frame_elems, dtype=torch.float32).pin_memory()
-                    new_host = self._host_bufs[hk]
-                    if host[slot] is not None and new_host is not host[slot]:
-                        # the batch size changed: results still parked in the old buffer must be handed out first
-                        return new_host
-                    host[slot] = new_host
                 ins = engines[slot].input_tensors()
                 if "done" in ev[slot]:
                     h2d.wait_event(ev[slot]["done"])      # the previous compute on this slot no longer reads its inputs
@@ -169,7 +238,11 @@ class _AchelousBase(nn.Module):
                     if self.has_pc:
                         ins[2].copy_(xp, non_blocking=True)
                     ev[slot]["in"] = h2d.record_event()
-                return None
+
+            def hand_out():
+                eng, hb, copied = pending.pop(0)
+                copied.synchronize()
+                return eng.unpack(hb)
 
             it = iter(batches)
             nxt = next(it, None)
@@ -178,49 +251,38 @@ class _AchelousBase(nn.Module):
             while nxt is not None:
                 slot = i & 1
                 if not staged:
-                    deferred = stage_in(slot, nxt)
-                    if deferred is not None:              # drain everything, then rebind the slot to the new buffer size
-                        while pending:
-                            prev = pending.pop(0)
-                            ev[prev]["copied"].synchronize()
-                            yield views(prev)
-                        host[slot] = deferred
-                        stage_in(slot, nxt)
+                    stage_in(slot, nxt)
                 eng = engines[slot]
-                # results of the batch that used this slot two iterations ago must be handed out before reuse
-                while pending and pending[0] == slot:
-                    ev[slot]["copied"].synchronize()
-                    pending.pop(0)
-                    yield views(slot)
                 main.wait_event(ev[slot]["in"])
                 if "copied" in ev[slot]:
-                    main.wait_event(ev[slot]["copied"])   # the previous D2H of this slot's output buffer has finished
+                    main.wait_event(ev[slot]["copied"])   # the previous D2H out of this slot's device buffer has finished
                 eng.forward_static()
                 ev[slot]["done"] = main.record_event()
+                hb = host_buffer(eng, i)
+                # the host buffer's previous occupant (batch i - NH) was handed out at least two requests ago
+                assert all(p[1] is not hb for p in pending)
                 d2h.wait_event(ev[slot]["done"])
                 with torch.cuda.stream(d2h):
-                    host[slot].copy_(eng.packed_out, non_blocking=True)
+                    hb.copy_(eng.packed_out, non_blocking=True)
                     ev[slot]["copied"] = d2h.record_event()
-                pending.append(slot)
-                # stage the NEXT batch's inputs now, while this batch computes (same-size batches: the common case)
+                pending.append((eng, hb, ev[slot]["copied"]))
+                # stage the NEXT batch's inputs now, while this batch computes
                 nxt = next(it, None)
                 staged = False
                 if nxt is not None:
-                    oslot = (i + 1) & 1
-                    same = engines[oslot] is not None and engines[oslot].B == nxt[0].shape[0]
-                    if same:
-                        stage_in(oslot, nxt)
-                        staged = True
+                    stage_in((i + 1) & 1, nxt)
+                    staged = True
                 # hand out the previous batch while this one is in flight
                 if len(pending) == 2:
-                    prev = pending.pop(0)
-                    ev[prev]["copied"].synchronize()
-                    yield views(prev)
+                    yield hand_out()
                 i += 1
             while pending:
-                prev = pending.pop(0)
-                ev[prev]["copied"].synchronize()
-                yield views(prev)
+                yield hand_out()
+
+
+def _bump_weights_epoch(module, incompatible_keys):
+    """load_state_dict post-hook: parameter contents (or, with assign=True, the Parameter objects) changed"""
+    module._weights_epoch += 1
 
 
 class Achelous(_AchelousBase):
@@ -242,9 +304,11 @@ class Achelous(_AchelousBase):
                                                 radar_channels=radar_channels, resolution=resolution)
         self.det_head = Hd.DecoupleHead(num_classes=num_det, phi=phi, nano_head=nano_head)
 
-    def forward(self, x, x_radar, x_point_clouds):
-        det, se, lane, pc = self._run(x, x_radar, x_point_clouds)
-        return det, se, lane, pc
+    def forward(self, x, x_radar, x_point_clouds, outputs="raw", **compact_options):
+        """outputs="raw" (default): the reference's return value.  outputs="compact": a CompactOutputs record (engine.py) -
+        NMS rows, uint8 argmax maps and point classes computed inside the same launch plan; options: conf_thres, nms_thres,
+        max_det, keep_classes (achelous.py:297 keeps (0, 8)), image_shape=(h, w) for masks at the original image size."""
+        return self._run(x, x_radar, x_point_clouds, outputs, **compact_options)
 
 
 class Achelous3T(_AchelousBase):
@@ -260,6 +324,9 @@ class Achelous3T(_AchelousBase):
                                                 radar_channels=radar_channels, resolution=resolution)
         self.det_head = Hd.DecoupleHead(num_classes=num_det, phi=phi, nano_head=nano_head)
 
-    def forward(self, x, x_radar):
-        det, se, lane, _ = self._run(x, x_radar, None)
+    def forward(self, x, x_radar, outputs="raw", **compact_options):
+        out = self._run(x, x_radar, None, outputs, **compact_options)
+        if outputs == "compact":
+            return out
+        det, se, lane, _ = out
         return det, se, lane

@@ -229,6 +229,10 @@ ACH_API int ach_xca_fold(const float* qkv, long long qkv_bs, const float* temper
  * out (B, heads*d, H*W) = softmax(q k^T / sqrt(d)) v per (group, head).  dim_head must be 8. */
 ACH_API int ach_mvit_attention(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head,
                                int H, int W, void* stream);
+/* The same contract with QK^T and PV on tcgen05 (Q and P in tensor memory).  Parity-tested; not on the default plan because the
+ * CUDA-core kernel is faster at d = 8.  Shapes outside its shared-memory layout are rejected, never rerouted. */
+ACH_API int ach_mvit_attention_tc(const float* qkv, long long qkv_bs, float* out, long long out_bs, int B, int heads, int dim_head,
+                                  int H, int W, void* stream);
 
 /* EdgeViT blocks (backbone/vision/edgevit_modules/edgevit.py, backbone='ev'):
  * ach_subsample: out (B, C, ceil(H/sr), ceil(W/sr)) = x[:, :, ::sr, ::sr]  (the sampler nn.AvgPool2d(1, sr), :66,76).
@@ -319,6 +323,11 @@ typedef struct AchUpGhostHead {
 } AchUpGhostHead;
 ACH_API int ach_up_ghost_head_supported(int c_in, int init, int k_out);
 ACH_API int ach_up_ghost_head(const AchUpGhostHead* p, void* stream);
+/* Compact variant: instead of the K logit planes (p->out is ignored) writes mask (B, 2h, 2w) uint8 = first-maximum class index
+ * over exactly those logits (= torch.argmax(out, 1), which is all achelous.py:283-297 keeps of them), batch stride mask_bs
+ * bytes; a class whose bit in keep_mask is clear is written as 0 (achelous.py:297 keeps classes {0, 8}: keep_mask 0x101). */
+ACH_API int ach_up_ghost_head_argmax(const AchUpGhostHead* p, unsigned char* mask, long long mask_bs, unsigned keep_mask,
+                                     void* stream);
 
 /* One whole decoder stage at its output resolution: the GhostModule of stage s (as ach_up_ghost, Cn = Ci) followed by
  * the NEXT stage's Upsample 1x1 conv + BN + ReLU (w1t K-major [2*Ci][32], BN scale folded; c1 bias [32]) and the next
@@ -382,6 +391,12 @@ ACH_API int ach_decode_outputs(const float* const* levels, const long long* leve
 ACH_API long long ach_nms_workspace_bytes(int B, int A);
 ACH_API int ach_nms(const float* decoded, int B, int A, int K, float conf_thres, float nms_thres, float* kept,
             int* kept_idx, int* counts, void* workspace, long long workspace_bytes, void* stream);
+/* ach_nms_rows: the same NMS writing only the first max_keep rows (score-descending) of image b at kept + b*kept_bs (floats;
+ * rows behind the survivors are zero-filled) and the TRUE survivor count at counts + b*counts_bs (ints): the detection part
+ * of the compact per-frame output record (decode + NMS inside the launch plan, achelous.py:259-275). */
+ACH_API int ach_nms_rows(const float* decoded, int B, int A, int K, float conf_thres, float nms_thres, float* kept,
+                 long long kept_bs, int max_keep, int* counts, long long counts_bs, void* workspace,
+                 long long workspace_bytes, void* stream);
 
 /* Segmentation post-process on device: the caller-side sequence of achelous.py:283-318
  * (softmax over classes -> letterbox crop rows [y_off, y_off+nh) x cols [x_off, x_off+nw) -> cv2.resize INTER_LINEAR to
@@ -390,6 +405,17 @@ ACH_API int ach_nms(const float* decoded, int B, int A, int K, float conf_thres,
 ACH_API int ach_seg_softmax(const float* x, long long x_bs, float* out, long long out_bs, int B, int K, int P, void* stream);
 ACH_API int ach_seg_resize_argmax(const float* prob, long long prob_bs, int B, int K, int H, int W, int y_off, int x_off, int nh,
                                   int nw, unsigned char* out, int OH, int OW, void* stream);
+/* ach_seg_softmax_resize_argmax: both steps in one pass over the LOGITS (no probability map in HBM), bit-identical class map;
+ * out batch stride out_bs bytes; classes whose keep_mask bit is clear are written as 0 (achelous.py:297).
+ * ach_seg_argmax_u8: argmax at network resolution, (B, K, P) logits -> (B, P) uint8 (P % 4 == 0).
+ * ach_logsoftmax_argmax_t: (B, K, N) point logits -> (B, N) uint8 = argmax of log_softmax over K (achelous.py:262). */
+ACH_API int ach_seg_softmax_resize_argmax(const float* logits, long long bs, int B, int K, int H, int W, int y_off, int x_off,
+                                          int nh, int nw, unsigned char* out, long long out_bs, int OH, int OW,
+                                          unsigned keep_mask, void* stream);
+ACH_API int ach_seg_argmax_u8(const float* x, long long x_bs, int B, int K, int P, unsigned keep_mask, unsigned char* out,
+                              long long out_bs, void* stream);
+ACH_API int ach_logsoftmax_argmax_t(const float* x, long long x_bs, unsigned char* out, long long out_bs, int B, int K, int N,
+                                    void* stream);
 
 /* Input pre-processing on device (achelous.py:200-246, utils/utils.py:20-54).
  * Image: Pillow's two-pass 8-bit BICUBIC resize (Resample.c; coefficient tables `bounds` [out][2] = (first source

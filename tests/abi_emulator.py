@@ -464,6 +464,75 @@ def ach_up_ghost_head(s):
     fview(s.out, (B, K, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(torch.cat([p, q], 1))
 
 
+def u8view(ptr, shape, strides):
+    extent = 1 + sum((s - 1) * st for s, st in zip(shape, strides))
+    arr = np.ctypeslib.as_array((C.c_uint8 * extent).from_address(ptr))
+    return torch.from_numpy(np.lib.stride_tricks.as_strided(arr, shape, strides))
+
+
+def _apply_keep(am, keep_mask):
+    keep = torch.tensor([(keep_mask >> k) & 1 for k in range(32)], dtype=torch.bool)
+    return torch.where(keep[am], am, torch.zeros_like(am))
+
+
+def ach_up_ghost_head_argmax(s, mask, mask_bs, keep_mask):
+    B, K, h, w = s.B, s.K, s.h, s.w
+    logits = torch.empty(B, K, 2 * h, 2 * w)
+    ach_up_ghost_head(_Shim(s, out=logits.data_ptr(), out_bs=logits.stride(0)))
+    u8view(mask, (B, 2 * h, 2 * w), (mask_bs, 2 * w, 1)).copy_(_apply_keep(logits.argmax(1), keep_mask).to(torch.uint8))
+
+
+def ach_seg_argmax_u8(x, x_bs, B, K, P, keep_mask, out, out_bs):
+    xv = fview(x, (B, K, P), (x_bs, P, 1))
+    u8view(out, (B, P), (out_bs, 1)).copy_(_apply_keep(xv.argmax(1), keep_mask).to(torch.uint8))
+
+
+def ach_seg_softmax_resize_argmax(logits, bs, B, K, H, W, y_off, x_off, nh, nw, out, out_bs, OH, OW, keep_mask):
+    import cv2
+    xv = fview(logits, (B, K, H, W), (bs, H * W, W, 1))
+    o = u8view(out, (B, OH, OW), (out_bs, OW, 1))
+    for b in range(B):   # achelous.py:283-296
+        pr = F.softmax(xv[b].permute(1, 2, 0), dim=-1).numpy()[y_off:y_off + nh, x_off:x_off + nw]
+        pr = cv2.resize(pr, (OW, OH), interpolation=cv2.INTER_LINEAR)
+        if pr.ndim == 2:
+            pr = pr[:, :, None]
+        o[b].copy_(_apply_keep(torch.from_numpy(pr.argmax(-1)), keep_mask).to(torch.uint8))
+
+
+def ach_logsoftmax_argmax_t(x, x_bs, out, out_bs, B, K, N):
+    xv = fview(x, (B, K, N), (x_bs, N, 1))
+    u8view(out, (B, N), (out_bs, 1)).copy_(F.log_softmax(xv.transpose(1, 2), dim=-1).argmax(-1).to(torch.uint8))
+
+
+def ach_decode_outputs(levels, level_bs, hs, ws, n, out, B, K, input_h, input_w):
+    from oracle.postprocess import decode_outputs
+    maps = [fview(levels[i], (B, 5 + K, hs[i], ws[i]), (level_bs[i], hs[i] * ws[i], ws[i], 1)) for i in range(n)]
+    A = sum(hs[i] * ws[i] for i in range(n))
+    fview(out, (B, A, 5 + K), (A * (5 + K), 5 + K, 1)).copy_(decode_outputs(maps, (input_h, input_w)))
+
+
+def ach_nms_rows(decoded, B, A, K, conf_thres, nms_thres, kept, kept_bs, max_keep, counts, counts_bs, ws, ws_bytes):
+    """rows of utils_bbox.non_max_suppression before the letterbox un-warp, restated with the oracle's pieces"""
+    from oracle.postprocess import batched_nms_coordinate_trick
+    pred = fview(decoded, (B, A, 5 + K), (A * (5 + K), 5 + K, 1)).clone()
+    xy, wh = pred[:, :, 0:2].clone(), pred[:, :, 2:4].clone()
+    pred[:, :, 0:2] = xy - wh / 2
+    pred[:, :, 2:4] = xy + wh / 2
+    rows = fview(kept, (B, max_keep, 7), (kept_bs, 7, 1))
+    cnt = np.lib.stride_tricks.as_strided(np.ctypeslib.as_array((C.c_int32 * (1 + (B - 1) * counts_bs)).from_address(counts)), (B,), (counts_bs * 4,))
+    rows.zero_()
+    for b in range(B):
+        ip = pred[b]
+        conf, cls = torch.max(ip[:, 5:5 + K], 1, keepdim=True)
+        cand = torch.nonzero(ip[:, 4] * conf[:, 0] >= conf_thres).flatten()
+        det = torch.cat((ip[:, :5], conf, cls.float()), 1)[cand].numpy()
+        keep = batched_nms_coordinate_trick(det[:, :4], (det[:, 4] * det[:, 5]).astype(np.float32), det[:, 6], nms_thres)
+        det = det[keep]
+        cnt[b] = len(det)
+        m = min(len(det), max_keep)
+        rows[b, :m] = torch.from_numpy(det[:m])
+
+
 def iview(ptr, shape):
     n = 1
     for d in shape:
@@ -515,7 +584,9 @@ EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, a
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
                                      ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
-                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT, ach_s2d, ach_ef_attention, ach_upsample2x_hp)}
+                                     ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT, ach_s2d, ach_ef_attention, ach_upsample2x_hp,
+                                     ach_up_ghost_head_argmax, ach_seg_argmax_u8, ach_seg_softmax_resize_argmax, ach_logsoftmax_argmax_t,
+                                     ach_decode_outputs, ach_nms_rows)}
 
 
 def _unwrap(a):

@@ -78,3 +78,64 @@ def test_repack_tracks_parameter_updates():
     assert eng._signature() != sig
     eng.repack()
     assert torch.allclose(eng._weights[key][0], before * 2.0)
+
+
+@pytest.mark.parametrize("image_shape,keep,fuse", [(None, None, True), (None, (0, 8), False), ((97, 211), (0, 8), True)])
+def test_compact_plan_matches_raw_plan(image_shape, keep, fuse):
+    """outputs="compact": decode + NMS rows, uint8 class maps and point classes produced INSIDE the plan equal what the
+    reference's caller derives from the raw outputs (achelous.py:259-297: decode_outputs -> non_max_suppression, softmax ->
+    [crop -> cv2.resize] -> argmax -> class-mask rule, argmax over point classes)."""
+    import numpy as np
+    from oracle import postprocess as OP
+    torch.set_num_threads(4)
+    model = Achelous(phi="S0", backbone="en", **MODEL_KW).eval()
+    model.fuse_seg_decoder = fuse
+    model.load_state_dict(fill_state_dict(model.state_dict(), seed=2), strict=True)
+    with torch.no_grad():                                  # bias the obj logits so that a useful number of boxes survive
+        for k in range(3):
+            model.det_head.obj_preds[k].bias += 2.0
+            model.det_head.reg_preds[k].bias[2:] += 1.3
+    B = 2
+    x, xr, pc = make_inputs(B, seed=21)
+    outs = {}
+    spec = dict(conf_thres=0.3, nms_thres=0.45, max_det=40, keep_classes=keep, image_shape=image_shape)
+    for mode, compact in (("raw", None), ("compact", spec)):
+        eng = Engine(model, B, "cpu", dry_run=True, compact=compact)
+        ins = eng.input_tensors()
+        ins[0].copy_(x), ins[1].copy_(xr), ins[2].copy_(pc)
+        emulate_engine(eng)
+        outs[mode] = eng.output_views()
+        if mode == "compact":
+            names = " ".join(fn.__name__ for fn, _ in eng.ops)
+            assert ("ach_up_ghost_head_argmax" in names) == (fuse and image_shape is None)     # fused argmax head only at network resolution
+            assert ("out.se_logits" in eng._bufs) == (not fuse or image_shape is not None)
+    det, se, lane, pcs = outs["raw"]
+    c = outs["compact"]
+    assert torch.equal(c.pc_cls.long(), pcs.argmax(-1))
+    keep_lut = torch.ones(9, dtype=torch.bool) if keep is None else torch.tensor([k in keep for k in range(9)])
+    if image_shape is None:
+        am = se.argmax(1)
+        assert torch.equal(c.se_mask.long(), torch.where(keep_lut[am], am, torch.zeros_like(am)))
+        assert torch.equal(c.lane_mask.long(), lane.argmax(1))
+    else:
+        for b in range(B):
+            _, am = OP.seg_postprocess(se[b], image_shape, True)
+            am = torch.from_numpy(am)
+            assert torch.equal(c.se_mask[b].long(), torch.where(keep_lut[am], am, torch.zeros_like(am)))
+            assert torch.equal(c.lane_mask[b].long(), torch.from_numpy(OP.seg_postprocess(lane[b], image_shape, True)[1]))
+    decoded = OP.decode_outputs([d.clone() for d in det], (320, 320))
+    ref_rows, _ = OP.non_max_suppression(decoded, 7, (320, 320), np.array([320, 320]), False, conf_thres=0.3, nms_thres=0.45,
+                                         return_indices=True)
+    n_trunc = 0
+    for b in range(B):
+        n = ref_rows[b].shape[0]
+        assert int(c.det_count[b]) == n and n > 0
+        m = min(n, 40)
+        n_trunc += n > 40
+        # rows before the letterbox un-warp: (x1, y1, x2, y2) normalised; the oracle returns them un-warped to a 320x320 image, y first
+        mine = c.det_rows[b, :m].numpy()
+        ref = ref_rows[b][:m]
+        assert np.array_equal(mine[:, 4:], ref[:, 4:])
+        assert np.allclose(mine[:, [1, 0, 3, 2]] * 320.0, ref[:, :4], rtol=0, atol=1e-3)
+        assert not c.det_rows[b, m:].any()
+    assert n_trunc > 0      # the cap was exercised

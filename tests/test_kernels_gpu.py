@@ -521,15 +521,15 @@ def test_pw_conv_tc(case):
 
 @pytest.mark.parametrize("tc", [1, 0], ids=["tcgen05", "cuda-cores"])
 @pytest.mark.parametrize("H,W", [(40, 40), (20, 20), (10, 10), (6, 14), (52, 52), (2, 2)])
-def test_mvit_attention(H, W, tc, monkeypatch):
+def test_mvit_attention(H, W, tc):
     B, heads, d = 2, 4, 8
     P = H * W
-    monkeypatch.setenv("ACH_MVIT_TC", str(tc))   # read at every launch
+    emu.EMULATORS["ach_mvit_attention_tc"] = emu.EMULATORS["ach_mvit_attention"]   # same contract, separate entry point
 
     def make(A):
         A.new("qkv", R(B, 3 * heads * d + 5, P) * 1.5), A.new("out", torch.zeros(B, heads * d, P))
         return (A.ptr("qkv", 5 * P), (3 * heads * d + 5) * P, A.ptr("out"), heads * d * P, B, heads, d, H, W)
-    run_both("ach_mvit_attention", make, ["out"])
+    run_both("ach_mvit_attention_tc" if tc else "ach_mvit_attention", make, ["out"])
 
 
 @pytest.mark.parametrize("Cc,H,W", [(32, 80, 80), (96, 20, 20), (5, 6, 10)])
@@ -618,9 +618,9 @@ def test_pn2_interp3(N1, S, C2):
     run_both("ach_pn2_interp3", make, ["out"])
 
 
-@pytest.mark.parametrize("stages,off_scale", [(1, 3.0), (2, 3.0), (1, 0.5)])   # offsets beyond / within the staged window halo
+@pytest.mark.parametrize("off_scale", [3.0, 0.5])   # offsets beyond / within the staged window halo
 @pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (8, 13, 21), (16, 24, 20), (8, 160, 160)])
-def test_rc_deform_tc(Cc, H, W, stages, off_scale, monkeypatch):
+def test_rc_deform_tc(Cc, H, W, off_scale):
     B = 2
     lib = _lib.load()
     n_om, n_reg = lib.ach_pack_pw_tc_elems(Cc * 9, 27), lib.ach_pack_pw_tc_elems(9 * Cc, Cc)
@@ -650,7 +650,6 @@ def test_rc_deform_tc(Cc, H, W, stages, off_scale, monkeypatch):
         return [("ach_pack_pw_tc", (A.ptr("w_om_tap"), Cc * 9, 27, 28, A.ptr("omh"), A.ptr("oml"))),
                 ("ach_pack_pw_tc", (A.ptr("w_reg_tap"), 9 * Cc, Cc, ldr, A.ptr("rgh"), A.ptr("rgl"))),
                 ("ach_rc_deform_tc", (s, A.ptr("omh"), A.ptr("oml"), A.ptr("rgh"), A.ptr("rgl")))]
-    monkeypatch.setenv("ACH_RC_TC_STAGES", str(stages))   # read at every launch (getenv in the C ABI)
     run_seq(make, ["out"], rtol=1e-4)
 
 
