@@ -77,7 +77,7 @@ def _ceil4(n):
 
 
 class Engine:
-    def __init__(self, model, batch, device, use_graph=True, dry_run=False, n_points=None, compact=None):
+    def __init__(self, model, batch, device, use_graph=True, dry_run=False, n_points=None, compact=None, out=None):
         """dry_run=True builds the plan and packs the weights without a GPU (host-logic tests only):
         nothing can be launched from such an engine.  `model` is the module that OWNS the parameters (under
         nn.DataParallel: the wrapped module, not a replica); `device` may differ from the parameters' device -
@@ -93,6 +93,7 @@ class Engine:
         self.res = model.resolution
         self.n_points = int(model.n_points if n_points is None else n_points)
         self.compact = dict(compact_spec(compact) if isinstance(compact, dict) else compact) if compact else None
+        self._out = out        # caller-owned packed output rows (e.g. this rank's slice of an all-gather buffer: in-place gather)
         self.ops = []          # (cfunc, args) - stream appended at call time
         self.op_names = []
         self.op_bytes = []
@@ -1423,6 +1424,17 @@ class Engine:
         self.pw_bias("pn2.h2", prefix + ".conv2", h, h2)
         self._pc_out(h2, num_class, N)
 
+    def _adopt_out(self, dtype, width):
+        """The packed output buffer: allocated here, or the caller's rows (B, width) - e.g. this rank's slice of the all-gather
+        destination, so that the gather is in place and no staging copy exists"""
+        if self._out is None:
+            return torch.zeros(self.B, width, device=self.device, dtype=dtype)
+        o = self._out
+        if (o.dtype != dtype or tuple(o.shape) != (self.B, width) or o.stride(1) != 1 or o.device != self.device or o.data_ptr() % 16
+                or (o.stride(0) * o.element_size()) % 16):
+            raise _lib.AchelousKernelError(f"out buffer must be a 16-byte aligned ({self.B}, {width}) {dtype} view on {self.device}")
+        return o
+
     # ------------------------------------------------------------------ plan
     def _build(self):
         m = self.model
@@ -1443,7 +1455,7 @@ class Engine:
         self.r_in = self.buf("in.radar", m.radar_channels, R, R)
         masks = None
         if self.compact is None:
-            self.packed_out = torch.empty(B, self.frame_elems, device=self.device, dtype=torch.float32)
+            self.packed_out = self._adopt_out(torch.float32, self.frame_elems)
             base, bs = self.packed_out.data_ptr(), self.packed_out.stride(0)
 
             def oview(i, C_, H, W):
@@ -1462,7 +1474,7 @@ class Engine:
                 off = _align16(off + nbytes)
             self.rec["shape"] = (md, mh, mw)
             self.frame_bytes = off
-            self.packed_out = torch.zeros(B, off, device=self.device, dtype=torch.uint8)
+            self.packed_out = self._adopt_out(torch.uint8, off)
             base, bs = self.packed_out.data_ptr(), self.packed_out.stride(0)
             raw_det = torch.empty(B, sum(sizes[:3]), device=self.device, dtype=torch.float32)
             self._bufs["out.det_raw"] = raw_det

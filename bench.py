@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""Headline benchmark: frames/sec of the full 5-task Achelous forward (EN-GDF-PN-S0, 320x320 RGB +
-320x320 radar map + 512 points), batch 64 per GPU, on N B200s.
+"""Headline benchmark: frames/sec of the full 5-task Achelous forward (320x320 RGB + 320x320 radar map + 512 points) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config en_s0|mv_s0|en_s2_pn2] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM (CUDA
-graph replay of the whole launch plan [+ one NCCL all-gather of the packed outputs when N > 1]);
-`e2e` = the same metric through the public nn.Module surface with pinned HOST inputs and a
-device->host read of all outputs inside the timed region; `roofline` = the dominant kernel timed live
-with CUDA events; `cpu_baseline` = the CPU oracle port timed on the box's host cores.
-`--impl reference` times the reference's algorithm on the host CPU (the oracle port: the reference
-itself is Python under /root/reference and cannot travel to the GPU box)."""
+Prints ONE JSON line (rank 0).
+  value        device-timed throughput of the RAW forward (the reference's return value: fp32 logits, the parity artefact), inputs
+               resident in HBM, CUDA-graph replay of the whole launch plan [+ one in-place NCCL all-gather of the packed outputs
+               when N > 1].  K steps are timed `--repeats` times (barrier + synchronize on both sides, max over ranks each time);
+               the MEDIAN repeat is reported.
+  compact      the same loop with outputs="compact" (decode + NMS rows, uint8 class maps, point classes produced inside the
+               plan - what achelous.py:259-297 derives from the logits; 0.23 MB instead of 4.6 MB per frame to gather)
+  e2e          the same metric through the public nn.Module surface with pinned HOST inputs and a device->host read of the
+               results inside the timed region: Achelous.stream_forward(compact=True); `raw_logits_value` = the same with the
+               raw fp32 outputs copied out (PCIe-bound)
+  roofline     the dominant kernel timed live with CUDA events
+  cpu_baseline the reference's own PyTorch forward (oracle/_ref = staged unmodified reference files; the oracle port when that
+               is absent or, for config 4, because the reference ships no PointNet++) on the box's host cores
+`--impl reference` times that CPU implementation alone, same metric / config."""
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -25,17 +32,23 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec full 5-task forward @320x320+512pts"
 UNIT = "frames/s"
-MODEL_KW = dict(num_det=7, num_seg=9, phi="S0", resolution=320, backbone="en", neck="gdf", pc_seg="pn", pc_channels=5,
-                pc_classes=8, nano_head=True, spp=True)
-WORKLOAD = "EN-GDF-PN-S0 inference, 320x320 RGB + radar map + 512 pts"
+BASE_KW = dict(num_det=7, num_seg=9, resolution=320, neck="gdf", pc_channels=5, pc_classes=8, nano_head=True, spp=True)
+CONFIGS = {   # BASELINE.json configs[1], [2], [3]
+    "en_s0": dict(kw=dict(BASE_KW, phi="S0", backbone="en", pc_seg="pn"), batch=64,
+                  workload="EN-GDF-PN-S0 inference, 320x320 RGB + radar map + 512 pts"),
+    "mv_s0": dict(kw=dict(BASE_KW, phi="S0", backbone="mv", pc_seg="pn"), batch=64,
+                  workload="MV-GDF-PN-S0 inference (MobileViT backbone), 320x320 RGB + radar map + 512 pts"),
+    "en_s2_pn2": dict(kw=dict(BASE_KW, phi="S2", backbone="en", pc_seg="pn2"), batch=32,
+                      workload="EN-GDF-PN2-S2 inference (PointNet++ head: builder-defined, the reference ships none), 320x320 RGB + radar map + 512 pts"),
+}
 
 
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return json.load(f), "measured"
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -49,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -85,53 +98,112 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def time_cpu_oracle(batch, steps, warmup, threads):
-    import torch
-    from achelous_b200.nets.Achelous import Achelous
-    from achelous_b200.synthetic import make_inputs
-    from achelous_b200.weights import fill_state_dict
-    from oracle import functional as OF
-    torch.set_num_threads(threads)
-    spec = Achelous(**MODEL_KW).state_dict()
-    sd = fill_state_dict(spec, seed=0)
-    x, xr, pc = make_inputs(batch, seed=1234)
-    ts = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        OF.achelous_forward(sd, x, xr, pc, phi="S0", backbone="en")
-        if i >= warmup:
-            ts.append(time.perf_counter() - t0)
-    return ts
+# ---------------------------------------------------------------------------------------------- CPU arm
+class CpuForward:
+    """The reference's CPU forward for one config: the UNMODIFIED reference module (kind "reference": /root/reference or the staged
+    copy oracle/_ref) when it can be imported and implements the config, else the oracle port (kind "port")."""
+
+    def __init__(self, cfg_name):
+        import torch
+        from achelous_b200.nets.Achelous import Achelous
+        from achelous_b200.weights import fill_state_dict
+        cfg = CONFIGS[cfg_name]
+        kw = cfg["kw"]
+        self.kw = kw
+        self.kind, self.how, self.model = "port", "oracle/functional.py (PyTorch CPU fp32 restatement)", None
+        spec = Achelous(**kw).state_dict()
+        self.sd = fill_state_dict(spec, seed=0)
+        if kw["pc_seg"] == "pn":       # the reference has no PointNet++ (SURVEY.md §0.2): config 4 can only be timed as the port
+            try:
+                from oracle.ref_loader import load_reference, reference_available, reference_kind
+                if reference_available():
+                    ns = load_reference()
+                    m = ns.Achelous(**kw).eval()
+                    m.load_state_dict(self.sd, strict=True)
+                    self.model, self.kind = m.eval(), "reference"
+                    self.how = f"unmodified reference nets/Achelous.py:49-53 ({reference_kind()}), PyTorch CPU fp32, torch.no_grad()"
+            except Exception as e:   # pragma: no cover
+                self.how += f" [reference import failed: {type(e).__name__}: {e}]"
+        self.torch = torch
+
+    def __call__(self, x, xr, pc):
+        if self.model is not None:
+            with self.torch.no_grad():
+                return self.model(x, xr, pc)
+        from oracle import functional as OF
+        return OF.achelous_forward(self.sd, x, xr, pc, phi=self.kw["phi"], backbone=self.kw["backbone"], pc_seg=self.kw["pc_seg"])
+
+    def time(self, batch, threads, warmup, steps):
+        from achelous_b200.synthetic import make_inputs
+        self.torch.set_num_threads(threads)
+        x, xr, pc = make_inputs(batch, seed=1234)
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            self(x, xr, pc)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+        return ts
+
+
+def thread_counts(cores):
+    n, out = 1, []
+    while n < cores:
+        out.append(n)
+        n *= 2
+    return out + [cores]
+
+
+def cpu_sweep(fwd, cores, warm, timed, budget_s):
+    """B=1, torch threads swept over 1, 2, 4, ..., cores; best median kept.  Also tries one batched point
+    (B=8, all cores) - a throughput-minded CPU user would batch.  Stops adding points when the time budget is spent."""
+    t_start, tried, best = time.perf_counter(), [], None
+    for batch, th in [(1, n) for n in thread_counts(cores)] + [(8, cores)]:
+        if time.perf_counter() - t_start > budget_s and best is not None:
+            break
+        ts = fwd.time(batch, th, warm, timed)
+        fps = batch / statistics.median(ts)
+        tried.append({"batch": batch, "threads": th, "frames_per_s": round(fps, 3)})
+        if best is None or fps > best[0]:
+            best = (fps, batch, th)
+    return best, tried
 
 
 def run_reference(args):
-    """CPU arm: the oracle port (same ATen CPU kernels the reference's eager forward runs) on all host threads."""
+    """CPU arm: the reference's own forward on the host cores, best (batch, threads) point of a short sweep, then K timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     cores = os.cpu_count() or 1
-    batch = 8
-    ts = time_cpu_oracle(batch, args.steps, max(args.warmup, 1), cores)
+    fwd = CpuForward(args.config)
+    best, tried = cpu_sweep(fwd, cores, 1, 2, budget_s=60.0)
+    _, batch, th = best
+    ts = fwd.time(batch, th, max(args.warmup, 1), args.steps)
     total = sum(ts)
     value = batch * len(ts) / total
+    cfg = CONFIGS[args.config]
+    sample = (f"{len(ts)} steps x {batch} frame(s) at {th} torch threads (best point of a sweep over B=1 x threads {thread_counts(cores)} and "
+              f"B=8 x {cores}); {fwd.how}")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "batch_per_step": batch, "device": "host CPU", "torch_threads": cores},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{len(ts)} steps x {batch} frames, oracle port (PyTorch CPU fp32), torch threads={cores}"},
+            "config": {"workload": cfg["workload"], "config": args.config, "batch_per_step": batch, "device": "host CPU", "torch_threads": th,
+                       "host_cores": cores, "sweep": tried},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": fwd.kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--config", default="en_s0", choices=list(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step (default: the config's BASELINE batch)")
+    ap.add_argument("--repeats", type=int, default=5, help="the K timed steps are measured this many times; the median is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -139,10 +211,12 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from achelous_b200.engine import Engine, compact_spec
     from achelous_b200.nets.Achelous import Achelous
     from achelous_b200.synthetic import make_inputs
     from achelous_b200.weights import fill_state_dict
 
+    cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -151,35 +225,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    B = args.batch
+    B = args.batch or cfg["batch"]
     W = max(args.warmup, 3)
     K = args.steps
+    R = max(args.repeats, 1)
 
-    model = Achelous(**MODEL_KW).eval()
+    model = Achelous(**cfg["kw"]).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=0), strict=True)
     model = model.to(dev)
     x, xr, pc = make_inputs(B, seed=1234 + rank)
     xd, xrd, pcd = x.to(dev), xr.to(dev), pc.to(dev)
-    model(xd, xrd, pcd)  # builds the plan, packs weights, captures the CUDA graph
-    eng = next(iter(model._engines.values()))
-    if world > 1:
-        gathered = [torch.empty(world * B, eng.frame_elems, device=dev) for _ in range(2)]
-        staging = torch.empty_like(eng.packed_out)
-        comm = torch.cuda.Stream(dev)
-    step_no = [0]
-
-    def step():
-        """forward on this rank's 64 frames, then ONE all-gather of the packed outputs (all ranks end up with all
-        frames' results).  The gather runs on a side stream from a staging copy, so it overlaps the next step's kernels."""
-        eng.forward_static()
-        if world > 1:
-            main = torch.cuda.current_stream(dev)
-            main.wait_stream(comm)                     # previous gather has consumed the staging buffer
-            staging.copy_(eng.packed_out)
-            comm.wait_stream(main)
-            with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered[step_no[0] & 1], staging)
-            step_no[0] += 1
+    comm = torch.cuda.Stream(dev) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -187,77 +243,140 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident throughput
-    for _ in range(W):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ncu_range = os.environ.get("ACH_NCU_RANGE") == "1"   # `ncu --profile-from-start off`: profile exactly the timed steps
-    if ncu_range:
-        torch.cuda.cudart().cudaProfilerStart()
-    e0.record()
-    for _ in range(K):
-        step()
-    e1.record()
-    barrier()
-    if ncu_range:
-        torch.cuda.cudart().cudaProfilerStop()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = t.item()
+    class Loop:
+        """Device-resident step: forward on this rank's B frames [+ ONE all-gather of the packed outputs, in place: the plan writes
+        straight into this rank's rows of the gather buffer; two plans / buffers alternate so the gather of step i (side stream)
+        overlaps the kernels of step i+1]."""
+
+        def __init__(self, compact):
+            ckey = compact_spec() if compact else None
+            if world == 1:
+                self.engines = [Engine(model, B, dev, compact=ckey)]
+                self.gathered = None
+            else:
+                probe = Engine(model, 1, "cpu", dry_run=True, compact=ckey)      # row width / dtype of the packed output
+                width, dtype = probe.packed_out.shape[1], probe.packed_out.dtype
+                self.gathered = [torch.zeros(world * B, width, device=dev, dtype=dtype) for _ in range(2)]
+                self.engines = [Engine(model, B, dev, compact=ckey, out=g[rank * B:(rank + 1) * B]) for g in self.gathered]
+                self.done = [None, None]
+            for e in self.engines:
+                for dst, src in zip(e.input_tensors(), (xd, xrd, pcd)):
+                    dst.copy_(src)
+                e.forward_static()          # packs weights, captures the CUDA graph
+            torch.cuda.synchronize()
+            self.i = 0
+
+        def step(self):
+            s = self.i % len(self.engines)
+            eng = self.engines[s]
+            if world > 1:
+                main = torch.cuda.current_stream(dev)
+                if self.done[s] is not None:
+                    main.wait_event(self.done[s])              # the gather that read this buffer two steps ago has finished
+                eng.forward_static()
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    dist.all_gather_into_tensor(self.gathered[s], eng.packed_out)    # in place: input IS rows [rank*B, (rank+1)*B)
+                    self.done[s] = comm.record_event()
+            else:
+                eng.forward_static()
+            self.i += 1
+
+        def timed(self, sampler=None):
+            for _ in range(W):
+                self.step()
+            barrier()
+            if sampler is not None:
+                sampler.start()
+            reps = []
+            ncu_range = os.environ.get("ACH_NCU_RANGE") == "1"   # `ncu --profile-from-start off`: profile exactly the timed steps
+            for _ in range(R):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                if ncu_range:
+                    torch.cuda.cudart().cudaProfilerStart()
+                e0.record()
+                for _ in range(K):
+                    self.step()
+                if world > 1:
+                    torch.cuda.current_stream(dev).wait_stream(comm)   # the step's all-gather is part of the step
+                e1.record()
+                barrier()
+                if ncu_range:
+                    torch.cuda.cudart().cudaProfilerStop()
+                t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                reps.append(t.item())
+            clocks = sampler.stop() if sampler is not None else None
+            return statistics.median(reps), reps, clocks
+
+    # ---------------- device-resident throughput: raw outputs (headline), then the compact record
+    raw = Loop(compact=False)
+    eng = raw.engines[0]
+    ms_total, reps_raw, clocks = raw.timed(ClockSampler(local_rank) if rank == 0 else None)
     value = world * B * K / (ms_total * 1e-3)
+
+    # on-hardware check of SURVEY.md §8e: gathered rows of every rank == a single-GPU forward of the same frames, bitwise
+    gather_check = None
+    if world > 1:
+        last = (raw.i - 1) % 2
+        barrier()
+        if rank == 0:
+            ok = True
+            for r in range(world):
+                xs, xrs, pcs = make_inputs(B, seed=1234 + r)
+                d, s_, l_, p_ = model(xs[:2].to(dev), xrs[:2].to(dev), pcs[:2].to(dev))
+                gd, gs, gl, gp = eng.unpack(raw.gathered[last][r * B:r * B + 2])
+                ok &= all(torch.equal(a, b) for a, b in zip(list(d) + [s_, l_, p_], list(gd) + [gs, gl, gp]))
+            gather_check = "bitwise-ok" if ok else "MISMATCH"
+        barrier()
+    del raw
+    torch.cuda.empty_cache()
+
+    cmp_loop = Loop(compact=True)
+    ms_c, reps_c, _ = cmp_loop.timed()
+    compact = {"value": world * B * K / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c / K,
+               "bytes_per_frame": cmp_loop.engines[0].packed_out.shape[1], "launches_per_step": len(cmp_loop.engines[0].ops),
+               "what": "forward(outputs='compact'): NMS rows (conf 0.35, IoU 0.35, <= 256 per frame), uint8 argmax class maps (320x320) and point "
+                       "classes produced inside the launch plan" + (" + in-place all-gather of the compact records" if world > 1 else "")}
+    del cmp_loop
+    torch.cuda.empty_cache()
 
     # ---------------- end to end through the nn.Module surface with pinned host buffers
     xh, xrh, pch = x.pin_memory(), xr.pin_memory(), pc.pin_memory()
-    det0, se0, lane0, pc0 = model(xd, xrd, pcd)
-    host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in list(det0) + [se0, lane0, pc0]]
     h2d = sum(t_.numel() * 4 for t_ in (xh, xrh, pch))
-    d2h = sum(t_.numel() * 4 for t_ in host_out)
 
-    def e2e_serial_step():
-        det, se, lane, pcs = model(xh, xrh, pch)  # H2D copies of the pinned inputs happen inside forward()
-        for h_, t_ in zip(host_out, list(det) + [se, lane, pcs]):
-            h_.copy_(t_, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the results on the host
-
-    for _ in range(2):
-        e2e_serial_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_serial_step()
-    barrier()
-    t_ser = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ser, op=dist.ReduceOp.MAX)
-    e2e_serial = world * B * K / t_ser.item()
-
-    # pipelined public API: Achelous.stream_forward overlaps the H2D of batch i+1 and the D2H of batch i-1 with batch i
     def host_batches(n):
         for _ in range(n):
             yield (xh, xrh, pch)
 
-    checksum = 0.0
-    for out in model.stream_forward(host_batches(3)):
-        checksum += float(out[3][0, 0, 0])       # touch the host result
-    barrier()
-    t0 = time.perf_counter()
-    n_out = 0
-    for out in model.stream_forward(host_batches(K)):
-        checksum += float(out[3][0, 0, 0])
-        n_out += 1
-    barrier()
-    assert n_out == K
-    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / t_e2e.item()
+    def e2e(compact_mode):
+        touch = (lambda o: float(o.det_count[0]) + float(o.se_mask[0, 0, 0])) if compact_mode else (lambda o: float(o[3][0, 0, 0]))
+        chk = 0.0
+        for out in model.stream_forward(host_batches(3), compact=compact_mode):
+            chk += touch(out)                        # the caller reads the host result
+        reps = []
+        for _ in range(R):
+            barrier()
+            t0 = time.perf_counter()
+            n_out = 0
+            for out in model.stream_forward(host_batches(K), compact=compact_mode):
+                chk += touch(out)
+                n_out += 1
+            barrier()
+            assert n_out == K
+            t = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            reps.append(t.item())
+        return world * B * K / statistics.median(reps)
+
+    e2e_compact = e2e(True)
+    d2h_compact = B * next(e for k, e in model._engines.items() if k[4] is not None).packed_out.shape[1]
+    e2e_raw = e2e(False)
+    d2h_raw = B * eng.frame_elems * 4
+    model._host_bufs.clear()
 
     # ---------------- input pre-processing on device (SURVEY.md §8f rank 2): raw camera frames / radar maps / point tables
     pre = None
@@ -289,39 +408,41 @@ def main():
 
     if rank == 0:
         peaks, which = load_peaks()
-        if roof is not None:
+        if roof is not None and roof.get("achieved") is not None:
             roof["peak"] = peaks["hbm_gbs"]
             roof["frac"] = roof["achieved"] / peaks["hbm_gbs"]
             roof["peak_source"] = which
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            best = None
-            for th in sorted({1, max(1, cores // 2), cores}):
-                ts = time_cpu_oracle(1, 3, 1, th)
-                fps = len(ts) / sum(ts)
-                if best is None or fps > best[0]:
-                    best = (fps, th)
-            cpu = {"value": best[0], "unit": UNIT, "cores": best[1], "kind": "port",
-                   "sample": f"B=1, 3 timed forwards per thread count in {{1,{max(1, cores // 2)},{cores}}} of {cores} host cores, best kept; "
-                             "oracle port = the reference's ATen CPU ops"}
+            fwd = CpuForward(args.config)
+            best, tried = cpu_sweep(fwd, cores, 1, 3, budget_s=25.0)
+            cpu = {"value": best[0], "unit": UNIT, "cores": best[2], "kind": fwd.kind,
+                   "sample": f"median of 3 forwards per point, best point B={best[1]} x {best[2]} threads of {tried} on {cores} host cores; {fwd.how}"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                           "parallelism": f"dp{world}: frames sharded, one NCCL all-gather of packed outputs" if world > 1 else "single GPU",
-                           "cuda_graph": True, "l2": "per-step activations (~8 GB) and inputs (158 MB) exceed the 126 MB L2",
+                "config": {"workload": cfg["workload"], "config": args.config, "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": (f"dp{world}: frames sharded, one in-place NCCL all-gather of the packed outputs per step" if world > 1
+                                           else "single GPU"),
+                           "outputs": "raw fp32 logits (the reference's return value)",
+                           "cuda_graph": True, "l2": "per-step activations (~4 GB) and inputs (158 MB) exceed the 126 MB L2",
                            "weights": "random init (seeded, de-vacuated)"},
+                "repeats": {"n": R, "ms_per_step_each": [round(r_ / K, 4) for r_ in reps_raw], "reported": "median"},
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "how": "Achelous.stream_forward (public pipelined API): every batch is copied host->device from pinned memory, "
-                               "run, and its 6 outputs copied device->host; copies overlap the neighbouring batches' kernels (inputs staged one batch "
-                               "ahead); wall clock",
-                        "serial_forward_value": e2e_serial,
-                        "serial_how": "Achelous.forward(pinned host tensors) then .copy_ of the 6 outputs to pinned host, one batch at a time"},
+                "compact": compact,
+                "e2e": {"value": e2e_compact, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_compact,
+                        "how": "Achelous.stream_forward(compact=True) (public pipelined API): every batch is copied host->device from pinned "
+                               "memory, run, and its compact result record (NMS rows + uint8 class maps + point classes: what achelous.py:259-297 "
+                               "keeps of the logits) copied device->host and read; copies overlap the neighbouring batches' kernels; wall clock, "
+                               "median of the repeats",
+                        "raw_logits_value": e2e_raw, "raw_logits_d2h_bytes_per_step": d2h_raw,
+                        "raw_logits_how": "stream_forward() with the raw fp32 outputs (4.6 MB per frame) copied out instead"},
                 "gpu_launches": K * len(eng.ops),
                 "launches_per_step": len(eng.ops),
                 "roofline": roof, "cpu_baseline": cpu, "preprocess": pre}
+        if gather_check is not None:
+            line["gather_check"] = gather_check
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -341,11 +462,10 @@ def measure_dominant(eng, K, torch):
     torch.cuda.synchronize()
     t = [evs[i].elapsed_time(evs[i + 1]) for i in range(n)]
     total = sum(t)
-    top = max(range(n), key=lambda i: t[i])
+    modelled = [i for i in range(n) if eng.algorithmic_bytes(i) is not None]
+    top = max(modelled, key=lambda i: t[i])
     fn, a = eng.ops[top]
     nbytes = eng.algorithmic_bytes(top)
-    if nbytes is None:
-        return {"bound": "hbm", "kernel": eng.op_names[top], "achieved": None, "unit": "GB/s", "traffic": None}
     # the launch before it in the plan rewrites its input, so caches are in plan-order state; the tensors are > L2
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -356,7 +476,7 @@ def measure_dominant(eng, K, torch):
     ms = e0.elapsed_time(e1) / K
     traffic = None
     # dram__bytes_read+write of this launch from the newest committed `ncu --set full` capture that holds it
-    for name in ("r1s2_traffic.json", "r1_traffic.json"):
+    for name in ("r2_traffic.json", "r1s2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 traffic = json.load(f).get(eng.op_names[top], {}).get("dram_bytes")
@@ -364,10 +484,17 @@ def measure_dominant(eng, K, torch):
             traffic = None
         if traffic is not None:
             break
+    # time-weighted roofline fraction of the whole plan: sum(algorithmic bytes) / sum(time) over the modelled launches
+    plan_bytes = sum(eng.algorithmic_bytes(i) for i in modelled)
+    plan_ms = sum(t[i] for i in modelled)
     return {"bound": "hbm", "kernel": f"{eng.op_names[top]} ({fn.__name__})", "share_of_step": t[top] / total,
             "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "algorithmic_bytes": nbytes, "launch_ms": ms, "traffic": traffic,
-            "note": "the top launch by time; every kernel on this path is HBM-bound by arithmetic intensity, the kernels themselves are "
-                    "issue / shared-memory-pipe bound (profiles/r1s2_ncu_summary.txt)"}
+            "plan": {"modelled_launches": len(modelled), "of": n, "algorithmic_bytes": plan_bytes, "eager_ms": plan_ms,
+                     "achieved": plan_bytes / (plan_ms * 1e-3) / 1e9},
+            "top5": [{"kernel": eng.op_names[i], "ms": round(t[i], 4),
+                      "GB/s": round(eng.algorithmic_bytes(i) / (t[i] * 1e-3) / 1e9, 1) if eng.algorithmic_bytes(i) else None}
+                     for i in sorted(range(n), key=lambda i: -t[i])[:5]],
+            "note": "the top launch by time; every kernel on this path is HBM-bound by arithmetic intensity"}
 
 
 if __name__ == "__main__":

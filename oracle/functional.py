@@ -5,7 +5,7 @@ TEST INFRASTRUCTURE - see ``oracle/__init__.py``.  Every function cites the
 reference file:line it restates (paths relative to /root/reference).  Pinned by
 ``tests/test_oracle_vs_golden.py`` against fixtures generated from the
 unmodified reference (``tests/golden/make_golden.py``) and, when
-``/root/reference`` is present, against the reference itself
+the reference is importable (``/root/reference`` or the staged copy ``oracle/_ref``), against the reference itself
 (``tests/test_oracle_vs_reference.py``).
 
 ``torchvision.ops.deform_conv2d`` (third-party, pinned torchvision==0.12.0 in

@@ -1,9 +1,12 @@
-"""Import the UNMODIFIED reference (``/root/reference``) on CPU.
+"""Import the UNMODIFIED reference on CPU: from ``/root/reference`` where that exists (this container), else from the
+byte-identical staged copy ``oracle/_ref/`` (``oracle/stage_reference.py``; what travels to the GPU box).
 
 Test infrastructure: used by ``tests/golden/make_golden.py`` (fixture
 generation) and by the ``needs_reference`` tests that pin ``oracle/`` against
-the real reference.  ``/root/reference`` does not exist on the GPU box, so
-nothing that runs there may call into this module.
+the real reference, and by ``bench.py``'s CPU-baseline legs (the thing being
+timed there, never the product).  ``/root/reference`` does not exist on the
+GPU box: there this module resolves to the staged copy, or reports the
+reference as unavailable.
 
 The reference imports a few packages at module top that are absent from this
 image and are not on the inference path: ``thop`` /
@@ -17,11 +20,26 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ACHELOUS_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root():
+    for root in (os.environ.get("ACHELOUS_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if root and os.path.isfile(os.path.join(root, "nets", "Achelous.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "nets", "Achelous.py"))
+
+
+def reference_kind() -> str:
+    """'source tree' (/root/reference) or 'staged copy' (oracle/_ref) - reported next to every timing of the reference"""
+    return "staged copy oracle/_ref" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(_STAGED) else f"source tree {REFERENCE_ROOT}"
 
 
 def _install_shims():

@@ -77,3 +77,66 @@ def test_seg_postprocess_on_device(shape, lb):
         diff = mine[b] != am
         assert (diff & safe).sum() == 0
         assert diff.mean() < 2e-3
+
+
+@pytest.mark.parametrize("n_boxes,seed", [(37, 2), (700, 3), (1500, 5), (2100, 4)])
+def test_nms_vs_torchvision_batched_nms_on_cuda(n_boxes, seed):
+    """utils/utils_bbox.py:125 calls torchvision.ops.boxes.batched_nms on the device the predictions live on.  Its CPU build
+    switches to the per-class branch above 1000 candidates (boxes.numel() > 4000), the CUDA build keeps the coordinate trick up
+    to 100 000 - so the reference ON A GPU is pinned here, against torchvision's own CUDA kernel, incl. > 1000 candidates."""
+    tv = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(seed)
+    B, A, K = 3, 2100, 7
+    pred = np.zeros((B, A, 5 + K), np.float32)
+    pred[..., 0:2] = rng.uniform(0.2, 0.8, (B, A, 2))
+    pred[..., 2:4] = rng.uniform(0.05, 0.4, (B, A, 2))
+    pred[..., 4] = 0.01
+    for b in range(B):
+        idx = rng.choice(A, n_boxes, replace=False)
+        pred[b, idx, 4] = np.round(rng.uniform(0.5, 1.0, n_boxes), 2)
+    pred[..., 5:] = np.round(rng.uniform(0.5, 1.0, (B, A, K)), 1)
+    t = torch.from_numpy(pred).cuda()
+    kept, kept_idx, counts = UB.nms_device(t.clone(), K, 0.2, 0.45)
+    # the reference's per-image sequence (utils_bbox.py:95-130), on CUDA tensors
+    box = t.clone()
+    box[:, :, 0:2] = t[:, :, 0:2] - t[:, :, 2:4] / 2
+    box[:, :, 2:4] = t[:, :, 0:2] + t[:, :, 2:4] / 2
+    for b in range(B):
+        conf, cls = torch.max(box[b, :, 5:5 + K], 1, keepdim=True)
+        mask = (box[b, :, 4] * conf[:, 0] >= 0.2)
+        det = torch.cat((box[b, :, :5], conf, cls.float()), 1)[mask]
+        keep = tv.ops.boxes.batched_nms(det[:, :4], det[:, 4] * det[:, 5], det[:, 6], 0.45)
+        ref_rows = det[keep]
+        ref_idx = torch.nonzero(mask).flatten()[keep]
+        n = int(counts[b])
+        assert n == ref_rows.shape[0], (b, n, ref_rows.shape[0])
+        assert torch.equal(kept_idx[b, :n].long(), ref_idx)
+        assert torch.equal(kept[b, :n], ref_rows)
+
+
+def test_nms_rows_compact_record():
+    """ach_nms_rows: first max_keep rows + true count at caller strides, zeros behind the survivors"""
+    import ctypes as C
+    from achelous_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    B, A, K, MK = 2, 2100, 7, 16
+    pred = np.zeros((B, A, 5 + K), np.float32)
+    pred[..., 0:2] = rng.uniform(0.1, 0.9, (B, A, 2))
+    pred[..., 2:4] = rng.uniform(0.02, 0.1, (B, A, 2))
+    pred[..., 4] = rng.uniform(0, 1, (B, A))
+    pred[1, :, 4] = 0.0                                   # image 1: no candidates
+    pred[..., 5:] = rng.uniform(0.3, 1.0, (B, A, K))
+    t = torch.from_numpy(pred).cuda()
+    kept, kept_idx, counts = UB.nms_device(t.clone(), K, 0.5, 0.4)
+    rec = torch.full((B, 64 + MK * 7), 7.0, device="cuda")
+    cnt = rec.view(torch.int32)
+    ws_bytes = lib.ach_nms_workspace_bytes(B, A)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.ach_nms_rows(t.data_ptr(), B, A, K, 0.5, 0.4, rec.data_ptr() + 64 * 4, rec.stride(0), MK, cnt.data_ptr(), rec.stride(0),
+                                ws.data_ptr(), ws_bytes, torch.cuda.current_stream().cuda_stream), "ach_nms_rows")
+    torch.cuda.synchronize()
+    assert int(counts[0]) > MK and int(counts[1]) == 0
+    assert cnt[:, 0].tolist() == counts.tolist()
+    assert torch.equal(rec[0, 64:].view(MK, 7), kept[0, :MK]) and not rec[1, 64:].any()
+    assert (rec[:, 1:64] == 7.0).all()
