@@ -171,19 +171,65 @@ __global__ void __launch_bounds__(NMS_T) nms_kernel(const float* __restrict__ de
     }
     __syncthreads();
 
-    // ---- D. greedy sweep
-    for (int i = 0; i < n; ++i) {
-        if (removed[i]) continue;  // uniform: shared memory, written before the last barrier
-        const float4 bi = s_box[i];
-        const float ai = s_area[i];
-        for (int j = i + 1 + tid; j < n; j += NMS_T) {
+    // ---- D. greedy sweep in rank order, 32 boxes (one warp's worth) per round.  Invariant at the start of a round: every box of
+    // the chunk has already been tested against every box kept in earlier chunks.  Warp 0 then resolves the chunk sequentially
+    // (box k, if it survives, suppresses the later boxes of the chunk: shuffles, no block barrier); all threads apply the chunk's
+    // survivors to the boxes behind the chunk.  Same decisions as the one-box-at-a-time sweep with n/32 instead of n barriers
+    // (the per-box version cost 0.71 ms for 64 images, one block barrier per kept box).
+    __shared__ float4 k_box[32];
+    __shared__ float k_area[32];
+    __shared__ int k_n;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        if (tid < 32) {
+            const int r = c0 + tid;
+            const bool valid = r < n;
+            bool dead = valid ? removed[r] != 0 : true;
+            const float4 bx = valid ? s_box[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ar = valid ? s_area[r] : 0.f;
+            for (int k = 0; k < 32; ++k) {
+                const unsigned alive = ~__ballot_sync(0xffffffffu, dead);
+                if (!((alive >> k) & 1u)) continue;            // warp-uniform
+                const float4 bk = make_float4(__shfl_sync(0xffffffffu, bx.x, k), __shfl_sync(0xffffffffu, bx.y, k),
+                                              __shfl_sync(0xffffffffu, bx.z, k), __shfl_sync(0xffffffffu, bx.w, k));
+                const float ak = __shfl_sync(0xffffffffu, ar, k);
+                if (tid > k && !dead) {
+                    const float w = fmaxf(__fsub_rn(fminf(bk.z, bx.z), fmaxf(bk.x, bx.x)), 0.f);
+                    const float h = fmaxf(__fsub_rn(fminf(bk.w, bx.w), fmaxf(bk.y, bx.y)), 0.f);
+                    const float inter = __fmul_rn(w, h);
+                    if (inter > 0.f) {   // disjoint pair (every cross-class pair after the shift): IoU = 0 never exceeds a threshold >= 0
+                        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ak, ar), inter));
+                        if (iou > nms_thres) dead = true;
+                    }
+                }
+            }
+            if (valid) removed[r] = dead ? 1 : 0;
+            const unsigned alive = ~__ballot_sync(0xffffffffu, dead);
+            if (!dead) {
+                const int slot = __popc(alive & ((1u << tid) - 1u));
+                k_box[slot] = bx;
+                k_area[slot] = ar;
+            }
+            if (tid == 0) k_n = __popc(alive);
+        }
+        __syncthreads();
+        const int kn = k_n;
+        for (int j = c0 + 32 + tid; j < n; j += NMS_T) {
             if (removed[j]) continue;
             const float4 bj = s_box[j];
-            const float w = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
-            const float h = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
-            const float inter = __fmul_rn(w, h);
-            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, s_area[j]), inter));
-            if (iou > nms_thres) removed[j] = 1;
+            const float aj = s_area[j];
+            for (int k = 0; k < kn; ++k) {
+                const float4 bi = k_box[k];
+                const float w = fmaxf(__fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)), 0.f);
+                const float h = fmaxf(__fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)), 0.f);
+                const float inter = __fmul_rn(w, h);
+                if (inter > 0.f) {
+                    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(k_area[k], aj), inter));
+                    if (iou > nms_thres) {
+                        removed[j] = 1;
+                        break;
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -252,6 +298,7 @@ extern "C" int ach_nms(const float* decoded, int B, int A, int K, float conf_thr
     using namespace ach;
     ACH_REQUIRE(decoded && kept && kept_idx && counts && workspace, "ach_nms: null arg");
     ACH_REQUIRE(B > 0 && A > 0 && K >= 1, "ach_nms: bad dims");
+    ACH_REQUIRE(nms_thres >= 0.f, "ach_nms: nms_thres must be >= 0");
     ACH_REQUIRE(A <= NMS_MAX_A, "ach_nms: A=%d anchors per image exceeds the supported %d", A, NMS_MAX_A);
     ACH_REQUIRE(workspace_bytes >= ach_nms_workspace_bytes(B, A), "ach_nms: workspace too small");
     ACH_REQUIRE(aligned16(workspace), "ach_nms: workspace must be 16-byte aligned");
@@ -267,6 +314,7 @@ extern "C" int ach_nms_rows(const float* decoded, int B, int A, int K, float con
     using namespace ach;
     ACH_REQUIRE(decoded && kept && counts && workspace, "ach_nms_rows: null arg");
     ACH_REQUIRE(B > 0 && A > 0 && K >= 1 && max_keep > 0 && max_keep <= A, "ach_nms_rows: bad dims");
+    ACH_REQUIRE(nms_thres >= 0.f, "ach_nms_rows: nms_thres must be >= 0");
     ACH_REQUIRE(kept_bs >= 7LL * max_keep && counts_bs >= 1, "ach_nms_rows: strides smaller than one image's record");
     ACH_REQUIRE(A <= NMS_MAX_A, "ach_nms_rows: A=%d anchors per image exceeds the supported %d", A, NMS_MAX_A);
     ACH_REQUIRE(workspace_bytes >= ach_nms_workspace_bytes(B, A), "ach_nms_rows: workspace too small");

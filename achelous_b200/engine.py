@@ -1029,6 +1029,7 @@ class Engine:
         self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
         dec = self.seg_decoder_fused if self.model.fuse_seg_decoder else self.seg_decoder
         masks = masks or {}
+        self.wait(6, 0)                    # the fusion + detection lane forks here: it needs the FPN maps, not the decoders
         self.cur_lane = 3                  # the two decoders are independent of each other
         self.wait(3, 0)
         dec("lane", prefix, sa_lane, w, out_lane, mask=masks.get("lane"))
@@ -1104,6 +1105,7 @@ class Engine:
         sa_lane = self.shuffle_attention("fpn.sa_lane", prefix + ".stage_3_lane_seg", f3)
         sa_se = self.shuffle_attention("fpn.sa_se", prefix + ".stage_3_semantic_seg", f3)
         self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
+        self.wait(6, 0)                    # the fusion + detection lane forks here: it needs the FPN maps, not the decoders
         self.cur_lane = 3                  # the two decoders are independent of each other
         self.wait(3, 0)
         self.seg_decoder_csp("lane", prefix, sa_lane, w, out_lane)
@@ -1500,6 +1502,14 @@ class Engine:
             else:
                 raise NotImplementedError(f"pc_seg={m.pc_seg!r}")
         ire = "image_radar_encoder"
+        # Stream lanes (parallel branches of the captured graph).  A lane forks from lane 0 at the point its first wait() is
+        # recorded, so the order of the blocks below is the dependency structure: the radar encoder depends on nothing but its
+        # input and forks at the very start (recorded after the neck it used to wait for backbone, neck AND the semantic decoder);
+        # fusion + detection (+ decode + NMS) fork when the FPN maps exist and run beside the two decoders.
+        self.cur_lane = 2
+        self.wait(2, 0)
+        radar = self.rcnet(self.r_in, ire + ".radar_encoder", m.phi)
+        self.cur_lane = 0
         if m.backbone == "en":
             feats = self.edgenext(self.x_in, ire + ".fpn.backbone", m.phi)
         elif m.backbone == "ev":
@@ -1509,22 +1519,20 @@ class Engine:
         else:
             feats = self.mobilevit(self.x_in, ire + ".fpn.backbone", m.phi)
         maps = (self.gdf_neck if m.neck == "gdf" else self.cdf_neck)(feats, ire + ".fpn", m.phi, out_se, out_lane, masks=masks)
-        self.cur_lane = 2                  # radar encoder: independent until the fusion stages
-        self.wait(2, 0)
-        radar = self.rcnet(self.r_in, ire + ".radar_encoder", m.phi)
-        self.cur_lane = 0
-        self.wait(0, 2)
+        self.cur_lane = 6                  # forked inside the neck (wait(6, 0) before the decoders); joins the radar lane here
+        self.wait(6, 2)
         fused = [self.fuse_stage(s, ire, maps[2 - i], radar[i]) for i, s in enumerate((3, 4, 5))]
-        for k, lane in enumerate((0, 4, 5)):   # the three detection levels are independent
-            if lane:
+        for k, lane in enumerate((6, 4, 5)):   # the three detection levels are independent
+            if lane != 6:
                 self.cur_lane = lane
-                self.wait(lane, 0)
+                self.wait(lane, 6)
             self.det_level(k, "det_head", fused[k], det_views[k], K)
-        self.cur_lane = 0
+        self.cur_lane = 6
         if self.compact is not None:
-            self.wait(0, 4)
-            self.wait(0, 5)
+            self.wait(6, 4)
+            self.wait(6, 5)
             self._det_finish(det_views, K)
+        self.cur_lane = 0
         self.sync_end = [(0, l) for l in sorted(set(self.op_lane)) if l]
         self._cpu64 = {}
         self._sig = self._signature()

@@ -235,6 +235,10 @@ def main():
     model = model.to(dev)
     x, xr, pc = make_inputs(B, seed=1234 + rank)
     xd, xrd, pcd = x.to(dev), xr.to(dev), pc.to(dev)
+    # with purely random head weights ~1200 of the 2100 anchors per image pass conf >= 0.35 - unrealistically many
+    # for the NMS inside the compact plan; shift the objectness bias so that ~120 candidates per image pass (as the golden
+    # fixtures do, tests/golden/make_golden.py:calibrate_obj_bias).  Kernel times of the raw forward do not depend on values.
+    obj_bias, n_cand = calibrate_obj_bias(model, xd[:8], xrd[:8], pcd[:8], torch)
     comm = torch.cuda.Stream(dev) if world > 1 else None
 
     def barrier():
@@ -336,7 +340,10 @@ def main():
 
     cmp_loop = Loop(compact=True)
     ms_c, reps_c, _ = cmp_loop.timed()
+    kept = cmp_loop.engines[0].output_views().det_count.float()
     compact = {"value": world * B * K / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c / K,
+               "nms": {"obj_bias": obj_bias, "candidates_per_frame_mean": round(n_cand, 1), "kept_per_frame_mean": round(kept.mean().item(), 1),
+                       "kept_per_frame_max": int(kept.max().item())},
                "bytes_per_frame": cmp_loop.engines[0].packed_out.shape[1], "launches_per_step": len(cmp_loop.engines[0].ops),
                "what": "forward(outputs='compact'): NMS rows (conf 0.35, IoU 0.35, <= 256 per frame), uint8 argmax class maps (320x320) and point "
                        "classes produced inside the launch plan" + (" + in-place all-gather of the compact records" if world > 1 else "")}
@@ -446,6 +453,23 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def calibrate_obj_bias(model, x, xr, pc, torch, conf=0.35, target=120):
+    det = model(x, xr, pc)[0]
+    flat = torch.cat([d.flatten(2) for d in det], 2)  # (B, 5+K, A)
+    cls = torch.sigmoid(flat[:, 5:]).max(1)[0]
+    lo, hi = -20.0, 20.0
+    for _ in range(30):
+        mid = (lo + hi) / 2
+        n = ((torch.sigmoid(flat[:, 4] + mid) * cls) >= conf).float().sum(1).mean().item()
+        lo, hi = (mid, hi) if n < target else (lo, mid)
+    bias = round((lo + hi) / 2, 3)
+    with torch.no_grad():
+        for k in range(3):
+            model.det_head.obj_preds[k].bias += bias      # in-place: the engines repack on their next forward
+    n = ((torch.sigmoid(flat[:, 4] + bias) * cls) >= conf).float().sum(1).mean().item()
+    return bias, n
 
 
 def measure_dominant(eng, K, torch):

@@ -234,6 +234,7 @@ def fourier_pos(p, H, W, hidden=32, temperature=10000.0):
     pos_x = torch.stack((pos_x[:, :, 0::2].sin(), pos_x[:, :, 1::2].cos()), dim=3).flatten(2)
     pos_y = torch.stack((pos_y[:, :, 0::2].sin(), pos_y[:, :, 1::2].cos()), dim=3).flatten(2)
     pos = torch.cat((pos_y, pos_x), dim=2).permute(2, 0, 1).unsqueeze(0)
+    pos = pos.to(p.sub("token_projection")("weight").dtype)   # no-op in fp32; lets the tests run this oracle in float64 as "truth"
     return conv(pos, p.sub("token_projection"))
 
 

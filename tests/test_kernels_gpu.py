@@ -529,6 +529,11 @@ def test_mvit_attention(H, W, tc):
     def make(A):
         A.new("qkv", R(B, 3 * heads * d + 5, P) * 1.5), A.new("out", torch.zeros(B, heads * d, P))
         return (A.ptr("qkv", 5 * P), (3 * heads * d + 5) * P, A.ptr("out"), heads * d * P, B, heads, d, H, W)
+    if tc and H * W > 4 * 640:
+        # beyond the tensor-core kernel's shared-memory layout: the entry point must refuse loudly, not reroute
+        with pytest.raises(_lib.AchelousKernelError, match="do not fit"):
+            run_both("ach_mvit_attention_tc", make, ["out"])
+        return
     run_both("ach_mvit_attention_tc" if tc else "ach_mvit_attention", make, ["out"])
 
 

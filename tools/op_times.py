@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--pc-seg", default="pn")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--tc", default="default", help="default | all | off")
+    ap.add_argument("--compact", action="store_true", help="time the outputs='compact' plan")
     ap.add_argument("--out", default="gpurun_out/op_times.json")
     a = ap.parse_args()
     kw = dict(num_det=7, num_seg=9, phi=a.phi, resolution=320, backbone=a.backbone, neck=a.neck, pc_seg=a.pc_seg, pc_channels=5,
@@ -35,7 +36,7 @@ def main():
         model.use_tensor_cores = "all" if a.tc == "all" else False
     model = model.cuda()
     x, xr, pc = [t.cuda() for t in make_inputs(a.batch, seed=1)]
-    model(x, xr, pc)
+    model(x, xr, pc, outputs="compact" if a.compact else "raw")
     torch.cuda.synchronize()
     eng = next(iter(model._engines.values()))
     stream = torch.cuda.current_stream().cuda_stream
