@@ -17,6 +17,7 @@
 // take them as immediate constant operands - no load instructions for weights at all.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma_common.cuh"
 
 namespace ach {
 
@@ -100,15 +101,8 @@ __global__ void __launch_bounds__(256) up_ghost_kernel(const AchUpGhost p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// ach_up_ghost_head: 30x30 output tile; x1 on 34x34 (16 channels, shared memory), x2 recomputed on the fly,
-// head primary p on 32x32 (one 1x4 column strip per thread = exactly 256 work items), then the head's
-// cheap dw3x3 from shared p.  p aliases the low-res tile (dead after x1 is built).
-constexpr int UH_T = 30;
-constexpr int UH_P = UH_T + 2;           // 32
-constexpr int UH_X1 = UH_T + 4;          // 34
-constexpr int UH_V = UH_X1 / 2 + 3;      // 20
+// ach_up_ghost_head: last decoder stage + head GhostModule.  All per-channel weights travel as kernel parameters.
 constexpr int UH_C = 16;                 // channels of v / x1 / x2
-constexpr int UH_X1P = UH_X1 + 1;        // row pitch
 
 template <int INIT, int KOUT>
 struct UpGhostHeadParams {
@@ -125,148 +119,284 @@ struct UpGhostHeadParams {
     float b4[KOUT - INIT];
 };
 
-// ARGMAX: instead of the K logit planes the kernel writes the per-pixel class index (first maximum, like torch.argmax
-// over the very same fp32 logits) as one byte - 4*K bytes per pixel less to write, copy out and all-gather
-// (achelous.py:283-297 only ever uses the argmax of these maps).  Classes whose bit in keep_mask is clear are mapped to 0
-// (the reference's `output_seg[(output_seg != 0) & (output_seg != 8)] = 0`).
+// ------------------------------------------------------------------------------------------------
+// ach_up_ghost_head ("v3").  ARGMAX: instead of the K logit planes the kernel writes the per-pixel class index (first maximum,
+// like torch.argmax over the very same fp32 logits) as one byte - achelous.py:283-297 only ever uses the argmax of these maps;
+// classes whose bit in keep_mask is clear are mapped to 0 (`output_seg[(output_seg != 0) & (output_seg != 8)] = 0`).
+// History (profiles/r2_head_kernel.md): the round-1 kernel kept the 16-channel x1 tile in shared memory (103 KB, one scalar LDS
+// per value and consumer; ncu: issue 62 %, l1tex 64 %, 24 % warps active; 0.411 ms).  A version with x1 built chunk-wise in shared
+// memory by separable passes cut the instruction count by a third and got SLOWER (0.47 ms) - ten CTA barriers per tile at 2-3
+// resident CTAs leave it latency bound (issue 35 %, barrier stall 1.6 per issue).  This version (0.247 ms) has NO barrier and no
+// shared-memory round trip in its main loop:
+//   * bilinear x2 with align_corners has a STATIC index pattern: out[2m] mixes v[m-1], v[m]; out[2m+1] mixes v[m], v[m+1]
+//     (2m*(w-1)/(2w-1) = m - m/(2w-1)); only the weights move with the position.  So the 4 x 6 x1 window a thread needs for its
+//     2 x 4 pixels is the separable interpolation of a 4 x 5 low-resolution patch, and is rebuilt in REGISTERS from the patch
+//     (12 8-byte shared loads) with per-thread weights computed once - image borders, the clamp at the last row / column and the
+//     dw conv's zero padding are folded into those weights (v + b1 is interpolated, so zero weights give relu(0) = 0);
+//   * the low-resolution tile of all 16 channels (24 x 24 x 16 floats, 36 KB) arrives by ONE 4-D TMA box copy per CTA
+//     (cp.async.bulk.tensor, out-of-image rows / columns zero-filled by the copy engine: no index arithmetic, no LDG / STS);
+//   * 32 x 40 output tiles, 2 x 4 pixels per thread, packed FFMA2 on horizontally adjacent pixels with the weights as uniform
+//     scalars from the constant bank, STG.128 / one STG.32 of four class bytes (ARGMAX) on the way out.
+constexpr int H3_TW = 32, H3_TH = 40, H3_T = 192;
+constexpr int H3_PH = H3_TH + 2, H3_PP = 40;          // p tile: rows (global ty0 - 1 + pr), pitch (36 columns used: tx0 - 1 + pc)
+constexpr int H3_VR = 24, H3_VP = 24;                 // low-resolution tile: rows (ty0/2 - 2 + r), columns (tx0/2 - 4 + c)
+constexpr int H3_VC = 2;                              // first used tile column: the box starts 2 columns early because the innermost
+                                                      // TMA start coordinate must be a multiple of 16 bytes (tools/probe/tma_probe.cu)
+constexpr int H3_VELEMS = UH_C * H3_VR * H3_VP;
+static_assert(H3_TW / 2 + 5 + H3_VC <= H3_VP + 1 && H3_TH / 2 + 4 <= H3_VR && (H3_TW / 2) % 4 == 0, "low-resolution tile too small for the output tile");
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+// weights (wa, wb) on the static source pair (a, a + 1) for destination index g of an axis of out_size = 2 * in_size pixels;
+// both 0 outside the image.  ATen's own source index / lambda (bilin_src) decides; the static pair is only the addressing.
+__device__ __forceinline__ void static_lerp_weights(int g, int out_size, int in_size, float scale, int a, float& wa, float& wb) {
+    wa = 0.f;
+    wb = 0.f;
+    if (g < 0 || g >= out_size) return;
+    int i0, i1;
+    float l;
+    bilin_src(g, scale, in_size, i0, i1, l);
+    if (i1 == i0) l = 0.f;                       // clamped at the last row / column: the value is v[i0]
+    const int d = i0 - a;
+    if (d == 0) { wa = 1.f - l; wb = l; }
+    else if (d == 1) { wb = 1.f; }                // g == 0: l == 0 exactly, the value is v[0] = v[a + 1]
+    else if (d == -1) { wb = 0.f; wa = 1.f; }     // scale * (out_size - 1) rounded just below in_size - 1: l = 1 - O(1e-6), value v[a]
+    else __trap();                                // cannot happen for out_size == 2 * in_size
+}
+
 template <int INIT, int KOUT, bool ARGMAX>
-__global__ void __launch_bounds__(256, 2) up_ghost_head_kernel(const float* __restrict__ v, long long v_bs, float* __restrict__ out,
-                                                               long long out_bs, int h, int w,
-                                                               const __grid_constant__ UpGhostHeadParams<INIT, KOUT> P,
-                                                               unsigned char* __restrict__ mask, long long mask_bs, unsigned keep_mask) {
-    extern __shared__ __align__(16) float smem[];
-    float* x1s = smem;                                  // [16][34][35]
-    float* vs = smem + UH_C * UH_X1 * UH_X1P;           // [16][20][21]
-    float* ps = vs;                                     // [INIT][32][33]  (aliases vs)
-    constexpr int VP = UH_V + 1, PP = UH_P + 1;
-    static_assert(INIT * UH_P * PP <= UH_C * UH_V * VP, "p tile must fit in the low-res tile");
+__global__ void __maxnreg__(112) up_ghost_head3_kernel(const __grid_constant__ CUtensorMap tmv, const float* __restrict__ v, long long v_bs,
+                                                        float* __restrict__ out, long long out_bs, int h, int w,
+                                                        const __grid_constant__ UpGhostHeadParams<INIT, KOUT> P,
+                                                        unsigned char* __restrict__ mask, long long mask_bs, unsigned keep_mask, int vec_ok,
+                                                        int use_tma) {
+    extern __shared__ __align__(128) float smem[];
+    float* vs = smem;                                    // [16][H3_VR][H3_VP]
+    float* ps = smem;                                    // [INIT][H3_PH][H3_PP]   (after the channel loop)
+    static_assert(INIT * H3_PH * H3_PP <= H3_VELEMS && KOUT - INIT <= INIT, "p tile must fit in the low-resolution tile");
+    __shared__ __align__(8) unsigned long long mbar;
 
-    const int H = 2 * h, W = 2 * w;
-    const int tiles_x = (W + UH_T - 1) / UH_T;
-    const int ty0 = (blockIdx.x / tiles_x) * UH_T, tx0 = (blockIdx.x % tiles_x) * UH_T;
+    const int H = 2 * h, W = 2 * w, tid = threadIdx.x;
+    const int tiles_x = (W + H3_TW - 1) / H3_TW;
+    const int ty0 = (blockIdx.x / tiles_x) * H3_TH, tx0 = (blockIdx.x % tiles_x) * H3_TW;
     const int b = blockIdx.y;
-    const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
-    const int vy0 = (int)(sy * (float)max(ty0 - 2, 0)), vx0 = (int)(sx * (float)max(tx0 - 2, 0));
-    const long long plane_lo = (long long)h * w, plane_hi = (long long)H * W;
-    const float* vb = v + (long long)b * v_bs;
+    const int R0 = ty0 / 2 - 2, C0 = tx0 / 2 - 2 - H3_VC;
+    const long long plane_hi = (long long)H * W;
 
-    // ---- low-res tile, all 16 channels
-    for (int i = threadIdx.x; i < UH_C * UH_V * UH_V; i += 256) {
-        const int c = i / (UH_V * UH_V);
-        const int r = i - c * (UH_V * UH_V);
-        const int yy = r / UH_V, xx = r - yy * UH_V;
-        const int gy = min(vy0 + yy, h - 1), gx = min(vx0 + xx, w - 1);
-        vs[(c * UH_V + yy) * VP + xx] = __ldg(vb + (long long)c * plane_lo + gy * w + gx);
+    if (use_tma) {
+        if (tid == 0) {
+            tma_mbar_init(tma_smem_u32(&mbar), 1);
+            tma_mbar_expect_tx(tma_smem_u32(&mbar), (uint32_t)H3_VELEMS * 4u);
+            tma_load_4d(tma_smem_u32(vs), &tmv, C0, R0, 0, b, tma_smem_u32(&mbar));
+        }
+    } else {   // views a tensor map cannot describe (row pitch not a multiple of 16 bytes): the same tile by plain loads
+        const float* vb = v + (long long)b * v_bs;
+        for (int i = tid; i < H3_VELEMS; i += H3_T) {
+            const int c = i / (H3_VR * H3_VP), r = (i / H3_VP) % H3_VR, x = i % H3_VP;
+            const int gy = R0 + r, gx = C0 + x;
+            vs[i] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? __ldg(vb + ((long long)c * h + gy) * w + gx) : 0.f;
+        }
+    }
+
+    // ---- per-thread interpolation weights (the tile is in flight meanwhile).  thread -> p rows 2*tr, 2*tr+1, p columns 4*tc .. 4*tc+3;
+    // x1 window rows i = 0..3 (global ty0 - 2 + 2*tr + i), columns j = 0..5 (global tx0 - 2 + 4*tc + j)
+    const int tr = tid / 9, tc = tid - tr * 9;
+    const bool p_thread = tid < (H3_PH / 2) * 9;
+    const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
+    float2 cwa[3], cwb[3];          // column weights, pairs (j, j + 1) for j = 0, 2, 4
+    float rwa[4], rwb[4];           // row weights
+    {
+        const int m0 = tx0 / 2 - 1 + 2 * tc, n0 = ty0 / 2 - 1 + tr;
+        const int gx0 = tx0 - 2 + 4 * tc, gy0 = ty0 - 2 + 2 * tr;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {   // static source columns of j = 2q: (m0 + q - 1, m0 + q); of j = 2q + 1: (m0 + q, m0 + q + 1)
+            static_lerp_weights(gx0 + 2 * q, W, w, sx, m0 + q - 1, cwa[q].x, cwb[q].x);
+            static_lerp_weights(gx0 + 2 * q + 1, W, w, sx, m0 + q, cwa[q].y, cwb[q].y);
+        }
+        static_lerp_weights(gy0 + 0, H, h, sy, n0 - 1, rwa[0], rwb[0]);
+        static_lerp_weights(gy0 + 1, H, h, sy, n0, rwa[1], rwb[1]);
+        static_lerp_weights(gy0 + 2, H, h, sy, n0, rwa[2], rwb[2]);
+        static_lerp_weights(gy0 + 3, H, h, sy, n0 + 1, rwa[3], rwb[3]);
+    }
+    float2 acc[2][2][INIT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < INIT; ++i) acc[r][q][i] = f2(P.b3[i], P.b3[i]);
+
+    if (use_tma) {
+        __syncthreads();                               // mbarrier initialised before anybody polls it
+        tma_mbar_wait(tma_smem_u32(&mbar), 0);
+    } else {
+        __syncthreads();
+    }
+
+    if (p_thread) {
+        const float* vt = vs + tr * H3_VP + H3_VC + 2 * tc;    // patch rows tr .. tr+3, columns H3_VC + 2*tc .. + 4
+#pragma unroll
+        for (int c = 0; c < UH_C; ++c) {
+            const float* vp = vt + c * (H3_VR * H3_VP);
+            const float b1 = P.b1[c];
+            // horizontal pass on (v + b1): t[r][q] = pair of x1 columns (2q, 2q + 1) of patch row r
+            float2 t[4][3];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 p01 = *reinterpret_cast<const float2*>(vp + r * H3_VP);
+                const float2 p23 = *reinterpret_cast<const float2*>(vp + r * H3_VP + 2);
+                const float2 p45 = *reinterpret_cast<const float2*>(vp + r * H3_VP + 4);
+                const float v0 = p01.x + b1, v1 = p01.y + b1, v2 = p23.x + b1, v3 = p23.y + b1, v4 = p45.x + b1;
+                t[r][0] = __ffma2_rn(cwb[0], f2(v1, v2), __fmul2_rn(cwa[0], f2(v0, v1)));
+                t[r][1] = __ffma2_rn(cwb[1], f2(v2, v3), __fmul2_rn(cwa[1], f2(v1, v2)));
+                t[r][2] = __ffma2_rn(cwb[2], f2(v3, v4), __fmul2_rn(cwa[2], f2(v2, v3)));
+            }
+            // vertical pass + relu: window rows 0..3 use patch rows (0,1), (1,2), (1,2), (2,3)
+            float2 x1w[4][3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ra = (i + 1) / 2;     // 0, 1, 1, 2
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float2 val = __ffma2_rn(f2(rwb[i], rwb[i]), t[ra + 1][q], __fmul2_rn(f2(rwa[i], rwa[i]), t[ra][q]));
+                    x1w[i][q] = f2(fmaxf(val.x, 0.f), fmaxf(val.y, 0.f));
+                }
+            }
+            // Ghost cheap op (dw 3x3 + BN + ReLU) and the head's primary 1x1 on the 2 x 4 pixels
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float2 d = f2(0.f, 0.f);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const float2 e0 = x1w[r + ky][q], e2 = x1w[r + ky][q + 1];
+                        const float w0 = P.w2[c * 9 + ky * 3], w1 = P.w2[c * 9 + ky * 3 + 1], w2_ = P.w2[c * 9 + ky * 3 + 2];
+                        d = __ffma2_rn(e0, f2(w0, w0), d);
+                        d = __ffma2_rn(f2(e0.y, e2.x), f2(w1, w1), d);
+                        d = __ffma2_rn(e2, f2(w2_, w2_), d);
+                    }
+                    d = __ffma2_rn(f2(P.s2[c], P.s2[c]), d, f2(P.b2[c], P.b2[c]));
+                    const float2 x2 = f2(fmaxf(d.x, 0.f), fmaxf(d.y, 0.f));
+                    const float2 x1c = f2(x1w[r + 1][q].y, x1w[r + 1][q + 1].x);
+#pragma unroll
+                    for (int i = 0; i < INIT; ++i) {
+                        const float wa = P.w3[c * INIT + i], wb = P.w3[(UH_C + c) * INIT + i];
+                        acc[r][q][i] = __ffma2_rn(x1c, f2(wa, wa), acc[r][q][i]);
+                        acc[r][q][i] = __ffma2_rn(x2, f2(wb, wb), acc[r][q][i]);
+                    }
+                }
+        }
+    }
+    __syncthreads();                                   // every thread is done with the low-resolution tile: p may overwrite it
+
+    // ---- p = relu(acc), 0 outside the image (= zero padding of the head's dw conv)
+    if (p_thread) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int pr = 2 * tr + r, gy = ty0 - 1 + pr;
+            const bool rin = gy >= 0 && gy < H;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int gx = tx0 - 1 + 4 * tc + 2 * q;
+                const bool in0 = rin && gx >= 0 && gx < W, in1 = rin && gx + 1 >= 0 && gx + 1 < W;
+#pragma unroll
+                for (int i = 0; i < INIT; ++i)
+                    *reinterpret_cast<float2*>(ps + (i * H3_PH + pr) * H3_PP + 4 * tc + 2 * q) =
+                        f2(in0 ? fmaxf(acc[r][q][i].x, 0.f) : 0.f, in1 ? fmaxf(acc[r][q][i].y, 0.f) : 0.f);
+            }
+        }
     }
     __syncthreads();
 
-    // ---- x1 = relu(up(v) + b1) on the 34x34 halo tile (0 outside the image = dw zero padding)
-    for (int i = threadIdx.x; i < UH_X1 * UH_X1; i += 256) {
-        const int yy = i / UH_X1, xx = i - yy * UH_X1;
-        const int gy = ty0 - 2 + yy, gx = tx0 - 2 + xx;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        int y0 = 0, y1 = 0, x0 = 0, x1 = 0;
-        float ly = 0.f, lx = 0.f;
-        if (in) {
-            bilin_src(gy, sy, h, y0, y1, ly);
-            bilin_src(gx, sx, w, x0, x1, lx);
-            y0 -= vy0; y1 -= vy0; x0 -= vx0; x1 -= vx0;
-        }
-        const float hy = 1.f - ly, hx = 1.f - lx;
+    // ---- outputs: thread -> rows 2*orow, 2*orow + 1, columns 4*og .. 4*og + 3; channels [0, INIT) = p, [INIT, KOUT) = relu(s4*dw3x3(p)+b4)
+    if (tid < (H3_TH / 2) * (H3_TW / 4)) {
+        const int og = tid & 7, orow = tid >> 3;
+        const int gx = tx0 + 4 * og;
+        float best[2][4];
+        int arg[2][4];
 #pragma unroll
-        for (int c = 0; c < UH_C; ++c) {
-            const float* vc = vs + c * UH_V * VP;
-            float val = hy * (hx * vc[y0 * VP + x0] + lx * vc[y0 * VP + x1]) + ly * (hx * vc[y1 * VP + x0] + lx * vc[y1 * VP + x1]);
-            val = in ? fmaxf(val + P.b1[c], 0.f) : 0.f;
-            x1s[(c * UH_X1 + yy) * UH_X1P + xx] = val;
-        }
-    }
-    __syncthreads();  // vs is dead from here on; ps (alias) may be written
-
-    // ---- head primary p = relu(w3 . [x1, x2] + b3) on the 32x32 tile, x2 = relu(s2*dw3x3(x1)+b2) on the fly.
-    // thread -> column `col` (0..31), strip of 4 rows starting at 4*strip (0..7): 6x3 x1 values serve 4 pixels.
-    {
-        const int col = threadIdx.x & 31, strip = threadIdx.x >> 5;
-        float acc[4][INIT];
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+            for (int x = 0; x < 4; ++x) { best[r][x] = -INFINITY; arg[r][x] = 0; }
+        // one channel's four values of output row 2*orow + r: stored at once, or folded into the running first-maximum
+        auto emit = [&](int r, int k, float a0, float a1, float a2, float a3) {
+            const int gy = ty0 + 2 * orow + r;
+            if (ARGMAX) {
+                const float a[4] = {a0, a1, a2, a3};
 #pragma unroll
-            for (int i = 0; i < INIT; ++i) acc[r][i] = P.b3[i];
+                for (int x = 0; x < 4; ++x)
+                    if (a[x] > best[r][x] || (a[x] == best[r][x] && k < arg[r][x])) { best[r][x] = a[x]; arg[r][x] = k; }
+            } else if (gy < H && gx < W) {
+                float* ob = out + (long long)b * out_bs + (long long)k * plane_hi + (long long)gy * W + gx;
+                if (vec_ok) {
+                    *reinterpret_cast<float4*>(ob) = make_float4(a0, a1, a2, a3);
+                } else {
+                    ob[0] = a0;
+                    if (gx + 1 < W) ob[1] = a1;
+                    if (gx + 2 < W) ob[2] = a2;
+                    if (gx + 3 < W) ob[3] = a3;
+                }
+            }
+        };
 #pragma unroll
-        for (int c = 0; c < UH_C; ++c) {
-            const float* xc = x1s + (c * UH_X1 + 4 * strip) * UH_X1P + col;  // x1 row (4*strip), col: p pixel (r, col) centre = x1[r+1][col+1]
-            float win[6][3];
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) win[r][k] = xc[r * UH_X1P + k];
+        for (int k = 0; k < INIT; ++k) {
+            const float* pb = ps + (k * H3_PH + 2 * orow) * H3_PP + 4 * og;
+            float win[4][6];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                float d = 0.f;
+                if (k < KOUT - INIT || r == 1 || r == 2) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(pb + r * H3_PP);
+                    const float2 b2 = *reinterpret_cast<const float2*>(pb + r * H3_PP + 4);
+                    win[r][0] = a4.x; win[r][1] = a4.y; win[r][2] = a4.z; win[r][3] = a4.w; win[r][4] = b2.x; win[r][5] = b2.y;
+                }
+            }
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+            for (int r = 0; r < 2; ++r) emit(r, k, win[r + 1][1], win[r + 1][2], win[r + 1][3], win[r + 1][4]);
+            if (k < KOUT - INIT) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) d = fmaf(win[r + ky][kx], P.w2[c * 9 + ky * 3 + kx], d);
-                const float x2 = fmaxf(fmaf(P.s2[c], d, P.b2[c]), 0.f);
-                const float x1c = win[r + 1][1];
+                for (int r = 0; r < 2; ++r) {
+                    float2 d[2];
 #pragma unroll
-                for (int i = 0; i < INIT; ++i) {
-                    acc[r][i] = fmaf(x1c, P.w3[c * INIT + i], acc[r][i]);
-                    acc[r][i] = fmaf(x2, P.w3[(UH_C + c) * INIT + i], acc[r][i]);
+                    for (int q = 0; q < 2; ++q) {
+                        d[q] = f2(0.f, 0.f);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float wk = P.w4[k * 9 + ky * 3 + kx];
+                                d[q] = __ffma2_rn(f2(win[r + ky][2 * q + kx], win[r + ky][2 * q + kx + 1]), f2(wk, wk), d[q]);
+                            }
+                        d[q] = __ffma2_rn(f2(P.s4[k], P.s4[k]), d[q], f2(P.b4[k], P.b4[k]));
+                    }
+                    emit(r, INIT + k, fmaxf(d[0].x, 0.f), fmaxf(d[0].y, 0.f), fmaxf(d[1].x, 0.f), fmaxf(d[1].y, 0.f));
                 }
             }
         }
+        if (ARGMAX) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int py = 4 * strip + r;
-            const int gy = ty0 - 1 + py, gx = tx0 - 1 + col;
-            const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+            for (int r = 0; r < 2; ++r) {
+                const int gy = ty0 + 2 * orow + r;
+                if (gy >= H || gx >= W) continue;
+                unsigned packed = 0;
 #pragma unroll
-            for (int i = 0; i < INIT; ++i) ps[(i * UH_P + py) * PP + col] = in ? fmaxf(acc[r][i], 0.f) : 0.f;
-        }
-    }
-    __syncthreads();
-
-    // ---- outputs: channels [0, INIT) = p, [INIT, KOUT) = relu(s4 * dw3x3(p) + b4)
-    float* ob = ARGMAX ? nullptr : out + (long long)b * out_bs;
-    unsigned char* mb = ARGMAX ? mask + (long long)b * mask_bs : nullptr;
-    for (int i = threadIdx.x; i < UH_T * UH_T; i += 256) {
-        const int yy = i / UH_T, xx = i - yy * UH_T;
-        const int gy = ty0 + yy, gx = tx0 + xx;
-        if (gy >= H || gx >= W) continue;
-        const long long o = (long long)gy * W + gx;
-        float best = -INFINITY;
-        int arg = 0;
+                for (int x = 0; x < 4; ++x) packed |= (unsigned)(((keep_mask >> arg[r][x]) & 1u) ? arg[r][x] : 0) << (8 * x);
+                unsigned char* mb = mask + (long long)b * mask_bs + (long long)gy * W + gx;
+                if (vec_ok) {
+                    *reinterpret_cast<unsigned*>(mb) = packed;
+                } else {
 #pragma unroll
-        for (int k = 0; k < INIT; ++k) {
-            const float val = ps[(k * UH_P + yy + 1) * PP + xx + 1];
-            if (ARGMAX) {
-                if (val > best) { best = val; arg = k; }
-            } else {
-                ob[k * plane_hi + o] = val;
+                    for (int x = 0; x < 4; ++x)
+                        if (gx + x < W) mb[x] = (unsigned char)(packed >> (8 * x));
+                }
             }
         }
-#pragma unroll
-        for (int k = 0; k < KOUT - INIT; ++k) {
-            float d = 0.f;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) d = fmaf(ps[(k * UH_P + yy + ky) * PP + xx + kx], P.w4[k * 9 + ky * 3 + kx], d);
-            const float val = fmaxf(fmaf(P.s4[k], d, P.b4[k]), 0.f);
-            if (ARGMAX) {
-                if (val > best) { best = val; arg = INIT + k; }
-            } else {
-                ob[(INIT + k) * plane_hi + o] = val;
-            }
-        }
-        if (ARGMAX) mb[o] = (unsigned char)(((keep_mask >> arg) & 1u) ? arg : 0);
     }
 }
 
 template <int INIT, int KOUT, bool ARGMAX>
-static int launch_head(const AchUpGhostHead& a, cudaStream_t st, unsigned char* mask = nullptr, long long mask_bs = 0,
-                       unsigned keep_mask = 0xffffffffu) {
+static int launch_head3(const AchUpGhostHead& a, cudaStream_t st, unsigned char* mask = nullptr, long long mask_bs = 0,
+                        unsigned keep_mask = 0xffffffffu) {
     UpGhostHeadParams<INIT, KOUT> P;
     memcpy(P.b1, a.b1, sizeof(P.b1));
     memcpy(P.w2, a.w2, sizeof(P.w2));
@@ -277,14 +407,24 @@ static int launch_head(const AchUpGhostHead& a, cudaStream_t st, unsigned char* 
     memcpy(P.w4, a.w4, sizeof(P.w4));
     memcpy(P.s4, a.s4, sizeof(P.s4));
     memcpy(P.b4, a.b4, sizeof(P.b4));
-    constexpr size_t smem = (size_t)(UH_C * UH_X1 * UH_X1P + UH_C * UH_V * (UH_V + 1)) * sizeof(float);
+    constexpr size_t smem = (size_t)H3_VELEMS * sizeof(float);
     static PerDeviceOnce attr_once;
     if (attr_once.first()) {
-        cudaFuncSetAttribute(up_ghost_head_kernel<INIT, KOUT, ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(up_ghost_head3_kernel<INIT, KOUT, ARGMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     const int H = 2 * a.h, W = 2 * a.w;
-    dim3 grid(cdiv(W, UH_T) * cdiv(H, UH_T), a.B);
-    up_ghost_head_kernel<INIT, KOUT, ARGMAX><<<grid, 256, smem, st>>>(a.v, a.v_bs, a.out, a.out_bs, a.h, a.w, P, mask, mask_bs, keep_mask);
+    // 16-byte stores need every row start aligned: W % 4 == 0 and aligned bases / batch strides
+    int vec_ok = W % 4 == 0;
+    if (ARGMAX)
+        vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(mask) & 3u) == 0 && mask_bs % 4 == 0;
+    else
+        vec_ok = vec_ok && aligned16(a.out) && a.out_bs % 4 == 0;
+    alignas(64) CUtensorMap tmv;
+    memset(&tmv, 0, sizeof(tmv));
+    const int use_tma = tma_map_planes(&tmv, a.v, a.w, a.h, UH_C, a.B, a.v_bs, H3_VP, H3_VR, UH_C) ? 1 : 0;
+    dim3 grid(cdiv(W, H3_TW) * cdiv(H, H3_TH), a.B);
+    up_ghost_head3_kernel<INIT, KOUT, ARGMAX><<<grid, H3_T, smem, st>>>(tmv, a.v, a.v_bs, a.out, a.out_bs, a.h, a.w, P, mask, mask_bs, keep_mask,
+                                                                         vec_ok, use_tma);
     return check_launch("ach_up_ghost_head");
 }
 
@@ -313,8 +453,8 @@ extern "C" int ach_up_ghost_head(const AchUpGhostHead* pp, void* stream) {
     ACH_REQUIRE(a.B > 0 && a.B <= 65535 && a.h > 1 && a.w > 1, "ach_up_ghost_head: bad dims");
     ACH_REQUIRE(ach_up_ghost_head_supported(a.C, a.init, a.K), "ach_up_ghost_head: (C=%d, init=%d, K=%d) not instantiated", a.C, a.init, a.K);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (a.init == 1) return launch_head<1, 2, false>(a, st);
-    return launch_head<5, 9, false>(a, st);
+    if (a.init == 1) return launch_head3<1, 2, false>(a, st);
+    return launch_head3<5, 9, false>(a, st);
 }
 
 extern "C" int ach_up_ghost_head_argmax(const AchUpGhostHead* pp, unsigned char* mask, long long mask_bs, unsigned keep_mask,
@@ -326,8 +466,8 @@ extern "C" int ach_up_ghost_head_argmax(const AchUpGhostHead* pp, unsigned char*
     ACH_REQUIRE(mask_bs >= 4LL * a.h * a.w, "ach_up_ghost_head_argmax: mask batch stride smaller than one map");
     ACH_REQUIRE(ach_up_ghost_head_supported(a.C, a.init, a.K), "ach_up_ghost_head_argmax: (C=%d, init=%d, K=%d) not instantiated", a.C, a.init, a.K);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (a.init == 1) return launch_head<1, 2, true>(a, st, mask, mask_bs, keep_mask);
-    return launch_head<5, 9, true>(a, st, mask, mask_bs, keep_mask);
+    if (a.init == 1) return launch_head3<1, 2, true>(a, st, mask, mask_bs, keep_mask);
+    return launch_head3<5, 9, true>(a, st, mask, mask_bs, keep_mask);
 }
 
 // ------------------------------------------------------------------------------------------------
