@@ -1600,8 +1600,11 @@ class Engine:
                 self._launch_all()  # warm-up: module loading, function attributes
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
-                # thread_local: nn.DataParallel runs one Python thread per GPU, each may be capturing its own plan
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                # nn.DataParallel runs one Python thread per GPU, each may be capturing its own plan: thread_local error mode, and
+                # a capture stream of THIS device (torch.cuda.graph's default capture stream is one process-wide stream on
+                # whichever device captured first - a replica on another GPU then records an empty graph)
+                cap = torch.cuda.Stream(self.device)
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
                     self._launch_all()
                 self.graph = g
             self.graph.replay()

@@ -238,7 +238,9 @@ def main():
     # with purely random head weights ~1200 of the 2100 anchors per image pass conf >= 0.35 - unrealistically many
     # for the NMS inside the compact plan; shift the objectness bias so that ~120 candidates per image pass (as the golden
     # fixtures do, tests/golden/make_golden.py:calibrate_obj_bias).  Kernel times of the raw forward do not depend on values.
-    obj_bias, n_cand = calibrate_obj_bias(model, xd[:8], xrd[:8], pcd[:8], torch)
+    # Calibrated on the SAME frames on every rank (rank 0's): all ranks must run identical weights.
+    cal = [t.to(dev) for t in make_inputs(8, seed=1234)]
+    obj_bias, n_cand = calibrate_obj_bias(model, cal[0], cal[1], cal[2], torch)
     comm = torch.cuda.Stream(dev) if world > 1 else None
 
     def barrier():
