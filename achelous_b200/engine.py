@@ -236,8 +236,15 @@ class Engine:
 
     # ------------------------------------------------------------------ op recorders
     def pw(self, name, x0, out, wt, O, x1=None, scale=None, bias=None, pbias=None, res=None, gamma=None, ln=False,
-           ln_eps=1e-6, act=ACT_NONE, wt_bs=0, ldw=None, reduce_max=False, out_bs=None):
+           ln_eps=1e-6, act=ACT_NONE, wt_bs=0, ldw=None, reduce_max=False, out_bs=None, frames=None):
+        """frames = (b0, nb): the launch covers frames [b0, b0 + nb) of every view only (shared weights, no reduce_max / pbias)"""
         P = x0.H * x0.W
+        B_ = self.B
+        if frames is not None:
+            b0, B_ = frames
+            assert wt_bs == 0 and not reduce_max and pbias is None and x1 is None
+            shift = lambda v: None if v is None else v._replace(ptr=v.ptr + b0 * v.bs * 4)
+            x0, out, res = shift(x0), shift(out), shift(res)
         s = AchPwConv()
         s.x0, s.x0_bs, s.c0 = x0.ptr, x0.bs, x0.C
         s.x1, s.x1_bs, s.c1 = (x1.ptr, x1.bs, x1.C) if x1 is not None else (None, 0, 0)
@@ -254,24 +261,29 @@ class Engine:
         else:
             assert out.C == O and out.H * out.W == P, (name, out, O, P)
             s.out, s.out_bs = out.ptr, out.bs
-        s.B, s.O, s.P = self.B, O, P
+        s.B, s.O, s.P = B_, O, P
         s.ln, s.ln_eps, s.act, s.reduce_max = int(ln), ln_eps, act, int(reduce_max)
         self._keep.append(s)
         K_ = s.c0 + s.c1
-        nb = 4 * (self.B * K_ * P + (self.B * O if reduce_max else self.B * O * P) + (self.B * O * P if res is not None else 0)
-                  + K_ * s.ldw * (self.B if wt_bs else 1))
+        nb = 4 * (B_ * K_ * P + (B_ * O if reduce_max else B_ * O * P) + (B_ * O * P if res is not None else 0)
+                  + K_ * s.ldw * (B_ if wt_bs else 1))
         tc_mode = self.model.use_tensor_cores
         # measured on B200: the warp-specialised tcgen05 kernel beats (or ties) the SIMT GEMM on every shared-weight layer with
         # >= 16 outputs (32 -> 16 at 320^2: 0.51 -> 0.47 ms); below that the two are within noise of each other
         tc_ok = tc_mode in (True, "all") and O >= 16
         if tc_ok and wt_bs == 0 and isinstance(wt, torch.Tensor) and not self.in_pack:
             # tcgen05 path: weights re-packed on the device into hi/lo UMMA tile images whenever they change
-            n = self.lib.ach_pack_pw_tc_elems(K_, O)
-            hi = self._zeros(n)
-            lo = self._zeros(n)
-            self._keep += [hi, lo]
-            self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt.data_ptr(), K_, O, s.ldw, hi.data_ptr(), lo.data_ptr())))
-            wsum = self._w(name + ".wsum", lambda wt=wt, O=O: wt.detach().cpu()[:, :O].double().sum(0)) if ln else None
+            ck = (wt.data_ptr(), K_, O, s.ldw, bool(ln))          # launches that share a weight tensor share its packed tiles
+            cache = self.__dict__.setdefault("_tc_tiles", {})
+            if ck not in cache:
+                n = self.lib.ach_pack_pw_tc_elems(K_, O)
+                hi = self._zeros(n)
+                lo = self._zeros(n)
+                self._keep += [hi, lo]
+                self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt.data_ptr(), K_, O, s.ldw, hi.data_ptr(), lo.data_ptr())))
+                wsum = self._w(name + ".wsum", lambda wt=wt, O=O: wt.detach().cpu()[:, :O].double().sum(0)) if ln else None
+                cache[ck] = (hi, lo, wsum)
+            hi, lo, wsum = cache[ck]
             self._add(name, self.lib.ach_pw_conv_tc, C.byref(s), hi.data_ptr(), lo.data_ptr(), self._ptr(wsum), nbytes=nb)
             return
         self._add(name, self.lib.ach_pw_conv, C.byref(s), nbytes=nb)
@@ -405,13 +417,37 @@ class Engine:
     def mlp_res(self, name, prefix, x_ln_src, res, out):
         """LN -> Linear(4C) -> GELU -> Linear(C) -> gamma -> + res   (conv_encoder.py:23-31, sdta_encoder.py:64-73)"""
         Cc = x_ln_src.C
-        h = self.buf(name + ".h", 4 * Cc, x_ln_src.H, x_ln_src.W)
+        P = x_ln_src.H * x_ln_src.W
         wt1, b1 = self._ln_fold_linear(name + ".pw1", prefix + ".pwconv1", prefix + ".norm")
-        self.pw(name + ".pw1", x_ln_src, h, wt1, 4 * Cc, bias=b1, ln=True, ln_eps=1e-6, act=ACT_GELU)
         wt2 = self._w(name + ".pw2.wt", lambda: self._kmajor(self._p(prefix + ".pwconv2.weight")))
         b2 = self._vec(name + ".pw2.b", lambda: self._p(prefix + ".pwconv2.bias"))
         gm = self._vec(name + ".gamma", lambda: self._p(prefix + ".gamma"))
-        self.pw(name + ".pw2", h, out, wt2, Cc, bias=b2, res=res, gamma=gm)
+        # The 4C-wide hidden tensor is written by pw1 and read once by pw2.  For the whole batch it is far larger than the L2
+        # (B=64, C=32 at 80^2: 210 MB); run the pair per group of frames through ONE small hidden buffer that stays L2-resident
+        # (dirty lines are overwritten by the next group instead of being written back), as long as a group still fills the GPU.
+        hid_bytes = 4 * 4 * Cc * P
+        nb = self.B
+        g_max = getattr(self.model, "mlp_group_bytes", 0)
+        if g_max and hid_bytes * self.B > g_max and self.model.use_tensor_cores:
+            tiles = (P + 127) // 128 * ((4 * Cc + 127) // 128)
+            nb = max(1, min(self.B, g_max // hid_bytes))
+            while nb < self.B and nb * tiles < getattr(self.model, "mlp_group_min_tiles", 444):   # a group still fills a wave of CTAs
+                nb += 1
+        if nb >= self.B:
+            h = self.buf(name + ".h", 4 * Cc, x_ln_src.H, x_ln_src.W)
+            self.pw(name + ".pw1", x_ln_src, h, wt1, 4 * Cc, bias=b1, ln=True, ln_eps=1e-6, act=ACT_GELU)
+            self.pw(name + ".pw2", h, out, wt2, Cc, bias=b2, res=res, gamma=gm)
+            return
+        ht = torch.empty(nb, 4 * Cc, x_ln_src.H, x_ln_src.W, device=self.device, dtype=torch.float32)
+        self._bufs[name + ".h"] = ht
+        hv = View(ht.data_ptr(), ht.stride(0), 4 * Cc, x_ln_src.H, x_ln_src.W)
+        for gi, b0 in enumerate(range(0, self.B, nb)):
+            n = min(nb, self.B - b0)
+            sfx = "" if gi == 0 else f"@{b0}"
+            # the hidden view always starts at the buffer's first frame: shift it back by b0
+            hshift = hv._replace(ptr=hv.ptr - b0 * hv.bs * 4)
+            self.pw(name + ".pw1" + sfx, x_ln_src, hshift, wt1, 4 * Cc, bias=b1, ln=True, ln_eps=1e-6, act=ACT_GELU, frames=(b0, n))
+            self.pw(name + ".pw2" + sfx, hshift, out, wt2, Cc, bias=b2, res=res, gamma=gm, frames=(b0, n))
 
     def conv_encoder(self, name, prefix, x, k):
         d = self.buf(name + ".dw", x.C, x.H, x.W)

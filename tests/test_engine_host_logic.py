@@ -139,3 +139,24 @@ def test_compact_plan_matches_raw_plan(image_shape, keep, fuse):
         assert np.allclose(mine[:, [1, 0, 3, 2]] * 320.0, ref[:, :4], rtol=0, atol=1e-3)
         assert not c.det_rows[b, m:].any()
     assert n_trunc > 0      # the cap was exercised
+
+
+def test_grouped_mlp_plan_equals_whole_batch_plan():
+    """The LN -> Linear(4C) -> GELU -> Linear pairs run per group of frames through one small (L2-resident) hidden buffer when the
+    whole-batch hidden tensor is large; same arithmetic per frame, so the outputs must be IDENTICAL to the ungrouped plan."""
+    torch.set_num_threads(4)
+    model = Achelous(phi="S0", backbone="en", **MODEL_KW).eval()
+    model.load_state_dict(fill_state_dict(model.state_dict(), seed=2), strict=True)
+    B = 3
+    x, xr, pc = make_inputs(B, seed=23)
+    outs = []
+    for group_bytes in (0, 1):
+        model.mlp_group_bytes, model.mlp_group_min_tiles = group_bytes, 1       # 1 byte: one frame per group
+        eng = Engine(model, B, "cpu", dry_run=True)
+        if group_bytes:
+            assert sum(n.startswith("bb.s0.0.pw1") for n in eng.op_names) == B and eng._bufs["bb.s0.0.h"].shape[0] == 1
+        ins = eng.input_tensors()
+        ins[0].copy_(x), ins[1].copy_(xr), ins[2].copy_(pc)
+        emulate_engine(eng)
+        outs.append(eng.packed_out.clone())
+    assert torch.equal(outs[0], outs[1])

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--tc", default="default", help="default | all | off")
     ap.add_argument("--compact", action="store_true", help="time the outputs='compact' plan")
+    ap.add_argument("--mlp-group-mb", type=float, default=None, help="override model.mlp_group_bytes (0: whole batch)")
     ap.add_argument("--out", default="gpurun_out/op_times.json")
     a = ap.parse_args()
     kw = dict(num_det=7, num_seg=9, phi=a.phi, resolution=320, backbone=a.backbone, neck=a.neck, pc_seg=a.pc_seg, pc_channels=5,
@@ -32,6 +33,8 @@ def main():
     model = Achelous(**kw).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=0))
     model.use_cuda_graph = False
+    if a.mlp_group_mb is not None:
+        model.mlp_group_bytes = int(a.mlp_group_mb * (1 << 20))
     if a.tc != "default":
         model.use_tensor_cores = "all" if a.tc == "all" else False
     model = model.cuda()
