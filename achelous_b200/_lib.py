@@ -27,6 +27,11 @@ class AchPwConv(C.Structure):
                 ("ln", I), ("ln_eps", F), ("act", I), ("reduce_max", I)]
 
 
+class AchMlp(C.Structure):
+    _fields_ = [("x", VP), ("res", VP), ("b1", VP), ("b2", VP), ("gamma", VP), ("out", VP),
+                ("x_bs", LL), ("res_bs", LL), ("out_bs", LL), ("B", I), ("C", I), ("P", I), ("ln_eps", F)]
+
+
 class AchDwConv(C.Structure):
     _fields_ = [("x", VP), ("xadd", VP), ("w", VP), ("scale", VP), ("bias", VP), ("post", VP), ("out", VP),
                 ("x_bs", LL), ("xadd_bs", LL), ("out_bs", LL),
@@ -72,6 +77,10 @@ _SIGNATURES = {
     "ach_pack_pw_tc_elems": ([I, I], LL),
     "ach_pack_pw_tc": ([VP, I, I, I, VP, VP, VP], I),
     "ach_pw_conv_tc": ([C.POINTER(AchPwConv), VP, VP, VP, VP], I),
+    "ach_pack_pw_tc_nt_elems": ([I, I, I], LL),
+    "ach_pack_pw_tc_nt": ([VP, I, I, I, I, VP, VP, VP], I),
+    "ach_mlp_tc_supported": ([I], I),
+    "ach_mlp_tc": ([C.POINTER(AchMlp), VP, VP, VP, VP, VP, VP], I),
     "ach_dw_conv": ([C.POINTER(AchDwConv), VP], I),
     "ach_conv_dense": ([C.POINTER(AchConvDense), VP], I),
     "ach_layernorm_cf": ([VP, LL, VP, VP, VP, LL, I, I, I, F, VP], I),

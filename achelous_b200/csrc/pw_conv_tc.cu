@@ -74,6 +74,22 @@ extern "C" int ach_pack_pw_tc(const float* wt, int K, int O, int ldw, float* w_h
     return check_launch("ach_pack_pw_tc");
 }
 
+/* explicit tile width (the fused MLP kernel wants W1 in 32-column tiles and W2 in one C-column tile) */
+extern "C" long long ach_pack_pw_tc_nt_elems(int K, int O, int NT) {
+    using namespace ach;
+    if (NT <= 0 || NT % 8 != 0) return -1;
+    return (long long)cdiv(O, NT) * cdiv(K, TC_KC) * NT * TC_KC;
+}
+
+extern "C" int ach_pack_pw_tc_nt(const float* wt, int K, int O, int ldw, int NT, float* w_hi, float* w_lo, void* stream) {
+    using namespace ach;
+    ACH_REQUIRE(wt && w_hi && w_lo && K > 0 && O > 0 && ldw >= O, "ach_pack_pw_tc_nt: bad args");
+    ACH_REQUIRE(NT >= 16 && NT <= 256 && NT % 16 == 0, "ach_pack_pw_tc_nt: NT=%d must be a multiple of 16 in [16, 256]", NT);
+    const long long total = ach_pack_pw_tc_nt_elems(K, O, NT);
+    pack_pw_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(wt, K, O, ldw, NT, cdiv(K, TC_KC), w_hi, w_lo, total);
+    return check_launch("ach_pack_pw_tc_nt");
+}
+
 extern "C" int ach_pw_conv_tc(const AchPwConv* pp, const float* w_hi, const float* w_lo, const float* wsum, void* stream) {
     using namespace ach;
     const AchPwConv& p = *pp;

@@ -17,7 +17,7 @@ from collections import namedtuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConv3x3Tc, AchConvDense, AchDwConv, AchPwConv, AchRcDeform, AchUpGhost,
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, AchConv3x3Tc, AchConvDense, AchDwConv, AchMlp, AchPwConv, AchRcDeform, AchUpGhost,
                    AchUpGhostHead, AchUpGhostPw2)
 from .nets import holders as Hd
 
@@ -425,6 +425,29 @@ class Engine:
         # The 4C-wide hidden tensor is written by pw1 and read once by pw2.  For the whole batch it is far larger than the L2
         # (B=64, C=32 at 80^2: 210 MB); run the pair per group of frames through ONE small hidden buffer that stays L2-resident
         # (dirty lines are overwritten by the next group instead of being written back), as long as a group still fills the GPU.
+        tc_mode = self.model.use_tensor_cores
+        if (tc_mode in (True, "all") and getattr(self.model, "fuse_mlp", True) and not self.in_pack
+                and self.lib.ach_mlp_tc_supported(Cc) and P % 4 == 0):
+            # ONE launch: the hidden tile lives in tensor memory (csrc/mlp_tc.cu); W1 in 32-column tiles, W2 as one C-column tile
+            def tiles(wt, K_, O, NT):
+                n = self.lib.ach_pack_pw_tc_nt_elems(K_, O, NT)
+                hi, lo = self._zeros(n), self._zeros(n)
+                self._keep += [hi, lo]
+                self.pack_ops.append((self.lib.ach_pack_pw_tc_nt, (wt.data_ptr(), K_, O, wt.shape[-1], NT, hi.data_ptr(), lo.data_ptr())))
+                return hi, lo
+            h1, l1 = tiles(wt1, Cc, 4 * Cc, 32)
+            h2, l2 = tiles(wt2, 4 * Cc, Cc, Cc)
+            wsum = self._w(name + ".pw1.wsum", lambda wt=wt1, O=4 * Cc: wt.detach().cpu()[:, :O].double().sum(0))
+            s = AchMlp()
+            s.x, s.x_bs, s.res, s.res_bs, s.out, s.out_bs = x_ln_src.ptr, x_ln_src.bs, res.ptr, res.bs, out.ptr, out.bs
+            s.b1, s.b2, s.gamma = b1.data_ptr(), b2.data_ptr(), gm.data_ptr()
+            s.B, s.C, s.P, s.ln_eps = self.B, Cc, P, 1e-6
+            assert x_ln_src.C == res.C == out.C == Cc
+            self._keep.append(s)
+            nbytes = 4 * (3 * self.B * Cc * P + 2 * 4 * Cc * Cc)
+            self._add(name + ".mlp", self.lib.ach_mlp_tc, C.byref(s), h1.data_ptr(), l1.data_ptr(), h2.data_ptr(), l2.data_ptr(),
+                      wsum.data_ptr(), nbytes=nbytes)
+            return
         hid_bytes = 4 * 4 * Cc * P
         nb = self.B
         g_max = getattr(self.model, "mlp_group_bytes", 0)

@@ -43,6 +43,7 @@ class _AchelousBase(nn.Module):
         self.seg_tensor_cores = True   # chained decoder stages: the two 1x1 convs of ach_up_ghost_pw2 on tcgen05 (needs use_tensor_cores)
         self.fuse_seg_decoder = True   # False: block-by-block decoder (keeps every reference intermediate)
         self.fuse_seg_chain = True     # decoder stages chained through ach_up_ghost_pw2 (no full-width maps in HBM)
+        self.fuse_mlp = True           # LN -> Linear(4C) -> GELU -> Linear -> gamma -> + res as ONE tcgen05 launch (hidden tile in tensor memory)
         self.mlp_group_bytes = 0          # > 0: LN->Linear->GELU->Linear pairs run per group of frames whose 4C-wide hidden tensor fits this
         #                                   many bytes (L2-resident between the two GEMMs).  Measured on B200 at B=64: 5.12 ms whole batch,
         #                                   5.56 / 5.30 / 5.20 ms at 24 / 48 / 96 MB groups (more, smaller launches lose more than L2 hits win)

@@ -86,6 +86,32 @@ ACH_API long long ach_pack_pw_tc_elems(int K, int O);
 ACH_API int ach_pack_pw_tc(const float* wt, int K, int O, int ldw, float* w_hi, float* w_lo, void* stream);
 ACH_API int ach_pw_conv_tc(const AchPwConv* p, const float* w_hi, const float* w_lo, const float* wsum, void* stream);
 
+/* Fused inverted-bottleneck MLP of the EdgeNeXt encoders on tcgen05 (3xTF32), one launch per block:
+ *   out[b, :, p] = res[b, :, p] + gamma * (W2 . gelu(LN(x[b, :, p]) . W1 + b1) + b2)
+ * x, res, out are (B, C, P) views (x 16-byte aligned, P % 4 == 0); the 4C-wide hidden activations exist only in tensor memory.
+ * LayerNorm over channels without affine (its affine is folded into W1 / b1 by the host; wsum1[n] = sum_k W1[k][n] of the
+ * folded weights, as for ach_pw_conv_tc).  Weights pre-packed by ach_pack_pw_tc_nt:
+ *   w1_hi/lo <- K-major [C][>= 4C] with NT = 32,   w2_hi/lo <- K-major [4C][>= C] with NT = C.
+ * Same arithmetic as ach_pw_conv_tc(ln, GELU) followed by ach_pw_conv_tc(bias, gamma, res).
+ * Replaces conv_encoder.py:23-31 and sdta_encoder.py:64-73 (norm -> pwconv1 -> act -> pwconv2 -> gamma -> + input).
+ * C in {32, 48, 64, 96} (ach_mlp_tc_supported); other widths use the two GEMM launches. */
+typedef struct AchMlp {
+    const float* x;
+    const float* res;
+    const float* b1;      /* [4C] */
+    const float* b2;      /* [C] */
+    const float* gamma;   /* [C] */
+    float* out;
+    long long x_bs, res_bs, out_bs;
+    int B, C, P;
+    float ln_eps;
+} AchMlp;
+ACH_API long long ach_pack_pw_tc_nt_elems(int K, int O, int NT);
+ACH_API int ach_pack_pw_tc_nt(const float* wt, int K, int O, int ldw, int NT, float* w_hi, float* w_lo, void* stream);
+ACH_API int ach_mlp_tc_supported(int C);
+ACH_API int ach_mlp_tc(const AchMlp* p, const float* w1_hi, const float* w1_lo, const float* w2_hi, const float* w2_lo,
+                       const float* wsum1, void* stream);
+
 /* Depthwise k x k convolution (k in {3,5,7,9}, stride 1 or 2, pad k/2):
  *   out[b,c] = act(scale[c] * dw(x[b,c] + xadd[b,c]) + bias[c]) + post[c]      (post broadcast over b)
  * w is [C][k*k].  Replaces nn.Conv2d(groups=C): conv_encoder.py:10, sdta_encoder.py:23 (cascade

@@ -79,9 +79,9 @@ def _tc_tile_n(O):
     return 32 if O <= 32 else (64 if O <= 64 else 128)
 
 
-def _tc_index(K, O):
-    """(o, k) of every element of the UMMA tile image written by ach_pack_pw_tc."""
-    NT, KC = _tc_tile_n(O), 16
+def _tc_index(K, O, NT=None):
+    """(o, k) of every element of the UMMA tile image written by ach_pack_pw_tc (ach_pack_pw_tc_nt: explicit tile width)."""
+    NT, KC = NT or _tc_tile_n(O), 16
     n_ot, n_kc = -(-O // NT), -(-K // KC)
     i = torch.arange(n_ot * n_kc * NT * KC)
     blk, r = i // (NT * KC), i % (NT * KC)
@@ -93,9 +93,41 @@ def _tc_index(K, O):
     return o, k
 
 
-def ach_pack_pw_tc(wt, K, O, ldw, w_hi, w_lo):
+def ach_pack_pw_tc_nt(wt, K, O, ldw, NT, w_hi, w_lo):
+    ach_pack_pw_tc(wt, K, O, ldw, w_hi, w_lo, NT)
+
+
+def _tc_unpack_nt(w_hi, w_lo, K, O, NT):
+    """K-major [K][ceil4(O)] matrix back from a hi/lo tile image"""
+    o, k = _tc_index(K, O, NT)
+    n = o.numel()
+    tiles = fview(w_hi, (n,), (1,)) + fview(w_lo, (n,), (1,))
+    ok = (o < O) & (k < K)
+    wt = torch.zeros(K, (O + 3) // 4 * 4)
+    wt[k[ok], o[ok]] = tiles[ok]
+    return wt
+
+
+def ach_mlp_tc(s, w1_hi, w1_lo, w2_hi, w2_lo, wsum1):
+    """out = res + gamma * (W2 . gelu(LN(x) . W1 + b1) + b2): the two ach_pw_conv contracts back to back"""
+    B, Cc, P = s.B, s.C, s.P
+    w1 = _tc_unpack_nt(w1_hi, w1_lo, Cc, 4 * Cc, 32).double()[:, :4 * Cc]
+    w2 = _tc_unpack_nt(w2_hi, w2_lo, 4 * Cc, Cc, Cc).double()[:, :Cc]
+    assert torch.allclose(_vec(wsum1, 4 * Cc), w1.sum(0).float(), rtol=1e-5, atol=1e-6)
+    x = fview(s.x, (B, Cc, P), (s.x_bs, P, 1)).double()
+    u = x.mean(1, keepdim=True)
+    v = (x - u).pow(2).mean(1, keepdim=True)
+    xn = (x - u) / torch.sqrt(v + s.ln_eps)
+    h = torch.einsum("ko,bkp->bop", w1, xn) + _vec(s.b1, 4 * Cc).double()[None, :, None]
+    h = F.gelu(h.float()).double()
+    y = (torch.einsum("ko,bkp->bop", w2, h) + _vec(s.b2, Cc).double()[None, :, None]).float()
+    y = fview(s.res, (B, Cc, P), (s.res_bs, P, 1)) + _vec(s.gamma, Cc)[None, :, None] * y
+    fview(s.out, (B, Cc, P), (s.out_bs, P, 1)).copy_(y)
+
+
+def ach_pack_pw_tc(wt, K, O, ldw, w_hi, w_lo, NT=None):
     w = fview(wt, (K, O), (ldw, 1))
-    o, k = _tc_index(K, O)
+    o, k = _tc_index(K, O, NT)
     ok = (o < O) & (k < K)
     vals = torch.zeros(o.numel())
     vals[ok] = w[k[ok], o[ok]]
@@ -583,7 +615,7 @@ def ach_pn2_interp3(xyz1, xyz1_bs, xyz2, xyz2_bs, pts2, pts2_bs, B, C2, N1, S, o
 EMULATORS = {f.__name__: f for f in (ach_pw_conv, ach_dw_conv, ach_conv_dense, ach_layernorm_cf, ach_upsample2x, ach_spp_maxpool,
                                      ach_shuffle_attention, ach_plane_mean, ach_eca_fuse, ach_avgpool3, ach_avgpool3_cl, ach_rc_deform, ach_xca_fold,
                                      ach_fc, ach_logsoftmax_t, ach_copy_add, ach_add, ach_fill, ach_up_ghost, ach_up_ghost_head,
-                                     ach_pack_pw_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
+                                     ach_pack_pw_tc, ach_pack_pw_tc_nt, ach_mlp_tc, ach_pw_conv_tc, ach_mvit_attention, ach_ln_s2d, ach_pn2_fps, ach_pn2_group,
                                      ach_pn2_group_max, ach_pn2_interp3, ach_rc_deform_tc, ach_up_ghost_pw2, ach_conv3x3_tc, ach_up_ghost_pw2_tc, ach_subsample, ach_mhsa, ach_dw_convT, ach_s2d, ach_ef_attention, ach_upsample2x_hp,
                                      ach_up_ghost_head_argmax, ach_seg_argmax_u8, ach_seg_softmax_resize_argmax, ach_logsoftmax_argmax_t,
                                      ach_decode_outputs, ach_nms_rows)}

@@ -147,6 +147,7 @@ def test_grouped_mlp_plan_equals_whole_batch_plan():
     torch.set_num_threads(4)
     model = Achelous(phi="S0", backbone="en", **MODEL_KW).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=2), strict=True)
+    model.fuse_mlp = False      # the two-launch path (the fused kernel needs no hidden buffer at all)
     B = 3
     x, xr, pc = make_inputs(B, seed=23)
     outs = []
@@ -160,3 +161,25 @@ def test_grouped_mlp_plan_equals_whole_batch_plan():
         emulate_engine(eng)
         outs.append(eng.packed_out.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_fused_mlp_plan_is_used_and_matches_two_launch_plan():
+    """ach_mlp_tc replaces the pw1 / pw2 pair wherever the width is instantiated (EN-S0: stages 0-2); through the CPU emulator both
+    plans evaluate the same fp64 arithmetic, so the packed weights (32-column W1 tiles, one C-column W2 tile) are what is pinned here."""
+    torch.set_num_threads(4)
+    model = Achelous(phi="S0", backbone="en", **MODEL_KW).eval()
+    model.load_state_dict(fill_state_dict(model.state_dict(), seed=5), strict=True)
+    B = 2
+    x, xr, pc = make_inputs(B, seed=29)
+    outs = []
+    for fuse in (True, False):
+        model.fuse_mlp = fuse
+        eng = Engine(model, B, "cpu", dry_run=True)
+        n_mlp = sum(n.endswith(".mlp") for n in eng.op_names)
+        n_pw1 = sum(n.endswith(".pw1") for n in eng.op_names)
+        assert (n_mlp, n_pw1) == ((10, 2) if fuse else (0, 12))     # C = 176 (stage 3) keeps the two GEMM launches
+        ins = eng.input_tensors()
+        ins[0].copy_(x), ins[1].copy_(xr), ins[2].copy_(pc)
+        emulate_engine(eng)
+        outs.append(eng.packed_out.clone())
+    assert rel_err(outs[0], outs[1]) < 1e-6

@@ -31,6 +31,7 @@ def build(phi, bb, wseed, graph=True, fuse="chain", tc=True, neck="gdf"):
     model.fuse_seg_decoder = bool(fuse)
     model.fuse_seg_chain = fuse == "chain"
     model.use_tensor_cores = tc
+    model.fuse_mlp = bool(fuse)     # the blockwise mode also keeps the MLP blocks as two GEMM launches
     sd = fill_state_dict(model.state_dict(), seed=wseed)
     model.load_state_dict(sd, strict=True)
     model.use_cuda_graph = graph
