@@ -65,9 +65,70 @@ __device__ __forceinline__ void mlp_bulk_g2s(uint32_t dst, const void* src, uint
                  "r"(mbar)
                  : "memory");
 }
+// mbarrier wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes (or the hint expires)
+// instead of polling - v2's MMA / loader warps spent ~12 % of the SM's issue slots in try_wait / branch / yield loops
+__device__ __forceinline__ void mlp_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MLP_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra MLP_WAIT_DONE;\n\t"
+        "bra MLP_WAIT_LOOP;\n\t"
+        "MLP_WAIT_DONE:\n\t"
+        "}\n" ::"r"(mbar), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
 __device__ __forceinline__ void mlp_wait_tc(uint32_t mbar, uint32_t parity) {   // barrier wait + ordering of the following tcgen05 ops
-    mbar_wait(mbar, parity);
+    mlp_wait(mbar, parity);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// Issue-side helpers for a WARP-UNIFORM MMA loop: every lane runs the loop (so that ptxas keeps descriptors, TMEM addresses and
+// barrier addresses in uniform registers - under an `if (lane == 0)` it wraps every UTCHMMA in an ELECT / 4 x R2UR / BRA.ANY
+// waterfall, ~10 instructions per MMA on one warp: ncu showed the C = 96 kernel bound by exactly that), one elected lane issues.
+__device__ __forceinline__ void mlp_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t elected) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void mlp_commit(uint32_t mbar, uint32_t elected) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "setp.ne.b32 e, %1, 0;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(mbar), "r"(elected)
+        : "memory");
+}
+
+// apply_act(ACT_GELU) (common.cuh: erf by Abramowitz-Stegun 7.1.26 on MUFU.RCP / MUFU.EX2) for two values at once on Blackwell's
+// packed fp32 pipe (FFMA2 / FMUL2: two independent IEEE operations per issue slot).  Element-wise the same operations in the same
+// order as the scalar form - negations are moved into the constants, which is exact - so the results are bit-identical; the GELU
+// epilogue is what bounds this kernel and this halves its FMA / MUL issue slots.
+__device__ __forceinline__ float2 mlp_gelu2(float2 v) {
+    const float2 h = __fmul2_rn(v, make_float2(0.5f, 0.5f));
+    const float2 z = __fmul2_rn(v, make_float2(0.70710678118654752440f, 0.70710678118654752440f));
+    const float2 ax = make_float2(fabsf(z.x), fabsf(z.y));
+    const float2 d = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), ax, make_float2(1.0f, 1.0f));
+    const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));   // arguments >= 1
+    // -poly (all coefficient signs flipped): erf = 1 - poly * e = fma(-poly, e, 1)
+    float2 np = __ffma2_rn(make_float2(-1.061405429f, -1.061405429f), t, make_float2(1.453152027f, 1.453152027f));
+    np = __ffma2_rn(np, t, make_float2(-1.421413741f, -1.421413741f));
+    np = __ffma2_rn(np, t, make_float2(0.284496736f, 0.284496736f));
+    np = __ffma2_rn(np, t, make_float2(-0.254829592f, -0.254829592f));
+    np = __fmul2_rn(np, t);
+    float2 q = __fmul2_rn(ax, ax);
+    q = __fmul2_rn(q, make_float2(-1.4426950408889634f, -1.4426950408889634f));   // (-ax * ax) * log2(e)
+    const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));              // underflow -> 0 -> erf = +-1
+    const float2 r = __ffma2_rn(np, e, make_float2(1.0f, 1.0f));
+    const float2 erf = make_float2(copysignf(r.x, z.x), copysignf(r.y, z.y));
+    return __ffma2_rn(h, erf, h);
 }
 
 struct MlpBars {   // per slot
@@ -93,10 +154,11 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
     __shared__ __align__(8) MlpBars bars[SLOTS];
     __shared__ __align__(8) uint64_t bar_w1_full[S1], bar_w1_free[S1], bar_w2_full[S2], bar_w2_free[S2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ float2 s_c1[4 * C];   // per hidden column {wsum1, b1}
+    __shared__ float4 s_c1[2 * C];   // per PAIR of hidden columns {wsum1[n], wsum1[n+1], b1[n], b1[n+1]}
     __shared__ float2 s_c2[C];       // per output {b2, gamma}
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the shuffle makes the warp index provably warp-uniform for the compiler (uniform registers in the MMA / loader loops)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int P = p.P;
     const int tile_stride = SLOTS * (int)gridDim.x;   // distance between consecutive tiles of one slot
 
@@ -130,74 +192,74 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 4 * C; i += Cfg::THREADS) s_c1[i] = make_float2(wsum1[i], p.b1[i]);
+    for (int i = tid; i < 2 * C; i += Cfg::THREADS) s_c1[i] = make_float4(wsum1[2 * i], wsum1[2 * i + 1], p.b1[2 * i], p.b1[2 * i + 1]);
     for (int i = tid; i < C; i += Cfg::THREADS) s_c2[i] = make_float2(p.b2[i], p.gamma[i]);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
 
-    if (warp >= 8 && warp < 10) {
+    // register re-allocation between the warpgroups: the MMA / loader warps need few registers, the epilogue warps hold the chunk
+    // (32 accumulator values + their hi/lo terms) AND the prefetched residual rows: 4 x 40 + 8 x 232 = 12 x 168
+    if (warp >= 8) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");   // one instruction for the whole warpgroup (warps 8-11)
+      if (warp < 10) {
         // ================================================================== MMA warp of slot (warp - 8); one lane issues
         const int slot = warp - 8;
         if (slot < SLOTS) {
             MlpBars& bs = bars[slot];
             constexpr uint32_t idesc1 = tf32_idesc(32), idesc2 = tf32_idesc(C);
             const uint32_t w1r_s = smem_u32(w1r), w2r_s = smem_u32(w2r);
-            const uint32_t t_slot = tmem_d + (uint32_t)(slot * SLOT_COLS);
+            // __shfl_sync(.., 0) tells the compiler the TMEM base (read from shared memory) is warp-uniform
+            const uint32_t t_slot = __shfl_sync(0xffffffffu, tmem_d, 0) + (uint32_t)(slot * SLOT_COLS);
             uint32_t q1 = 0, q2 = 0;   // weight chunks consumed so far (ring positions)
             int k = 0;                 // tiles of this slot so far
+            const uint32_t elected = lane == 0 ? 1u : 0u;
             // GEMM 1 of hidden chunk j: accumulator of group sg <- XA . W1[:, 32j .. 32j+31]
             auto gemm1 = [&](int j, int sg) {
                 const uint32_t s = RESIDENT ? (uint32_t)j : q1 % S1;
-                if (!RESIDENT || k == 0) mbar_wait(smem_u32(&bar_w1_full[s]), RESIDENT ? 0u : (q1 / S1) & 1u);
-                if (lane == 0) {
-                    const uint32_t b_hi = w1r_s + s * (uint32_t)W_STAGE * 4u;
-                    const uint64_t dh = kmajor_desc(b_hi, 32, 0), dl = kmajor_desc(b_hi + W_HALF_BYTES, 32, 0);
-                    const uint32_t acc = t_slot + (uint32_t)(G0 + sg * 96);
+                if (!RESIDENT || k == 0) mlp_wait(smem_u32(&bar_w1_full[s]), RESIDENT ? 0u : (q1 / S1) & 1u);
+                const uint32_t b_hi = w1r_s + s * (uint32_t)W_STAGE * 4u;
+                const uint64_t dh = kmajor_desc(b_hi, 32, 0), dl = kmajor_desc(b_hi + W_HALF_BYTES, 32, 0);
+                const uint32_t acc = t_slot + (uint32_t)(G0 + sg * 96);
 #pragma unroll
-                    for (int kc = 0; kc < KC; ++kc) {
+                for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint32_t ah = t_slot + (uint32_t)(XA0 + kc * 32 + ks * 8), al = ah + 16u;
-                            const uint64_t off = (uint64_t)((kc * 2048 + ks * 1024) >> 4);   // the descriptor's address field counts 16-byte units
-                            mma_tf32_ts(acc, ah, dh + off, idesc1, (kc > 0 || ks > 0) ? 1u : 0u);
-                            mma_tf32_ts(acc, al, dh + off, idesc1, 1u);
-                            mma_tf32_ts(acc, ah, dl + off, idesc1, 1u);
-                        }
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t ah = t_slot + (uint32_t)(XA0 + kc * 32 + ks * 8), al = ah + 16u;
+                        const uint64_t off = (uint64_t)((kc * 2048 + ks * 1024) >> 4);   // the descriptor's address field counts 16-byte units
+                        mlp_mma(acc, ah, dh + off, idesc1, (kc > 0 || ks > 0) ? 1u : 0u, elected);
+                        mlp_mma(acc, al, dh + off, idesc1, 1u, elected);
+                        mlp_mma(acc, ah, dl + off, idesc1, 1u, elected);
                     }
-                    tc_commit(smem_u32(&bs.acc1_full[sg]));
-                    if (!RESIDENT) tc_commit(smem_u32(&bar_w1_free[s]));
-                    if (j == NJ - 1) tc_commit(smem_u32(&bs.xa_free));   // every GEMM 1 of the tile has read XA
                 }
-                __syncwarp();
+                mlp_commit(smem_u32(&bs.acc1_full[sg]), elected);
+                if (!RESIDENT) mlp_commit(smem_u32(&bar_w1_free[s]), elected);
+                if (j == NJ - 1) mlp_commit(smem_u32(&bs.xa_free), elected);   // every GEMM 1 of the tile has read XA
                 ++q1;
             };
             // GEMM 2 of hidden chunk j: output accumulator `buf` (+)= A2 of group sg . W2[32j .. 32j+31, :]
             auto gemm2 = [&](int j, int sg, int buf) {
                 const uint32_t s = RESIDENT ? (uint32_t)j : q2 % S2;
-                if (!RESIDENT || k == 0) mbar_wait(smem_u32(&bar_w2_full[s]), RESIDENT ? 0u : (q2 / S2) & 1u);
-                if (lane == 0) {
-                    const uint32_t b_hi = w2r_s + s * (uint32_t)W_STAGE * 4u;
-                    const uint64_t dh = kmajor_desc(b_hi, C, 0), dl = kmajor_desc(b_hi + W_HALF_BYTES, C, 0);
-                    const uint32_t a2 = t_slot + (uint32_t)(G0 + sg * 96 + 32);
-                    const uint32_t acc = t_slot + (uint32_t)(buf * C);
+                if (!RESIDENT || k == 0) mlp_wait(smem_u32(&bar_w2_full[s]), RESIDENT ? 0u : (q2 / S2) & 1u);
+                const uint32_t b_hi = w2r_s + s * (uint32_t)W_STAGE * 4u;
+                const uint64_t dh = kmajor_desc(b_hi, C, 0), dl = kmajor_desc(b_hi + W_HALF_BYTES, C, 0);
+                const uint32_t a2 = t_slot + (uint32_t)(G0 + sg * 96 + 32);
+                const uint32_t acc = t_slot + (uint32_t)(buf * C);
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
+                for (int kk = 0; kk < 2; ++kk) {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint32_t ah = a2 + (uint32_t)(kk * 16 + ks * 8), al = ah + 32u;
-                            const uint64_t off = (uint64_t)((kk * C * 64 + ks * 2 * (C / 8) * 128) >> 4);
-                            mma_tf32_ts(acc, ah, dh + off, idesc2, (j > 0 || kk > 0 || ks > 0) ? 1u : 0u);
-                            mma_tf32_ts(acc, al, dh + off, idesc2, 1u);
-                            mma_tf32_ts(acc, ah, dl + off, idesc2, 1u);
-                        }
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t ah = a2 + (uint32_t)(kk * 16 + ks * 8), al = ah + 32u;
+                        const uint64_t off = (uint64_t)((kk * C * 64 + ks * 2 * (C / 8) * 128) >> 4);
+                        mlp_mma(acc, ah, dh + off, idesc2, (j > 0 || kk > 0 || ks > 0) ? 1u : 0u, elected);
+                        mlp_mma(acc, al, dh + off, idesc2, 1u, elected);
+                        mlp_mma(acc, ah, dl + off, idesc2, 1u, elected);
                     }
-                    tc_commit(smem_u32(&bs.a2_free[sg]));
-                    if (!RESIDENT) tc_commit(smem_u32(&bar_w2_free[s]));
-                    if (j == NJ - 1) tc_commit(smem_u32(&bs.acc2_full[buf]));
                 }
-                __syncwarp();
+                mlp_commit(smem_u32(&bs.a2_free[sg]), elected);
+                if (!RESIDENT) mlp_commit(smem_u32(&bar_w2_free[s]), elected);
+                if (j == NJ - 1) mlp_commit(smem_u32(&bs.acc2_full[buf]), elected);
                 ++q2;
             };
 #pragma unroll 1
@@ -232,7 +294,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
                 }
             }
         }
-    } else if (warp >= 10) {
+      } else {
         // ================================================================== loader warps: activation tiles per slot (+ weights: warp 10)
         const int slot = warp - 10;
         if (lane == 0 && slot < SLOTS) {
@@ -242,7 +304,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             int k = 0;
             auto load_x = [&](int item, int t) {
                 const int pt = item % n_pt, b = item / n_pt;
-                if (t > 0) mbar_wait(smem_u32(&bs.x_empty), (uint32_t)(t - 1) & 1u);   // every group of the slot has read the previous tile
+                if (t > 0) mlp_wait(smem_u32(&bs.x_empty), (uint32_t)(t - 1) & 1u);   // every group of the slot has read the previous tile
                 const uint32_t full = smem_u32(&bs.x_full);
                 tma_mbar_expect_tx(full, (uint32_t)C * TC_M * 4u);   // boxes are always complete: out-of-range pixels are zero-filled
 #pragma unroll
@@ -253,7 +315,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
                 uint64_t* fullb = first ? bar_w1_full : bar_w2_full;
                 uint64_t* freeb = first ? bar_w1_free : bar_w2_free;
                 const uint32_t s = RESIDENT ? (uint32_t)j : q % (uint32_t)ns;
-                if (!RESIDENT && q >= (uint32_t)ns) mbar_wait(smem_u32(&freeb[s]), (q / (uint32_t)ns - 1u) & 1u);   // the MMAs that read the stage are done
+                if (!RESIDENT && q >= (uint32_t)ns) mlp_wait(smem_u32(&freeb[s]), (q / (uint32_t)ns - 1u) & 1u);   // the MMAs that read the stage are done
                 const uint32_t full = smem_u32(&fullb[s]);
                 const uint32_t dst = (first ? w1r_s : w2r_s) + s * (uint32_t)W_STAGE * 4u;
                 const float* hi = (first ? w1_hi : w2_hi) + (long long)j * (C * 32);
@@ -298,8 +360,10 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             }
         }
         __syncwarp();
+      }
     } else {
         // ================================================================== epilogue groups (thread = pixel = TMEM lane)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
         const int g = warp >> 2, wq = warp & 3, px = wq * 32 + lane;
         const int slot = Cfg::TWO_SLOTS ? g : 0, sg = Cfg::TWO_SLOTS ? 0 : g;
         MlpBars& bs = bars[slot];
@@ -319,7 +383,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             it.b = item / n_pt;
             it.pp = pt * TC_M + px;
             it.p_ok = it.pp < P;
-            mbar_wait(smem_u32(&bs.x_full), (uint32_t)t & 1u);
+            mlp_wait(smem_u32(&bs.x_full), (uint32_t)t & 1u);
             if (t > 0) mlp_wait_tc(smem_u32(&bs.xa_free), (uint32_t)(t - 1) & 1u);   // GEMM 1 of the previous tile no longer reads XA
             const float* gs = xs_slot + px;
             // LayerNorm running sums, shifted by the pixel's first channel to avoid cancellation; two partial sums per statistic
@@ -367,35 +431,37 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             it.ms = (shift + t1) * it.rs;
             return it;
         };
+        // residual rows of this group's output units, requested at the top of a tile's last chunk and consumed by its output epilogue
+        // (v2 issued them right before the accumulator read: 6 % of all stall samples sat on their first use)
+        constexpr int NU = C / 16 / SG;   // 16-column output units per group
+        float rr[NU * 16];
+        auto load_res = [&](const Item& it) {
+            if (it.p_ok) {
+                const float* rptr = p.res + (long long)it.b * p.res_bs + it.pp;
+#pragma unroll
+                for (int n = 0; n < NU; ++n) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) rr[n * 16 + i] = __ldg(rptr + (long long)(16 * (sg + n * SG) + i) * P);
+                }
+            }
+        };
         // output epilogue of tile t_k: this group's 16-column units of accumulator k % NBUF -> + b2, * gamma, + residual -> stores
         auto final_epilogue = [&](const Item& done, int t_k) {
             const int buf = t_k % NBUF;
-            const float* rptr = p.res + (long long)done.b * p.res_bs + done.pp;
             float* optr = p.out + (long long)done.b * p.out_bs + done.pp;
-            float rr[16];
-            if (done.p_ok) {   // first unit's residuals before the accumulator wait
-#pragma unroll
-                for (int i = 0; i < 16; ++i) rr[i] = __ldg(rptr + (long long)(16 * sg + i) * P);
-            }
             mlp_wait_tc(smem_u32(&bs.acc2_full[buf]), (uint32_t)(t_k / NBUF) & 1u);
-#pragma unroll 1
-            for (int uu = sg; uu < C / 16; uu += SG) {
+#pragma unroll
+            for (int n = 0; n < NU; ++n) {
+                const int uu = sg + n * SG;
                 uint32_t r[16];
                 tmem_ld16(t_lane + (uint32_t)(buf * C + 16 * uu), r);
                 if (done.p_ok) {
-                    float y[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 c = s_c2[16 * uu + i];
                         // the GEMM kernel's epilogue with rs = scale = 1, ms = 0 (acc + b2), then gamma * y + res
-                        y[i] = fmaf(c.y, __uint_as_float(r[i]) + c.x, rr[i]);
+                        optr[(long long)(16 * uu + i) * P] = fmaf(c.y, __uint_as_float(r[i]) + c.x, rr[n * 16 + i]);
                     }
-                    if (uu + SG < C / 16) {   // next unit's residuals before this unit's stores
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) rr[i] = __ldg(rptr + (long long)(16 * (uu + SG) + i) * P);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) optr[(long long)(16 * uu + i) * P] = y[i];
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -416,7 +482,10 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             for (int r = 0; r < R; ++r, ++u) {
                 const int j = r * SG + sg;
                 // the next tile's A operand before the last chunk: the chunk stream then crosses the tile boundary without a gap
-                if (r == R - 1 && next < total_items) nxt = produce_xa(next, k + 1);
+                if (r == R - 1) {
+                    load_res(cur);
+                    if (next < total_items) nxt = produce_xa(next, k + 1);
+                }
                 // ---- hidden chunk j: accumulator -> LayerNorm fix-up + bias + GELU -> hi/lo A operand of GEMM 2
                 mlp_wait_tc(smem_u32(&bs.acc1_full[sg]), u & 1u);
                 uint32_t ra[16], rb[16];
@@ -425,17 +494,23 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mlp_mbar_arrive(smem_u32(&bs.acc1_drained[sg]));   // GEMM 1 of this group's next chunk may start now
+                const float2 rs2 = make_float2(cur.rs, cur.rs), nms2 = make_float2(-cur.ms, -cur.ms);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float2 c = s_c1[j * 32 + 16 * h + i];
-                        // same expression as the GEMM kernel's epilogue with scale = 1: act(rs * acc - ms * wsum + bias)
-                        float y = fmaf(cur.rs, __uint_as_float(h == 0 ? ra[i] : rb[i]), fmaf(-cur.ms, c.x, c.y));
-                        y = apply_act(y, ACT_GELU);
-                        hi[i] = __float_as_uint(y) & 0xffffe000u;
-                        lo[i] = __float_as_uint(y - __uint_as_float(hi[i]));
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 c = s_c1[j * 16 + 8 * h + i];
+                        const float2 a = h == 0 ? make_float2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]))
+                                                : make_float2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
+                        // same expression as the GEMM kernel's epilogue with scale = 1: act(rs * acc - ms * wsum + bias), two columns at a time
+                        float2 y = __ffma2_rn(rs2, a, __ffma2_rn(nms2, make_float2(c.x, c.y), make_float2(c.z, c.w)));
+                        y = mlp_gelu2(y);
+                        hi[2 * i] = __float_as_uint(y.x) & 0xffffe000u;
+                        hi[2 * i + 1] = __float_as_uint(y.y) & 0xffffe000u;
+                        const float2 l = __ffma2_rn(make_float2(__uint_as_float(hi[2 * i]), __uint_as_float(hi[2 * i + 1])), make_float2(-1.0f, -1.0f), y);   // y - hi, exact
+                        lo[2 * i] = __float_as_uint(l.x);
+                        lo[2 * i + 1] = __float_as_uint(l.y);
                     }
                     if (h == 0 && u > 0) mlp_wait_tc(smem_u32(&bs.a2_free[sg]), (u - 1u) & 1u);   // GEMM 2 of the previous chunk has read the slot
                     tmem_st16(t_a2 + (uint32_t)(16 * h), hi);
