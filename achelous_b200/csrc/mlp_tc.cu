@@ -495,27 +495,33 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
                 __syncwarp();
                 if (lane == 0) mlp_mbar_arrive(smem_u32(&bs.acc1_drained[sg]));   // GEMM 1 of this group's next chunk may start now
                 const float2 rs2 = make_float2(cur.rs, cur.rs), nms2 = make_float2(-cur.ms, -cur.ms);
+                // all 16 column pairs as independent chains in ONE block (v3 split them in two halves around the A2-slot wait: ncu showed
+                // 31 % of the epilogue warps' samples on fixed-latency dependencies - with two warps per scheduler the chunk needs the ILP),
+                // and only then the wait for GEMM 2 of the previous chunk, which by now has long completed
+                uint32_t hi0[16], lo0[16], hi1[16], lo1[16];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t hi[16], lo[16];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 c = s_c1[j * 16 + 8 * h + i];
-                        const float2 a = h == 0 ? make_float2(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1]))
-                                                : make_float2(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]));
-                        // same expression as the GEMM kernel's epilogue with scale = 1: act(rs * acc - ms * wsum + bias), two columns at a time
-                        float2 y = __ffma2_rn(rs2, a, __ffma2_rn(nms2, make_float2(c.x, c.y), make_float2(c.z, c.w)));
-                        y = mlp_gelu2(y);
-                        hi[2 * i] = __float_as_uint(y.x) & 0xffffe000u;
-                        hi[2 * i + 1] = __float_as_uint(y.y) & 0xffffe000u;
-                        const float2 l = __ffma2_rn(make_float2(__uint_as_float(hi[2 * i]), __uint_as_float(hi[2 * i + 1])), make_float2(-1.0f, -1.0f), y);   // y - hi, exact
-                        lo[2 * i] = __float_as_uint(l.x);
-                        lo[2 * i + 1] = __float_as_uint(l.y);
+                for (int i = 0; i < 16; ++i) {
+                    const float4 c = s_c1[j * 16 + i];
+                    const float2 a = i < 8 ? make_float2(__uint_as_float(ra[2 * (i & 7)]), __uint_as_float(ra[2 * (i & 7) + 1]))
+                                           : make_float2(__uint_as_float(rb[2 * (i & 7)]), __uint_as_float(rb[2 * (i & 7) + 1]));
+                    // same expression as the GEMM kernel's epilogue with scale = 1: act(rs * acc - ms * wsum + bias), two columns at a time
+                    float2 y = __ffma2_rn(rs2, a, __ffma2_rn(nms2, make_float2(c.x, c.y), make_float2(c.z, c.w)));
+                    y = mlp_gelu2(y);
+                    const uint32_t h0 = __float_as_uint(y.x) & 0xffffe000u, h1 = __float_as_uint(y.y) & 0xffffe000u;
+                    const float2 l = __ffma2_rn(make_float2(__uint_as_float(h0), __uint_as_float(h1)), make_float2(-1.0f, -1.0f), y);   // y - hi, exact
+                    if (i < 8) {
+                        hi0[2 * (i & 7)] = h0, hi0[2 * (i & 7) + 1] = h1;
+                        lo0[2 * (i & 7)] = __float_as_uint(l.x), lo0[2 * (i & 7) + 1] = __float_as_uint(l.y);
+                    } else {
+                        hi1[2 * (i & 7)] = h0, hi1[2 * (i & 7) + 1] = h1;
+                        lo1[2 * (i & 7)] = __float_as_uint(l.x), lo1[2 * (i & 7) + 1] = __float_as_uint(l.y);
                     }
-                    if (h == 0 && u > 0) mlp_wait_tc(smem_u32(&bs.a2_free[sg]), (u - 1u) & 1u);   // GEMM 2 of the previous chunk has read the slot
-                    tmem_st16(t_a2 + (uint32_t)(16 * h), hi);
-                    tmem_st16(t_a2 + (uint32_t)(32 + 16 * h), lo);
                 }
+                if (u > 0) mlp_wait_tc(smem_u32(&bs.a2_free[sg]), (u - 1u) & 1u);   // GEMM 2 of the previous chunk has read the slot
+                tmem_st16(t_a2, hi0);
+                tmem_st16(t_a2 + 16u, hi1);
+                tmem_st16(t_a2 + 32u, lo0);
+                tmem_st16(t_a2 + 48u, lo1);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
