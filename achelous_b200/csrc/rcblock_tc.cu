@@ -38,7 +38,9 @@ constexpr int RCT_TW = 16, RCT_TH = 8;   // pixel tile (RCT_TW * RCT_TH == TC_M)
 constexpr int RCT_R = 3;                 // halo of the staged window: 1 (3x3 tap) + |offset| < 2 + the +1 bilinear corner
 constexpr int RCT_WW = RCT_TW + 2 * RCT_R, RCT_WH = RCT_TH + 2 * RCT_R;
 
-template <int C, int STAGES>
+// PK = k handed to the tensor core per push (16, or 32 with a single A stage: C = 3 has K = 27, so each of its two GEMMs is ONE push -
+// half the CTA barriers, tcgen05.wait::st and elected-thread MMA issues per tile)
+template <int C, int STAGES, int PK>
 __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, const float* __restrict__ wom_hi,
                                                            const float* __restrict__ wom_lo, const float* __restrict__ wreg_hi,
                                                            const float* __restrict__ wreg_lo, int n_tx, int n_ty, int total_items) {
@@ -47,7 +49,8 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     constexpr int CP = (C + 3) & ~3;
     constexpr int Q = CP / 4;
     constexpr int B_ELEMS = RCT_N * TC_KC;
-    static_assert(RCT_ACOL + STAGES * 32 <= RCT_TMEM_COLS, "A stages do not fit the TMEM allocation");
+    static_assert(PK == 16 || PK == 32, "k per push");
+    static_assert(RCT_ACOL + STAGES * 2 * PK <= RCT_TMEM_COLS, "A stages do not fit the TMEM allocation");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* b_all = reinterpret_cast<float*>(smem_raw);           // [2 GEMMs][NCH][hi | lo][B_ELEMS]
     float4* win = reinterpret_cast<float4*>(b_all + 2 * NCH * 2 * B_ELEMS);   // [Q][RCT_WH][RCT_WW] pooled window (zero outside the image)
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     const int H = p.H, W = p.W, P = H * W;
 
     // hands the 16 k in vbuf (this thread's pixel) to the tensor core as chunk `chunk` of GEMM `g`
-    auto push_chunk = [&](const float (&vbuf)[TC_KC], int g, int chunk) {
+    auto push_chunk = [&](const float (&vbuf)[PK], int g, int chunk) {   // chunk counts pushes of PK k
         const uint32_t s = n % STAGES;
         if (n >= (uint32_t)STAGES) {   // the MMAs that read this A stage are done
             mbar_wait(smem_u32(&mbar[s]), (n / STAGES - 1u) & 1u);
@@ -107,26 +110,31 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
         // The A operand goes to TENSOR memory: this thread's lane, 16 hi columns then 16 lo columns - no shared-memory
         // store, no proxy fence, and the MMA does not re-read A through the shared-memory pipe (ncu on the shared-memory
         // A ring: l1tex 83 % busy, of which ~35 % were the tensor core's own operand reads at N = 32).
-        uint32_t hi[TC_KC], lo[TC_KC];
+        const uint32_t a_col = (uint32_t)RCT_ACOL + s * (2u * PK);   // stage: PK hi columns, then PK lo columns
 #pragma unroll
-        for (int j = 0; j < TC_KC; ++j) {
-            hi[j] = __float_as_uint(vbuf[j]) & 0xffffe000u;
-            lo[j] = __float_as_uint(vbuf[j] - __uint_as_float(hi[j]));
+        for (int h = 0; h < PK / 16; ++h) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                hi[j] = __float_as_uint(vbuf[16 * h + j]) & 0xffffe000u;
+                lo[j] = __float_as_uint(vbuf[16 * h + j] - __uint_as_float(hi[j]));
+            }
+            tmem_st16(t_lane + a_col + 16u * h, hi);
+            tmem_st16(t_lane + a_col + PK + 16u * h, lo);
         }
-        const uint32_t a_col = (uint32_t)RCT_ACOL + s * 32u;
-        tmem_st16(t_lane + a_col, hi);
-        tmem_st16(t_lane + a_col + 16u, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t b_hi_s = b_all_s + (uint32_t)((g * NCH + chunk) * 2) * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
             const uint32_t col = tmem_d + (uint32_t)(g * RCT_N);
 #pragma unroll
-            for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                const uint32_t ah = tmem_d + a_col + (uint32_t)ks * 8u, al = ah + 16u;
-                const uint64_t bh = kmajor_desc(b_hi_s, RCT_N, ks), bl = kmajor_desc(b_lo_s, RCT_N, ks);
+            for (int ks = 0; ks < PK / 8; ++ks) {
+                const int c16 = chunk * (PK / 16) + ks / 2;   // 16-k weight tile (tiles past NCH do not exist: their k are zero padding)
+                if (c16 >= NCH) break;
+                const uint32_t b_hi_s = b_all_s + (uint32_t)((g * NCH + c16) * 2) * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
+                const uint32_t ah = tmem_d + a_col + (uint32_t)ks * 8u, al = ah + PK;
+                const uint64_t bh = kmajor_desc(b_hi_s, RCT_N, ks & 1), bl = kmajor_desc(b_lo_s, RCT_N, ks & 1);
                 mma_tf32_ts(col, ah, bh, idesc, (chunk == 0 && ks == 0) ? 0u : 1u);
                 mma_tf32_ts(col, al, bh, idesc, 1u);
                 mma_tf32_ts(col, ah, bl, idesc, 1u);
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
 
         // ---- GEMM 1: offsets / modulators = 3x3 conv of the pooled map (implicit im2col, k = tap*C + ch, zero padding)
         {
-            float vbuf[TC_KC];
+            float vbuf[PK];
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const float4* src = win + (ly_ + RCT_R + t / 3 - 1) * RCT_WW + (lx_ + RCT_R + t % 3 - 1);
@@ -197,13 +205,13 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
                     for (int e = 0; e < 4; ++e) {
                         if (q * 4 + e < C) {
                             const int k = t * C + q * 4 + e;   // compile-time
-                            vbuf[k % TC_KC] = v[e];
-                            if ((k % TC_KC) == TC_KC - 1 || k == K1 - 1) {
+                            vbuf[k % PK] = v[e];
+                            if ((k % PK) == PK - 1 || k == K1 - 1) {
                                 if (k == K1 - 1) {
 #pragma unroll
-                                    for (int z = (k % TC_KC) + 1; z < TC_KC; ++z) vbuf[z] = 0.f;
+                                    for (int z = (k % PK) + 1; z < PK; ++z) vbuf[z] = 0.f;
                                 }
-                                push_chunk(vbuf, 0, k / TC_KC);
+                                push_chunk(vbuf, 0, k / PK);
                             }
                         }
                     }
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
 
         // ---- modulated deformable sampling, k = tap*C + ch, streamed 16 k at a time into GEMM 2
         {
-            float vbuf[TC_KC];
+            float vbuf[PK];
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
                 const float py = (float)(y - 1 + t / 3) + om[2 * t];
@@ -241,45 +249,63 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
                 // four corners are immediate offsets from one shared-memory address.
                 const int ry0 = y0 - wy0, rx0 = x0 - wx0;
                 const bool inwin = (unsigned)ry0 < (unsigned)(RCT_WH - 1) && (unsigned)rx0 < (unsigned)(RCT_WW - 1);
-                float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
-                const float4* wbase = win + ry0 * RCT_WW + rx0;
-                int i00 = 0, i01 = 0, i10 = 0, i11 = 0;
-                if (!inwin) {
-                    // offset beyond the halo: per-corner validity and clamped global gathers (dcn semantics spelled out)
+                const float w00 = hy * hx, w01 = hy * lx, w10 = ly * hx, w11 = ly * lx;
+                // Offsets beyond the halo are rare; the global-gather fallback is a WARP-UNIFORM branch, so the fast path carries none
+                // of its instructions (ncu on the if-converted version: 36 predicated-off LDG and ~300 index instructions per tile,
+                // a quarter of everything the kernel issued).
+                float sv[Q][4];   // bilinear sample of every channel at this tap (before the modulator)
+                if (__any_sync(0xffffffffu, !inwin)) {
+                    // per-corner validity and clamped global gathers (dcn semantics spelled out); in-window lanes read the window
                     const bool in = (py > -1.f) && (py < (float)H) && (px > -1.f) && (px < (float)W);
                     const bool y0ok = in && y0 >= 0, y1ok = in && (y0 + 1 <= H - 1);
                     const bool x0ok = x0 >= 0, x1ok = (x0 + 1 <= W - 1);
-                    w00 = (y0ok && x0ok) ? w00 : 0.f;
-                    w01 = (y0ok && x1ok) ? w01 : 0.f;
-                    w10 = (y1ok && x0ok) ? w10 : 0.f;
-                    w11 = (y1ok && x1ok) ? w11 : 0.f;
+                    const float v00 = (inwin || (y0ok && x0ok)) ? w00 : 0.f, v01 = (inwin || (y0ok && x1ok)) ? w01 : 0.f;
+                    const float v10 = (inwin || (y1ok && x0ok)) ? w10 : 0.f, v11 = (inwin || (y1ok && x1ok)) ? w11 : 0.f;
                     const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
                     const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
-                    i00 = (yc0 * W + xc0) * Q, i01 = (yc0 * W + xc1) * Q, i10 = (yc1 * W + xc0) * Q, i11 = (yc1 * W + xc1) * Q;
+                    const int i00 = (yc0 * W + xc0) * Q, i01 = (yc0 * W + xc1) * Q, i10 = (yc1 * W + xc0) * Q, i11 = (yc1 * W + xc1) * Q;
+                    const float4* wbase = win + (inwin ? ry0 * RCT_WW + rx0 : 0);
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        float4 a4, b4, c4, d4;
+                        if (inwin) {
+                            const float4* wq = wbase + q * (RCT_WH * RCT_WW);
+                            a4 = wq[0], b4 = wq[1], c4 = wq[RCT_WW], d4 = wq[RCT_WW + 1];
+                        } else {
+                            a4 = __ldg(pooled + i00 + q), b4 = __ldg(pooled + i01 + q), c4 = __ldg(pooled + i10 + q), d4 = __ldg(pooled + i11 + q);
+                        }
+                        sv[q][0] = v00 * a4.x + v01 * b4.x + v10 * c4.x + v11 * d4.x;
+                        sv[q][1] = v00 * a4.y + v01 * b4.y + v10 * c4.y + v11 * d4.y;
+                        sv[q][2] = v00 * a4.z + v01 * b4.z + v10 * c4.z + v11 * d4.z;
+                        sv[q][3] = v00 * a4.w + v01 * b4.w + v10 * c4.w + v11 * d4.w;
+                    }
+                } else {
+                    const float4* wbase = win + ry0 * RCT_WW + rx0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float4* wq = wbase + q * (RCT_WH * RCT_WW);
+                        const float4 a4 = wq[0], b4 = wq[1], c4 = wq[RCT_WW], d4 = wq[RCT_WW + 1];
+                        sv[q][0] = w00 * a4.x + w01 * b4.x + w10 * c4.x + w11 * d4.x;
+                        sv[q][1] = w00 * a4.y + w01 * b4.y + w10 * c4.y + w11 * d4.y;
+                        sv[q][2] = w00 * a4.z + w01 * b4.z + w10 * c4.z + w11 * d4.z;
+                        sv[q][3] = w00 * a4.w + w01 * b4.w + w10 * c4.w + w11 * d4.w;
+                    }
                 }
+                // (the chunk hand-over contains CTA barriers: it stays outside the warp-dependent branch)
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    float4 a4, b4, c4, d4;
-                    if (inwin) {
-                        const float4* wq = wbase + q * (RCT_WH * RCT_WW);
-                        a4 = wq[0], b4 = wq[1], c4 = wq[RCT_WW], d4 = wq[RCT_WW + 1];
-                    } else {
-                        a4 = __ldg(pooled + i00 + q), b4 = __ldg(pooled + i01 + q), c4 = __ldg(pooled + i10 + q), d4 = __ldg(pooled + i11 + q);
-                    }
-                    const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
-                    const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         if (q * 4 + e < C) {
                             const int k = t * C + q * 4 + e;   // compile-time
                             // same expression as the SIMT kernel / torchvision: mask * bilinear value
-                            vbuf[k % TC_KC] = m * (w00 * a[e] + w01 * bb[e] + w10 * cc[e] + w11 * dd[e]);
-                            if ((k % TC_KC) == TC_KC - 1 || k == K1 - 1) {
+                            vbuf[k % PK] = m * sv[q][e];
+                            if ((k % PK) == PK - 1 || k == K1 - 1) {
                                 if (k == K1 - 1) {
 #pragma unroll
-                                    for (int z = (k % TC_KC) + 1; z < TC_KC; ++z) vbuf[z] = 0.f;
+                                    for (int z = (k % PK) + 1; z < PK; ++z) vbuf[z] = 0.f;
                                 }
-                                push_chunk(vbuf, 1, k / TC_KC);
+                                push_chunk(vbuf, 1, k / PK);
                             }
                         }
                     }
@@ -321,7 +347,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(RCT_TMEM_COLS) : "memory");
 }
 
-template <int C, int STAGES>
+template <int C, int STAGES, int PK>
 static int launch_rc_tc_s(const AchRcDeform& p, const float* wom_hi, const float* wom_lo, const float* wreg_hi, const float* wreg_lo,
                           cudaStream_t st) {
     constexpr int NCH = (C * 9 + TC_KC - 1) / TC_KC;
@@ -330,16 +356,16 @@ static int launch_rc_tc_s(const AchRcDeform& p, const float* wom_hi, const float
     static int ctas_per_wave_dev[ACH_MAX_DEVICES] = {};
     int& ctas_per_wave = ctas_per_wave_dev[current_device()];
     if (!ctas_per_wave) {
-        cudaFuncSetAttribute(rc_deform_tc_kernel<C, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(rc_deform_tc_kernel<C, STAGES, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        ctas_per_wave = sms * tc_ctas_per_sm(rc_deform_tc_kernel<C, STAGES>, 128, smem, RCT_TMEM_COLS);
+        ctas_per_wave = sms * tc_ctas_per_sm(rc_deform_tc_kernel<C, STAGES, PK>, 128, smem, RCT_TMEM_COLS);
     }
     const int n_tx = cdiv(p.W, RCT_TW), n_ty = cdiv(p.H, RCT_TH);
     const long long total = (long long)n_tx * n_ty * p.B;
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);
-    rc_deform_tc_kernel<C, STAGES><<<grid, 128, smem, st>>>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, n_tx, n_ty, (int)total);
+    rc_deform_tc_kernel<C, STAGES, PK><<<grid, 128, smem, st>>>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, n_tx, n_ty, (int)total);
     return check_launch("ach_rc_deform_tc");
 }
 
@@ -347,7 +373,8 @@ template <int C>
 static int launch_rc_tc(const AchRcDeform& p, const float* wom_hi, const float* wom_lo, const float* wreg_hi, const float* wreg_lo,
                         cudaStream_t st) {
     // two A stages in tensor memory (a 1-stage build was the better one only while A still lived in shared memory: DESIGN.md §7)
-    return launch_rc_tc_s<C, 2>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
+    if constexpr (C * 9 <= 32) return launch_rc_tc_s<C, 1, 32>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);   // one push per GEMM
+    else return launch_rc_tc_s<C, 2, 16>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
 }
 
 }  // namespace ach
