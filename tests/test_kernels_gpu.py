@@ -208,6 +208,7 @@ def test_dw_conv(case):
 # ------------------------------------------------------------------ conv_dense
 CD_CASES = [
     dict(B=2, Cin=3, H=320, W=320, O=32, k=4, s=4, p=0, ln=1),
+    dict(B=3, Cin=3, H=64, W=48, O=24, k=4, s=4, p=0, act=1, scale=1),   # patchify kernel, partial last CTA, O < 32
     dict(B=2, Cin=32, H=80, W=80, O=48, k=2, s=2, p=0),
     dict(B=2, Cin=96, H=20, W=20, O=176, k=2, s=2, p=0),
     dict(B=2, Cin=3, H=320, W=320, O=8, k=3, s=2, p=1),

@@ -41,7 +41,10 @@ int main(int argc, char** argv) {
                     {4, 32, 24, 16, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 32x24x16"}, {4, 24, 24, 8, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 24x24x8"},
                     {4, 24, 24, 4, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 24x24x4"}, {4, 24, 12, 16, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 24x12x16"},
                     {3, 24, 24, 16, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 24x24x16 (C*B folded)"}, {3, 24, 24, 8, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 24x24x8"},
-                    {3, 32, 24, 16, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 32x24x16"}};
+                    {3, 32, 24, 16, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "3d 32x24x16"},
+                    {4, 36, 33, 3, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 36x33x3"}, {4, 36, 32, 3, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 36x32x3"},
+                    {4, 32, 33, 3, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 32x33x3"}, {4, 36, 33, 4, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 36x33x4"},
+                    {4, 36, 33, 11, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 36x33x11"}, {4, 20, 18, 16, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "4d 20x18x16"}};
     for (const Case& cs : cases) {
         if (++idx != only && only >= 0) continue;
         alignas(64) CUtensorMap tm;
