@@ -45,6 +45,7 @@ struct MlpCfg {
     static constexpr int NBUF = (C == 32 || C == 64) ? 2 : 1;   // output accumulators per slot
     static constexpr int SLOT_COLS = NBUF * C + 2 * C + SG * 96;
     static constexpr bool RESIDENT = TWO_SLOTS;                 // all weight tiles stay in shared memory
+    static constexpr int CL = RESIDENT ? 1 : 2;                 // thread-block cluster: streamed weight tiles are multicast to CL CTAs
     static constexpr int S1 = RESIDENT ? NJ : 4;                // W1 stages
     static constexpr int S2 = RESIDENT ? NJ : 3;                // W2 stages
     static constexpr int W_STAGE = C * 64;                      // floats per stage: hi [C x 32] | lo [C x 32]
@@ -52,6 +53,7 @@ struct MlpCfg {
     static constexpr size_t SMEM = (size_t)(SLOTS * C * TC_M + (S1 + S2) * W_STAGE) * sizeof(float);
     static_assert(NJ % SG == 0 && R >= 2, "chunk rounds");
     static_assert(SLOTS * SLOT_COLS <= 512, "TMEM budget");
+    static_assert(CL == 1 || CL == 2, "the half-stage multicast protocol is written for pairs");
 };
 
 __device__ __forceinline__ void mlp_mbar_init(uint32_t mbar, uint32_t count) {
@@ -131,6 +133,46 @@ __device__ __forceinline__ float2 mlp_gelu2(float2 v) {
     return __ffma2_rn(h, erf, h);
 }
 
+__device__ __forceinline__ void mlp_commit_mc(uint32_t mbar, uint32_t elected, uint16_t cta_mask) {   // arrive on the barrier at this offset in the masked CTAs
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "setp.ne.b32 e, %1, 0;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t"
+        "}\n" ::"r"(mbar), "r"(elected), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void mlp_bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar), "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mlp_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void mlp_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// elect.sync: ONE lane of the (converged) warp gets true - and the compiler knows it, so tcgen05.mma / commit inside the branch are
+// emitted once, with uniform-register operands and no per-instruction ELECT / vote / branch "waterfall" (with `lane == 0` as the
+// predicate every UTCHMMA carried ~10 such instructions; ncu showed the single MMA warp of the C = 96 kernel issue-bound on them
+// while the tensor pipe sat at 25 % and the epilogue groups waited 60 % of the time for accumulators)
+__device__ __forceinline__ bool mlp_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 struct MlpBars {   // per slot
     uint64_t x_full, x_empty, xa_full, xa_free, acc2_full[2], acc2_empty[2];
     uint64_t acc1_full[2], acc1_drained[2], a2_full[2], a2_free[2];   // per group of the slot
@@ -139,12 +181,15 @@ struct MlpBars {   // per slot
 template <int C>
 __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
     mlp_tc_kernel(const AchMlp p, const float* __restrict__ w1_hi, const float* __restrict__ w1_lo, const float* __restrict__ w2_hi,
-                  const float* __restrict__ w2_lo, const float* __restrict__ wsum1, int n_pt, int total_items,
+                  const float* __restrict__ w2_lo, const float* __restrict__ wsum1, int n_pt, int real_items, int total_items,
                   const __grid_constant__ CUtensorMap tmx) {
+    // total_items bounds the tile loops; items >= real_items are phantom tiles (zero-filled loads, no stores): with a cluster every CTA
+    // runs the same number of tiles so that the multicast weight stream is consumed in lockstep
     using Cfg = MlpCfg<C>;
     constexpr int NJ = Cfg::NJ, KC = Cfg::KC, SLOTS = Cfg::SLOTS, SG = Cfg::SG, R = Cfg::R, NBUF = Cfg::NBUF;
     constexpr int S1 = Cfg::S1, S2 = Cfg::S2, W_STAGE = Cfg::W_STAGE, SLOT_COLS = Cfg::SLOT_COLS;
     constexpr bool RESIDENT = Cfg::RESIDENT;
+    constexpr int CL = Cfg::CL;
     constexpr int XA0 = NBUF * C, G0 = NBUF * C + 2 * C;         // column offsets inside a slot
     constexpr uint32_t W_HALF_BYTES = (uint32_t)C * 32u * 4u;    // hi (or lo) part of a weight stage
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -153,6 +198,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
     float* w2r = w1r + S1 * W_STAGE;                   // [S2][hi | lo]
     __shared__ __align__(8) MlpBars bars[SLOTS];
     __shared__ __align__(8) uint64_t bar_w1_full[S1], bar_w1_free[S1], bar_w2_full[S2], bar_w2_free[S2];
+    __shared__ __align__(8) uint64_t bar_w1_pfree[S1], bar_w2_pfree[S2];   // the peer CTA's MMAs have read the stage (this CTA multicasts into it)
     __shared__ uint32_t tmem_base_s;
     __shared__ float4 s_c1[2 * C];   // per PAIR of hidden columns {wsum1[n], wsum1[n+1], b1[n], b1[n+1]}
     __shared__ float2 s_c2[C];       // per output {b2, gamma}
@@ -185,10 +231,12 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
         for (int i = 0; i < S1; ++i) {
             mlp_mbar_init(smem_u32(&bar_w1_full[i]), 1);
             mlp_mbar_init(smem_u32(&bar_w1_free[i]), 1);
+            mlp_mbar_init(smem_u32(&bar_w1_pfree[i]), CL > 1 ? CL - 1 : 1);
         }
         for (int i = 0; i < S2; ++i) {
             mlp_mbar_init(smem_u32(&bar_w2_full[i]), 1);
             mlp_mbar_init(smem_u32(&bar_w2_free[i]), 1);
+            mlp_mbar_init(smem_u32(&bar_w2_pfree[i]), CL > 1 ? CL - 1 : 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -198,6 +246,8 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
+    const uint32_t crank = CL > 1 ? mlp_cluster_rank() : 0u;
+    if (CL > 1) mlp_cluster_sync();   // every CTA's barriers are initialised before the leader's first multicast lands
 
     // register re-allocation between the warpgroups: the MMA / loader warps need few registers, the epilogue warps hold the chunk
     // (32 accumulator values + their hi/lo terms) AND the prefetched residual rows: 4 x 40 + 8 x 232 = 12 x 168
@@ -214,7 +264,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             const uint32_t t_slot = __shfl_sync(0xffffffffu, tmem_d, 0) + (uint32_t)(slot * SLOT_COLS);
             uint32_t q1 = 0, q2 = 0;   // weight chunks consumed so far (ring positions)
             int k = 0;                 // tiles of this slot so far
-            const uint32_t elected = lane == 0 ? 1u : 0u;
+            const bool elected = mlp_elect_one();   // the same lane for the whole kernel: the warp is converged here
             // GEMM 1 of hidden chunk j: accumulator of group sg <- XA . W1[:, 32j .. 32j+31]
             auto gemm1 = [&](int j, int sg) {
                 const uint32_t s = RESIDENT ? (uint32_t)j : q1 % S1;
@@ -228,14 +278,22 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
                     for (int ks = 0; ks < 2; ++ks) {
                         const uint32_t ah = t_slot + (uint32_t)(XA0 + kc * 32 + ks * 8), al = ah + 16u;
                         const uint64_t off = (uint64_t)((kc * 2048 + ks * 1024) >> 4);   // the descriptor's address field counts 16-byte units
-                        mlp_mma(acc, ah, dh + off, idesc1, (kc > 0 || ks > 0) ? 1u : 0u, elected);
-                        mlp_mma(acc, al, dh + off, idesc1, 1u, elected);
-                        mlp_mma(acc, ah, dl + off, idesc1, 1u, elected);
+                        if (elected) {
+                            mma_tf32_ts(acc, ah, dh + off, idesc1, (kc > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32_ts(acc, al, dh + off, idesc1, 1u);
+                            mma_tf32_ts(acc, ah, dl + off, idesc1, 1u);
+                        }
                     }
                 }
-                mlp_commit(smem_u32(&bs.acc1_full[sg]), elected);
-                if (!RESIDENT) mlp_commit(smem_u32(&bar_w1_free[s]), elected);
-                if (j == NJ - 1) mlp_commit(smem_u32(&bs.xa_free), elected);   // every GEMM 1 of the tile has read XA
+                if (elected) {
+                    tc_commit(smem_u32(&bs.acc1_full[sg]));
+                    if (!RESIDENT) {
+                        tc_commit(smem_u32(&bar_w1_free[s]));
+                        if (CL > 1) mlp_commit_mc(smem_u32(&bar_w1_pfree[s]), 1u, (uint16_t)(1u << (crank ^ 1u)));   // tell the peer
+                    }
+                    if (j == NJ - 1) tc_commit(smem_u32(&bs.xa_free));   // every GEMM 1 of the tile has read XA
+                }
+                __syncwarp();
                 ++q1;
             };
             // GEMM 2 of hidden chunk j: output accumulator `buf` (+)= A2 of group sg . W2[32j .. 32j+31, :]
@@ -252,14 +310,22 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
                     for (int ks = 0; ks < 2; ++ks) {
                         const uint32_t ah = a2 + (uint32_t)(kk * 16 + ks * 8), al = ah + 32u;
                         const uint64_t off = (uint64_t)((kk * C * 64 + ks * 2 * (C / 8) * 128) >> 4);
-                        mlp_mma(acc, ah, dh + off, idesc2, (j > 0 || kk > 0 || ks > 0) ? 1u : 0u, elected);
-                        mlp_mma(acc, al, dh + off, idesc2, 1u, elected);
-                        mlp_mma(acc, ah, dl + off, idesc2, 1u, elected);
+                        if (elected) {
+                            mma_tf32_ts(acc, ah, dh + off, idesc2, (j > 0 || kk > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32_ts(acc, al, dh + off, idesc2, 1u);
+                            mma_tf32_ts(acc, ah, dl + off, idesc2, 1u);
+                        }
                     }
                 }
-                mlp_commit(smem_u32(&bs.a2_free[sg]), elected);
-                if (!RESIDENT) mlp_commit(smem_u32(&bar_w2_free[s]), elected);
-                if (j == NJ - 1) mlp_commit(smem_u32(&bs.acc2_full[buf]), elected);
+                if (elected) {
+                    tc_commit(smem_u32(&bs.a2_free[sg]));
+                    if (!RESIDENT) {
+                        tc_commit(smem_u32(&bar_w2_free[s]));
+                        if (CL > 1) mlp_commit_mc(smem_u32(&bar_w2_pfree[s]), 1u, (uint16_t)(1u << (crank ^ 1u)));
+                    }
+                    if (j == NJ - 1) tc_commit(smem_u32(&bs.acc2_full[buf]));
+                }
+                __syncwarp();
                 ++q2;
             };
 #pragma unroll 1
@@ -314,15 +380,27 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
                 const int ns = first ? S1 : S2;
                 uint64_t* fullb = first ? bar_w1_full : bar_w2_full;
                 uint64_t* freeb = first ? bar_w1_free : bar_w2_free;
+                uint64_t* pfreeb = first ? bar_w1_pfree : bar_w2_pfree;
                 const uint32_t s = RESIDENT ? (uint32_t)j : q % (uint32_t)ns;
-                if (!RESIDENT && q >= (uint32_t)ns) mlp_wait(smem_u32(&freeb[s]), (q / (uint32_t)ns - 1u) & 1u);   // the MMAs that read the stage are done
+                if (!RESIDENT && q >= (uint32_t)ns) {   // the MMAs that read the stage are done (re-arming the barrier needs that in every CTA)
+                    mlp_wait(smem_u32(&freeb[s]), (q / (uint32_t)ns - 1u) & 1u);
+                    if (CL > 1) mlp_wait(smem_u32(&pfreeb[s]), (q / (uint32_t)ns - 1u) & 1u);   // ... and in the peer, whose stage this CTA writes too
+                }
                 const uint32_t full = smem_u32(&fullb[s]);
                 const uint32_t dst = (first ? w1r_s : w2r_s) + s * (uint32_t)W_STAGE * 4u;
                 const float* hi = (first ? w1_hi : w2_hi) + (long long)j * (C * 32);
                 const float* lo = (first ? w1_lo : w2_lo) + (long long)j * (C * 32);
                 tma_mbar_expect_tx(full, 2u * W_HALF_BYTES);
-                mlp_bulk_g2s(dst, hi, W_HALF_BYTES, full);
-                mlp_bulk_g2s(dst + W_HALF_BYTES, lo, W_HALF_BYTES, full);
+                if (CL > 1) {
+                    // the two CTAs of a cluster each fetch HALF of the stage (rank 0 the hi tiles, rank 1 the lo tiles) and multicast it
+                    // into both ring stages, completing both barriers: per SM half the bulk-copy requests for the same weight stream
+                    // (the stream - 576 KB per tile at C = 96 - is latency bound: the rings hold 7 x 24 KB and cannot be deeper)
+                    if (crank == 0) mlp_bulk_g2s_mc(dst, hi, W_HALF_BYTES, full, (uint16_t)3);
+                    else mlp_bulk_g2s_mc(dst + W_HALF_BYTES, lo, W_HALF_BYTES, full, (uint16_t)3);
+                } else {
+                    mlp_bulk_g2s(dst, hi, W_HALF_BYTES, full);
+                    mlp_bulk_g2s(dst + W_HALF_BYTES, lo, W_HALF_BYTES, full);
+                }
                 ++q;
             };
             const int first_item = blockIdx.x + slot * (int)gridDim.x;
@@ -338,25 +416,48 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
 #pragma unroll 1
                 for (int item = first_item; item + tile_stride < total_items; item += tile_stride, ++k) load_x(item + tile_stride, k + 1);
             } else {
-                // weight chunks in exactly the order the MMA warp consumes them (a blocking wait on one ring can then never starve the other)
+                // streamed weights: this thread feeds the W1 ring (and the activation tiles), warp 11 the W2 ring - each blocks only on its
+                // own ring's free barriers, so both run as far ahead as their stages allow.  (A single thread issuing both rings in MMA
+                // order stalled the W1 prefetch behind the W2 stage that only frees at the end of a round: ~5 us per 2-chunk round
+                // where tensor core and epilogue need ~1.2 us.)
 #pragma unroll 1
                 for (int item = first_item; item < total_items; item += tile_stride, ++k) {
-                    const bool next_tile = item + tile_stride < total_items;
-                    if (k == 0) {
 #pragma unroll 1
-                        for (int sg = 0; sg < SG; ++sg) load_w(sg, true, q1);
-                    }
-                    if (next_tile) load_x(item + tile_stride, k + 1);
-#pragma unroll 1
-                    for (int r = 0; r < R; ++r) {
-                        if (r + 1 < R || next_tile) {
-#pragma unroll 1
-                            for (int sg = 0; sg < SG; ++sg) load_w(((r + 1) % R) * SG + sg, true, q1);
-                        }
-#pragma unroll 1
-                        for (int sg = 0; sg < SG; ++sg) load_w(r * SG + sg, false, q2);
+                    for (int j = 0; j < NJ; ++j) {
+                        load_w(j, true, q1);
+                        if (j == SG - 1 && item + tile_stride < total_items) load_x(item + tile_stride, k + 1);
                     }
                 }
+            }
+        } else if (lane == 0 && !RESIDENT && slot == 1) {
+            // ---- W2 ring (streamed weights only; with resident weights warp 11 is the second slot's activation loader above)
+            const uint32_t w1r_s = smem_u32(w1r), w2r_s = smem_u32(w2r);
+            uint32_t q2 = 0;
+            auto load_w2 = [&](int j) {
+                const uint32_t s = q2 % (uint32_t)S2;
+                if (q2 >= (uint32_t)S2) {
+                    mlp_wait(smem_u32(&bar_w2_free[s]), (q2 / (uint32_t)S2 - 1u) & 1u);
+                    if (CL > 1) mlp_wait(smem_u32(&bar_w2_pfree[s]), (q2 / (uint32_t)S2 - 1u) & 1u);
+                }
+                const uint32_t full = smem_u32(&bar_w2_full[s]);
+                const uint32_t dst = w2r_s + s * (uint32_t)W_STAGE * 4u;
+                const float* hi = w2_hi + (long long)j * (C * 32);
+                const float* lo = w2_lo + (long long)j * (C * 32);
+                tma_mbar_expect_tx(full, 2u * W_HALF_BYTES);
+                if (CL > 1) {
+                    if (crank == 0) mlp_bulk_g2s_mc(dst, hi, W_HALF_BYTES, full, (uint16_t)3);
+                    else mlp_bulk_g2s_mc(dst + W_HALF_BYTES, lo, W_HALF_BYTES, full, (uint16_t)3);
+                } else {
+                    mlp_bulk_g2s(dst, hi, W_HALF_BYTES, full);
+                    mlp_bulk_g2s(dst + W_HALF_BYTES, lo, W_HALF_BYTES, full);
+                }
+                ++q2;
+            };
+            (void)w1r_s;
+#pragma unroll 1
+            for (int item = blockIdx.x; item < total_items; item += tile_stride) {
+#pragma unroll 1
+                for (int j = 0; j < NJ; ++j) load_w2(j);
             }
         }
         __syncwarp();
@@ -382,7 +483,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             const int pt = item % n_pt;
             it.b = item / n_pt;
             it.pp = pt * TC_M + px;
-            it.p_ok = it.pp < P;
+            it.p_ok = it.pp < P && item < real_items;
             mlp_wait(smem_u32(&bs.x_full), (uint32_t)t & 1u);
             if (t > 0) mlp_wait_tc(smem_u32(&bs.xa_free), (uint32_t)(t - 1) & 1u);   // GEMM 1 of the previous tile no longer reads XA
             const float* gs = xs_slot + px;
@@ -547,6 +648,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(512) : "memory");
+    if (CL > 1) mlp_cluster_sync();   // no CTA leaves while a peer may still signal its barriers
 }
 
 template <int C>
@@ -573,8 +675,27 @@ static int launch_mlp(const AchMlp& p, const float* w1_hi, const float* w1_lo, c
     ACH_REQUIRE(total < (1LL << 30), "ach_mlp_tc: too many tiles");
     // persistent: one CTA per SM (the kernel owns all 512 TMEM columns); with two slots a CTA wants at least two tiles
     const long long want = Cfg::SLOTS == 2 ? (total + 1) / 2 : total;
-    const int grid = (int)(want < sms ? want : sms);
-    mlp_tc_kernel<C><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(p, w1_hi, w1_lo, w2_hi, w2_lo, wsum1, n_pt, (int)total, tmx);
+    int grid = (int)(want < sms ? want : sms);
+    long long bound = total;
+    if (Cfg::CL > 1) {   // whole clusters, and the same number of tiles (real or phantom) in every CTA
+        grid = (grid + Cfg::CL - 1) / Cfg::CL * Cfg::CL;
+        if (grid > sms) grid -= Cfg::CL;
+        bound = (total + grid - 1) / grid * grid;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Cfg::CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = Cfg::CL > 1 ? 1 : 0;
+    const int real_i = (int)total, bound_i = (int)bound;
+    cudaLaunchKernelEx(&cfg, mlp_tc_kernel<C>, p, w1_hi, w1_lo, w2_hi, w2_lo, wsum1, n_pt, real_i, bound_i, tmx);
     return check_launch("ach_mlp_tc");
 }
 
