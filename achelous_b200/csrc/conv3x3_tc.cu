@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(C3_THREADS, NT == 128 ? 2 : 3)
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float2 s_ep[NT];   // per output of the current tile: {scale, bias}
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = (int)tc_uniform((uint32_t)(tid >> 5)), lane = tid & 31;   // warp index provably uniform
     const int H = p.H, W = p.W, P = H * W;
     constexpr int A_COL0 = NT;
     constexpr int TMEM_COLS = c3_tmem_cols(NT);
@@ -86,8 +86,10 @@ __global__ void __launch_bounds__(C3_THREADS, NT == 128 ? 2 : 3)
     const uint32_t b_ring_s = smem_u32(b_ring);
 
     if (warp == C3_PROD / 32) {
-        // ================================================================== MMA + weight-TMA thread
-        if (lane == 0) {
+        // ================================================================== MMA + weight-TMA warp (warp-uniform loop, one elected lane issues: tc_common.cuh)
+        {
+            const bool elected = tc_elect_one();
+            const uint32_t tmem_u = tc_uniform(tmem_d);
             constexpr uint32_t idesc = tf32_idesc(NT);
             constexpr uint32_t B_LBO = (NT / 8) * 128;
             int pit = 0, p_item = blockIdx.x, p_c = 0;
@@ -99,13 +101,15 @@ __global__ void __launch_bounds__(C3_THREADS, NT == 128 ? 2 : 3)
                 const long long blk = ((long long)(p_item % n_ot) * n_chunks + p_c) * B_ELEMS;
                 const uint32_t full = smem_u32(&bar_full_b[sb]);
                 const uint32_t dst = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(2u * B_ELEMS * 4u) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                             "l"(w_hi + blk), "r"(B_ELEMS * 4u), "r"(full)
-                             : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + B_ELEMS * 4u),
-                             "l"(w_lo + blk), "r"(B_ELEMS * 4u), "r"(full)
-                             : "memory");
+                if (elected) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(2u * B_ELEMS * 4u) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                                 "l"(w_hi + blk), "r"(B_ELEMS * 4u), "r"(full)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + B_ELEMS * 4u),
+                                 "l"(w_lo + blk), "r"(B_ELEMS * 4u), "r"(full)
+                                 : "memory");
+                }
                 ++pit;
                 if (++p_c == n_chunks) {
                     p_c = 0;
@@ -128,19 +132,22 @@ __global__ void __launch_bounds__(C3_THREADS, NT == 128 ? 2 : 3)
                     mbar_wait(smem_u32(&bar_full_b[sb]), (uint32_t)(it / C3_SB) & 1u);
                     mbar_wait(smem_u32(&bar_full_a[sa]), (uint32_t)(it / C3_SA) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi_t = tmem_d + (uint32_t)(A_COL0 + sa * 32), a_lo_t = a_hi_t + 16u;
-                    const uint32_t b_hi_s = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
+                    const uint32_t a_hi_t = tmem_u + (uint32_t)(A_COL0 + sa * 32), a_lo_t = a_hi_t + 16u;
+                    const uint32_t b_hi_s = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u;
+                    const uint64_t dh = make_desc(b_hi_s, B_LBO, 128u, 0), dl = make_desc(b_hi_s + B_ELEMS * 4u, B_LBO, 128u, 0);
+                    if (elected) {
 #pragma unroll
-                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                        const uint32_t ah = a_hi_t + (uint32_t)ks * 8u, al = a_lo_t + (uint32_t)ks * 8u;
-                        const uint64_t bh = make_desc(b_hi_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
-                        const uint64_t bl = make_desc(b_lo_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
-                        mma_tf32_ts(tmem_d, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                        mma_tf32_ts(tmem_d, al, bh, idesc, 1u);
-                        mma_tf32_ts(tmem_d, ah, bl, idesc, 1u);
+                        for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                            const uint32_t ah = a_hi_t + (uint32_t)ks * 8u, al = a_lo_t + (uint32_t)ks * 8u;
+                            const uint64_t off = (uint64_t)((ks * 2 * B_LBO) >> 4);   // the descriptor's address field counts 16-byte units
+                            mma_tf32_ts(tmem_u, ah, dh + off, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32_ts(tmem_u, al, dh + off, idesc, 1u);
+                            mma_tf32_ts(tmem_u, ah, dl + off, idesc, 1u);
+                        }
+                        tc_commit(smem_u32(&bar_mma[sa]));
+                        if (c == n_chunks - 1) tc_commit(smem_u32(&bar_acc_full));
                     }
-                    tc_commit(smem_u32(&bar_mma[sa]));
-                    if (c == n_chunks - 1) tc_commit(smem_u32(&bar_acc_full));
+                    __syncwarp();
                 }
             }
         }

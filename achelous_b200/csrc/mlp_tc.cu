@@ -157,22 +157,6 @@ __device__ __forceinline__ void mlp_cluster_sync() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// elect.sync: ONE lane of the (converged) warp gets true - and the compiler knows it, so tcgen05.mma / commit inside the branch are
-// emitted once, with uniform-register operands and no per-instruction ELECT / vote / branch "waterfall" (with `lane == 0` as the
-// predicate every UTCHMMA carried ~10 such instructions; ncu showed the single MMA warp of the C = 96 kernel issue-bound on them
-// while the tensor pipe sat at 25 % and the epilogue groups waited 60 % of the time for accumulators)
-__device__ __forceinline__ bool mlp_elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-
 struct MlpBars {   // per slot
     uint64_t x_full, x_empty, xa_full, xa_free, acc2_full[2], acc2_empty[2];
     uint64_t acc1_full[2], acc1_drained[2], a2_full[2], a2_free[2];   // per group of the slot
@@ -264,7 +248,7 @@ __global__ void __launch_bounds__(MlpCfg<C>::THREADS, 1)
             const uint32_t t_slot = __shfl_sync(0xffffffffu, tmem_d, 0) + (uint32_t)(slot * SLOT_COLS);
             uint32_t q1 = 0, q2 = 0;   // weight chunks consumed so far (ring positions)
             int k = 0;                 // tiles of this slot so far
-            const bool elected = mlp_elect_one();   // the same lane for the whole kernel: the warp is converged here
+            const bool elected = tc_elect_one();   // the same lane for the whole kernel: the warp is converged here
             // GEMM 1 of hidden chunk j: accumulator of group sg <- XA . W1[:, 32j .. 32j+31]
             auto gemm1 = [&](int j, int sg) {
                 const uint32_t s = RESIDENT ? (uint32_t)j : q1 % S1;

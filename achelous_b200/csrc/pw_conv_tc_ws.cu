@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
     __shared__ float s_ln[HALVES][TC_M][2];
     __shared__ __align__(16) float4 s_ep[NT];   // per output of the current tile: {scale, scale*wsum, bias + scale*pbias, gamma}
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the shuffle makes the warp index provably warp-uniform for the compiler (uniform registers / branches in the role loops)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int K = p.c0 + p.c1, P = p.P;
     // TMEM columns: [0, NT) accumulator, then WS_SA A-operand stages of 32 columns (hi k 0..15 | lo k 0..15)
     constexpr int A_COL0 = NT;
@@ -125,8 +126,14 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == WS_PROD / 32) {
-        // ================================================================== MMA + weight-TMA thread
-        if (lane == 0) {
+        // ================================================================== MMA + weight-TMA warp
+        // Every lane runs the loop and the barrier waits (warp-uniform control flow: descriptors, TMEM and barrier addresses live in
+        // uniform registers), ONE lane chosen by elect.sync issues.  Under the former `if (lane == 0)` ptxas wrapped every UTCHMMA /
+        // UBLKCP in an ELECT + 4 x R2UR + vote + branch "waterfall" (~10 instructions per MMA on this single warp): the same finding
+        // as in mlp_tc.cu, where it bounded the kernel.
+        {
+            const bool elected = tc_elect_one();
+            const uint32_t tmem_u = tc_uniform(tmem_d);
             constexpr uint32_t idesc = tf32_idesc(NT);
             constexpr uint32_t B_LBO = (NT / 8) * 128;
             int pit = 0, p_item = blockIdx.x, p_c = 0;   // weight prefetch cursor: chunk counter, (item, chunk)
@@ -138,9 +145,11 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
                 const long long blk = ((long long)(p_item % n_ot) * n_kchunks + p_c) * B_ELEMS;
                 const uint32_t full = smem_u32(&bar_full_b[sb]);
                 const uint32_t dst = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u;
-                mbar_expect_tx(full, 2u * B_ELEMS * 4u);
-                bulk_g2s(dst, w_hi + blk, B_ELEMS * 4u, full);
-                bulk_g2s(dst + B_ELEMS * 4u, w_lo + blk, B_ELEMS * 4u, full);
+                if (elected) {
+                    mbar_expect_tx(full, 2u * B_ELEMS * 4u);
+                    bulk_g2s(dst, w_hi + blk, B_ELEMS * 4u, full);
+                    bulk_g2s(dst + B_ELEMS * 4u, w_lo + blk, B_ELEMS * 4u, full);
+                }
                 ++pit;
                 if (++p_c == n_kchunks) {
                     p_c = 0;
@@ -163,19 +172,22 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
                     mbar_wait(smem_u32(&bar_full_b[sb]), (uint32_t)(it / WS_SB) & 1u);
                     mbar_wait(smem_u32(&bar_full_a[sa]), (uint32_t)(it / WS_SA) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi_t = tmem_d + (uint32_t)(A_COL0 + sa * 32), a_lo_t = a_hi_t + 16u;
-                    const uint32_t b_hi_s = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
+                    const uint32_t a_hi_t = tmem_u + (uint32_t)(A_COL0 + sa * 32), a_lo_t = a_hi_t + 16u;
+                    const uint32_t b_hi_s = b_ring_s + (uint32_t)sb * 2u * B_ELEMS * 4u;
+                    const uint64_t dh = make_desc(b_hi_s, B_LBO, 128u, 0), dl = make_desc(b_hi_s + B_ELEMS * 4u, B_LBO, 128u, 0);
+                    if (elected) {
 #pragma unroll
-                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                        const uint32_t ah = a_hi_t + (uint32_t)ks * 8u, al = a_lo_t + (uint32_t)ks * 8u;
-                        const uint64_t bh = make_desc(b_hi_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
-                        const uint64_t bl = make_desc(b_lo_s + ks * 2 * B_LBO, B_LBO, 128u, 0);
-                        mma_tf32_ts(tmem_d, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                        mma_tf32_ts(tmem_d, al, bh, idesc, 1u);
-                        mma_tf32_ts(tmem_d, ah, bl, idesc, 1u);
+                        for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                            const uint32_t ah = a_hi_t + (uint32_t)ks * 8u, al = a_lo_t + (uint32_t)ks * 8u;
+                            const uint64_t off = (uint64_t)((ks * 2 * B_LBO) >> 4);   // the descriptor's address field counts 16-byte units
+                            mma_tf32_ts(tmem_u, ah, dh + off, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32_ts(tmem_u, al, dh + off, idesc, 1u);
+                            mma_tf32_ts(tmem_u, ah, dl + off, idesc, 1u);
+                        }
+                        tc_commit(smem_u32(&bar_mma[sa]));
+                        if (c == n_kchunks - 1) tc_commit(smem_u32(&bar_acc_full));
                     }
-                    tc_commit(smem_u32(&bar_mma[sa]));
-                    if (c == n_kchunks - 1) tc_commit(smem_u32(&bar_acc_full));
+                    __syncwarp();
                 }
             }
         }

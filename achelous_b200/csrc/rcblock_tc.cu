@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     __shared__ __align__(8) uint64_t mbar[STAGES];
     __shared__ uint32_t tmem_base_s;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = (int)tc_uniform((uint32_t)(tid >> 5));   // warp index provably uniform
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(RCT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = tmem_base_s;
+    const uint32_t tmem_d = tc_uniform(tmem_base_s);
     const uint32_t t_lane = tmem_d + ((uint32_t)(warp * 32) << 16);
     const uint32_t b_all_s = smem_u32(b_all);
     constexpr uint32_t idesc = tf32_idesc(RCT_N);
@@ -125,21 +125,24 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {   // warp-uniform branch, one elected lane issues (tc_common.cuh: no per-MMA waterfall on the warp all others wait for)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t col = tmem_d + (uint32_t)(g * RCT_N);
+            if (tc_elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < PK / 8; ++ks) {
-                const int c16 = chunk * (PK / 16) + ks / 2;   // 16-k weight tile (tiles past NCH do not exist: their k are zero padding)
-                if (c16 >= NCH) break;
-                const uint32_t b_hi_s = b_all_s + (uint32_t)((g * NCH + c16) * 2) * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
-                const uint32_t ah = tmem_d + a_col + (uint32_t)ks * 8u, al = ah + PK;
-                const uint64_t bh = kmajor_desc(b_hi_s, RCT_N, ks & 1), bl = kmajor_desc(b_lo_s, RCT_N, ks & 1);
-                mma_tf32_ts(col, ah, bh, idesc, (chunk == 0 && ks == 0) ? 0u : 1u);
-                mma_tf32_ts(col, al, bh, idesc, 1u);
-                mma_tf32_ts(col, ah, bl, idesc, 1u);
+                for (int ks = 0; ks < PK / 8; ++ks) {
+                    const int c16 = chunk * (PK / 16) + ks / 2;   // 16-k weight tile (tiles past NCH do not exist: their k are zero padding)
+                    if (c16 >= NCH) break;
+                    const uint32_t b_hi_s = b_all_s + (uint32_t)((g * NCH + c16) * 2) * B_ELEMS * 4u, b_lo_s = b_hi_s + B_ELEMS * 4u;
+                    const uint32_t ah = tmem_d + a_col + (uint32_t)ks * 8u, al = ah + PK;
+                    const uint64_t bh = kmajor_desc(b_hi_s, RCT_N, ks & 1), bl = kmajor_desc(b_lo_s, RCT_N, ks & 1);
+                    mma_tf32_ts(col, ah, bh, idesc, (chunk == 0 && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(col, al, bh, idesc, 1u);
+                    mma_tf32_ts(col, ah, bl, idesc, 1u);
+                }
+                tc_commit(smem_u32(&mbar[s]));
             }
-            tc_commit(smem_u32(&mbar[s]));
+            __syncwarp();
         }
         ++n;
     };

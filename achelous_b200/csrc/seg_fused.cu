@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
     const int h = p.h, w = p.w, H = 2 * h, W = 2 * w;
     const int tiles_x = (W + UP_TW - 1) / UP_TW;
     const int ty0 = (blockIdx.x / tiles_x) * UP_TH, tx0 = (blockIdx.x % tiles_x) * UP_TW;
-    const int b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, half = tid >> 7;
+    const int b = blockIdx.y, tid = threadIdx.x, warp = (int)tc_uniform((uint32_t)(tid >> 5)), half = warp >> 2;   // provably warp-uniform
     const float sy = (float)(h - 1) / (float)(H - 1), sx = (float)(w - 1) / (float)(W - 1);
     const int vy0 = (int)(sy * (float)max(ty0 - 1, 0)), vx0 = (int)(sx * (float)max(tx0 - 1, 0));
     const long long plane_lo = (long long)h * w, plane_hi = (long long)H * W;
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
     __syncthreads();
 
     const int col = tid & 31, rp = tid >> 5;
-    const uint32_t tm = tmem_base_s + (uint32_t)(half * HALF_COLS);          // this half's columns
+    const uint32_t tm = tc_uniform(tmem_base_s) + (uint32_t)(half * HALF_COLS);          // this half's columns
     const uint32_t t_lane = tm + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t mb = smem_u32(&mbar[half]);
     const uint32_t b1_s = smem_u32(b1t), b2_s = smem_u32(b2t);
@@ -729,20 +729,23 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-        if ((tid & 127) == 0) {
+        if ((warp & 3) == 0) {   // warp-uniform branch, one elected lane issues (tc_common.cuh)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int c = 0; c < n_chunks; ++c) {
-                const uint32_t bh_s = b_s + (uint32_t)(c * 2) * BT * 4u, bl_s = bh_s + BT * 4u;
+            if (tc_elect_one()) {
+                for (int c = 0; c < n_chunks; ++c) {
+                    const uint32_t bh_s = b_s + (uint32_t)(c * 2) * BT * 4u, bl_s = bh_s + BT * 4u;
 #pragma unroll
-                for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                    const uint32_t ah = tm + (uint32_t)(c * TC_KC + ks * 8), al = ah + (uint32_t)AK;
-                    const uint64_t bh = kmajor_desc(bh_s, 32, ks), bl = kmajor_desc(bl_s, 32, ks);
-                    mma_tf32_ts(tm + 2u * AK, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                    mma_tf32_ts(tm + 2u * AK, al, bh, idesc, 1u);
-                    mma_tf32_ts(tm + 2u * AK, ah, bl, idesc, 1u);
+                    for (int ks = 0; ks < TC_KC / 8; ++ks) {
+                        const uint32_t ah = tm + (uint32_t)(c * TC_KC + ks * 8), al = ah + (uint32_t)AK;
+                        const uint64_t bh = kmajor_desc(bh_s, 32, ks), bl = kmajor_desc(bl_s, 32, ks);
+                        mma_tf32_ts(tm + 2u * AK, ah, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        mma_tf32_ts(tm + 2u * AK, al, bh, idesc, 1u);
+                        mma_tf32_ts(tm + 2u * AK, ah, bl, idesc, 1u);
+                    }
                 }
+                tc_commit(mb);
             }
-            tc_commit(mb);
+            __syncwarp();
         }
         mbar_wait(mb, commits & 1u);
         ++commits;

@@ -106,6 +106,24 @@ __device__ __forceinline__ void split_store(float* hi, float* lo, const float (&
     *reinterpret_cast<float4*>(lo) = l;
 }
 
+// Issue pattern for tcgen05.mma / bulk copies from a warp: run the surrounding loop WARP-UNIFORMLY (every lane; warp index and TMEM base
+// passed through tc_uniform so that ptxas can prove uniformity and keep descriptors / addresses in uniform registers) and issue
+// under `if (tc_elect_one())`.  With `if (lane == 0)` / `if (tid == 0)` as the guard ptxas cannot tell that one lane is active and
+// wraps every UTCHMMA in an ELECT + R2UR + vote + branch "waterfall" (~10 instructions per MMA, on the one warp everything waits for):
+// ncu on mlp_tc.cu showed a kernel bound by exactly that with the tensor pipe at 25 %.
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t tc_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 __device__ __forceinline__ void tc_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
