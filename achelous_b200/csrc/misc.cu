@@ -268,40 +268,70 @@ __global__ void __launch_bounds__(128) avgpool3_cl_kernel(const float* __restric
     float4* op = reinterpret_cast<float4*>(out + (long long)blockIdx.y * out_bs) + (long long)(y * W + x0) * Q;
     for (int q = 0; q < Q; ++q) {
         float o[4][4];   // [channel in quad][pixel]
+        if (vec) {
+            // all 12 row vectors of the quad (4 channels x 3 rows) are requested BEFORE the first one is used: ncu showed 7 long-scoreboard
+            // stalls per issued instruction with the loads interleaved with their shuffles (1.8 TB/s on a pure streaming kernel)
+            float4 m[4][3];
+            float lf[4][3], rt[4][3];
+            const bool need_l = x0 > 0 && !lane_l, need_r = x0 + 4 < W && !lane_r;   // neighbour strip not held by the adjacent lane
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = q * 4 + e;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (c < C) {
-                const float* xp = xb + (long long)c * P;
+            for (int e = 0; e < 4; ++e) {
+                const int c = q * 4 + e;
 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy) {
                     const int yy = y + dy;
-                    const bool row_ok = yy >= 0 && yy < H;      // warp-uniform except where a warp straddles two rows
-                    const float* r = xp + (row_ok ? yy : y) * W;
+                    const bool ok = c < C && yy >= 0 && yy < H;
+                    const float* r = xb + (long long)(ok ? c : 0) * P + (ok ? yy : y) * W;
+                    m[e][dy + 1] = ok ? __ldg(reinterpret_cast<const float4*>(r + x0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    lf[e][dy + 1] = (ok && need_l) ? __ldg(r + x0 - 1) : 0.f;
+                    rt[e][dy + 1] = (ok && need_r) ? __ldg(r + x0 + 4) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const float4 mm = m[e][dy];
+                    const float lft = __shfl_up_sync(0xffffffffu, mm.w, 1), rgt = __shfl_down_sync(0xffffffffu, mm.x, 1);
                     float v[6];
-                    if (vec) {
-                        // one aligned 16-byte load for the 4 centre columns; the two outer columns come from the neighbouring
-                        // lanes' vectors (ncu on the scalar version: l1tex 85 % busy, 18 strided 4-byte loads per channel)
-                        const float4 m = __ldg(reinterpret_cast<const float4*>(r + x0));
-                        v[1] = m.x, v[2] = m.y, v[3] = m.z, v[4] = m.w;
-                        const float lft = __shfl_up_sync(0xffffffffu, m.w, 1), rgt = __shfl_down_sync(0xffffffffu, m.x, 1);
-                        v[0] = x0 == 0 ? 0.f : (lane_l ? lft : __ldg(r + x0 - 1));
-                        v[5] = x0 + 4 >= W ? 0.f : (lane_r ? rgt : __ldg(r + x0 + 4));
-                    } else {
+                    v[1] = mm.x, v[2] = mm.y, v[3] = mm.z, v[4] = mm.w;
+                    v[0] = x0 == 0 ? 0.f : (lane_l ? lft : lf[e][dy]);
+                    v[5] = x0 + 4 >= W ? 0.f : (lane_r ? rgt : rt[e][dy]);
+                    const int yy = y + dy - 1;
+                    if (yy >= 0 && yy < H) {   // rows outside the image are skipped, as in avgpool3_kernel (same summation order)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] += v[j] + v[j + 1] + v[j + 2];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[e][j] = acc[j] / 9.0f;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = q * 4 + e;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if (c < C) {
+                    const float* xp = xb + (long long)c * P;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int yy = y + dy;
+                        if (yy < 0 || yy >= H) continue;
+                        const float* r = xp + yy * W;
+                        float v[6];
 #pragma unroll
                         for (int j = 0; j < 6; ++j) {
                             const int xc = x0 - 1 + j;
                             v[j] = (xc >= 0 && xc < W) ? __ldg(r + xc) : 0.f;
                         }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[j] += v[j] + v[j + 1] + v[j + 2];   // same summation order as avgpool3_kernel
                     }
-                    if (!row_ok) continue;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[j] += v[j] + v[j + 1] + v[j + 2];   // same summation order as avgpool3_kernel
                 }
-            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[e][j] = acc[j] / 9.0f;
+                for (int j = 0; j < 4; ++j) o[e][j] = acc[j] / 9.0f;
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
