@@ -154,8 +154,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     };
 
     // asynchronous (cp.async, zero-filled outside the image) copy of an item's pooled window into shared memory
-    auto fill_window = [&](int item) {
-        const int tx_i = item % n_tx, ty_i = (item / n_tx) % n_ty, b = item / (n_tx * n_ty);
+    auto fill_window = [&](int tx_i, int ty_i, int b) {
         const int wy0 = ty_i * RCT_TH - RCT_R, wx0 = tx_i * RCT_TW - RCT_R;
         const float4* __restrict__ pooled = reinterpret_cast<const float4*>(p.pooled + (long long)b * p.pooled_bs);
         for (int i = tid; i < RCT_WH * RCT_WW; i += 128) {
@@ -170,17 +169,28 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
                              : "memory");
         }
     };
-    if ((int)blockIdx.x < total_items) fill_window(blockIdx.x);
+    // tile coordinates advance incrementally by the (pre-divided) grid stride: the three runtime divisions per tile of the direct
+    // decode (I2F / MUFU.RCP / F2I sequences at the top of the loop) were the single hottest stall site in ncu's source view
+    int tx_i = (int)blockIdx.x % n_tx, ty_i = ((int)blockIdx.x / n_tx) % n_ty, b = (int)blockIdx.x / (n_tx * n_ty);
+    const int step_x = (int)gridDim.x % n_tx, step_y = ((int)gridDim.x / n_tx) % n_ty, step_b = (int)gridDim.x / (n_tx * n_ty);
+    auto advance = [&](int& tx, int& ty, int& bb) {
+        tx += step_x;
+        ty += step_y;
+        bb += step_b;
+        if (tx >= n_tx) { tx -= n_tx; ++ty; }
+        if (ty >= n_ty) { ty -= n_ty; ++bb; }
+    };
+    if ((int)blockIdx.x < total_items) fill_window(tx_i, ty_i, b);
 
 #pragma unroll 1
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int tx_i = item % n_tx, ty_i = (item / n_tx) % n_ty, b = item / (n_tx * n_ty);
         const int ly_ = tid / RCT_TW, lx_ = tid % RCT_TW;     // position inside the tile
         const int y = ty_i * RCT_TH + ly_, x = tx_i * RCT_TW + lx_;
         const bool ok = y < H && x < W;
         const int pix = y * W + x;
         const int wy0 = ty_i * RCT_TH - RCT_R, wx0 = tx_i * RCT_TW - RCT_R;   // image coordinates of the window origin
         const float4* __restrict__ pooled = reinterpret_cast<const float4*>(p.pooled + (long long)b * p.pooled_bs);
+        float* __restrict__ out_item = p.out + (long long)b * p.out_bs;   // (b advances to the next item before the epilogue)
 
         // residual input: requested now, consumed in the epilogue (ncu on the first v3: 24 % of all stall samples sat on
         // these loads when they were issued there)
@@ -316,7 +326,8 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
             }
         }
         // every gather of this item precedes the barrier of the last push_chunk: the window can take the next item's data
-        if (item + (int)gridDim.x < total_items) fill_window(item + gridDim.x);
+        advance(tx_i, ty_i, b);   // (the epilogue below uses this item's pix / xres / ok, computed above)
+        if (item + (int)gridDim.x < total_items) fill_window(tx_i, ty_i, b);
         wait_all();
         float acc[16];
         {
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
 #pragma unroll
                 for (int i = 0; i < CP / 4; ++i) fma4_bcast(z + 4 * i, acc[c], w4[i]);
             }
-            float* __restrict__ orow = p.out + (long long)b * p.out_bs + pix;
+            float* __restrict__ orow = out_item + pix;
 #pragma unroll
             for (int o = 0; o < C; ++o) orow[(long long)o * P] = xres[o] + fmaxf(fmaf(s_scale[o], z[o], s_bias[o]), 0.f);
         }
