@@ -10,20 +10,28 @@
 // channel held in registers.  Epilogue: folded BN/bias, activation, optional broadcast post-add
 // (positional encoding), 128-bit stores when the row pitch allows.
 #include "common.cuh"
+#include "tma_common.cuh"
 #include <cstdlib>
 
 namespace ach {
 
 constexpr int DW_NX = 4;  // outputs per thread along x
 
+// use_tma: the halo tile of the CPB channels arrives as ONE tensor-map box (zero-filled outside the image = the conv's zero padding);
+// the box has to start at a 16-byte aligned column, XO = (-pad) mod 4 columns left of the tile, which only shifts the register
+// segment (ncu on the warp-per-row staging loop at the MobileViT stride-2 layers: 9 long-scoreboard stalls per issue, 1.2 TB/s).
 template <int KS, int S>
-__global__ void __launch_bounds__(256) dw_conv_kernel(const AchDwConv p, int TH, int TW, int CPB, int tiles_x) {
-    extern __shared__ __align__(16) float smem[];
-    constexpr int SEG = (DW_NX - 1) * S + KS;      // input values per kernel row per thread
+__global__ void __launch_bounds__(256) dw_conv_kernel(const AchDwConv p, int TH, int TW, int CPB, int tiles_x, const __grid_constant__ CUtensorMap tmx,
+                                                      int use_tma) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int XO_T = (4 - ((KS / 2) & 3)) & 3;
+    constexpr int SEG = (DW_NX - 1) * S + KS + XO_T;   // input values per kernel row per thread (incl. the TMA column shift)
     constexpr int SEG4 = (SEG + 3) / 4;            // as float4 loads
+    const int xo = use_tma ? XO_T : 0;
     const int IH = (TH - 1) * S + KS;
     const int IW = (TW - 1) * S + KS;
-    const int IWp = ((IW + 3) & ~3) + 4;           // 16B-aligned rows + slack for the last segment's over-read
+    const int IWp = ((IW + XO_T + 3) & ~3) + 4;    // 16B-aligned rows + slack for the last segment's over-read
+    __shared__ __align__(8) uint64_t mbar;
     float* tile = smem;                            // [CPB][IH][IWp]
     float* wsm = smem + CPB * IH * IWp;            // [CPB][KS*KS]
 
@@ -38,12 +46,17 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const AchDwConv p, int TH,
     const long long plane_in = (long long)p.H * p.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (use_tma && threadIdx.x == 0) {
+        tma_mbar_init(tma_smem_u32(&mbar), 1);
+        tma_mbar_expect_tx(tma_smem_u32(&mbar), (uint32_t)(CPB * IH * IWp) * 4u);   // always the full box: missing channels are zero-filled
+        tma_load_4d(tma_smem_u32(tile), &tmx, ix0 - XO_T, iy0, c_base, b, tma_smem_u32(&mbar));
+    }
     for (int i = threadIdx.x; i < nch * KS * KS; i += 256) wsm[i] = p.w[(long long)c_base * KS * KS + i];
 
     // ---- stage the halo tile: one warp per (channel, row)
     const float* xb = p.x + (long long)b * p.x_bs;
     const float* ab = p.xadd ? p.xadd + (long long)b * p.xadd_bs : nullptr;
-    for (int r = warp; r < nch * IH; r += 8) {
+    for (int r = warp; !use_tma && r < nch * IH; r += 8) {
         const int c = r / IH;
         const int yy = r - c * IH;
         const int gy = iy0 + yy;
@@ -61,6 +74,7 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const AchDwConv p, int TH,
         }
     }
     __syncthreads();
+    if (use_tma) tma_mbar_wait(tma_smem_u32(&mbar), 0);
 
     const int th = min(TH, p.Ho - ty0);
     const int tw = min(TW, p.Wo - tx0);
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const AchDwConv p, int TH,
 #pragma unroll
             for (int kx = 0; kx < KS; ++kx)
 #pragma unroll
-                for (int j = 0; j < DW_NX; ++j) acc[j] = fmaf(seg[j * S + kx], wk[ky * KS + kx], acc[j]);
+                for (int j = 0; j < DW_NX; ++j) acc[j] = fmaf(seg[j * S + kx + xo], wk[ky * KS + kx], acc[j]);
         }
         const int ch = c_base + c;
         const float s = p.scale ? p.scale[ch] : 1.f;
@@ -266,17 +280,22 @@ static int launch_dw(const AchDwConv& p, cudaStream_t st) {
     TH = cdiv(p.Ho, cdiv(p.Ho, TH));           // balance the rows over the tiles
     int CPB = max(1, 256 / (TH * strips));     // >= 1 strip per thread per pass
     CPB = min(CPB, p.C);
+    constexpr int XO_T = (4 - ((KS / 2) & 3)) & 3;
     const int IH = (TH - 1) * S + KS, IW = (TW - 1) * S + KS;
-    const int IWp = ((IW + 3) & ~3) + 4;
+    const int IWp = ((IW + XO_T + 3) & ~3) + 4;
     while (CPB > 1 && (size_t)CPB * (IH * IWp + KS * KS) * 4 > 96 * 1024) --CPB;
     const size_t smem = (size_t)CPB * (IH * IWp + KS * KS) * sizeof(float);
+    alignas(64) CUtensorMap tmx;
+    memset(&tmx, 0, sizeof(tmx));
+    const int use_tma = (!p.xadd && p.W % 4 == 0 && IWp <= 256 && IH <= 256 && CPB <= 256 &&
+                         tma_map_planes(&tmx, p.x, p.W, p.H, p.C, p.B, p.x_bs, IWp, IH, CPB)) ? 1 : 0;
     const int tiles_x = cdiv(p.Wo, TW), tiles_y = cdiv(p.Ho, TH);
     static PerDeviceOnce attr_once;
     if (attr_once.first()) {
         cudaFuncSetAttribute(dw_conv_kernel<KS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     }
     dim3 grid(tiles_x * tiles_y, cdiv(p.C, CPB), p.B);
-    dw_conv_kernel<KS, S><<<grid, 256, smem, st>>>(p, TH, TW, CPB, tiles_x);
+    dw_conv_kernel<KS, S><<<grid, 256, smem, st>>>(p, TH, TW, CPB, tiles_x, tmx, use_tma);
     return check_launch("ach_dw_conv");
 }
 

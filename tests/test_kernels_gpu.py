@@ -523,7 +523,8 @@ def test_pw_conv_tc(case):
 
 
 # ------------------------------------------------------------------ fused LN -> Linear -> GELU -> Linear -> gamma -> + res
-@pytest.mark.parametrize("Cc,B,P", [(32, 2, 6400), (32, 3, 132), (48, 2, 1600), (48, 1, 4), (64, 2, 1600), (96, 3, 400), (96, 2, 100), (32, 40, 1664)])
+@pytest.mark.parametrize("Cc,B,P", [(32, 2, 6400), (32, 3, 132), (48, 2, 1600), (48, 1, 4), (64, 2, 1600), (96, 3, 400), (96, 2, 100), (32, 40, 1664),
+                                     (96, 40, 400), (64, 37, 520), (48, 50, 1600), (96, 1, 128)])   # > 148 tiles: phantom tiles in the CTA pairs, odd tile counts
 def test_mlp_tc(Cc, B, P):
     """ach_mlp_tc against the emulator, and against the two ach_pw_conv_tc launches it replaces (same arithmetic: bit for bit)"""
     lib = _lib.load()
