@@ -329,12 +329,17 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
         advance(tx_i, ty_i, b);   // (the epilogue below uses this item's pix / xres / ok, computed above)
         if (item + (int)gridDim.x < total_items) fill_window(tx_i, ty_i, b);
         wait_all();
-        float acc[16];
+        float acc[C > 16 ? 32 : 16];
         {
             uint32_t r[16];
             tmem_ld16(t_lane + (uint32_t)RCT_N, r);
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(r[i]);
+            if constexpr (C > 16) {
+                tmem_ld16(t_lane + (uint32_t)RCT_N + 16u, r);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[16 + i] = __uint_as_float(r[i]);
+            }
         }
 
         // ---- 1x1 conv + folded BN + ReLU + residual
@@ -393,7 +398,7 @@ static int launch_rc_tc(const AchRcDeform& p, const float* wom_hi, const float* 
 
 }  // namespace ach
 
-extern "C" int ach_rc_deform_tc_supported(int C) { return C == 3 || C == 8 || C == 12 || C == 16; }
+extern "C" int ach_rc_deform_tc_supported(int C) { return C == 3 || C == 8 || C == 12 || C == 16 || C == 24; }
 
 extern "C" int ach_rc_deform_tc(const AchRcDeform* pp, const float* wom_hi, const float* wom_lo, const float* wreg_hi,
                                 const float* wreg_lo, void* stream) {
@@ -412,8 +417,9 @@ extern "C" int ach_rc_deform_tc(const AchRcDeform* pp, const float* wom_hi, cons
         case 8: return launch_rc_tc<8>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
         case 12: return launch_rc_tc<12>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
         case 16: return launch_rc_tc<16>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);
+        case 24: return launch_rc_tc<24>(p, wom_hi, wom_lo, wreg_hi, wreg_lo, st);   // 20 x 20 maps: the SIMT kernel has one thread per pixel there (5 warps per SM)
         default: break;
     }
-    set_error("ach_rc_deform_tc: C=%d not instantiated (3, 8, 12, 16); use ach_rc_deform", p.C);
+    set_error("ach_rc_deform_tc: C=%d not instantiated (3, 8, 12, 16, 24); use ach_rc_deform", p.C);
     return ACH_ERR_INVALID;
 }

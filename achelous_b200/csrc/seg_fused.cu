@@ -137,6 +137,10 @@ struct UpGhostHeadParams {
 //     (cp.async.bulk.tensor, out-of-image rows / columns zero-filled by the copy engine: no index arithmetic, no LDG / STS);
 //   * 32 x 40 output tiles, 2 x 4 pixels per thread, packed FFMA2 on horizontally adjacent pixels with the weights as uniform
 //     scalars from the constant bank, STG.128 / one STG.32 of four class bytes (ARGMAX) on the way out.
+#ifndef H3_UNROLL_N
+#define H3_UNROLL_N 4
+#endif
+constexpr int H3_UNROLL = H3_UNROLL_N;   // channel-loop unroll of the head kernel (16 = full: 92 KB of SASS, ncu: 1.75 no-instruction stalls per issue)
 constexpr int H3_TW = 32, H3_TH = 40, H3_T = 192;
 constexpr int H3_PH = H3_TH + 2, H3_PP = 40;          // p tile: rows (global ty0 - 1 + pr), pitch (36 columns used: tx0 - 1 + pc)
 constexpr int H3_VR = 24, H3_VP = 24;                 // low-resolution tile: rows (ty0/2 - 2 + r), columns (tx0/2 - 4 + c)
@@ -235,7 +239,7 @@ __global__ void __maxnreg__(112) up_ghost_head3_kernel(const __grid_constant__ C
 
     if (p_thread) {
         const float* vt = vs + tr * H3_VP + H3_VC + 2 * tc;    // patch rows tr .. tr+3, columns H3_VC + 2*tc .. + 4
-#pragma unroll
+#pragma unroll H3_UNROLL
         for (int c = 0; c < UH_C; ++c) {
             const float* vp = vt + c * (H3_VR * H3_VP);
             const float b1 = P.b1[c];

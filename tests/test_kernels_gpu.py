@@ -691,7 +691,7 @@ def test_pn2_interp3(N1, S, C2):
 
 
 @pytest.mark.parametrize("off_scale", [3.0, 0.5])   # offsets beyond / within the staged window halo
-@pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (8, 13, 21), (16, 24, 20), (8, 160, 160)])
+@pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (8, 13, 21), (16, 24, 20), (8, 160, 160), (24, 20, 20), (24, 13, 9)])
 def test_rc_deform_tc(Cc, H, W, off_scale):
     B = 2
     lib = _lib.load()
