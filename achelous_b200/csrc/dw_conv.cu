@@ -264,6 +264,10 @@ template <int KS>
 static int launch_rows_k(const AchDwConv& p, cudaStream_t st) {
     // rows per thread: 8 on tall planes (halo re-reads (R + KS - 1) / R stay small), otherwise a divisor of H
     if (p.H >= 40 && KS <= 5) return launch_rows<KS, 8>(p, st);
+    // small planes (10 x 10): few threads each running thousands of straight-line instructions once (64 KB+ of SASS at k = 9,
+    // R = 5) are instruction-fetch / latency bound - 2 rows per thread gives 2.5x the threads and a third of the code; the extra halo
+    // re-reads hit L1 / L2 (the planes are tiny)
+    if (p.H <= 10) return launch_rows<KS, 2>(p, st);   // measured: 10 x 10 k = 9 0.036 -> 0.022 ms; 20 x 20 k = 7 slightly slower (stays at 5 rows)
     if (p.H % 5 == 0) return launch_rows<KS, 5>(p, st);
     return launch_rows<KS, 4>(p, st);
 }
