@@ -57,18 +57,42 @@ __global__ void __launch_bounds__(256) ln_s2d_kernel(const float* __restrict__ x
     if (p >= P) return;
     const int y = p / W, xx = p - y * W;
     const float* xb = x + (long long)blockIdx.y * x_bs + p;
-    float mean = 0.f;
-    for (int c = 0; c < C; ++c) mean += xb[(long long)c * P];
-    mean /= (float)C;
-    float var = 0.f;
-    for (int c = 0; c < C; ++c) {
-        const float d = xb[(long long)c * P] - mean;
-        var = fmaf(d, d, var);
+    // statistics in ONE pass over the channels, 8 independent loads in flight at a time (the three dependent runtime-length loops of the
+    // first version left 15 long-scoreboard stalls per issued instruction).  Sums are taken of (x - x[0]): no cancellation in
+    // E[d^2] - E[d]^2 for LayerNorm-sized variances, same scheme as the GEMM kernels' fused LayerNorm.
+    const float shift = xb[0];
+    float s1 = 0.f, s2 = 0.f;
+    int c = 0;
+    for (; c + 8 <= C; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = xb[(long long)(c + j) * P];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float d = v[j] - shift;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+        }
     }
-    const float rstd = 1.0f / sqrtf(var / (float)C + eps);
+    for (; c < C; ++c) {
+        const float d = xb[(long long)c * P] - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+    }
+    const float m1 = s1 / (float)C;
+    const float mean = shift + m1;
+    const float rstd = 1.0f / sqrtf(fmaxf(s2 / (float)C - m1 * m1, 0.f) + eps);
     const int Po = (H / 2) * (W / 2);
     float* ob = out + (long long)blockIdx.y * out_bs + (long long)(((y & 1) << 1) | (xx & 1)) * Po + (y >> 1) * (W / 2) + (xx >> 1);
-    for (int c = 0; c < C; ++c) ob[(long long)c * 4 * Po] = w[c] * ((xb[(long long)c * P] - mean) * rstd) + bb[c];
+    c = 0;
+    for (; c + 8 <= C; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = xb[(long long)(c + j) * P];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ob[(long long)(c + j) * 4 * Po] = w[c + j] * ((v[j] - mean) * rstd) + bb[c + j];
+    }
+    for (; c < C; ++c) ob[(long long)c * 4 * Po] = w[c] * ((xb[(long long)c * P] - mean) * rstd) + bb[c];
 }
 
 // ------------------------------------------------------------------ bilinear x2, align_corners=True
