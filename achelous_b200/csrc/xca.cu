@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) xca_fold_kernel(const float* __restrict__
 
     // 4. fold into the projection: rows h*d + j of the per-frame K-major weight
     float* wo = wt_eff + (long long)b * wt_eff_bs;
-    if ((d & 3) == 0) {
+    if ((d & 3) == 0 && (d >> 2) * ldw >= 256) {   // (small heads keep one output per thread: d = 12 would leave 144 threads busy)
         // one output column o (coalesced) and FOUR consecutive j per thread: a projection value is loaded once for four FMAs, the four
         // attention values are one 16-byte broadcast (2 loads per 4 FMAs instead of 2 per FMA; same sum order over i per output)
         const int dq = d >> 2;
