@@ -136,6 +136,15 @@ _SIGNATURES = {
     "ach_nms_workspace_bytes": ([I, I], LL),
     "ach_nms": ([VP, I, I, I, F, F, VP, VP, VP, VP, LL, VP], I),
     "ach_nms_rows": ([VP, I, I, I, F, F, VP, LL, I, VP, LL, VP, LL, VP], I),
+    "ach_peer_alloc": ([LL, C.POINTER(VP)], I),
+    "ach_peer_free": ([VP], I),
+    "ach_peer_handle_bytes": ([], I),
+    "ach_peer_export": ([VP, C.c_char_p], I),
+    "ach_peer_open": ([C.c_char_p, C.POINTER(VP)], I),
+    "ach_peer_close": ([VP], I),
+    "ach_peer_copy": ([VP, VP, LL, VP], I),
+    "ach_peer_signal": ([VP, I, C.c_uint, VP], I),
+    "ach_peer_wait": ([VP, I, C.c_uint, VP], I),
 }
 
 EXPORTED_SYMBOLS = ["ach_last_error"] + list(_SIGNATURES)

@@ -6,7 +6,7 @@
 
 Prints ONE JSON line (rank 0).
   value        device-timed throughput of the RAW forward (the reference's return value: fp32 logits, the parity artefact), inputs
-               resident in HBM, CUDA-graph replay of the whole launch plan [+ one in-place NCCL all-gather of the packed outputs
+               resident in HBM, CUDA-graph replay of the whole launch plan [+ one in-place all-gather of the packed outputs (copy-engine pushes over NVLink peer memory)
                when N > 1].  K steps are timed `--repeats` times (barrier + synchronize on both sides, max over ranks each time);
                the MEDIAN repeat is reported.
   compact      the same loop with outputs="compact" (decode + NMS rows, uint8 class maps, point classes produced inside the
@@ -213,6 +213,7 @@ def main():
     import torch.distributed as dist
     from achelous_b200.engine import Engine, compact_spec
     from achelous_b200.nets.Achelous import Achelous
+    from achelous_b200.peer_gather import PeerGather
     from achelous_b200.synthetic import make_inputs
     from achelous_b200.weights import fill_state_dict
 
@@ -242,6 +243,9 @@ def main():
     cal = [t.to(dev) for t in make_inputs(8, seed=1234)]
     obj_bias, n_cand = calibrate_obj_bias(model, cal[0], cal[1], cal[2], torch)
     comm = torch.cuda.Stream(dev) if world > 1 else None
+    # output collection: copy-engine pushes over NVLink peer memory (achelous_b200/peer_gather.py); ACH_BENCH_GATHER=nccl times the
+    # NCCL all-gather it replaced (A/B line in profiles/)
+    gather_mode = [os.environ.get("ACH_BENCH_GATHER", "peer"), None]
 
     def barrier():
         if world > 1:
@@ -256,13 +260,28 @@ def main():
 
         def __init__(self, compact):
             ckey = compact_spec() if compact else None
+            self.pg = None
             if world == 1:
                 self.engines = [Engine(model, B, dev, compact=ckey)]
                 self.gathered = None
             else:
                 probe = Engine(model, 1, "cpu", dry_run=True, compact=ckey)      # row width / dtype of the packed output
                 width, dtype = probe.packed_out.shape[1], probe.packed_out.dtype
-                self.gathered = [torch.zeros(world * B, width, device=dev, dtype=dtype) for _ in range(2)]
+                if gather_mode[0] == "peer":
+                    try:
+                        self.pg = PeerGather(B, width, dtype, dev)
+                    except Exception as e:                                        # no IPC / no peer access on this box: say so, use NCCL
+                        gather_mode[:] = ["nccl", f"{type(e).__name__}: {e}"[:200]]
+                    flag = torch.tensor([1 if self.pg is not None else 0], device=dev)
+                    dist.all_reduce(flag, op=dist.ReduceOp.MIN)                   # all ranks take the same path
+                    if flag.item() == 0 and self.pg is not None:
+                        self.pg.close()
+                        self.pg = None
+                        gather_mode[:] = ["nccl", "peer mapping failed on another rank"]
+                if self.pg is not None:
+                    self.gathered = [self.pg.slot(s_) for s_ in range(2)]
+                else:
+                    self.gathered = [torch.zeros(world * B, width, device=dev, dtype=dtype) for _ in range(2)]
                 self.engines = [Engine(model, B, dev, compact=ckey, out=g[rank * B:(rank + 1) * B]) for g in self.gathered]
                 self.done = [None, None]
             for e in self.engines:
@@ -282,11 +301,24 @@ def main():
                 eng.forward_static()
                 comm.wait_stream(main)
                 with torch.cuda.stream(comm):
-                    dist.all_gather_into_tensor(self.gathered[s], eng.packed_out)    # in place: input IS rows [rank*B, (rank+1)*B)
+                    if self.pg is not None:
+                        seq = self.i + 1
+                        self.pg.push(s, seq, comm)             # copy-engine pushes of this rank's rows into every peer's slot
+                        self.pg.wait(s, seq, comm)             # ... the step's gather is complete when all ranks' rows are here
+                        self.pg.release(s, seq, comm)          # (the consumer of the gathered rows would run before this)
+                    else:
+                        dist.all_gather_into_tensor(self.gathered[s], eng.packed_out)    # in place: input IS rows [rank*B, (rank+1)*B)
                     self.done[s] = comm.record_event()
             else:
                 eng.forward_static()
             self.i += 1
+
+        def close(self):
+            self.engines = None
+            self.gathered = None
+            if self.pg is not None:
+                self.pg.close()
+                self.pg = None
 
         def timed(self, sampler=None):
             for _ in range(W):
@@ -337,8 +369,7 @@ def main():
                 ok &= all(torch.equal(a, b) for a, b in zip(list(d) + [s_, l_, p_], list(gd) + [gs, gl, gp]))
             gather_check = "bitwise-ok" if ok else "MISMATCH"
         barrier()
-    del raw
-    torch.cuda.empty_cache()
+    # (`raw` stays alive: `eng` below keeps writing into its rows of the peer-mapped gather buffer)
 
     cmp_loop = Loop(compact=True)
     ms_c, reps_c, _ = cmp_loop.timed()
@@ -349,13 +380,11 @@ def main():
                "bytes_per_frame": cmp_loop.engines[0].packed_out.shape[1], "launches_per_step": len(cmp_loop.engines[0].ops),
                "what": "forward(outputs='compact'): NMS rows (conf 0.35, IoU 0.35, <= 256 per frame), uint8 argmax class maps (320x320) and point "
                        "classes produced inside the launch plan" + (" + in-place all-gather of the compact records" if world > 1 else "")}
+    cmp_loop.close()
     del cmp_loop
     torch.cuda.empty_cache()
 
     # ---------------- end to end through the nn.Module surface with pinned host buffers
-    xh, xrh, pch = x.pin_memory(), xr.pin_memory(), pc.pin_memory()
-    h2d = sum(t_.numel() * 4 for t_ in (xh, xrh, pch))
-
     def host_batches(n):
         for _ in range(n):
             yield (xh, xrh, pch)
@@ -381,10 +410,18 @@ def main():
             reps.append(t.item())
         return world * B * K / statistics.median(reps)
 
-    e2e_compact = e2e(True)
-    d2h_compact = B * next(e for k, e in model._engines.items() if k[4] is not None).packed_out.shape[1]
-    e2e_raw = e2e(False)
-    d2h_raw = B * eng.frame_elems * 4
+    # pinned staging buffers and the copy-driving thread on the GPU's own NUMA node (achelous_b200/hostmem.py); restored afterwards
+    # so that the CPU baseline below still sees every host core
+    from achelous_b200.hostmem import near_gpu
+    numa = {}
+    import contextlib
+    with (near_gpu(local_rank, numa) if os.environ.get("ACH_BENCH_NUMA", "1") != "0" else contextlib.nullcontext()):
+        xh, xrh, pch = x.pin_memory(), xr.pin_memory(), pc.pin_memory()
+        h2d = sum(t_.numel() * 4 for t_ in (xh, xrh, pch))
+        e2e_compact = e2e(True)
+        d2h_compact = B * next(e for k, e in model._engines.items() if k[4] is not None).packed_out.shape[1]
+        e2e_raw = e2e(False)
+        d2h_raw = B * eng.frame_elems * 4
     model._host_bufs.clear()
 
     # ---------------- input pre-processing on device: raw camera frames / radar maps / point tables
@@ -432,7 +469,9 @@ def main():
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": cfg["workload"], "config": args.config, "batch_per_gpu": B, "global_batch": B * world,
-                           "parallelism": (f"dp{world}: frames sharded, one in-place NCCL all-gather of the packed outputs per step" if world > 1
+                           "parallelism": (f"dp{world}: frames sharded, one in-place all-gather of the packed outputs per step ("
+                                            + ("copy-engine pushes over NVLink peer memory, achelous_b200/peer_gather.py" if gather_mode[0] == "peer"
+                                               else "NCCL" + (f"; peer path unavailable: {gather_mode[1]}" if gather_mode[1] else "")) + ")" if world > 1
                                            else "single GPU"),
                            "outputs": "raw fp32 logits (the reference's return value)",
                            "cuda_graph": True, "l2": "per-step activations (~4 GB) and inputs (158 MB) exceed the 126 MB L2",
@@ -446,13 +485,15 @@ def main():
                                "keeps of the logits) copied device->host and read; copies overlap the neighbouring batches' kernels; wall clock, "
                                "median of the repeats",
                         "raw_logits_value": e2e_raw, "raw_logits_d2h_bytes_per_step": d2h_raw,
-                        "raw_logits_how": "stream_forward() with the raw fp32 outputs (4.6 MB per frame) copied out instead"},
+                        "raw_logits_how": "stream_forward() with the raw fp32 outputs (4.6 MB per frame) copied out instead",
+                        "host_placement": numa},
                 "gpu_launches": K * len(eng.ops),
                 "launches_per_step": len(eng.ops),
                 "roofline": roof, "cpu_baseline": cpu, "preprocess": pre}
         if gather_check is not None:
             line["gather_check"] = gather_check
         print(json.dumps(line), flush=True)
+    raw.close()
     if world > 1:
         dist.destroy_process_group()
 

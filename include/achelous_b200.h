@@ -460,6 +460,24 @@ ACH_API int ach_pre_resize_v_norm(const unsigned char* tmp, long long tmp_bs, in
 ACH_API int ach_pre_radar(const void* src, long long src_bs, int is_f64, int B, long long n, float* out, long long out_bs, void* stream);
 ACH_API int ach_pre_points(const double* feat, int n_rows, int C, const int* idx, int B, int N, float* out, void* stream);
 
+/* Output collection over NVLink peer memory (replaces the gather half of nn.DataParallel's scatter / gather,
+ * /root/reference/achelous.py:176-177, for one-process-per-GPU serving).  Every rank owns one allocation from ach_peer_alloc
+ * (plain cudaMalloc, zero-filled), exports it (ach_peer_export -> ach_peer_handle_bytes() opaque bytes, shipped to the other
+ * processes by the host), and maps the peers' allocations with ach_peer_open.  ach_peer_copy is a stream-ordered copy-engine
+ * transfer between such pointers (no SM work).  ach_peer_signal: after everything earlier on `stream`, store `value` (release,
+ * system scope) to flags[i] for i < n (n <= 64; `flags` is a DEVICE array of pointers, usually into peers' allocations; NULL
+ * entries are skipped).  ach_peer_wait: the stream does not advance until local words flags[0..n) have all reached `value`
+ * (wrap-safe signed comparison; acquire, system scope; one spinning warp). */
+ACH_API int ach_peer_alloc(long long bytes, void** ptr);
+ACH_API int ach_peer_free(void* ptr);
+ACH_API int ach_peer_handle_bytes(void);
+ACH_API int ach_peer_export(void* ptr, unsigned char* handle);
+ACH_API int ach_peer_open(const unsigned char* handle, void** ptr);
+ACH_API int ach_peer_close(void* ptr);
+ACH_API int ach_peer_copy(void* dst, const void* src, long long bytes, void* stream);
+ACH_API int ach_peer_signal(unsigned* const* flags, int n, unsigned value, void* stream);
+ACH_API int ach_peer_wait(const unsigned* flags, int n, unsigned value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

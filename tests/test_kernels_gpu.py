@@ -375,7 +375,8 @@ def test_rc_deform(Cc, H, W, cl):
     run_both("ach_rc_deform", make, ["out"], rtol=1e-4)
 
 
-@pytest.mark.parametrize("Cc,heads,N", [(48, 4, 1600), (96, 4, 400), (176, 4, 100), (64, 8, 1600), (144, 8, 400), (288, 8, 100)])
+@pytest.mark.parametrize("Cc,heads,N", [(48, 4, 1600), (96, 4, 400), (176, 4, 100), (64, 8, 1600), (144, 8, 400), (288, 8, 100),
+                                        (32, 4, 36), (48, 4, 196), (36, 4, 260)])   # one chunk (no cluster), ragged last chunks, odd head dim
 def test_xca_fold(Cc, heads, N):
     B = 2
     ldw = (Cc + 3) // 4 * 4
