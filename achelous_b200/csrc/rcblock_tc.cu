@@ -33,6 +33,10 @@ namespace ach {
 constexpr int RCT_N = 32;   // MMA N for both GEMMs (27 offset/modulator outputs; C <= 16 conv outputs)
 constexpr int RCT_ACOL = 2 * RCT_N;      // TMEM columns [0, 64): the two accumulators; from 64: A-operand stages (hi 16 | lo 16)
 constexpr int RCT_TMEM_COLS = 128;
+// launch bound (CTAs per SM) per channel count: tensor memory allows 4 CTAs per SM (4 x 128 columns), so nothing is gained below 128
+// registers - without a bound ptxas squeezed the folded C = 3 build into 72 registers by SPILLING the prefetched residual (the spill
+// store then waits for the global load: the top stall line of that build, 0.303 -> 0.326 ms); C = 12 / 16 keep 3 CTAs, C = 24 two
+__host__ __device__ constexpr int rct_min_ctas(int C) { return C <= 8 ? 4 : (C <= 16 ? 3 : 2); }
 
 constexpr int RCT_TW = 16, RCT_TH = 8;   // pixel tile (RCT_TW * RCT_TH == TC_M); a warp covers 2 rows of 16 pixels
 constexpr int RCT_R = 3;                 // halo of the staged window: 1 (3x3 tap) + |offset| < 2 + the +1 bilinear corner
@@ -41,7 +45,7 @@ constexpr int RCT_WW = RCT_TW + 2 * RCT_R, RCT_WH = RCT_TH + 2 * RCT_R;
 // PK = k handed to the tensor core per push (16, or 32 with a single A stage: C = 3 has K = 27, so each of its two GEMMs is ONE push -
 // half the CTA barriers, tcgen05.wait::st and elected-thread MMA issues per tile)
 template <int C, int STAGES, int PK>
-__global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, const float* __restrict__ wom_hi,
+__global__ void __launch_bounds__(128, rct_min_ctas(C)) rc_deform_tc_kernel(const AchRcDeform p, const float* __restrict__ wom_hi,
                                                            const float* __restrict__ wom_lo, const float* __restrict__ wreg_hi,
                                                            const float* __restrict__ wreg_lo, int n_tx, int n_ty, int total_items) {
     constexpr int K1 = C * 9;
@@ -50,13 +54,18 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
     constexpr int Q = CP / 4;
     constexpr int B_ELEMS = RCT_N * TC_KC;
     static_assert(PK == 16 || PK == 32, "k per push");
+    // v5: the host folds everything linear into the two GEMMs (engine.py:rc_tc_fold): offset bias + tap coordinate, -log2(e) on the
+    // modulator rows, and 2 * BN scale * weight_conv1 into the deformable-conv weights.  With a spare k column in the last push
+    // (ONES) the constants are an extra weight row against a constant-1 operand column; otherwise (C = 16) they are added from p.b_om
+    // / p.bias.  Per pixel this removes the C x C epilogue GEMM (C^2 FMAs + C^2/4 shared loads), 27 bias adds, 18 int->float
+    // conversions and 18 multiplies.
+    constexpr bool ONES = (K1 % PK) != 0;
     static_assert(RCT_ACOL + STAGES * 2 * PK <= RCT_TMEM_COLS, "A stages do not fit the TMEM allocation");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* b_all = reinterpret_cast<float*>(smem_raw);           // [2 GEMMs][NCH][hi | lo][B_ELEMS]
     float4* win = reinterpret_cast<float4*>(b_all + 2 * NCH * 2 * B_ELEMS);   // [Q][RCT_WH][RCT_WW] pooled window (zero outside the image)
-    __shared__ __align__(16) float s_w1[C * CP];    // [c][o]
     __shared__ float s_bom[32];
-    __shared__ float s_scale[CP], s_bias[CP];
+    __shared__ float s_bias[CP];
     __shared__ __align__(8) uint64_t mbar[STAGES];
     __shared__ uint32_t tmem_base_s;
 
@@ -69,15 +78,8 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
         for (int i = 0; i < STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[i])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < C * CP; i += 128) {
-        const int c = i / CP, o = i - c * CP;
-        s_w1[i] = (o < C) ? p.w1[c * C + o] : 0.f;
-    }
     if (tid < 32) s_bom[tid] = (tid < 27) ? p.b_om[tid] : 0.f;
-    if (tid < CP) {
-        s_scale[tid] = (tid < C) ? p.scale[tid] : 0.f;
-        s_bias[tid] = (tid < C) ? p.bias[tid] : 0.f;
-    }
+    if (tid < CP) s_bias[tid] = (tid < C) ? p.bias[tid] : 0.f;
     // weight tiles: chunk c of GEMM g at b_all + ((g*NCH + c)*2 + {0: hi, 1: lo}) * B_ELEMS
     for (int i = tid; i < NCH * B_ELEMS / 4; i += 128) {
         const int c = i / (B_ELEMS / 4), r = i - c * (B_ELEMS / 4);
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
                             if ((k % PK) == PK - 1 || k == K1 - 1) {
                                 if (k == K1 - 1) {
 #pragma unroll
-                                    for (int z = (k % PK) + 1; z < PK; ++z) vbuf[z] = 0.f;
+                                    for (int z = (k % PK) + 1; z < PK; ++z) vbuf[z] = (ONES && z == K1 % PK) ? 1.f : 0.f;
                                 }
                                 push_chunk(vbuf, 0, k / PK);
                             }
@@ -237,22 +239,27 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
             uint32_t r[16];
             tmem_ld16(t_lane + 0u, r);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) om[i] = __uint_as_float(r[i]) + s_bom[i];
+            for (int i = 0; i < 16; ++i) om[i] = ONES ? __uint_as_float(r[i]) : __uint_as_float(r[i]) + s_bom[i];
             tmem_ld16(t_lane + 16u, r);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) om[16 + i] = __uint_as_float(r[i]) + s_bom[16 + i];
+            for (int i = 0; i < 16; ++i) om[16 + i] = ONES ? __uint_as_float(r[i]) : __uint_as_float(r[i]) + s_bom[16 + i];
         }
 
         // ---- modulated deformable sampling, k = tap*C + ch, streamed 16 k at a time into GEMM 2
         {
             float vbuf[PK];
+            // converted HERE (volatile: ptxas hoisted the two conversions above GEMM 1 and then spilled them - the spill store was the
+            // hottest stall line of the first folded build)
+            float yf, xf;
+            asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(yf) : "r"(y));
+            asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(xf) : "r"(x));
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
-                const float py = (float)(y - 1 + t / 3) + om[2 * t];
-                const float px = (float)(x - 1 + t % 3) + om[2 * t + 1];
-                // mask = 2*sigmoid(z) = 2 / (1 + 2^(-z*log2 e)) on MUFU.EX2 + MUFU.RCP (relative error <= 2^-21; the
-                // denominator is >= 1, and z -> -inf gives 2/inf = 0 like the exact form)
-                const float m = 2.0f * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * om[18 + t]));
+                const float py = yf + om[2 * t];          // (the tap's own coordinate is part of the folded offset constant)
+                const float px = xf + om[2 * t + 1];
+                // mask / 2 = sigmoid(z) = 1 / (1 + 2^(-z*log2 e)) on MUFU.EX2 + MUFU.RCP (relative error <= 2^-21; the denominator is >= 1,
+                // and z -> -inf gives 1/inf = 0 like the exact form); om[18 + t] already is -z*log2 e, the 2 sits in the GEMM 2 weights
+                const float m = rcp_approx(1.0f + ex2_approx(om[18 + t]));
                 const float fy = floorf(py), fx = floorf(px);
                 const int y0 = (int)fy, x0 = (int)fx;
                 const float ly = py - fy, lx = px - fx;
@@ -311,12 +318,12 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
                     for (int e = 0; e < 4; ++e) {
                         if (q * 4 + e < C) {
                             const int k = t * C + q * 4 + e;   // compile-time
-                            // same expression as the SIMT kernel / torchvision: mask * bilinear value
+                            // mask * bilinear value, as in torchvision
                             vbuf[k % PK] = m * sv[q][e];
                             if ((k % PK) == PK - 1 || k == K1 - 1) {
                                 if (k == K1 - 1) {
 #pragma unroll
-                                    for (int z = (k % PK) + 1; z < PK; ++z) vbuf[z] = 0.f;
+                                    for (int z = (k % PK) + 1; z < PK; ++z) vbuf[z] = (ONES && z == K1 % PK) ? 1.f : 0.f;
                                 }
                                 push_chunk(vbuf, 1, k / PK);
                             }
@@ -342,20 +349,11 @@ __global__ void __launch_bounds__(128) rc_deform_tc_kernel(const AchRcDeform p, 
             }
         }
 
-        // ---- 1x1 conv + folded BN + ReLU + residual
+        // ---- (1x1 conv and BatchNorm are inside GEMM 2) ReLU + residual
         if (ok) {
-            float z[CP];
-#pragma unroll
-            for (int o = 0; o < CP; ++o) z[o] = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float4* w4 = reinterpret_cast<const float4*>(s_w1 + c * CP);
-#pragma unroll
-                for (int i = 0; i < CP / 4; ++i) fma4_bcast(z + 4 * i, acc[c], w4[i]);
-            }
             float* __restrict__ orow = out_item + pix;
 #pragma unroll
-            for (int o = 0; o < C; ++o) orow[(long long)o * P] = xres[o] + fmaxf(fmaf(s_scale[o], z[o], s_bias[o]), 0.f);
+            for (int o = 0; o < C; ++o) orow[(long long)o * P] = xres[o] + fmaxf(ONES ? acc[o] : acc[o] + s_bias[o], 0.f);
         }
         // the next item's first MMA overwrites the accumulators: order this item's TMEM reads before it
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -404,7 +402,7 @@ extern "C" int ach_rc_deform_tc(const AchRcDeform* pp, const float* wom_hi, cons
                                 const float* wreg_lo, void* stream) {
     using namespace ach;
     const AchRcDeform& p = *pp;
-    ACH_REQUIRE(p.x && p.pooled && p.b_om && p.w1 && p.scale && p.bias && p.out && wom_hi && wom_lo && wreg_hi && wreg_lo,
+    ACH_REQUIRE(p.x && p.pooled && p.b_om && p.bias && p.out && wom_hi && wom_lo && wreg_hi && wreg_lo,
                 "ach_rc_deform_tc: null arg");
     ACH_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0 && (long long)p.B * p.H * p.W < (1LL << 31), "ach_rc_deform_tc: bad dims");
     ACH_REQUIRE(p.pooled_cl && aligned16(p.pooled) && p.pooled_bs % 4 == 0,

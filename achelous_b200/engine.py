@@ -76,6 +76,42 @@ def _ceil4(n):
     return (n + 3) // 4 * 4
 
 
+def rc_tc_push_k(C_):
+    """k handed to the tensor core per push by ach_rc_deform_tc (rcblock_tc.cu): 32 when a whole GEMM fits one push"""
+    return 32 if 9 * C_ <= 32 else 16
+
+
+def rc_tc_fold(w_offmod, b_offmod, w_reg, w1, scale, bias):
+    """Operands of ach_rc_deform_tc (include/achelous_b200.h) from the RCBlock's parameters, host float64.
+    Everything after the bilinear sampling of RadarEncoder.py:65-72 / dcn.py:49-63 is linear up to the ReLU -
+    deform_conv2d (no bias) -> weight_conv1 -> eval BatchNorm - so it collapses into ONE (9C x C) matrix
+    2 * diag(scale) . W1 . Wreg (the 2 of `2 * sigmoid`) and the bias; the tap coordinate (t/3 - 1, t%3 - 1) joins the offset
+    bias, and the modulator rows are pre-scaled by -log2(e) (sigmoid on ex2).  Where the push has a spare k column
+    (9C % push_k != 0) the constants ride in the GEMMs as an extra weight row against a constant-1 operand column.
+      w_offmod (27, C, 3, 3) = cat(offset_conv.weight, modulator_conv.weight), b_offmod (27,), w_reg (C, C, 3, 3), w1 (C, C),
+      scale / bias: folded BatchNorm(weight_conv1 + its bias)
+    -> w_om_tap (K, 28), consts (32,), w_reg_tap (K, ceil4(C)), bias (C,), K (= 9C + 1 with the constants row, else 9C)"""
+    C_ = w_reg.shape[0]
+    log2e = 1.4426950408889634
+    consts = torch.zeros(32, dtype=torch.float64)
+    t = torch.arange(9)
+    consts[0:18:2] = b_offmod[0:18:2] + (t // 3 - 1)
+    consts[1:18:2] = b_offmod[1:18:2] + (t % 3 - 1)
+    consts[18:27] = -log2e * b_offmod[18:27]
+    om = w_offmod.reshape(27, C_, 9).permute(2, 1, 0).reshape(9 * C_, 27).clone()      # rows k = tap * C + ch
+    om[:, 18:] *= -log2e
+    m = 2.0 * scale[:, None] * (w1.reshape(C_, C_) @ w_reg.reshape(C_, C_ * 9))            # (o, ch * 9 + tap)
+    reg = m.reshape(C_, C_, 9).permute(2, 1, 0).reshape(9 * C_, C_)
+    K = 9 * C_
+    if K % rc_tc_push_k(C_) != 0:
+        om = torch.cat([om, consts[None, :27]], 0)
+        reg = torch.cat([reg, bias[None, :].to(reg.dtype)], 0)
+        K += 1
+    om = torch.nn.functional.pad(om, (0, 1))
+    reg = torch.nn.functional.pad(reg, (0, _ceil4(C_) - C_))
+    return om, consts, reg, bias, K
+
+
 class Engine:
     def __init__(self, model, batch, device, use_graph=True, dry_run=False, n_points=None, compact=None, out=None):
         """dry_run=True builds the plan and packs the weights without a GPU (host-logic tests only):
@@ -1275,15 +1311,19 @@ class Engine:
             self._keep.append(s)
             nb_rc = 4 * self.B * cin * cur.H * cur.W * 3
             if use_tc:
-                # both contractions of the block as implicit GEMMs on tcgen05; weights packed on the device at (re)pack time
-                def w_om_tap(d=d, cin=cin):     # rows k = tap*C + ch (tap-major, like w_reg_tap), 27 outputs padded to 28
-                    wo = torch.cat([self._p(d + ".offset_conv.weight"), self._p(d + ".modulator_conv.weight")], 0)  # (27, C, 3, 3)
-                    return torch.nn.functional.pad(wo.reshape(27, cin, 9).permute(2, 1, 0).reshape(9 * cin, 27), (0, 1))
-                w_om_t = self._w(f"rc{i}.w_om_tap", w_om_tap)
-                w_reg_t = self._w(f"rc{i}.w_reg_tap", (lambda d=d, cin=cin: torch.nn.functional.pad(
-                    self._p(d + ".regular_conv.weight").reshape(cin, cin, 9).permute(2, 1, 0).reshape(9 * cin, cin), (0, _ceil4(cin) - cin))))
+                # both contractions of the block as implicit GEMMs on tcgen05, with everything linear folded into them on the host
+                # (rc_tc_fold); weights packed on the device at (re)pack time
+                def fold(d=d, bp=bp, cin=cin):
+                    sc, bi = self._bn_fold(bp + ".norm", 1e-5, self._p(bp + ".weight_conv1.bias"))
+                    return rc_tc_fold(torch.cat([self._p(d + ".offset_conv.weight"), self._p(d + ".modulator_conv.weight")], 0),
+                                      torch.cat([self._p(d + ".offset_conv.bias"), self._p(d + ".modulator_conv.bias")]),
+                                      self._p(d + ".regular_conv.weight"), self._p(bp + ".weight_conv1.weight"), sc, bi)
+                K_ = fold()[4]
+                w_om_t = self._w(f"rc{i}.w_om_tap", lambda fold=fold: fold()[0])
+                w_reg_t = self._w(f"rc{i}.w_reg_tap", lambda fold=fold: fold()[2])
+                s.b_om = self._vec(f"rc{i}.om_consts", lambda fold=fold: fold()[1]).data_ptr()
                 tiles = []
-                for wt_, K_, O_ in ((w_om_t, cin * 9, 27), (w_reg_t, 9 * cin, cin)):
+                for wt_, O_ in ((w_om_t, 27), (w_reg_t, cin)):
                     n_ = self.lib.ach_pack_pw_tc_elems(K_, O_)
                     hi = self._zeros(n_)
                     lo = self._zeros(n_)

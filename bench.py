@@ -370,6 +370,15 @@ def main():
             gather_check = "bitwise-ok" if ok else "MISMATCH"
         barrier()
     # (`raw` stays alive: `eng` below keeps writing into its rows of the peer-mapped gather buffer)
+    if os.environ.get("ACH_BENCH_LEGS") == "raw":      # A/B runs (e.g. ACH_BENCH_GATHER=nccl): the device-resident loop only
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                              "ms_per_step": ms_total / K, "legs": "raw", "gather": gather_mode, "gather_check": gather_check,
+                              "repeats": [round(r_ / K, 4) for r_ in reps_raw], "clocks": clocks}), flush=True)
+        raw.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cmp_loop = Loop(compact=True)
     ms_c, reps_c, _ = cmp_loop.timed()

@@ -232,13 +232,17 @@ typedef struct AchRcDeform {
 } AchRcDeform;
 ACH_API int ach_rc_deform(const AchRcDeform* p, void* stream);
 
-/* Tensor-core version of ach_rc_deform for C in {3, 8, 12, 16} (the high-resolution RCNet blocks): both dense
- * contractions run as implicit GEMMs on tcgen05 (3xTF32).  Weights pre-packed with ach_pack_pw_tc, both with
- * TAP-MAJOR rows k = tap*C + ch:
- *   wom_hi/lo  <- K-major [9*C][28] (18 offset + 9 modulator outputs), O = 27
- *   wreg_hi/lo <- K-major [9*C][ceil4(C)], O = C
- * The AchRcDeform fields w_om / w_reg are ignored; x, pooled (channel-last, pooled_cl must be 1), b_om, w1, scale,
- * bias, out as in ach_rc_deform.  Replaces RadarEncoder.py:65-72 + dcn.py:49-63 like ach_rc_deform. */
+/* Tensor-core version of ach_rc_deform for C in {3, 8, 12, 16, 24}: both dense contractions run as implicit GEMMs on
+ * tcgen05 (3xTF32), and everything LINEAR in the block is folded into them by the host (achelous_b200/engine.py:rc_tc_fold;
+ * deform_conv2d -> weight_conv1 -> eval BatchNorm has no non-linearity before the ReLU).  PK = 32 if 9C <= 32 else 16 is the
+ * k per tensor-core push; with 9C % PK != 0 a spare k column exists and the constants travel as weight row 9C (K = 9C + 1)
+ * against a constant-1 operand column, otherwise K = 9C.  Weights pre-packed with ach_pack_pw_tc, TAP-MAJOR rows k = tap*C + ch:
+ *   wom_hi/lo  <- K-major [K][28]: columns 0..17 offset conv, 18..26 = -log2(e) * modulator conv, (row 9C: b_om below)
+ *   wreg_hi/lo <- K-major [K][ceil4(C)] = 2 * diag(scale) . weight_conv1 . regular_conv, O = C, (row 9C: bias below)
+ * AchRcDeform fields read: x, pooled (channel-last, pooled_cl must be 1), out, the dims, and
+ *   b_om  32 floats: [2t] = offset bias + (t/3 - 1), [2t+1] = offset bias + (t%3 - 1), [18+t] = -log2(e) * modulator bias
+ *   bias  C floats: folded BatchNorm(weight_conv1 + its bias) bias
+ * (w_om, w_reg, w1, scale are ignored).  out = x + relu(GEMM 2).  Replaces RadarEncoder.py:65-72 + dcn.py:49-63. */
 ACH_API int ach_rc_deform_tc_supported(int C);
 ACH_API int ach_rc_deform_tc(const AchRcDeform* p, const float* wom_hi, const float* wom_lo, const float* wreg_hi,
                              const float* wreg_lo, void* stream);

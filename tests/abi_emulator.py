@@ -388,13 +388,31 @@ class _Shim:
 
 
 def ach_rc_deform_tc(s, wom_hi, wom_lo, wreg_hi, wreg_lo):
-    Cc = s.C
-    wom_tap = _tc_unpack(wom_hi, wom_lo, 9 * Cc, 27)                         # rows k = tap*C + ch
-    wom = torch.zeros(Cc * 9, 28)
-    wom[:, :27] = wom_tap.reshape(9, Cc, 27).permute(1, 0, 2).reshape(Cc * 9, 27)           # rows ch*9 + tap
-    wreg_tap = _tc_unpack(wreg_hi, wreg_lo, 9 * Cc, Cc)                      # rows k = tap*C + ch
-    wreg = wreg_tap.reshape(9, Cc, Cc).permute(1, 0, 2).reshape(Cc * 9, Cc).contiguous()   # rows ch*9 + tap
-    ach_rc_deform(_Shim(s, w_om=wom.data_ptr(), w_reg=wreg.data_ptr()))
+    """folded operands (engine.py:rc_tc_fold): offsets carry the tap coordinate, modulator rows -log2(e) * z, GEMM 2 carries
+    2 * BN scale * weight_conv1; the constants ride as weight row 9C where the push has a spare k column"""
+    B, Cc, H, W = s.B, s.C, s.H, s.W
+    P, K1 = H * W, 9 * Cc
+    pk = 32 if K1 <= 32 else 16
+    ones = K1 % pk != 0
+    K = K1 + 1 if ones else K1
+    wom = _tc_unpack(wom_hi, wom_lo, K, 27)                                  # rows k = tap*C + ch
+    wreg = _tc_unpack(wreg_hi, wreg_lo, K, Cc)
+    consts, bias = _vec(s.b_om, 27), _vec(s.bias, Cc)
+    if ones:                                                                 # the kernel takes the constants from the GEMM rows
+        assert torch.allclose(wom[K1], consts, rtol=1e-6, atol=1e-7) and torch.allclose(wreg[K1], bias, rtol=1e-6, atol=1e-7)
+        consts, bias = wom[K1], wreg[K1]
+    x = fview(s.x, (B, Cc, H, W), (s.x_bs, P, W, 1))
+    CP = (Cc + 3) // 4 * 4
+    pooled = fview(s.pooled, (B, P, CP), (s.pooled_bs, CP, 1))[:, :, :Cc].transpose(1, 2).reshape(B, Cc, H, W).clone()
+    w_om = wom[:K1].reshape(9, Cc, 27).permute(2, 1, 0).reshape(27, Cc, 3, 3)
+    om = F.conv2d(pooled, w_om, consts, 1, 1)
+    t = torch.arange(9)
+    tap = torch.stack([(t // 3 - 1), (t % 3 - 1)], 1).reshape(18).float()
+    offset = om[:, :18] - tap[None, :, None, None]
+    half_mask = 1.0 / (1.0 + torch.exp2(om[:, 18:]))
+    w_reg = wreg[:K1].reshape(9, Cc, Cc).permute(2, 1, 0).reshape(Cc, Cc, 3, 3)
+    y = deform_conv2d_3x3(pooled, offset, half_mask, w_reg) + bias[None, :, None, None]
+    fview(s.out, (B, Cc, H, W), (s.out_bs, P, W, 1)).copy_(x + F.relu(y))
 
 
 def ach_xca_fold(qkv, qkv_bs, temperature, proj_wt, ldw, wt_eff, wt_eff_bs, B, Cc, heads, N):

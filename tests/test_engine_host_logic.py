@@ -8,6 +8,9 @@ from achelous_b200.nets.Achelous import Achelous
 from achelous_b200.synthetic import make_inputs
 from achelous_b200.weights import fill_state_dict
 from oracle import functional as OF
+from achelous_b200 import _lib
+from achelous_b200._lib import AchRcDeform
+from tests import abi_emulator as emu
 from tests.abi_emulator import emulate_engine
 from tests.common import MODEL_KW, argmax_mismatch, rel_err
 
@@ -183,3 +186,62 @@ def test_fused_mlp_plan_is_used_and_matches_two_launch_plan():
         emulate_engine(eng)
         outs.append(eng.packed_out.clone())
     assert rel_err(outs[0], outs[1]) < 1e-6
+
+
+# ------------------------------------------------------------------ folded RCBlock operands (rcblock_tc.cu v5)
+class _Arena:
+    def __init__(self):
+        self.t = {}
+
+    def new(self, name, tensor):
+        self.t[name] = tensor.detach().to(torch.float32).clone().contiguous()
+        return self.t[name]
+
+    def ptr(self, name):
+        return self.t[name].data_ptr()
+
+
+R = torch.randn
+
+
+@pytest.mark.parametrize("Cc,H,W", [(3, 20, 24), (16, 12, 12)])
+def test_rc_deform_tc_emulator_matches_unfolded_block(Cc, H, W):
+    """the host fold (engine.rc_tc_fold) + the emulator's folded ach_rc_deform_tc == the unfolded RCBlock contract (ach_rc_deform)"""
+    from achelous_b200.engine import rc_tc_fold
+    torch.manual_seed(3)
+    B, CP = 2, (Cc + 3) // 4 * 4
+    A = _Arena()
+    A.new("x", R(B, Cc, H, W))
+    pc = torch.zeros(B, H * W, CP)
+    pc[:, :, :Cc] = R(B, H * W, Cc)
+    A.new("pooled", pc)
+    w_offmod, b_offmod = R(27, Cc, 3, 3) / (Cc * 9) ** 0.5, torch.rand(27) * 2 - 1
+    w_reg, w1, scale, bias = R(Cc, Cc, 3, 3) / (Cc * 9) ** 0.5, R(Cc, Cc) / Cc ** 0.5, torch.rand(Cc) + 0.5, R(Cc) * 0.1
+    outs = []
+    for folded in (False, True):
+        A.new("out", torch.zeros(B, Cc, H, W))
+        s = AchRcDeform()
+        s.x, s.pooled, s.out = A.ptr("x"), A.ptr("pooled"), A.ptr("out")
+        s.x_bs = s.out_bs = Cc * H * W
+        s.pooled_cl, s.pooled_bs = 1, CP * H * W
+        s.B, s.C, s.H, s.W = B, Cc, H, W
+        if not folded:
+            wom = torch.zeros(Cc * 9, 28)
+            wom[:, :27] = w_offmod.reshape(27, Cc * 9).t()
+            A.new("w_om", wom), A.new("b_om", b_offmod), A.new("w_reg", w_reg.reshape(Cc, Cc * 9).t()), A.new("w1", w1.t())
+            A.new("scale", scale), A.new("bias", bias)
+            for n in ("w_om", "b_om", "w_reg", "w1", "scale", "bias"):
+                setattr(s, n, A.ptr(n))
+            emu.ach_rc_deform(s)
+        else:
+            om, consts, reg, bias_f, K = rc_tc_fold(w_offmod.double(), b_offmod.double(), w_reg.double(), w1.double(), scale.double(), bias.double())
+            n_om, n_reg = _lib.load().ach_pack_pw_tc_elems(K, 27), _lib.load().ach_pack_pw_tc_elems(K, Cc)
+            A.new("w_om_tap", om), A.new("w_reg_tap", reg), A.new("consts", consts), A.new("bias_f", bias_f)
+            for n_, sz in (("omh", n_om), ("oml", n_om), ("rgh", n_reg), ("rgl", n_reg)):
+                A.new(n_, torch.zeros(sz))
+            s.b_om, s.bias = A.ptr("consts"), A.ptr("bias_f")
+            emu.ach_pack_pw_tc(A.ptr("w_om_tap"), K, 27, 28, A.ptr("omh"), A.ptr("oml"))
+            emu.ach_pack_pw_tc(A.ptr("w_reg_tap"), K, Cc, CP, A.ptr("rgh"), A.ptr("rgl"))
+            emu.ach_rc_deform_tc(s, A.ptr("omh"), A.ptr("oml"), A.ptr("rgh"), A.ptr("rgl"))
+        outs.append(A.t["out"].clone())
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-5 * outs[0].abs().max().item()

@@ -694,34 +694,46 @@ def test_pn2_interp3(N1, S, C2):
 @pytest.mark.parametrize("off_scale", [3.0, 0.5])   # offsets beyond / within the staged window halo
 @pytest.mark.parametrize("Cc,H,W", [(3, 64, 64), (3, 37, 29), (8, 40, 40), (12, 40, 40), (8, 13, 21), (16, 24, 20), (8, 160, 160), (24, 20, 20), (24, 13, 9)])
 def test_rc_deform_tc(Cc, H, W, off_scale):
+    """tensor-core RCBlock with HOST-FOLDED operands (engine.rc_tc_fold) on the GPU against the UNFOLDED block
+    (ach_rc_deform contract: 3x3 offset / modulator conv, 2 * sigmoid, deform conv, 1x1 conv, BN, ReLU, residual) on the host"""
+    from achelous_b200.engine import rc_tc_fold
     B = 2
     lib = _lib.load()
-    n_om, n_reg = lib.ach_pack_pw_tc_elems(Cc * 9, 27), lib.ach_pack_pw_tc_elems(9 * Cc, Cc)
-    ldr = (Cc + 3) // 4 * 4
-    CP = ldr
+    CP = (Cc + 3) // 4 * 4
 
     def make(A):
         A.new("x", R(B, Cc, H, W))
         pc = torch.zeros(B, H * W, CP)
         pc[:, :, :Cc] = R(B, H * W, Cc)
         A.new("pooled", pc)                       # channel-last [P][ceil4(C)]
-        w_om = torch.zeros(9 * Cc, 28)            # rows k = tap*C + ch
-        w_om[:, :27] = R(9 * Cc, 27) / (Cc * 9) ** 0.5
-        w_om[:, :18] *= off_scale
-        w_reg = torch.zeros(9 * Cc, ldr)
-        w_reg[:, :Cc] = R(9 * Cc, Cc) / (Cc * 9) ** 0.5
-        A.new("w_om_tap", w_om), A.new("w_reg_tap", w_reg), A.new("b_om", torch.rand(27) * 2 - 1), A.new("w1", R(Cc, Cc) / Cc ** 0.5)
-        A.new("scale", torch.rand(Cc) + 0.5), A.new("bias", R(Cc) * 0.1), A.new("out", torch.zeros(B, Cc, H, W))
-        for n_, sz in (("omh", n_om), ("oml", n_om), ("rgh", n_reg), ("rgl", n_reg)):
-            A.new(n_, torch.zeros(sz))
+        w_offmod = R(27, Cc, 3, 3) / (Cc * 9) ** 0.5
+        w_offmod[:18] *= off_scale
+        b_offmod = torch.rand(27) * 2 - 1
+        w_reg = R(Cc, Cc, 3, 3) / (Cc * 9) ** 0.5
+        w1 = R(Cc, Cc) / Cc ** 0.5                # (o, c)
+        scale, bias = torch.rand(Cc) + 0.5, R(Cc) * 0.1
+        A.new("out", torch.zeros(B, Cc, H, W))
         s = AchRcDeform()
-        s.x, s.pooled, s.b_om, s.w1 = (A.ptr(n) for n in ("x", "pooled", "b_om", "w1"))
-        s.scale, s.bias, s.out = A.ptr("scale"), A.ptr("bias"), A.ptr("out")
+        s.x, s.pooled, s.out = A.ptr("x"), A.ptr("pooled"), A.ptr("out")
         s.x_bs = s.out_bs = Cc * H * W
         s.pooled_cl, s.pooled_bs = 1, CP * H * W
         s.B, s.C, s.H, s.W = B, Cc, H, W
-        return [("ach_pack_pw_tc", (A.ptr("w_om_tap"), Cc * 9, 27, 28, A.ptr("omh"), A.ptr("oml"))),
-                ("ach_pack_pw_tc", (A.ptr("w_reg_tap"), 9 * Cc, Cc, ldr, A.ptr("rgh"), A.ptr("rgl"))),
+        if A.device.type == "cpu":                # the unfolded block, SIMT-kernel weight layouts (rows ch*9 + tap)
+            wom = torch.zeros(Cc * 9, 28)
+            wom[:, :27] = w_offmod.reshape(27, Cc * 9).t()
+            A.new("w_om", wom), A.new("b_om", b_offmod), A.new("w_reg", w_reg.reshape(Cc, Cc * 9).t()), A.new("w1", w1.t())
+            A.new("scale", scale), A.new("bias", bias)
+            for n in ("w_om", "b_om", "w_reg", "w1", "scale", "bias"):
+                setattr(s, n, A.ptr(n))
+            return [("ach_rc_deform", (s,))]
+        om, consts, reg, bias_f, K = rc_tc_fold(w_offmod.double(), b_offmod.double(), w_reg.double(), w1.double(), scale.double(), bias.double())
+        n_om, n_reg = lib.ach_pack_pw_tc_elems(K, 27), lib.ach_pack_pw_tc_elems(K, Cc)
+        A.new("w_om_tap", om), A.new("w_reg_tap", reg), A.new("consts", consts), A.new("bias", bias_f)
+        for n_, sz in (("omh", n_om), ("oml", n_om), ("rgh", n_reg), ("rgl", n_reg)):
+            A.new(n_, torch.zeros(sz))
+        s.b_om, s.bias = A.ptr("consts"), A.ptr("bias")
+        return [("ach_pack_pw_tc", (A.ptr("w_om_tap"), K, 27, 28, A.ptr("omh"), A.ptr("oml"))),
+                ("ach_pack_pw_tc", (A.ptr("w_reg_tap"), K, Cc, CP, A.ptr("rgh"), A.ptr("rgl"))),
                 ("ach_rc_deform_tc", (s, A.ptr("omh"), A.ptr("oml"), A.ptr("rgh"), A.ptr("rgl")))]
     run_seq(make, ["out"], rtol=1e-4)
 
