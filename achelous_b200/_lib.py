@@ -107,7 +107,7 @@ _SIGNATURES = {
     "ach_up_ghost_pw2_supported": ([I, I, I], I),
     "ach_up_ghost_pw2": ([C.POINTER(AchUpGhostPw2), VP], I),
     "ach_up_ghost_pw2_tc_supported": ([I, I, I], I),
-    "ach_up_ghost_pw2_tc": ([C.POINTER(AchUpGhostPw2), VP, VP, VP, VP, VP], I),
+    "ach_up_ghost_pw2_tc": ([C.POINTER(AchUpGhostPw2), VP, VP, VP, VP, VP, VP], I),
     "ach_up_ghost_head_supported": ([I, I, I], I),
     "ach_up_ghost_head": ([C.POINTER(AchUpGhostHead), VP], I),
     "ach_up_ghost_head_argmax": ([C.POINTER(AchUpGhostHead), VP, LL, C.c_uint, VP], I),

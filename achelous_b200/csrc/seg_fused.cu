@@ -637,8 +637,17 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_kernel(const AchUpGhostPw
 //   GEMM 1 (N = 32) -> D;  D + c1, ReLU, split -> tcgen05.st over the dead A columns;  GEMM 2 (N = 32, 16 used) -> D
 //   D -> 16 coalesced channel-plane stores.
 // Weights: ach_pack_pw_tc tiles of w1t (K = 2*CI, O = 32) and w2t (K = 32, O = 16), resident in shared memory.
+// The depthwise 3x3 taps and the per-channel affines travel as KERNEL PARAMETERS (constant bank), like the head kernel's: with them in
+// shared memory every FMA of the dw 3x3 had a broadcast LDS of its weight next to the LDS of its x1 value (ncu: LSU pipe 49 %,
+// l1tex 68 %, mio-throttle 1.3 per issue) - as immediates of the FMA they cost nothing.
 template <int CI>
-__global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhostPw2 p, const float* __restrict__ w1_hi,
+struct UpDwParams {
+    float w[CI * 12];   // per channel: 9 taps, s2, b2, b1
+};
+
+template <int CI>
+__global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhostPw2 p, const __grid_constant__ UpDwParams<CI> dwp,
+                                                                 const float* __restrict__ w1_hi,
                                                                  const float* __restrict__ w1_lo, const float* __restrict__ w2_hi,
                                                                  const float* __restrict__ w2_lo) {
     constexpr int K1 = 2 * CI, NCH1 = K1 / TC_KC, NCH2 = UP_C1 / TC_KC;
@@ -652,8 +661,7 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
     float* b2t = b1t + NCH1 * 2 * BT;                    // [NCH2][hi | lo][BT]
     float* x1s = b2t + NCH2 * 2 * BT;                    // [CI][18][35]
     float* vs = x1s + CI * UP_XH * UP_XP;                // [CI][12][20+1]
-    float* dws = vs + CI * UP_VH * (UP_VW + 1);          // [CI][12]: 9 taps, s2, b2, b1
-    float* c1s = dws + CI * 12;                          // [32]
+    float* c1s = vs + CI * UP_VH * (UP_VW + 1);          // [32]
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t tmem_base_s;
 
@@ -684,10 +692,6 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
         const int c = i / (BT / 4), r = i - c * (BT / 4);
         reinterpret_cast<float4*>(b2t)[(c * 2 + 0) * (BT / 4) + r] = __ldg(reinterpret_cast<const float4*>(w2_hi) + i);
         reinterpret_cast<float4*>(b2t)[(c * 2 + 1) * (BT / 4) + r] = __ldg(reinterpret_cast<const float4*>(w2_lo) + i);
-    }
-    for (int i = tid; i < CI * 12; i += 256) {
-        const int c = i / 12, k = i - c * 12;
-        dws[i] = k < 9 ? p.w2[c * 9 + k] : (k == 9 ? p.s2[c] : (k == 10 ? p.b2[c] : p.b1[c]));
     }
     if (tid < UP_C1) c1s[tid] = p.c1[tid];
     {
@@ -731,12 +735,12 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
             y0 -= vy0; y1 -= vy0; x0 -= vx0; x1 -= vx0;
         }
         const float hy = 1.f - ly, hx = 1.f - lx;
-#pragma unroll 4
+#pragma unroll
         for (int c = 0; c < CI; ++c) {
             const float* vc = vs + c * UP_VH * (UP_VW + 1);
             float val = hy * (hx * vc[y0 * (UP_VW + 1) + x0] + lx * vc[y0 * (UP_VW + 1) + x1]) +
                         ly * (hx * vc[y1 * (UP_VW + 1) + x0] + lx * vc[y1 * (UP_VW + 1) + x1]);
-            x1s[(c * UP_XH + yy) * UP_XP + xx] = in ? fmaxf(val + dws[c * 12 + 11], 0.f) : 0.f;
+            x1s[(c * UP_XH + yy) * UP_XP + xx] = in ? fmaxf(val + dwp.w[c * 12 + 11], 0.f) : 0.f;
         }
     }
     __syncthreads();
@@ -803,7 +807,7 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
                 } else {
                     const int c = k - CI;
                     const float* xc = xrow + c * UP_XH * UP_XP;
-                    const float* dk = dws + c * 12;
+                    const float* dk = dwp.w + c * 12;                   // compile-time offsets: constant-bank operands
                     float d = 0.f;
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
@@ -846,16 +850,18 @@ __global__ void __launch_bounds__(256, 2) up_ghost_pw2_tc_kernel(const AchUpGhos
 
 template <int CI>
 static int launch_up_ghost_pw2_tc(const AchUpGhostPw2& p, const float* w1_hi, const float* w1_lo, const float* w2_hi, const float* w2_lo,
-                                  cudaStream_t st) {
+                                  const float* dw_host, cudaStream_t st) {
     constexpr int NCH1 = 2 * CI / TC_KC, NCH2 = UP_C1 / TC_KC;
-    const size_t smem = (size_t)((NCH1 + NCH2) * 2 * 32 * TC_KC + CI * UP_XH * UP_XP + CI * UP_VH * (UP_VW + 1) + CI * 12 + UP_C1) * sizeof(float);
+    const size_t smem = (size_t)((NCH1 + NCH2) * 2 * 32 * TC_KC + CI * UP_XH * UP_XP + CI * UP_VH * (UP_VW + 1) + UP_C1) * sizeof(float);
+    UpDwParams<CI> dwp;
+    memcpy(dwp.w, dw_host, sizeof(dwp.w));
     static PerDeviceOnce attr_once;
     if (attr_once.first()) {
         cudaFuncSetAttribute(up_ghost_pw2_tc_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     const int H = 2 * p.h, W = 2 * p.w;
     dim3 grid(cdiv(W, UP_TW) * cdiv(H, UP_TH), p.B);
-    up_ghost_pw2_tc_kernel<CI><<<grid, 256, smem, st>>>(p, w1_hi, w1_lo, w2_hi, w2_lo);
+    up_ghost_pw2_tc_kernel<CI><<<grid, 256, smem, st>>>(p, dwp, w1_hi, w1_lo, w2_hi, w2_lo);
     return check_launch("ach_up_ghost_pw2_tc");
 }
 
@@ -897,17 +903,17 @@ extern "C" int ach_up_ghost_pw2_tc_supported(int ci, int c1, int n2) {
 }
 
 extern "C" int ach_up_ghost_pw2_tc(const AchUpGhostPw2* pp, const float* w1_hi, const float* w1_lo, const float* w2_hi, const float* w2_lo,
-                                   void* stream) {
+                                   const float* dw_host, void* stream) {
     using namespace ach;
     const AchUpGhostPw2& p = *pp;
-    ACH_REQUIRE(p.v && p.out && p.b1 && p.w2 && p.s2 && p.b2 && p.c1 && w1_hi && w1_lo && w2_hi && w2_lo, "ach_up_ghost_pw2_tc: null arg");
+    ACH_REQUIRE(p.v && p.out && p.c1 && w1_hi && w1_lo && w2_hi && w2_lo && dw_host, "ach_up_ghost_pw2_tc: null arg");
     ACH_REQUIRE(p.B > 0 && p.B <= 65535 && p.h > 1 && p.w > 1, "ach_up_ghost_pw2_tc: bad dims");
     ACH_REQUIRE(ach_up_ghost_pw2_tc_supported(p.Ci, p.C1, p.N2), "ach_up_ghost_pw2_tc: (Ci=%d, C1=%d, N2=%d) not instantiated", p.Ci, p.C1, p.N2);
     ACH_REQUIRE(aligned16(w1_hi) && aligned16(w1_lo) && aligned16(w2_hi) && aligned16(w2_lo), "ach_up_ghost_pw2_tc: weight tiles must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (p.Ci) {
-        case 16: return launch_up_ghost_pw2_tc<16>(p, w1_hi, w1_lo, w2_hi, w2_lo, st);
-        case 24: return launch_up_ghost_pw2_tc<24>(p, w1_hi, w1_lo, w2_hi, w2_lo, st);
-        default: return launch_up_ghost_pw2_tc<32>(p, w1_hi, w1_lo, w2_hi, w2_lo, st);
+        case 16: return launch_up_ghost_pw2_tc<16>(p, w1_hi, w1_lo, w2_hi, w2_lo, dw_host, st);
+        case 24: return launch_up_ghost_pw2_tc<24>(p, w1_hi, w1_lo, w2_hi, w2_lo, dw_host, st);
+        default: return launch_up_ghost_pw2_tc<32>(p, w1_hi, w1_lo, w2_hi, w2_lo, dw_host, st);
     }
 }

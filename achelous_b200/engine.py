@@ -1062,7 +1062,10 @@ class Engine:
                             self._keep += [hi, lo]
                             self.pack_ops.append((self.lib.ach_pack_pw_tc, (wt_.data_ptr(), K_, O_, wt_.shape[-1], hi.data_ptr(), lo.data_ptr())))
                             tiles += [hi.data_ptr(), lo.data_ptr()]
-                        self._add(n + ".up_ghost_pw2", self.lib.ach_up_ghost_pw2_tc, C.byref(u), *tiles, nbytes=nb_u)
+                        # depthwise taps + affines as kernel parameters (host array [Ci][12]: 9 taps, s2, b2, b1)
+                        dwh = self._h(n + ".chain.dw", (lambda w2f=w2f, s2f=s2f, b2f=b2f, b1f=b1f: torch.cat(
+                            [w2f(), s2f()[:, None], b2f()[:, None], b1f()[:, None]], 1)))
+                        self._add(n + ".up_ghost_pw2", self.lib.ach_up_ghost_pw2_tc, C.byref(u), *tiles, dwh, nbytes=nb_u)
                     else:
                         self._add(n + ".up_ghost_pw2", self.lib.ach_up_ghost_pw2, C.byref(u), nbytes=nb_u)
                     chained_v = vn

@@ -269,7 +269,7 @@ def main():
                 width, dtype = probe.packed_out.shape[1], probe.packed_out.dtype
                 if gather_mode[0] == "peer":
                     try:
-                        self.pg = PeerGather(B, width, dtype, dev)
+                        self.pg = PeerGather(B, width, dtype, dev, copy_streams=int(os.environ.get("ACH_PEER_STREAMS", "2")))
                     except Exception as e:                                        # no IPC / no peer access on this box: say so, use NCCL
                         gather_mode[:] = ["nccl", f"{type(e).__name__}: {e}"[:200]]
                     flag = torch.tensor([1 if self.pg is not None else 0], device=dev)

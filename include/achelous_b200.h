@@ -380,9 +380,13 @@ typedef struct AchUpGhostPw2 {
 ACH_API int ach_up_ghost_pw2_supported(int ci, int c1, int n2);
 ACH_API int ach_up_ghost_pw2(const AchUpGhostPw2* p, void* stream);
 /* Same stage with the two 1x1 convolutions on tcgen05 (3xTF32): w1_hi/lo = ach_pack_pw_tc tiles of w1t (K = 2*Ci, O = 32,
- * ldw = 32), w2_hi/lo = tiles of w2t (K = 32, O = 16, ldw = 16); the struct's w1t / w2t fields are ignored. */
+ * ldw = 32), w2_hi/lo = tiles of w2t (K = 32, O = 16, ldw = 16); the struct's w1t / w2t fields are ignored.  The depthwise
+ * stage's per-channel weights travel as KERNEL PARAMETERS: dw_host is a HOST array [Ci][12] = (9 taps of w2, s2, b2, b1) per
+ * channel, read at launch time (a captured CUDA graph therefore bakes them in: re-capture after changing them); the struct's
+ * device arrays b1 / w2 / s2 / b2 are ignored. */
 ACH_API int ach_up_ghost_pw2_tc_supported(int ci, int c1, int n2);
 ACH_API int ach_up_ghost_pw2_tc(const AchUpGhostPw2* p, const float* w1_hi, const float* w1_lo, const float* w2_hi, const float* w2_lo,
+                                const float* dw_host,
                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------

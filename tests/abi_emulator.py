@@ -496,10 +496,12 @@ def ach_up_ghost_pw2(s):
     fview(s.out, (B, N2, 2 * h, 2 * w), (s.out_bs, 4 * h * w, 2 * w, 1)).copy_(o)
 
 
-def ach_up_ghost_pw2_tc(s, w1_hi, w1_lo, w2_hi, w2_lo):
+def ach_up_ghost_pw2_tc(s, w1_hi, w1_lo, w2_hi, w2_lo, dw_host):
     w1 = _tc_unpack(w1_hi, w1_lo, 2 * s.Ci, s.C1).contiguous()
     w2 = _tc_unpack(w2_hi, w2_lo, s.C1, s.N2).contiguous()
-    ach_up_ghost_pw2(_Shim(s, w1t=w1.data_ptr(), w2t=w2.data_ptr()))
+    dw = fview(dw_host, (s.Ci, 12), (12, 1))           # HOST array: 9 taps, s2, b2, b1 per channel (kernel parameters)
+    w2d, s2, b2, b1 = dw[:, :9].contiguous(), dw[:, 9].contiguous(), dw[:, 10].contiguous(), dw[:, 11].contiguous()
+    ach_up_ghost_pw2(_Shim(s, w1t=w1.data_ptr(), w2t=w2.data_ptr(), w2=w2d.data_ptr(), s2=s2.data_ptr(), b2=b2.data_ptr(), b1=b1.data_ptr()))
 
 
 def ach_up_ghost_head(s):

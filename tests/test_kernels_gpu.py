@@ -803,12 +803,14 @@ def test_up_ghost_pw2_tc(Ci, h, w):
             A.new(nm, torch.zeros(sz))
         s = AchUpGhostPw2()
         s.v, s.v_bs, s.out, s.out_bs = A.ptr("v", h * w), (Ci + 1) * h * w, A.ptr("out"), N2 * 4 * h * w
-        for n in ("b1", "w2", "s2", "b2", "c1"):
+        for n in ("b1", "w2", "s2", "b2", "c1"):          # (the tensor-core entry reads c1 only; the emulator checks dw_host against the rest)
             setattr(s, n, A.ptr(n))
+        # depthwise weights as kernel parameters: HOST array [Ci][12] = 9 taps, s2, b2, b1
+        A.new("dw", torch.cat([A.t["w2"].cpu(), A.t["s2"].cpu()[:, None], A.t["b2"].cpu()[:, None], A.t["b1"].cpu()[:, None]], 1), host=True)
         s.B, s.Ci, s.C1, s.N2, s.h, s.w = B, Ci, C1, N2, h, w
         return [("ach_pack_pw_tc", (A.ptr("w1t"), 2 * Ci, C1, C1, A.ptr("h1"), A.ptr("l1"))),
                 ("ach_pack_pw_tc", (A.ptr("w2t"), C1, N2, N2, A.ptr("h2"), A.ptr("l2"))),
-                ("ach_up_ghost_pw2_tc", (s, A.ptr("h1"), A.ptr("l1"), A.ptr("h2"), A.ptr("l2")))]
+                ("ach_up_ghost_pw2_tc", (s, A.ptr("h1"), A.ptr("l1"), A.ptr("h2"), A.ptr("l2"), A.ptr("dw")))]
     run_seq(make, ["out"])
 
 

@@ -1,0 +1,86 @@
+"""Which launch stops being reproducible when OTHER kernels share the GPU with it?  Runs a victim op sequence of the B = 64 plan over and
+over on one stream while a noise op sequence loops on a second stream, and compares exact checksums of every plan buffer.
+
+    python tools/op_race_probe.py --victim pn.fstn.fill,pn.fstn.c3max --noise rc0.deform [--iters 300]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from achelous_b200 import _lib  # noqa: E402
+from achelous_b200.nets.Achelous import Achelous  # noqa: E402
+from achelous_b200.synthetic import make_inputs  # noqa: E402
+from achelous_b200.weights import fill_state_dict  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--victim", required=True)
+    ap.add_argument("--noise", default="")
+    ap.add_argument("--iters", type=int, default=300)
+    ap.add_argument("--noise-reps", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=64)
+    a = ap.parse_args()
+    kw = dict(num_det=7, num_seg=9, phi="S0", resolution=320, backbone="en", neck="gdf", pc_seg="pn", pc_channels=5, pc_classes=8,
+              nano_head=True, spp=True)
+    model = Achelous(**kw).eval()
+    model.load_state_dict(fill_state_dict(model.state_dict(), seed=0))
+    model.use_cuda_graph = False
+    model = model.cuda()
+    x, xr, pc = [t.cuda() for t in make_inputs(a.batch, seed=1234)]
+    model(x, xr, pc)
+    eng = next(iter(model._engines.values()))
+    eng.multi_stream = False
+    eng.forward_static()          # every buffer holds its single-stream value
+    torch.cuda.synchronize()
+    names = [n for n in eng._bufs if not n.startswith("in.")]
+    bufs = [eng._bufs[n] for n in names]
+    for i, t in enumerate(eng._keep):
+        if isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.dim() == 2 and t.shape[0] == a.batch and t.numel() < (1 << 22):
+            names.append(f"keep[{i}]{tuple(t.shape)}")
+            bufs.append(t)
+
+    def sums():
+        return torch.stack([b.contiguous().view(torch.int32).sum(dtype=torch.int64) for b in bufs])
+
+    def run(ops, stream):
+        for n in ops:
+            i = eng.op_names.index(n)
+            fn, args = eng.ops[i]
+            _lib.check(fn(*args, stream.cuda_stream), n)
+
+    def expand(spec):      # names, or prefixes ending in '*'
+        out = []
+        for tok in [t for t in spec.split(",") if t]:
+            out += [n for n in eng.op_names if n.startswith(tok[:-1])] if tok.endswith("*") else [tok]
+        return out
+    victim = expand(a.victim)
+    noise = expand(a.noise)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(sa):
+        run(victim, sa)
+        ref = sums()
+    torch.cuda.synchronize()
+    bad = {}
+    for it in range(a.iters):
+        if noise:
+            with torch.cuda.stream(sb):
+                for _ in range(a.noise_reps):
+                    run(noise, sb)
+        with torch.cuda.stream(sa):
+            run(victim, sa)
+            s = sums()
+        torch.cuda.synchronize()
+        for i in (s != ref).nonzero().flatten().tolist():
+            bad.setdefault(names[i], []).append(it)
+    tag = f"victim {a.victim} | noise {a.noise}"
+    if not bad:
+        print(f"OK   {tag}: {a.iters} runs identical")
+    else:
+        print(f"RACE {tag}: " + ", ".join(f"{n} x{len(v)}" for n, v in bad.items()))
+
+
+if __name__ == "__main__":
+    main()
