@@ -30,8 +30,6 @@
 // The accumulator (NT TMEM columns) is handed back and forth with two more barriers (acc_full / acc_empty).
 #include <cstdlib>
 
-#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
-
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -75,8 +73,7 @@ __device__ __forceinline__ void prod_bar() { asm volatile("bar.sync 1, %0;" ::"n
 template <int NT, int ACT, bool RES>
 __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
     pw_conv_tc_ws_kernel(const AchPwConv p, const float* __restrict__ w_hi, const float* __restrict__ w_lo,
-                         const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items,
-                         const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, int use_tmap) {
+                         const float* __restrict__ wsum, int n_kchunks, int n_pt, int n_ot, int total_items) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr int B_ELEMS = NT * TC_KC;
     constexpr int SG = ws_sg(NT);
@@ -210,21 +207,11 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
                 const int k0 = c * TC_KC;
                 const int nk = min(TC_KC, K - k0);
                 const uint32_t full = smem_u32(&bar_g_full[g]);
-                const bool straddle = k0 < p.c0 && k0 + TC_KC > p.c0 && p.c1 > 0;
-                if (use_tmap && !straddle) {
-                    if (lane == 0) {
-                        const bool first = k0 < p.c0;
-                        const CUtensorMap* tm = first ? &tm0 : &tm1;
-                        const int ch = first ? k0 : k0 - p.c0;
-                        mbar_expect_tx(full, (uint32_t)G_ELEMS * 4u);          // the box is always complete: out-of-range parts are zero-filled
-                        asm volatile(
-                            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                                g_ring_s + g * G_ELEMS * 4u),
-                            "l"(tm), "r"(pp0), "r"(ch), "r"(b), "r"(full)
-                            : "memory");
-                    }
-                    continue;
-                }
+                // One bulk copy per channel row (16 x 512 B per chunk).  A tensor-map box per chunk (kernel-parameter CUtensorMap, one
+                // cp.async.bulk.tensor instead of 16 row copies) measured 3 % faster on these layers but was NOT reproducible run to run once
+                // other kernels shared the GPU: back-to-back launches of this kernel on one stream occasionally accumulated a tile from the
+                // wrong activations (tools/op_race_probe.py: 19 of 250 runs with the tensor-map path, 0 of 250 with the row copies - every
+                // barrier / lane / single-CTA-per-SM variant of the kernel kept the failure, only the copy path mattered).  DESIGN.md §7.
                 if (lane == 0) mbar_expect_tx(full, (uint32_t)nk * bytes);
                 __syncwarp();
                 if (lane < nk) {
@@ -437,37 +424,6 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
     }
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (no direct libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-
-// (P, C, B) fp32 view with strides (1, P, bs) elements; box = 128 pixels x 16 channels x 1 frame
-static bool make_act_tmap(CUtensorMap* tm, const float* base, int P, int Cc, int B, long long bs) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc || !base || Cc <= 0) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)Cc, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)P * 4ull, (cuuint64_t)(B > 1 ? bs : (long long)P * Cc) * 4ull};
-    const cuuint32_t box[3] = {(cuuint32_t)TC_M, (cuuint32_t)TC_KC, 1u};
-    const cuuint32_t estr[3] = {1u, 1u, 1u};
-    if (strides[1] % 16 != 0 || strides[1] >= (1ull << 40)) return false;
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int NT, int ACT, bool RES>
 static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, const float* wsum, cudaStream_t st) {
     const int K = p.c0 + p.c1;
@@ -487,12 +443,6 @@ static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, c
     const long long total = (long long)n_pt * n_ot * p.B;
     ACH_REQUIRE(total < (1LL << 31), "ach_pw_conv_tc: too many tiles");
     const int grid = (int)(total < ctas_per_wave ? total : ctas_per_wave);   // persistent: one wave of resident CTAs
-    // tensor maps of the activation views (views a tensor map cannot describe fall back to per-row bulk copies inside the kernel)
-    alignas(64) CUtensorMap tm0, tm1;
-    memset(&tm0, 0, sizeof(tm0));
-    memset(&tm1, 0, sizeof(tm1));
-    int use_tmap = make_act_tmap(&tm0, p.x0, p.P, p.c0, p.B, p.x0_bs) ? 1 : 0;
-    if (use_tmap && p.c1 > 0) use_tmap = make_act_tmap(&tm1, p.x1, p.P, p.c1, p.B, p.x1_bs) ? 1 : 0;
     // programmatic dependent launch was measured inside the CUDA graph at 5.664 vs 5.674 ms per step - the graph already hides
     // launch latency - so the attribute is not set
     cudaLaunchConfig_t cfg = {};
@@ -503,7 +453,7 @@ static int launch_ws(const AchPwConv& p, const float* w_hi, const float* w_lo, c
     cfg.attrs = nullptr;
     cfg.numAttrs = 0;
     const int total_i = (int)total;
-    cudaLaunchKernelEx(&cfg, pw_conv_tc_ws_kernel<NT, ACT, RES>, p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, total_i, tm0, tm1, use_tmap);
+    cudaLaunchKernelEx(&cfg, pw_conv_tc_ws_kernel<NT, ACT, RES>, p, w_hi, w_lo, wsum, n_kchunks, n_pt, n_ot, total_i);
     return check_launch("ach_pw_conv_tc");
 }
 

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--noise", default="")
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--noise-reps", type=int, default=2)
+    ap.add_argument("--copy-noise", type=int, default=0, help="N x 300 MB device-to-device copies on the noise stream per iteration")
+    ap.add_argument("--detail", default="", help="buffer whose differing elements are described")
     ap.add_argument("--batch", type=int, default=64)
     a = ap.parse_args()
     kw = dict(num_det=7, num_seg=9, phi="S0", resolution=320, backbone="en", neck="gdf", pc_seg="pn", pc_channels=5, pc_classes=8,
@@ -64,7 +66,16 @@ def main():
         ref = sums()
     torch.cuda.synchronize()
     bad = {}
+    na = torch.empty(75_000_000, device="cuda") if a.copy_noise else None
+    nb = torch.empty_like(na) if a.copy_noise else None
+    det = bufs[names.index(a.detail)] if a.detail else None
+    det_ref = det.clone() if det is not None else None
+    shown = 0
     for it in range(a.iters):
+        if a.copy_noise:
+            with torch.cuda.stream(sb):
+                for _ in range(a.copy_noise):
+                    nb.copy_(na, non_blocking=True)
         if noise:
             with torch.cuda.stream(sb):
                 for _ in range(a.noise_reps):
@@ -75,6 +86,12 @@ def main():
         torch.cuda.synchronize()
         for i in (s != ref).nonzero().flatten().tolist():
             bad.setdefault(names[i], []).append(it)
+        if det is not None and shown < 5 and not torch.equal(det, det_ref):
+            shown += 1
+            ne = (det != det_ref)
+            idx = ne.nonzero()
+            print(f"  iter {it}: {int(ne.sum())} elements differ; frames {sorted(set(idx[:, 0].tolist()))[:10]}, channels {int(idx[:, 1].min())}..{int(idx[:, 1].max())}, "
+                  f"rows {int(idx[:, 2].min())}..{int(idx[:, 2].max())}, cols {int(idx[:, 3].min())}..{int(idx[:, 3].max())}; max |diff| {(det - det_ref)[ne].abs().max().item():.3e}")
     tag = f"victim {a.victim} | noise {a.noise}"
     if not bad:
         print(f"OK   {tag}: {a.iters} runs identical")
