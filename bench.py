@@ -552,7 +552,7 @@ def measure_dominant(eng, K, torch):
     ms = e0.elapsed_time(e1) / K
     traffic = None
     # dram__bytes_read+write of this launch from the newest committed `ncu --set full` capture that holds it
-    for name in ("r2_traffic.json", "r1s2_traffic.json", "r1_traffic.json"):
+    for name in ("r2_final_traffic.json", "r2_traffic.json", "r1s2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 traffic = json.load(f).get(eng.op_names[top], {}).get("dram_bytes")

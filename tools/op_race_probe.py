@@ -90,8 +90,21 @@ def main():
             shown += 1
             ne = (det != det_ref)
             idx = ne.nonzero()
-            print(f"  iter {it}: {int(ne.sum())} elements differ; frames {sorted(set(idx[:, 0].tolist()))[:10]}, channels {int(idx[:, 1].min())}..{int(idx[:, 1].max())}, "
-                  f"rows {int(idx[:, 2].min())}..{int(idx[:, 2].max())}, cols {int(idx[:, 3].min())}..{int(idx[:, 3].max())}; max |diff| {(det - det_ref)[ne].abs().max().item():.3e}")
+            W_ = det.shape[3]
+            pix = (idx[:, 2] * W_ + idx[:, 3])
+            lanes = sorted(set((pix % 128).tolist()))
+            runs, st = [], None
+            for v in lanes + [None]:
+                if st is None:
+                    st = prev = v
+                elif v is not None and v == prev + 1:
+                    prev = v
+                else:
+                    runs.append(f"{st}-{prev}")
+                    st = prev = v
+            print(f"  iter {it}: {int(ne.sum())} elements differ; frames {sorted(set(idx[:, 0].tolist()))[:10]}, channels {int(idx[:, 1].min())}..{int(idx[:, 1].max())} "
+                  f"({len(set(idx[:, 1].tolist()))} distinct), pixel tiles {sorted(set((pix // 128).tolist()))}, pixel-in-tile runs {runs}; "
+                  f"max |diff| {(det - det_ref)[ne].abs().max().item():.3e}; ref {det_ref[ne][:3].tolist()} cur {det[ne][:3].tolist()}")
     tag = f"victim {a.victim} | noise {a.noise}"
     if not bad:
         print(f"OK   {tag}: {a.iters} runs identical")
