@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
                     if (elected) {
 #pragma unroll
                         for (int ks = 0; ks < TC_KC / 8; ++ks) {
-                            const uint32_t ah = a_hi_t + (uint32_t)ks * 8u, al = a_lo_t + (uint32_t)ks * 8u;
+                            // NT = 128 (two producer threads per pixel): K-step ks of the stage is [hi 8 | lo 8] at column 16 * ks, written by
+                            // half ks with ONE 16-column store; one thread per pixel: [hi 16 | lo 16]
+                            const uint32_t ah = HALVES == 2 ? a_hi_t + (uint32_t)ks * 16u : a_hi_t + (uint32_t)ks * 8u;
+                            const uint32_t al = HALVES == 2 ? ah + 8u : a_lo_t + (uint32_t)ks * 8u;
                             const uint64_t off = (uint64_t)((ks * 2 * B_LBO) >> 4);   // the descriptor's address field counts 16-byte units
                             mma_tf32_ts(tmem_u, ah, dh + off, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                             mma_tf32_ts(tmem_u, al, dh + off, idesc, 1u);
@@ -286,11 +289,21 @@ __global__ void __launch_bounds__(ws_threads(NT), NT == 128 ? 2 : 3)
                     hi[e] = __float_as_uint(v0[e]) & 0xffffe000u;
                     lo[e] = __float_as_uint(v0[e] - __uint_as_float(hi[e]));
                 }
-                const uint32_t a_t = t_lane + (uint32_t)(A_COL0 + sa * 32 + half * KPT);
                 if constexpr (KPT == 8) {
-                    tmem_st8(a_t, hi);
-                    tmem_st8(a_t + 16u, lo);
+                    // The two threads of a pixel (warps w and w + 4) write the SAME tensor-memory lanes at the same time.  With their
+                    // columns interleaved ([hi h0 | hi h1 | lo h0 | lo h1], two 8-column stores each) one warp's store occasionally did
+                    // not land when both were released by the same late activation chunk: 32 pixels x all outputs of one tile wrong
+                    // (17 of 2 500 isolated launches under HBM-saturating copy traffic, tools/op_race_probe.py; only the NT = 128 build).
+                    // Each half now owns one contiguous, 16-column aligned block [hi 8 | lo 8] = exactly one MMA K-step, one store.
+                    uint32_t hl[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        hl[e] = hi[e];
+                        hl[8 + e] = lo[e];
+                    }
+                    tmem_st16(t_lane + (uint32_t)(A_COL0 + sa * 32 + half * 16), hl);
                 } else {
+                    const uint32_t a_t = t_lane + (uint32_t)(A_COL0 + sa * 32);
                     tmem_st16(a_t, hi);
                     tmem_st16(a_t + 16u, lo);
                 }
