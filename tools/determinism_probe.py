@@ -20,6 +20,9 @@ def main():
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--backbone", default="en")
+    ap.add_argument("--phi", default="S0")
+    ap.add_argument("--neck", default="gdf")
+    ap.add_argument("--pc-seg", default="pn")
     ap.add_argument("--copy-noise", action="store_true")
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--merge-lanes", default="", help="e.g. '2>0,3>0': ops of lane 2 / 3 are issued on lane 0 instead (bisecting which overlap matters)")
@@ -29,7 +32,7 @@ def main():
     ap.add_argument("--single-stream", action="store_true", help="eager launches on ONE stream (no lanes): separates missing cross-lane "
                     "dependencies from races inside a kernel")
     a = ap.parse_args()
-    kw = dict(num_det=7, num_seg=9, phi="S0", resolution=320, backbone=a.backbone, neck="gdf", pc_seg="pn", pc_channels=5, pc_classes=8,
+    kw = dict(num_det=7, num_seg=9, phi=a.phi, resolution=320, backbone=a.backbone, neck=a.neck, pc_seg=a.pc_seg, pc_channels=5, pc_classes=8,
               nano_head=True, spp=True)
     model = Achelous(**kw).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=0))
