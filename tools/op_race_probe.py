@@ -24,8 +24,12 @@ def main():
     ap.add_argument("--copy-noise", type=int, default=0, help="N x 300 MB device-to-device copies on the noise stream per iteration")
     ap.add_argument("--detail", default="", help="buffer whose differing elements are described")
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--backbone", default="en")
+    ap.add_argument("--phi", default="S0")
+    ap.add_argument("--neck", default="gdf")
+    ap.add_argument("--pc-seg", default="pn")
     a = ap.parse_args()
-    kw = dict(num_det=7, num_seg=9, phi="S0", resolution=320, backbone="en", neck="gdf", pc_seg="pn", pc_channels=5, pc_classes=8,
+    kw = dict(num_det=7, num_seg=9, phi=a.phi, resolution=320, backbone=a.backbone, neck=a.neck, pc_seg=a.pc_seg, pc_channels=5, pc_classes=8,
               nano_head=True, spp=True)
     model = Achelous(**kw).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=0))
