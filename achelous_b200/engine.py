@@ -1143,7 +1143,7 @@ class Engine:
         added by the kernel (tensor-core path), False when the caller still has to add it"""
         sc = self._vec(name + ".s", lambda: self._bn_fold(prefix + ".bn", 1e-3)[0])
         bi = self._vec(name + ".b", lambda: self._bn_fold(prefix + ".bn", 1e-3)[1])
-        if self.model.use_tensor_cores and x.C >= 12:   # below ~12 input channels the 16-wide K chunks are mostly padding
+        if self.model.use_tensor_cores and getattr(self.model, "conv3_tensor_cores", True) and x.C >= 12:   # below ~12 input channels the 16-wide K chunks are mostly padding
             self.conv3_tc(name, x, out, prefix + ".conv.weight", scale=sc, bias=bi, act=act, res=res)
             return True
         self.conv(name, x, out, self._pack_conv(name + ".w", prefix + ".conv.weight"), 3, 1, 1, scale=sc, bias=bi, act=act)
@@ -1204,11 +1204,12 @@ class Engine:
         sa_se = self.shuffle_attention("fpn.sa_se", prefix + ".stage_3_semantic_seg", f3)
         self.taps.update({"neck.spp": f5, "neck.fpn4": f4, "neck.fpn3": f3, "neck.sa_lane": sa_lane, "neck.sa_se": sa_se})
         self.wait(6, 0)                    # the fusion + detection lane forks here: it needs the FPN maps, not the decoders
-        self.cur_lane = 3                  # the two decoders are independent of each other
-        self.wait(3, 0)
+        # The two decoders share lane 0 here (the Ghost neck runs them on two lanes): with the lane decoder on its own lane 2 of 1 500
+        # graph replays under HBM-saturating copy traffic differed in a 1x1-conv tile of one decoder while the other decoder's
+        # conv3x3_tc launches shared the SMs; on one lane - or with the 3x3 convs on CUDA cores - 1 500 of 1 500 were identical
+        # (tools/determinism_probe.py --neck cdf).  Reproducibility first: the interaction is not understood yet.
         self.seg_decoder_csp("lane", prefix, sa_lane, w, out_lane)
         self._seg_finish("lane", out_lane)
-        self.cur_lane = 0
         self.seg_decoder_csp("se", prefix, sa_se, w, out_se)
         self._seg_finish("se", out_se)
         return (f5, m5), (f4, m4), (f3, m3)

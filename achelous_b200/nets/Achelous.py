@@ -41,6 +41,7 @@ class _AchelousBase(nn.Module):
         self.use_tensor_cores = True   # 1x1 convs / Linears on tcgen05 (3xTF32, fp32-accurate); False: fp32 CUDA-core GEMM
         self.rc_tensor_cores = True    # RCBlock contractions on tcgen05 for C in {3, 8, 12, 16} (needs use_tensor_cores); False: SIMT kernel
         self.seg_tensor_cores = True   # chained decoder stages: the two 1x1 convs of ach_up_ghost_pw2 on tcgen05 (needs use_tensor_cores)
+        self.conv3_tensor_cores = True  # dense 3x3 convs (CSP neck, MobileViT) as implicit GEMMs on tcgen05; False: conv_dense (CUDA cores)
         self.fuse_seg_decoder = True   # False: block-by-block decoder (keeps every reference intermediate)
         self.fuse_seg_chain = True     # decoder stages chained through ach_up_ghost_pw2 (no full-width maps in HBM)
         self.fuse_mlp = True           # LN -> Linear(4C) -> GELU -> Linear -> gamma -> + res as ONE tcgen05 launch (hidden tile in tensor memory)

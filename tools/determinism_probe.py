@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--merge-lanes", default="", help="e.g. '2>0,3>0': ops of lane 2 / 3 are issued on lane 0 instead (bisecting which overlap matters)")
     ap.add_argument("--only", default="", help="comma separated op-name prefixes: launch ONLY these ops (e.g. 'pn.,rc0.') - inputs of the others keep "
                     "the values of the first full run")
+    ap.add_argument("--no-conv3-tc", action="store_true", help="dense 3x3 convs on conv_dense (CUDA cores) instead of conv3x3_tc")
     ap.add_argument("--detail", default="", help="buffer name (as printed) whose differing elements are described")
     ap.add_argument("--single-stream", action="store_true", help="eager launches on ONE stream (no lanes): separates missing cross-lane "
                     "dependencies from races inside a kernel")
@@ -37,6 +38,7 @@ def main():
     model = Achelous(**kw).eval()
     model.load_state_dict(fill_state_dict(model.state_dict(), seed=0))
     model.use_cuda_graph = not (a.eager or a.single_stream)
+    model.conv3_tensor_cores = not a.no_conv3_tc
     model = model.cuda()
     x, xr, pc = [t.cuda() for t in make_inputs(a.batch, seed=1234)]
     model(x, xr, pc)
