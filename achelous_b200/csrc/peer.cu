@@ -18,14 +18,29 @@ __global__ void peer_signal_kernel(unsigned* const* flags, int n, unsigned value
     }
 }
 
+// A peer that died never raises its flag: after PEER_WAIT_LIMIT_NS the kernel traps (sticky CUDA error on this context - the
+// process fails loudly at its next synchronisation and the launcher tears the job down) instead of spinning forever on the GPU.
+constexpr unsigned long long PEER_WAIT_LIMIT_NS = 60ull * 1000ull * 1000ull * 1000ull;
+
 __global__ void peer_wait_kernel(const unsigned* flags, int n, unsigned value) {
     const int i = threadIdx.x;
     if (i < n) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         unsigned v;
+        unsigned spins = 0;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
             if ((int)(v - value) >= 0) break;
             __nanosleep(200);
+            if ((++spins & 0xfffu) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > PEER_WAIT_LIMIT_NS) {
+                    printf("ach_peer_wait: flag %d still %u after 60 s (waiting for %u) - a peer rank is gone\n", i, v, value);
+                    __trap();
+                }
+            }
         } while (true);
     }
 }

@@ -475,7 +475,8 @@ ACH_API int ach_pre_points(const double* feat, int n_rows, int C, const int* idx
  * transfer between such pointers (no SM work).  ach_peer_signal: after everything earlier on `stream`, store `value` (release,
  * system scope) to flags[i] for i < n (n <= 64; `flags` is a DEVICE array of pointers, usually into peers' allocations; NULL
  * entries are skipped).  ach_peer_wait: the stream does not advance until local words flags[0..n) have all reached `value`
- * (wrap-safe signed comparison; acquire, system scope; one spinning warp). */
+ * (wrap-safe signed comparison; acquire, system scope; one spinning warp; a word that has not arrived after 60 s traps
+ * the kernel - a sticky CUDA error instead of a GPU that spins forever on a dead peer). */
 ACH_API int ach_peer_alloc(long long bytes, void** ptr);
 ACH_API int ach_peer_free(void* ptr);
 ACH_API int ach_peer_handle_bytes(void);
