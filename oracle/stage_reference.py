@@ -37,8 +37,11 @@ def stage(verbose=True):
         os.makedirs(os.path.dirname(os.path.join(DST, rel)), exist_ok=True)
         shutil.copyfile(os.path.join(SRC, rel), os.path.join(DST, rel))
     n = 0
-    for root, _, files in os.walk(DST):      # byte-for-byte: the staged copy IS the reference
+    for root, dirs, files in os.walk(DST):      # byte-for-byte: the staged copy IS the reference
+        dirs[:] = [d for d in dirs if d != "__pycache__"]     # (left behind by importing the staged copy)
         for f in files:
+            if f == "STAGED_FROM" or f.endswith(".pyc"):      # this recipe's own marker from an earlier run
+                continue
             rel = os.path.relpath(os.path.join(root, f), DST)
             assert filecmp.cmp(os.path.join(DST, rel), os.path.join(SRC, rel), shallow=False), rel
             n += 1
