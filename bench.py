@@ -117,8 +117,10 @@ class CpuForward:
             try:
                 from oracle.ref_loader import load_reference, reference_available, reference_kind
                 if reference_available():
-                    ns = load_reference()
-                    m = ns.Achelous(**kw).eval()
+                    import contextlib
+                    with contextlib.redirect_stdout(sys.stderr):    # the reference's imports print hints: stdout carries ONE JSON line
+                        ns = load_reference()
+                        m = ns.Achelous(**kw).eval()
                     m.load_state_dict(self.sd, strict=True)
                     self.model, self.kind = m.eval(), "reference"
                     self.how = f"unmodified reference nets/Achelous.py:49-53 ({reference_kind()}), PyTorch CPU fp32, torch.no_grad()"

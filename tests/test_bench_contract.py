@@ -14,6 +14,8 @@ def _run(env_extra, *extra):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", *extra],
                          capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
+    # stdout carries the JSON line and nothing else (the reference's imports print install hints: they belong on stderr)
+    assert all(ln.startswith("{") for ln in out.stdout.splitlines() if ln.strip()), out.stdout[:500]
     return [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
 
 
